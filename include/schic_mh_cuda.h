@@ -1,0 +1,74 @@
+/*
+ * schic_mh_cuda.h -- entry points only the CUDA library (libschic_mh.so) exports, on top of
+ * include/schic_mh.h. They take DEVICE pointers (plain addresses, no torch types) so that
+ *   - bench.py can time the path with inputs already resident in HBM,
+ *   - the multi-GPU host layer (one process per GPU) can all-gather signatures / CSR shards with
+ *     NCCL through torch.distributed and hand the gathered buffers back to the kernels.
+ * The reference has no counterpart: scHiCExplorer never enables upstream's GPU flags
+ * (no gpu_hashing kwarg at scHicClusterMinHash.py:347-348, 402-404); these calls serve the same
+ * MinHash.fit / kneighbors sites as schic_mh.h.
+ */
+#ifndef SCHIC_MH_CUDA_H_
+#define SCHIC_MH_CUDA_H_
+
+#include "schic_mh.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Number of visible CUDA devices (0 and SCHIC_OK when there is no driver/GPU). */
+int schic_device_count(int32_t* n_out);
+
+/* MinHash.fit on a CSR shard already in HBM. The arrays are BORROWED (not copied) and must stay
+ * valid until the next fit or destroy. d_indptr [n_rows+1] int64 (absolute positions into
+ * d_indices/d_data), d_indices uint32, d_data float32 (may be NULL when fast=1). append must be 0. */
+int schic_mh_fit_csr_device(schic_mh_handle* h, int64_t n_rows, int64_t nnz, const int64_t* d_indptr,
+                            const uint32_t* d_indices, const float* d_data, int32_t append);
+
+/* MinHash.kneighbors with results left in HBM: d_idx [n_local,k] int32, d_dist [n_local,k] float32,
+ * d_nvalid [n_local] int32. Asynchronous on the handle's stream. */
+int schic_mh_kneighbors_device(schic_mh_handle* h, int32_t k, int32_t fast, int32_t* d_idx, float* d_dist,
+                               int32_t* d_nvalid);
+
+/* Device address of the local signature matrix (uint32 [n_local, H]) -- the send buffer of the
+ * signature all-gather. */
+int schic_mh_signatures_device(schic_mh_handle* h, void** d_sig_out, int64_t* n_rows_out);
+
+/* Distributed query: use an external (all-gathered, borrowed) database of n_total rows; this
+ * handle's local rows are database rows [row0, row0+n_local). d_sig_all uint32 [n_total, H];
+ * the CSR of the whole database (d_indptr_all/d_indices_all/d_data_all) is needed only for the
+ * exact rerank. Passing d_sig_all == NULL returns to the local database. */
+int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t row0, const uint32_t* d_sig_all,
+                                 const int64_t* d_indptr_all, const uint32_t* d_indices_all,
+                                 const float* d_data_all);
+
+/* Run on the caller's stream (a cudaStream_t, e.g. torch's current stream) instead of the
+ * handle's own. NULL selects the legacy default stream. */
+int schic_mh_set_stream(schic_mh_handle* h, void* cuda_stream);
+int schic_mh_synchronize(schic_mh_handle* h);
+
+/* CUDA-event time (ms) of the stages of the most recent fit + kneighbors on this handle:
+ * [0] h2d, [1] signatures (K1), [2] collisions (K3), [3] select, [4] rerank (K4), [5] graph (K5),
+ * [6] d2h, [7] sum. Synchronises the stream. */
+int schic_mh_stage_ms(schic_mh_handle* h, float* out, int32_t n_out);
+
+/* Number of kernels this handle has launched so far. */
+int schic_mh_launch_count(schic_mh_handle* h, int64_t* n_out);
+
+/* INT32 issue-rate micro-benchmark, Tint-op/s: out[0] LOP3, [1] IMAD, [2] 1:1 mix, [3] SM MHz,
+ * [4] SHF, [5] IMAD.HI, [6] VIMNMX, [7] VIMNMX3, [8] IADD; out must hold 12 doubles. */
+int schic_int32_peak(int32_t device, int32_t iters, double* out);
+
+/* Experiment hook: K1 with instruction-selection variant v on device-resident CSR; elapsed ms. */
+int schic_k1_variant_ms(int32_t variant, int64_t n_rows, int64_t nnz, const int64_t* d_indptr,
+                        const uint32_t* d_indices, int32_t n_hash, uint32_t* d_sig, int32_t reps, float* ms_out);
+
+/* Page-locked host memory for the e2e path (numpy arrays are built over it). */
+int schic_pinned_alloc(int64_t bytes, void** out);
+int schic_pinned_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCHIC_MH_CUDA_H_ */

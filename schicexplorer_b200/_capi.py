@@ -1,0 +1,275 @@
+"""ctypes binding of the C ABI declared in ``include/schic_mh.h`` / ``include/schic_mh_cuda.h``.
+
+The product loads exactly one library through :func:`cuda_api`:
+``schicexplorer_b200/csrc/libschic_mh.so`` (hand-written sm_100a kernels). There is no CPU
+fallback: if the library is missing, or no GPU is usable, the call raises. The class
+:class:`CApi` itself is path-agnostic so that the tests can bind the oracle's ``.so`` (which
+exports the same symbols) as the checker; nothing in this package references ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIB_PATH = os.path.join(_HERE, "csrc", "libschic_mh.so")
+
+
+class SchicError(RuntimeError):
+    """A C-ABI call returned a negative status (message from ``schic_mh_last_error``)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"[schic status {status}] {message}")
+        self.status = status
+
+
+class Params(C.Structure):
+    # field order mirrors struct schic_mh_params (include/schic_mh.h)
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("n_neighbors", C.c_int32),
+        ("number_of_hash_functions", C.c_int32),
+        ("hash_width", C.c_int32),
+        ("fast", C.c_int32),
+        ("absolute_numbers", C.c_int32),
+        ("minimal_blocks_in_common", C.c_int32),
+        ("excess_factor", C.c_int32),
+        ("max_bin_size", C.c_int64),
+        ("shingle_size", C.c_int32),
+        ("shingle", C.c_int32),
+        ("number_of_cores", C.c_int32),
+        ("device", C.c_int32),
+    ]
+
+
+# symbols every back end must export (include/schic_mh.h)
+BASE_SYMBOLS = (
+    "schic_mh_create", "schic_mh_destroy", "schic_mh_last_error", "schic_mh_backend",
+    "schic_mh_fit_csr", "schic_mh_n_fitted", "schic_mh_signatures", "schic_mh_collision_counts",
+    "schic_mh_kneighbors", "schic_mh_kneighbors_graph",
+)
+# symbols only the CUDA library exports (include/schic_mh_cuda.h)
+CUDA_SYMBOLS = (
+    "schic_mh_fit_csr_device", "schic_mh_kneighbors_device", "schic_mh_signatures_device",
+    "schic_mh_set_database_device", "schic_mh_set_stream", "schic_mh_stage_ms",
+    "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
+    "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free",
+)
+
+_vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(_vp)
+    return _vp(int(a))  # raw (device) address
+
+
+class CApi:
+    """One loaded back end. All methods raise :class:`SchicError` on a non-zero status."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        self.path = path
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.schic_mh_last_error.restype = C.c_char_p
+        L.schic_mh_backend.restype = C.c_char_p
+        L.schic_mh_create.argtypes = [C.POINTER(Params), C.POINTER(_vp)]
+        L.schic_mh_destroy.argtypes = [_vp]
+        L.schic_mh_fit_csr.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32]
+        L.schic_mh_n_fitted.argtypes = [_vp, C.POINTER(_i64)]
+        L.schic_mh_signatures.argtypes = [_vp, _vp]
+        L.schic_mh_collision_counts.argtypes = [_vp, _i64, _i64, _vp]
+        L.schic_mh_kneighbors.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
+        L.schic_mh_kneighbors_graph.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
+        self.backend = L.schic_mh_backend().decode()
+        self.is_cuda = self.backend == "cuda"
+        if self.is_cuda:
+            L.schic_mh_fit_csr_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _i32]
+            L.schic_mh_kneighbors_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
+            L.schic_mh_signatures_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_i64)]
+            L.schic_mh_set_database_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp]
+            L.schic_mh_set_stream.argtypes = [_vp, _vp]
+            L.schic_mh_stage_ms.argtypes = [_vp, _vp, _i32]
+            L.schic_mh_launch_count.argtypes = [_vp, C.POINTER(_i64)]
+            L.schic_mh_synchronize.argtypes = [_vp]
+            L.schic_int32_peak.argtypes = [_i32, _i32, _vp]
+            L.schic_k1_variant_ms.argtypes = [_i32, _i64, _i64, _vp, _vp, _i32, _vp, _i32, C.POINTER(C.c_float)]
+            L.schic_pinned_alloc.argtypes = [_i64, C.POINTER(_vp)]
+            L.schic_pinned_free.argtypes = [_vp]
+            L.schic_device_count.argtypes = [C.POINTER(_i32)]
+
+    # -- helpers ---------------------------------------------------------------------------
+    def check(self, status: int):
+        if status != 0:
+            raise SchicError(status, self.lib.schic_mh_last_error().decode(errors="replace"))
+
+    def has_symbols(self, names) -> list:
+        missing = []
+        for n in names:
+            try:
+                getattr(self.lib, n)
+            except AttributeError:
+                missing.append(n)
+        return missing
+
+    # -- include/schic_mh.h ----------------------------------------------------------------
+    def create(self, **kw) -> int:
+        p = Params()
+        p.struct_size = C.sizeof(Params)
+        p.n_neighbors = int(kw.get("n_neighbors", 5))
+        p.number_of_hash_functions = int(kw.get("number_of_hash_functions", 400))
+        p.hash_width = int(kw.get("hash_width", 32))
+        p.fast = int(bool(kw.get("fast", False)))
+        p.absolute_numbers = int(bool(kw.get("absolute_numbers", False)))
+        p.minimal_blocks_in_common = int(kw.get("minimal_blocks_in_common", 1))
+        p.excess_factor = int(kw.get("excess_factor", 1))
+        p.max_bin_size = int(kw.get("max_bin_size", 50))
+        p.shingle_size = int(kw.get("shingle_size", 4))
+        p.shingle = int(kw.get("shingle", 0))
+        p.number_of_cores = int(kw.get("number_of_cores", 0) or 0)
+        p.device = int(kw.get("device", -1))
+        h = _vp()
+        self.check(self.lib.schic_mh_create(C.byref(p), C.byref(h)))
+        return h.value
+
+    def destroy(self, h):
+        if h:
+            self.lib.schic_mh_destroy(_vp(h))
+
+    def fit_csr(self, h, indptr, indices, data, append: bool):
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        if indices.dtype.itemsize == 8:
+            indices = np.ascontiguousarray(indices).view(np.uint64)
+            bits = 64
+        else:
+            indices = np.ascontiguousarray(indices).view(np.uint32)
+            bits = 32
+        if data is not None:
+            data = np.ascontiguousarray(data, dtype=np.float32)
+        self.check(self.lib.schic_mh_fit_csr(_vp(h), len(indptr) - 1, _ptr(indptr), _ptr(indices), bits,
+                                             _ptr(data), int(append)))
+
+    def n_fitted(self, h) -> int:
+        n = _i64()
+        self.check(self.lib.schic_mh_n_fitted(_vp(h), C.byref(n)))
+        return n.value
+
+    def signatures(self, h, n_hash: int) -> np.ndarray:
+        out = np.empty((self.n_fitted(h), n_hash), dtype=np.uint32)
+        self.check(self.lib.schic_mh_signatures(_vp(h), _ptr(out)))
+        return out
+
+    def collision_counts(self, h, row0=0, row1=None) -> np.ndarray:
+        n = self.n_fitted(h)
+        row1 = n if row1 is None else row1
+        out = np.empty((row1 - row0, n), dtype=np.uint16)
+        self.check(self.lib.schic_mh_collision_counts(_vp(h), row0, row1, _ptr(out)))
+        return out
+
+    def kneighbors(self, h, k: int, fast: int = -1, n_rows=None):
+        n = self.n_fitted(h) if n_rows is None else n_rows
+        idx = np.empty((n, k), dtype=np.int32)
+        dist = np.empty((n, k), dtype=np.float32)
+        nv = np.empty(n, dtype=np.int32)
+        self.check(self.lib.schic_mh_kneighbors(_vp(h), k, fast, _ptr(idx), _ptr(dist), _ptr(nv)))
+        return idx, dist, nv
+
+    def kneighbors_graph(self, h, k: int, fast: int = -1, n_rows=None):
+        n = self.n_fitted(h) if n_rows is None else n_rows
+        indptr = np.empty(n + 1, dtype=np.int64)
+        indices = np.empty(n * k, dtype=np.int32)
+        data = np.empty(n * k, dtype=np.float32)
+        self.check(self.lib.schic_mh_kneighbors_graph(_vp(h), k, fast, _ptr(indptr), _ptr(indices), _ptr(data)))
+        nnz = int(indptr[-1])
+        return indptr, indices[:nnz], data[:nnz]
+
+    # -- include/schic_mh_cuda.h (device-pointer entry points) -------------------------------
+    def fit_csr_device(self, h, n_rows, nnz, d_indptr, d_indices, d_data, append: bool):
+        self.check(self.lib.schic_mh_fit_csr_device(_vp(h), n_rows, nnz, _ptr(d_indptr), _ptr(d_indices),
+                                                    _ptr(d_data), int(append)))
+
+    def kneighbors_device(self, h, k, fast, d_idx, d_dist, d_nvalid):
+        self.check(self.lib.schic_mh_kneighbors_device(_vp(h), k, fast, _ptr(d_idx), _ptr(d_dist), _ptr(d_nvalid)))
+
+    def signatures_device(self, h):
+        p, n = _vp(), _i64()
+        self.check(self.lib.schic_mh_signatures_device(_vp(h), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def set_database_device(self, h, n_total, row0, d_sig, d_indptr=None, d_indices=None, d_data=None):
+        self.check(self.lib.schic_mh_set_database_device(_vp(h), n_total, row0, _ptr(d_sig), _ptr(d_indptr),
+                                                         _ptr(d_indices), _ptr(d_data)))
+
+    def set_stream(self, h, stream: int):
+        self.check(self.lib.schic_mh_set_stream(_vp(h), _vp(stream)))
+
+    def stage_ms(self, h) -> dict:
+        out = np.zeros(8, dtype=np.float32)
+        self.check(self.lib.schic_mh_stage_ms(_vp(h), _ptr(out), 8))
+        names = ("h2d", "signatures", "collisions", "select", "rerank", "graph", "d2h", "total")
+        return dict(zip(names, out.tolist()))
+
+    def launch_count(self, h) -> int:
+        n = _i64()
+        self.check(self.lib.schic_mh_launch_count(_vp(h), C.byref(n)))
+        return n.value
+
+    def synchronize(self, h):
+        self.check(self.lib.schic_mh_synchronize(_vp(h)))
+
+    def int32_peak(self, device: int = -1, iters: int = 4096) -> dict:
+        """INT32 issue-rate micro-benchmark (Tint-op/s per SASS opcode) -- the roofline denominator."""
+        out = np.zeros(12, dtype=np.float64)
+        self.check(self.lib.schic_int32_peak(device, iters, _ptr(out)))
+        names = ("lop3", "imad", "mix_lop3_imad", "sm_mhz", "shf", "imad_hi", "vimnmx", "vimnmx3", "iadd")
+        return dict(zip(names, out.tolist()))
+
+    def k1_variant_ms(self, variant, n_rows, nnz, d_indptr, d_indices, n_hash, d_sig, reps=3) -> float:
+        ms = C.c_float()
+        self.check(self.lib.schic_k1_variant_ms(variant, n_rows, nnz, _ptr(d_indptr), _ptr(d_indices), n_hash,
+                                                _ptr(d_sig), reps, C.byref(ms)))
+        return ms.value
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array over page-locked host memory (freed when the array is collected)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = _vp()
+        self.check(self.lib.schic_pinned_alloc(n, C.byref(p)))
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        lib, addr = self.lib, p.value
+        import weakref
+        weakref.finalize(buf, lambda: lib.schic_pinned_free(_vp(addr)))
+        return arr
+
+    def device_count(self) -> int:
+        n = _i32()
+        self.check(self.lib.schic_device_count(C.byref(n)))
+        return n.value
+
+
+_cuda_api = None
+_lock = threading.Lock()
+
+
+def cuda_api() -> CApi:
+    """The product back end. Raises if the CUDA library is not built (no fallback)."""
+    global _cuda_api
+    with _lock:
+        if _cuda_api is None:
+            api = CApi(CUDA_LIB_PATH)
+            if not api.is_cuda:
+                raise RuntimeError(f"{CUDA_LIB_PATH} reports backend {api.backend!r}, expected 'cuda'")
+            _cuda_api = api
+    return _cuda_api

@@ -1,0 +1,662 @@
+// capi.cu -- C ABI (include/schic_mh.h, include/schic_mh_cuda.h) over the sm_100a kernels.
+//
+// Host-side orchestration of the hot path: device memory for the fitted set (CSR + signatures),
+// chunked H2D upload overlapped with K1 on a second stream, query blocking of the count matrix,
+// stage timing with CUDA events, and the D2H of the neighbour lists. There is no CPU compute
+// path in this file: without a usable GPU every entry point fails with SCHIC_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/schic_mh_cuda.h"
+#include "common.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            cudaGetLastError();                                                                   \
+            return fail(e__ == cudaErrorMemoryAllocation ? SCHIC_ERR_OOM : SCHIC_ERR_CUDA,        \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                     \
+        }                                                                                         \
+    } while (0)
+
+#define ST_TRY(expr)                \
+    do {                            \
+        int s__ = (expr);           \
+        if (s__ != 0) return s__;   \
+    } while (0)
+
+// Owning device buffer that can grow while keeping its contents.
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    int64_t cap = 0;   // elements
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    int reserve(int64_t n, int64_t keep, cudaStream_t s) {
+        if (n <= cap) return 0;
+        int64_t ncap = std::max<int64_t>(n, cap + cap / 2);
+        T* np = nullptr;
+        CU_TRY(cudaMalloc(&np, (size_t)ncap * sizeof(T)));
+        if (keep > 0 && p) {
+            cudaError_t e = cudaMemcpyAsync(np, p, (size_t)keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { cudaFree(np); return fail(SCHIC_ERR_CUDA, cudaGetErrorString(e)); }
+        }
+        if (p) cudaFree(p);
+        p = np;
+        cap = ncap;
+        return 0;
+    }
+};
+
+enum Stage { ST_H2D = 0, ST_SIG, ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_COUNT };
+
+}  // namespace
+
+struct schic_mh_handle {
+    schic_mh_params p{};
+    int device = 0;
+    cudaStream_t stream = nullptr;       // compute stream
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D uploads overlapped with K1
+    int64_t launches = 0;
+
+    // local fitted rows
+    int64_t n = 0, nnz = 0;
+    bool borrowed = false;
+    const int64_t* b_indptr = nullptr; const uint32_t* b_feat = nullptr; const float* b_val = nullptr;
+    DevBuf<int64_t> indptr; DevBuf<uint32_t> feat; DevBuf<uint32_t> feat_hi; DevBuf<float> val;
+    bool have_val = false, have_hi = false;
+    DevBuf<uint32_t> sig;
+    DevBuf<double> norm2; int64_t norm_rows = 0; const void* norm_of = nullptr;
+
+    // external database (distributed query)
+    bool ext = false;
+    int64_t db_n = 0, db_row0 = 0;
+    const uint32_t* db_sig = nullptr; const int64_t* db_indptr = nullptr;
+    const uint32_t* db_feat = nullptr; const float* db_val = nullptr;
+
+    // scratch of kneighbors
+    DevBuf<uint16_t> counts; DevBuf<int32_t> cand_idx, cand_cnt, cand_nv;
+    DevBuf<int32_t> out_idx, out_nv; DevBuf<float> out_dist;
+    DevBuf<int64_t> g_indptr; DevBuf<int32_t> g_indices; DevBuf<float> g_data;
+
+    // stage timing: accumulated event pairs of the last fit / kneighbors
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[ST_COUNT];
+    std::vector<cudaEvent_t> pool;      // every event ever created (owned)
+    std::vector<cudaEvent_t> free_ev;   // recycled
+    std::vector<cudaEvent_t> misc_ev;   // ordering events of the current fit (not stage timers)
+
+    const int64_t* d_indptr() const { return borrowed ? b_indptr : indptr.p; }
+    const uint32_t* d_feat() const { return borrowed ? b_feat : feat.p; }
+    const float* d_val() const { return borrowed ? b_val : (have_val ? val.p : nullptr); }
+};
+
+namespace {
+
+int use_device(const schic_mh_handle* h) {
+    CU_TRY(cudaSetDevice(h->device));
+    return 0;
+}
+
+cudaEvent_t get_event(schic_mh_handle* h) {
+    if (!h->free_ev.empty()) {
+        cudaEvent_t e = h->free_ev.back();
+        h->free_ev.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    h->pool.push_back(e);
+    return e;
+}
+
+cudaEvent_t get_misc_event(schic_mh_handle* h) {
+    cudaEvent_t e = get_event(h);
+    if (e) h->misc_ev.push_back(e);
+    return e;
+}
+
+struct StageTimer {
+    schic_mh_handle* h; Stage st; cudaStream_t s; cudaEvent_t a;
+    StageTimer(schic_mh_handle* hh, Stage stage, cudaStream_t stream) : h(hh), st(stage), s(stream) {
+        a = get_event(h);
+        if (a) cudaEventRecord(a, s);
+    }
+    ~StageTimer() {
+        cudaEvent_t b = get_event(h);
+        if (a && b) { cudaEventRecord(b, s); h->ev[st].push_back({a, b}); }
+    }
+};
+
+void reset_stage(schic_mh_handle* h, std::initializer_list<Stage> stages) {
+    for (Stage s : stages) {
+        for (auto& pr : h->ev[s]) { h->free_ev.push_back(pr.first); h->free_ev.push_back(pr.second); }
+        h->ev[s].clear();
+    }
+}
+
+int check(const schic_mh_handle* h) {
+    if (!h) return fail(SCHIC_ERR_INVALID_ARG, "null handle");
+    return 0;
+}
+
+void add_launches(schic_mh_handle* h, int n) { if (n > 0) h->launches += n; }
+
+// K1 on rows [r0, r1) of the handle's CSR (positions are absolute in the device arrays).
+int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t pos1, cudaStream_t s) {
+    const int H = h->p.number_of_hash_functions;
+    uint32_t* sig = h->sig.p + r0 * (int64_t)H;
+    int nl;
+    if (h->p.hash_width == 64)
+        nl = schic::launch_signatures64(h->d_indptr() + r0, h->d_feat(), h->have_hi ? h->feat_hi.p : nullptr,
+                                        r1 - r0, pos1 - pos0, pos0, H, sig, s);
+    else
+        nl = schic::launch_signatures32(h->d_indptr() + r0, h->d_feat(), r1 - r0, pos1 - pos0, pos0, H, sig, s);
+    if (nl < 0) return fail(SCHIC_ERR_CUDA, "K1 launch failed");
+    add_launches(h, nl);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const float* val, int64_t rows) {
+    if (h->norm_of == (const void*)indptr && h->norm_rows == rows) return 0;
+    ST_TRY(h->norm2.reserve(rows, 0, h->stream));
+    add_launches(h, schic::launch_row_norms(indptr, val, rows, 0, h->norm2.p, h->stream));
+    CU_TRY(cudaGetLastError());
+    h->norm_of = indptr;
+    h->norm_rows = rows;
+    return 0;
+}
+
+// The whole query side on device. Results land in h->out_idx / out_dist / out_nv ([n, k]) unless
+// caller-provided device outputs are given.
+int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx, float* d_dist, int32_t* d_nv) {
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    if (k < 1) return fail(SCHIC_ERR_INVALID_ARG, "k must be >= 1");
+    const bool fast = fast_arg < 0 ? h->p.fast != 0 : fast_arg != 0;
+    const int H = h->p.number_of_hash_functions;
+    const int64_t nq = h->n;
+    const int64_t ndb = h->ext ? h->db_n : h->n;
+    const int64_t row0 = h->ext ? h->db_row0 : 0;
+    const uint32_t* db_sig = h->ext ? h->db_sig : h->sig.p;
+    const int64_t* db_indptr = h->ext ? h->db_indptr : h->d_indptr();
+    const uint32_t* db_feat = h->ext ? h->db_feat : h->d_feat();
+    const float* db_val = h->ext ? h->db_val : h->d_val();
+    if (ndb >= h->p.max_bin_size)
+        return fail(SCHIC_ERR_UNSUPPORTED, "n_fitted >= max_bin_size: bucket pruning is not built yet");
+    if (k > ndb) k = (int)ndb;   // cannot have more neighbours than fitted rows; outputs keep stride k
+    const int64_t kc64 = fast ? (int64_t)k : std::min<int64_t>((int64_t)k * std::max(1, h->p.excess_factor), ndb);
+    const int kcand = (int)kc64;
+    if (!fast) {
+        if (!db_val || !db_feat) return fail(SCHIC_ERR_INVALID_ARG, "exact rerank needs the CSR values (fit with data)");
+        if (h->have_hi) return fail(SCHIC_ERR_UNSUPPORTED, "exact rerank supports 32-bit feature ids only");
+    }
+    reset_stage(h, {ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H});
+    cudaStream_t s = h->stream;
+
+    ST_TRY(h->cand_idx.reserve(nq * kcand, 0, s));
+    ST_TRY(h->cand_cnt.reserve(nq * kcand, 0, s));
+    ST_TRY(h->cand_nv.reserve(nq, 0, s));
+    if (!d_idx) {
+        ST_TRY(h->out_idx.reserve(nq * k, 0, s));
+        ST_TRY(h->out_dist.reserve(nq * k, 0, s));
+        ST_TRY(h->out_nv.reserve(nq, 0, s));
+        d_idx = h->out_idx.p; d_dist = h->out_dist.p; d_nv = h->out_nv.p;
+    }
+
+    // query blocking: the uint16 count matrix is produced and consumed in row blocks of <= 2 GiB
+    const int64_t ld = (ndb + 7) & ~(int64_t)7;
+    int64_t qb = std::max<int64_t>(128, ((int64_t)1 << 30) / ld);
+    qb = std::min<int64_t>((qb / 128) * 128, (nq + 127) / 128 * 128);
+    ST_TRY(h->counts.reserve(qb * ld, 0, s));
+    for (int64_t q0 = 0; q0 < nq; q0 += qb) {
+        const int64_t q1 = std::min(nq, q0 + qb);
+        {
+            StageTimer t(h, ST_COLL, s);
+            add_launches(h, schic::launch_collision_counts(h->sig.p + q0 * (int64_t)H, q1 - q0, db_sig, ndb, H,
+                                                          h->counts.p, ld, s));
+        }
+        {
+            StageTimer t(h, ST_SELECT, s);
+            const int nl = schic::launch_select_topk(h->counts.p, q1 - q0, ndb, ld, H, h->p.minimal_blocks_in_common,
+                                                     kcand, h->cand_idx.p + q0 * kcand, h->cand_cnt.p + q0 * kcand,
+                                                     h->cand_nv.p + q0, s);
+            if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k * excess_factor too large for the in-shared-memory select");
+            add_launches(h, nl);
+        }
+        CU_TRY(cudaGetLastError());
+    }
+    if (fast) {
+        StageTimer t(h, ST_SELECT, s);
+        add_launches(h, schic::launch_fast_distance(h->cand_idx.p, h->cand_cnt.p, h->cand_nv.p, nq, kcand, k, H,
+                                                   h->p.absolute_numbers, d_idx, d_dist, d_nv, s));
+    } else {
+        StageTimer t(h, ST_RERANK, s);
+        ST_TRY(ensure_norms(h, db_indptr, db_val, ndb));
+        const int nl = schic::launch_rerank(db_indptr, db_feat, db_val, 0, h->norm2.p, row0, nq, h->cand_idx.p,
+                                            h->cand_nv.p, kcand, k, d_idx, d_dist, d_nv, s);
+        if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k * excess_factor too large for the in-shared-memory rerank");
+        add_launches(h, nl);
+    }
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int effective_k(const schic_mh_handle* h, int k) {
+    const int64_t ndb = h->ext ? h->db_n : h->n;
+    return (int)std::min<int64_t>(k, ndb);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* schic_mh_last_error(void) { return g_err.c_str(); }
+const char* schic_mh_backend(void) { return "cuda"; }
+
+int schic_device_count(int32_t* n_out) {
+    if (!n_out) return fail(SCHIC_ERR_INVALID_ARG, "null argument");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *n_out = n;
+    return SCHIC_OK;
+}
+
+int schic_mh_create(const schic_mh_params* p, schic_mh_handle** out) {
+    if (!p || !out) return fail(SCHIC_ERR_INVALID_ARG, "null argument");
+    if (p->struct_size != (int32_t)sizeof(schic_mh_params))
+        return fail(SCHIC_ERR_INVALID_ARG, "schic_mh_params.struct_size mismatch");
+    if (p->number_of_hash_functions < 1 || p->number_of_hash_functions > 65535)
+        return fail(SCHIC_ERR_INVALID_ARG, "number_of_hash_functions must be in [1, 65535]");
+    if (p->hash_width != 32 && p->hash_width != 64) return fail(SCHIC_ERR_INVALID_ARG, "hash_width must be 32 or 64");
+    if (p->shingle != 0) return fail(SCHIC_ERR_UNSUPPORTED, "block combine (shingle) is off in the default HashSpec");
+    if (p->n_neighbors < 1) return fail(SCHIC_ERR_INVALID_ARG, "n_neighbors must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SCHIC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+    }
+    int dev = p->device;
+    if (dev < 0) CU_TRY(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(SCHIC_ERR_INVALID_ARG, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(SCHIC_ERR_NO_DEVICE, std::string("kernels are built for sm_100a only; device is ") + prop.name);
+    CU_TRY(cudaSetDevice(dev));
+    auto* h = new schic_mh_handle();
+    h->p = *p;
+    if (h->p.excess_factor < 1) h->p.excess_factor = 1;
+    if (h->p.max_bin_size < 1) h->p.max_bin_size = INT64_MAX;
+    h->device = dev;
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return fail(SCHIC_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    h->stream = h->own_stream;
+    *out = h;
+    return SCHIC_OK;
+}
+
+int schic_mh_destroy(schic_mh_handle* h) {
+    if (!h) return SCHIC_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (cudaEvent_t e : h->pool) cudaEventDestroy(e);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+    cudaGetLastError();
+    return SCHIC_OK;
+}
+
+int schic_mh_set_stream(schic_mh_handle* h, void* cuda_stream) {
+    ST_TRY(check(h));
+    h->stream = (cudaStream_t)cuda_stream;
+    return SCHIC_OK;
+}
+
+int schic_mh_synchronize(schic_mh_handle* h) {
+    ST_TRY(check(h));
+    ST_TRY(use_device(h));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    CU_TRY(cudaStreamSynchronize(h->copy_stream));
+    return SCHIC_OK;
+}
+
+int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
+                     int32_t index_bits, const float* data, int32_t append) {
+    ST_TRY(check(h));
+    if (n_rows < 0 || !indptr) return fail(SCHIC_ERR_INVALID_ARG, "bad CSR arguments");
+    if (index_bits != 32 && index_bits != 64) return fail(SCHIC_ERR_INVALID_ARG, "index_bits must be 32 or 64");
+    const int64_t nnz = indptr[n_rows] - indptr[0];
+    if (nnz < 0 || (nnz > 0 && !indices)) return fail(SCHIC_ERR_INVALID_ARG, "bad CSR arguments");
+    if (!h->p.fast && nnz > 0 && !data) return fail(SCHIC_ERR_INVALID_ARG, "data is required when fast=0");
+    for (int64_t r = 0; r < n_rows; ++r)
+        if (indptr[r + 1] < indptr[r]) return fail(SCHIC_ERR_INVALID_ARG, "indptr not monotone");
+    ST_TRY(use_device(h));
+    if (h->borrowed && append) return fail(SCHIC_ERR_UNSUPPORTED, "cannot append to a borrowed device CSR");
+    if (!append || h->borrowed) {
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        h->n = 0; h->nnz = 0; h->borrowed = false; h->have_val = false; h->have_hi = false;
+        h->norm_of = nullptr; h->ext = false;
+    }
+    reset_stage(h, {ST_H2D, ST_SIG});
+    for (cudaEvent_t e : h->misc_ev) h->free_ev.push_back(e);
+    h->misc_ev.clear();
+    h->norm_of = nullptr;
+    const int H = h->p.number_of_hash_functions;
+    const int64_t r0 = h->n, pos0 = h->nnz;
+    const bool want_val = data != nullptr;
+    if (r0 > 0 && want_val != h->have_val) return fail(SCHIC_ERR_INVALID_ARG, "partial_fit must be consistent about data");
+    const bool want_hi = index_bits == 64 && h->p.hash_width == 64;
+    cudaStream_t s = h->stream, cs = h->copy_stream;
+
+    ST_TRY(h->indptr.reserve(r0 + n_rows + 1, r0 + 1, s));
+    ST_TRY(h->feat.reserve(pos0 + nnz, pos0, s));
+    if (want_val) ST_TRY(h->val.reserve(pos0 + nnz, pos0, s));
+    if (want_hi) ST_TRY(h->feat_hi.reserve(pos0 + nnz, pos0, s));
+    ST_TRY(h->sig.reserve((r0 + n_rows) * (int64_t)H, r0 * (int64_t)H, s));
+
+    // rebased indptr (absolute positions in the device store)
+    std::vector<int64_t> ip(n_rows + 1);
+    for (int64_t r = 0; r <= n_rows; ++r) ip[r] = pos0 + (indptr[r] - indptr[0]);
+    // 32-bit feature ids (width 32 hashes (uint32)(f+1), so truncation is exact there)
+    const uint32_t* f32 = nullptr;
+    std::vector<uint32_t> lo, hi;
+    if (index_bits == 32) {
+        f32 = (const uint32_t*)indices + indptr[0];
+    } else {
+        const uint64_t* f64 = (const uint64_t*)indices + indptr[0];
+        lo.resize(nnz);
+        if (want_hi) hi.resize(nnz);
+        bool any_hi = false;
+        for (int64_t e = 0; e < nnz; ++e) {
+            lo[e] = (uint32_t)f64[e];
+            if (want_hi) hi[e] = (uint32_t)(f64[e] >> 32);
+            any_hi = any_hi || (f64[e] >> 32) != 0;
+        }
+        if (any_hi && !h->p.fast) return fail(SCHIC_ERR_UNSUPPORTED, "exact rerank supports feature ids < 2^32 only");
+        f32 = lo.data();
+    }
+
+    cudaEvent_t up0 = get_event(h), up1 = get_event(h);
+    if (up0) cudaEventRecord(up0, cs);
+    CU_TRY(cudaMemcpyAsync(h->indptr.p + r0, ip.data(), (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+    CU_TRY(cudaStreamSynchronize(cs));   // ip is a local vector
+    h->n = r0 + n_rows;
+    h->nnz = pos0 + nnz;
+    h->have_val = want_val;
+    h->have_hi = want_hi;
+
+    // Upload the feature ids in row-aligned chunks on the copy stream; K1 for chunk i runs on the
+    // compute stream while chunk i+1 is still in flight.
+    const int64_t kChunkNnz = (int64_t)8 << 20;
+    cudaEvent_t sig0 = get_event(h);
+    bool sig_started = false;
+    int64_t c0 = 0;
+    while (c0 < n_rows) {
+        int64_t c1 = c0 + 1;
+        while (c1 < n_rows && (ip[c1 + 1] - ip[c0]) <= kChunkNnz) ++c1;
+        const int64_t a = ip[c0] - pos0, b = ip[c1] - pos0;
+        if (b > a) {
+            CU_TRY(cudaMemcpyAsync(h->feat.p + pos0 + a, f32 + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, cs));
+            if (want_hi)
+                CU_TRY(cudaMemcpyAsync(h->feat_hi.p + pos0 + a, hi.data() + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, cs));
+        }
+        cudaEvent_t ready = get_misc_event(h);
+        if (!ready) return fail(SCHIC_ERR_CUDA, "cudaEventCreate failed");
+        CU_TRY(cudaEventRecord(ready, cs));
+        CU_TRY(cudaStreamWaitEvent(s, ready, 0));
+        if (!sig_started && sig0) { cudaEventRecord(sig0, s); sig_started = true; }
+        ST_TRY(hash_rows(h, r0 + c0, r0 + c1, ip[c0], ip[c1], s));
+        c0 = c1;
+    }
+    cudaEvent_t sig1 = get_event(h);
+    if (sig_started && sig1) { cudaEventRecord(sig1, s); h->ev[ST_SIG].push_back({sig0, sig1}); }
+    if (want_val && nnz > 0)
+        CU_TRY(cudaMemcpyAsync(h->val.p + pos0, data + indptr[0], (size_t)nnz * 4, cudaMemcpyHostToDevice, cs));
+    if (up0 && up1) { cudaEventRecord(up1, cs); h->ev[ST_H2D].push_back({up0, up1}); }
+    // the host vectors (lo/hi) and the caller's arrays must outlive the copies; later stages use
+    // the compute stream, so make it wait for the value upload as well
+    cudaEvent_t done = get_misc_event(h);
+    if (!done) return fail(SCHIC_ERR_CUDA, "cudaEventCreate failed");
+    CU_TRY(cudaEventRecord(done, cs));
+    CU_TRY(cudaStreamWaitEvent(s, done, 0));
+    CU_TRY(cudaStreamSynchronize(cs));
+    return SCHIC_OK;
+}
+
+int schic_mh_fit_csr_device(schic_mh_handle* h, int64_t n_rows, int64_t nnz, const int64_t* d_indptr,
+                            const uint32_t* d_indices, const float* d_data, int32_t append) {
+    ST_TRY(check(h));
+    if (append) return fail(SCHIC_ERR_UNSUPPORTED, "device-resident fit does not append");
+    if (n_rows < 0 || nnz < 0 || !d_indptr || (nnz > 0 && !d_indices)) return fail(SCHIC_ERR_INVALID_ARG, "bad CSR arguments");
+    if (!h->p.fast && !d_data) return fail(SCHIC_ERR_INVALID_ARG, "data is required when fast=0");
+    ST_TRY(use_device(h));
+    reset_stage(h, {ST_H2D, ST_SIG});
+    const int H = h->p.number_of_hash_functions;
+    h->borrowed = true; h->b_indptr = d_indptr; h->b_feat = d_indices; h->b_val = d_data;
+    h->have_val = d_data != nullptr; h->have_hi = false;
+    h->n = n_rows; h->nnz = nnz; h->norm_of = nullptr; h->ext = false;
+    ST_TRY(h->sig.reserve(n_rows * (int64_t)H, 0, h->stream));
+    // indptr[0] of a borrowed CSR: read back one value (8 bytes) -- positions are absolute
+    int64_t pos0 = 0;
+    CU_TRY(cudaMemcpyAsync(&pos0, d_indptr, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    {
+        StageTimer t(h, ST_SIG, h->stream);
+        ST_TRY(hash_rows(h, 0, n_rows, pos0, pos0 + nnz, h->stream));
+    }
+    return SCHIC_OK;
+}
+
+int schic_mh_n_fitted(const schic_mh_handle* h, int64_t* n_out) {
+    ST_TRY(check(h));
+    if (!n_out) return fail(SCHIC_ERR_INVALID_ARG, "null argument");
+    *n_out = h->n;
+    return SCHIC_OK;
+}
+
+int schic_mh_signatures(schic_mh_handle* h, uint32_t* out) {
+    ST_TRY(check(h));
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    if (!out) return fail(SCHIC_ERR_INVALID_ARG, "null argument");
+    ST_TRY(use_device(h));
+    CU_TRY(cudaMemcpyAsync(out, h->sig.p, (size_t)h->n * h->p.number_of_hash_functions * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return SCHIC_OK;
+}
+
+int schic_mh_signatures_device(schic_mh_handle* h, void** d_sig_out, int64_t* n_rows_out) {
+    ST_TRY(check(h));
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    if (!d_sig_out || !n_rows_out) return fail(SCHIC_ERR_INVALID_ARG, "null argument");
+    *d_sig_out = h->sig.p;
+    *n_rows_out = h->n;
+    return SCHIC_OK;
+}
+
+int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t row0, const uint32_t* d_sig_all,
+                                 const int64_t* d_indptr_all, const uint32_t* d_indices_all, const float* d_data_all) {
+    ST_TRY(check(h));
+    if (!d_sig_all) { h->ext = false; h->norm_of = nullptr; return SCHIC_OK; }
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "fit the local shard first");
+    if (row0 < 0 || row0 + h->n > n_total) return fail(SCHIC_ERR_INVALID_ARG, "local rows do not fit in the database");
+    h->ext = true; h->db_n = n_total; h->db_row0 = row0; h->db_sig = d_sig_all;
+    h->db_indptr = d_indptr_all; h->db_feat = d_indices_all; h->db_val = d_data_all;
+    h->norm_of = nullptr;
+    return SCHIC_OK;
+}
+
+int schic_mh_collision_counts(schic_mh_handle* h, int64_t row0, int64_t row1, uint16_t* out) {
+    ST_TRY(check(h));
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    if (row0 < 0 || row1 > h->n || row0 > row1 || !out) return fail(SCHIC_ERR_INVALID_ARG, "bad row range");
+    ST_TRY(use_device(h));
+    const int H = h->p.number_of_hash_functions;
+    const int64_t ndb = h->ext ? h->db_n : h->n;
+    const uint32_t* db_sig = h->ext ? h->db_sig : h->sig.p;
+    if (ndb >= h->p.max_bin_size)
+        return fail(SCHIC_ERR_UNSUPPORTED, "n_fitted >= max_bin_size: bucket pruning is not built yet");
+    const int64_t ld = (ndb + 7) & ~(int64_t)7;
+    const int64_t nq = row1 - row0;
+    if (nq == 0) return SCHIC_OK;
+    ST_TRY(h->counts.reserve(nq * ld, 0, h->stream));
+    add_launches(h, schic::launch_collision_counts(h->sig.p + row0 * (int64_t)H, nq, db_sig, ndb, H, h->counts.p, ld, h->stream));
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpy2DAsync(out, (size_t)ndb * 2, h->counts.p, (size_t)ld * 2, (size_t)ndb * 2, (size_t)nq,
+                             cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return SCHIC_OK;
+}
+
+int schic_mh_kneighbors_device(schic_mh_handle* h, int32_t k, int32_t fast, int32_t* d_idx, float* d_dist, int32_t* d_nvalid) {
+    ST_TRY(check(h));
+    if (!d_idx || !d_dist || !d_nvalid) return fail(SCHIC_ERR_INVALID_ARG, "null output");
+    ST_TRY(use_device(h));
+    if (h->n > 0 && k > effective_k(h, k)) return fail(SCHIC_ERR_INVALID_ARG, "k exceeds the number of fitted rows");
+    return kneighbors_on_device(h, k, fast, d_idx, d_dist, d_nvalid);
+}
+
+int schic_mh_kneighbors(schic_mh_handle* h, int32_t k, int32_t fast, int32_t* idx, float* dist, int32_t* n_valid) {
+    ST_TRY(check(h));
+    if (k < 1 || !idx || !dist) return fail(SCHIC_ERR_INVALID_ARG, "bad kneighbors arguments");
+    ST_TRY(use_device(h));
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    const int ke = effective_k(h, k);
+    ST_TRY(kneighbors_on_device(h, ke, fast, nullptr, nullptr, nullptr));
+    const int64_t n = h->n;
+    {
+        StageTimer t(h, ST_D2H, h->stream);
+        if (ke == k) {
+            CU_TRY(cudaMemcpyAsync(idx, h->out_idx.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaMemcpyAsync(dist, h->out_dist.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, h->stream));
+        } else {   // k > n_fitted: pad columns [ke, k)
+            for (int64_t e = 0; e < n * (int64_t)k; ++e) { idx[e] = -1; dist[e] = __builtin_inff(); }
+            CU_TRY(cudaMemcpy2DAsync(idx, (size_t)k * 4, h->out_idx.p, (size_t)ke * 4, (size_t)ke * 4, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaMemcpy2DAsync(dist, (size_t)k * 4, h->out_dist.p, (size_t)ke * 4, (size_t)ke * 4, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        }
+        if (n_valid) CU_TRY(cudaMemcpyAsync(n_valid, h->out_nv.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return SCHIC_OK;
+}
+
+int schic_mh_kneighbors_graph(schic_mh_handle* h, int32_t k, int32_t fast, int64_t* indptr, int32_t* indices, float* data) {
+    ST_TRY(check(h));
+    if (k < 1 || !indptr || !indices || !data) return fail(SCHIC_ERR_INVALID_ARG, "bad kneighbors_graph arguments");
+    ST_TRY(use_device(h));
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    const int ke = effective_k(h, k);
+    ST_TRY(kneighbors_on_device(h, ke, fast, nullptr, nullptr, nullptr));
+    const int64_t n = h->n;
+    cudaStream_t s = h->stream;
+    ST_TRY(h->g_indptr.reserve(n + 1, 0, s));
+    ST_TRY(h->g_indices.reserve(n * ke, 0, s));
+    ST_TRY(h->g_data.reserve(n * ke, 0, s));
+    {
+        StageTimer t(h, ST_GRAPH, s);
+        const int nl = schic::launch_graph_emit(h->out_idx.p, h->out_dist.p, h->out_nv.p, n, ke, h->g_indptr.p,
+                                                h->g_indices.p, h->g_data.p, s);
+        if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k too large for the in-shared-memory graph emit");
+        add_launches(h, nl);
+    }
+    CU_TRY(cudaGetLastError());
+    {
+        StageTimer t(h, ST_D2H, s);
+        CU_TRY(cudaMemcpyAsync(indptr, h->g_indptr.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        const int64_t nnz = indptr[n];
+        if (nnz > 0) {
+            CU_TRY(cudaMemcpyAsync(indices, h->g_indices.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaMemcpyAsync(data, h->g_data.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(s));
+    return SCHIC_OK;
+}
+
+int schic_mh_stage_ms(schic_mh_handle* h, float* out, int32_t n_out) {
+    ST_TRY(check(h));
+    if (!out || n_out < ST_COUNT + 1) return fail(SCHIC_ERR_INVALID_ARG, "out must hold 8 floats");
+    ST_TRY(use_device(h));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    CU_TRY(cudaStreamSynchronize(h->copy_stream));
+    float sum = 0.f;
+    for (int st = 0; st < ST_COUNT; ++st) {
+        float acc = 0.f;
+        for (auto& pr : h->ev[st]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) acc += ms; else cudaGetLastError();
+        }
+        out[st] = acc;
+        sum += acc;
+    }
+    out[ST_COUNT] = sum;
+    return SCHIC_OK;
+}
+
+int schic_mh_launch_count(schic_mh_handle* h, int64_t* n_out) {
+    ST_TRY(check(h));
+    if (!n_out) return fail(SCHIC_ERR_INVALID_ARG, "null argument");
+    *n_out = h->launches;
+    return SCHIC_OK;
+}
+
+int schic_int32_peak(int32_t device, int32_t iters, double* out) {
+    if (!out) return fail(SCHIC_ERR_INVALID_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SCHIC_ERR_NO_DEVICE, "no CUDA device"); }
+    if (device >= 0) CU_TRY(cudaSetDevice(device));
+    for (int i = 0; i < 12; ++i) out[i] = 0.0;
+    if (schic::run_int32_peak(iters < 64 ? 64 : iters, out, nullptr) < 0) return fail(SCHIC_ERR_CUDA, "int32 peak kernel failed");
+    return SCHIC_OK;
+}
+
+int schic_k1_variant_ms(int32_t variant, int64_t n_rows, int64_t nnz, const int64_t* d_indptr, const uint32_t* d_indices,
+                        int32_t n_hash, uint32_t* d_sig, int32_t reps, float* ms_out) {
+    if (!d_indptr || !d_indices || !d_sig || !ms_out || reps < 1) return fail(SCHIC_ERR_INVALID_ARG, "bad arguments");
+    int64_t pos0 = 0;
+    CU_TRY(cudaMemcpy(&pos0, d_indptr, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    if (schic::launch_signatures32_variant(variant, d_indptr, d_indices, n_rows, nnz, pos0, n_hash, d_sig, nullptr) < 0)
+        return fail(SCHIC_ERR_UNSUPPORTED, "variant not compiled in");
+    CU_TRY(cudaEventRecord(e0, nullptr));
+    for (int r = 0; r < reps; ++r)
+        schic::launch_signatures32_variant(variant, d_indptr, d_indices, n_rows, nnz, pos0, n_hash, d_sig, nullptr);
+    CU_TRY(cudaEventRecord(e1, nullptr));
+    CU_TRY(cudaEventSynchronize(e1));
+    CU_TRY(cudaEventElapsedTime(ms_out, e0, e1));
+    *ms_out /= (float)reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CU_TRY(cudaGetLastError());
+    return SCHIC_OK;
+}
+
+int schic_pinned_alloc(int64_t bytes, void** out) {
+    if (!out || bytes < 0) return fail(SCHIC_ERR_INVALID_ARG, "bad arguments");
+    CU_TRY(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
+    return SCHIC_OK;
+}
+
+int schic_pinned_free(void* p) {
+    if (p) CU_TRY(cudaFreeHost(p));
+    return SCHIC_OK;
+}
+
+}  // extern "C"

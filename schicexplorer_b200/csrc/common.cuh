@@ -1,0 +1,63 @@
+// common.cuh -- shared declarations of the sm_100a MinHash kNN kernels (host-side launchers).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/schic_mh.h"
+
+namespace schic {
+
+constexpr uint32_t kModulus = SCHIC_MH_MODULUS;  // 2^31 - 1; also the empty-row sentinel
+
+// ---- K1: MinHash signatures (k1_signatures.cu) ------------------------------------------
+// sig[row_offset + r][j] = min over the row's features f of wang32((f+1)(j+1)) mod M.
+// indptr [n_rows+1] (device, indptr[0] may be non-zero), feat = feature ids (device).
+// Launches a fill (sentinel) kernel and the hashing kernel on `stream`; returns launch count.
+int launch_signatures32(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
+                        int64_t indptr0, int H, uint32_t* d_sig /* first row of this batch */,
+                        cudaStream_t stream);
+// variant >= 0 selects an instruction-selection variant (only in builds with -DK1_ALL_VARIANTS).
+int launch_signatures32_variant(int variant, const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows,
+                                int64_t nnz, int64_t indptr0, int H, uint32_t* d_sig, cudaStream_t stream);
+int launch_signatures64(const int64_t* d_indptr, const uint32_t* d_feat_lo, const uint32_t* d_feat_hi,
+                        int64_t n_rows, int64_t nnz, int64_t indptr0, int H, uint32_t* d_sig,
+                        cudaStream_t stream);
+
+// ---- K3: collision counts (k3_collisions.cu) ---------------------------------------------
+// cnt[q][d] = #{j : sigQ[q][j] == sigD[d][j], value admissible}; uint16 row major [nq, ld_out].
+int launch_collision_counts(const uint32_t* d_sig_q, int64_t nq, const uint32_t* d_sig_db, int64_t ndb,
+                            int H, uint16_t* d_cnt, int64_t ld_out, cudaStream_t stream);
+
+// ---- K3b: threshold + top-k select + fast distance (k3_select.cu) --------------------------
+// For each query row: candidates with cnt >= min_blocks (and > 0), ordered by (cnt desc, idx asc),
+// first kcand kept. Writes idx [nq,kcand] (-1 padded), cnt [nq,kcand], n_valid [nq].
+int launch_select_topk(const uint16_t* d_cnt, int64_t nq, int64_t ndb, int64_t ld_cnt, int H,
+                       int min_blocks, int kcand, int32_t* d_idx, int32_t* d_cntsel, int32_t* d_nvalid,
+                       cudaStream_t stream);
+// dist = absolute ? cnt : 1 - cnt/H (fp32), first k of kcand columns; pads +inf / -1.
+int launch_fast_distance(const int32_t* d_idx_in, const int32_t* d_cnt_in, const int32_t* d_nvalid_in,
+                         int64_t nq, int kcand, int k, int H, int absolute, int32_t* d_idx_out,
+                         float* d_dist_out, int32_t* d_nvalid_out, cudaStream_t stream);
+
+// ---- K4: exact euclidean rerank (k4_rerank.cu) ----------------------------------------------
+// norms2[r] = sum of squares of row r (fp64).
+int launch_row_norms(const int64_t* d_indptr, const float* d_val, int64_t n_rows, int64_t indptr0,
+                     double* d_norm2, cudaStream_t stream);
+// For query q (database row q_row0+q) and each of its candidates: euclidean distance over the
+// union of supports; then order by (dist asc, idx asc), keep k. CSR arrays are the database's.
+int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* d_val, int64_t indptr0,
+                  const double* d_norm2, int64_t q_row0, int64_t nq, const int32_t* d_cand_idx,
+                  const int32_t* d_cand_nvalid, int kcand, int k, int32_t* d_idx_out, float* d_dist_out,
+                  int32_t* d_nvalid_out, cudaStream_t stream);
+
+// ---- K5: graph emit (k5_graph.cu) ---------------------------------------------------------
+// CSR of the kNN graph: indptr = exclusive scan of n_valid, rows sorted by column.
+int launch_graph_emit(const int32_t* d_idx, const float* d_dist, const int32_t* d_nvalid, int64_t nq, int k,
+                      int64_t* d_indptr, int32_t* d_indices, float* d_data, cudaStream_t stream);
+
+// ---- INT32 throughput micro-benchmark (int_peak.cu) -----------------------------------------
+// out[0] ALU-pipe (LOP3/SHF/IADD3) Tint-op/s, out[1] FMA-pipe (IMAD), out[2] 1:1 mix, out[3] SM MHz.
+int run_int32_peak(int iters, double* out4, cudaStream_t stream);
+
+}  // namespace schic
