@@ -1,0 +1,76 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """The CPU oracle (checker). Built on first use with g++."""
+    from oracle import build_oracle, oracle_api
+    build_oracle()
+    return oracle_api()
+
+
+@pytest.fixture(scope="session")
+def cuda():
+    """The product back end; fails loudly when the library or the GPU is missing."""
+    from schicexplorer_b200 import _capi
+    api = _capi.cuda_api()
+    assert api.device_count() > 0, "no CUDA device visible: -m gpu tests need a B200"
+    return api
+
+
+@pytest.fixture(scope="session")
+def fixture20():
+    """The reference's 20-cell test matrix (text dump of test_matrix.scool) as CSR."""
+    from schicexplorer_b200.loader import cells_to_csr, load_cells_npz
+    cells, chroms = load_cells_npz(os.path.join(GOLDEN, "fixture20.npz"))
+    X, names = cells_to_csr(cells, chroms)
+    return X, names, cells, chroms
+
+
+@pytest.fixture(scope="session")
+def golden20():
+    return np.load(os.path.join(GOLDEN, "golden20.npz"))
+
+
+# kwargs scHicClusterMinHash passes to MinHash in the default branch (scHicClusterMinHash.py:402-404)
+REF_KWARGS = dict(number_of_hash_functions=800, minimal_blocks_in_common=100, excess_factor=1, max_bin_size=100000,
+                  shingle_size=5, absolute_numbers=False)
+
+
+class Fitted:
+    """Small helper: one handle on one back end, fitted on a CSR."""
+
+    def __init__(self, api, X, fast=True, n_neighbors=20, **kw):
+        params = dict(REF_KWARGS)
+        params.update(kw)
+        self.api, self.H = api, params["number_of_hash_functions"]
+        self.h = api.create(n_neighbors=n_neighbors, fast=fast, **params)
+        data = None if fast else X.data.astype(np.float32)
+        api.fit_csr(self.h, X.indptr, X.indices, data, False)
+
+    def sig(self):
+        return self.api.signatures(self.h, self.H)
+
+    def close(self):
+        self.api.destroy(self.h)
+        self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -1,0 +1,284 @@
+"""GPU suite (-m gpu): the sm_100a kernels, called through the C ABI, against the CPU oracle on
+the same inputs. Bar: bit-exact for signatures, collision counts and neighbour indices;
+relative 1e-5 for reranked distances (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix, vstack
+
+from conftest import REF_KWARGS, Fitted
+from schicexplorer_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5   # north_star: "reranked distances within 1e-5 relative"
+
+
+def synth_csr(n, seed=11, **kw):
+    cfg = synth.small_config(n, config_id=seed, **kw)
+    ip, ix, dt, z = synth.generate_csr(cfg, workers=1)
+    return synth.to_scipy(cfg, ip, ix, dt)
+
+
+def assert_neighbours_equal_up_to_ties(idx, dist, nv, ridx, rdist, rnv, rtol):
+    assert np.array_equal(nv, rnv)
+    for c in range(len(nv)):
+        k = nv[c]
+        np.testing.assert_allclose(dist[c, :k], rdist[c, :k], rtol=rtol, atol=0)
+        if not np.array_equal(idx[c, :k], ridx[c, :k]):
+            # allowed only where distances tie (within tolerance): same sets per tie group
+            assert sorted(idx[c, :k].tolist()) == sorted(ridx[c, :k].tolist())
+            bad = idx[c, :k] != ridx[c, :k]
+            d = rdist[c, :k][bad]
+            assert np.allclose(dist[c, :k][bad], d, rtol=rtol)
+        assert (idx[c, k:] == -1).all() and np.isinf(dist[c, k:]).all()
+
+
+@pytest.mark.parametrize("width", [32, 64])
+def test_fixture_signatures_counts_bit_exact(cuda, oracle, fixture20, golden20, width):
+    X = fixture20[0]
+    with Fitted(cuda, X, hash_width=width) as g:
+        sig = g.sig()
+        assert np.array_equal(sig, golden20[f"sig{width}"])
+        assert np.array_equal(cuda.collision_counts(g.h), golden20[f"cnt{width}"])
+        assert np.array_equal(cuda.collision_counts(g.h, 3, 11), golden20[f"cnt{width}"][3:11])
+
+
+@pytest.mark.parametrize("fast", [True, False])
+def test_fixture_kneighbors_and_graph(cuda, oracle, fixture20, golden20, fast):
+    X = fixture20[0]
+    tag = "fast" if fast else "exact"
+    with Fitted(cuda, X, fast=fast) as g, Fitted(oracle, X, fast=fast) as o:
+        idx, dist, nv = cuda.kneighbors(g.h, 20)
+        assert_neighbours_equal_up_to_ties(idx, dist, nv, golden20[f"idx_{tag}"], golden20[f"dist_{tag}"],
+                                           golden20[f"nv_{tag}"], 0 if fast else RTOL)
+        if fast:
+            assert np.array_equal(idx, golden20["idx_fast"]) and np.array_equal(dist, golden20["dist_fast"])
+        gi, gc, gd = cuda.kneighbors_graph(g.h, 20)
+        oi, oc, od = oracle.kneighbors_graph(o.h, 20)
+        assert np.array_equal(gi, oi) and np.array_equal(gc, oc)
+        np.testing.assert_allclose(gd, od, rtol=0 if fast else RTOL)
+        # k smaller than / larger than n
+        i5, d5, n5 = cuda.kneighbors(g.h, 5)
+        oi5, od5, on5 = oracle.kneighbors(o.h, 5)
+        assert_neighbours_equal_up_to_ties(i5, d5, n5, oi5, od5, on5, 0 if fast else RTOL)
+        i30, d30, n30 = cuda.kneighbors(g.h, 30)
+        assert np.array_equal(n30, nv) and (i30[:, 20:] == -1).all()
+        assert np.array_equal(i30[:, :20], idx)
+
+
+@pytest.mark.parametrize("H", [1, 31, 32, 33, 160, 200, 800, 1200, 2000])
+def test_signatures_hash_count_sweep(cuda, oracle, H):
+    X = synth_csr(48, median_nnz=2500, min_nnz=1, max_nnz=9000)
+    with Fitted(cuda, X, number_of_hash_functions=H, minimal_blocks_in_common=1) as g, \
+            Fitted(oracle, X, number_of_hash_functions=H, minimal_blocks_in_common=1) as o:
+        assert np.array_equal(g.sig(), o.sig())
+        assert np.array_equal(cuda.collision_counts(g.h), oracle.collision_counts(o.h))
+
+
+def test_ragged_empty_and_tiny_rows(cuda, oracle):
+    X = synth_csr(40, median_nnz=3000, min_nnz=1, max_nnz=9000)
+    empty = csr_matrix((1, X.shape[1]))
+    one = csr_matrix(([3.0], ([0], [12345])), shape=(1, X.shape[1]))
+    last = csr_matrix(([1.0, 2.0], ([0, 0], [0, X.shape[1] - 1])), shape=(1, X.shape[1]))
+    Xe = vstack([empty, X[:9], empty, empty, one, X[9:], last, empty]).tocsr()
+    for fast in (True, False):
+        kw = dict(number_of_hash_functions=256, minimal_blocks_in_common=8, fast=fast)
+        with Fitted(cuda, Xe, **kw) as g, Fitted(oracle, Xe, **kw) as o:
+            sig = g.sig()
+            assert np.array_equal(sig, o.sig())
+            assert (sig[0] == 2147483647).all()
+            assert np.array_equal(cuda.collision_counts(g.h), oracle.collision_counts(o.h))
+            a, b = cuda.kneighbors(g.h, 6), oracle.kneighbors(o.h, 6)
+            assert_neighbours_equal_up_to_ties(*a, *b, 0 if fast else RTOL)
+
+
+def test_modulo_special_values_hit_the_exact_path(cuda, oracle):
+    """Features engineered so that wang32 output is 2M, 2M+1 or M (residues 0, 1, 0): the rare
+    outcomes of the two-minima trick in K1 must still be bit-exact."""
+    M = 2147483647
+
+    def inv_wang32(k):   # exact inverse of the mix, to find keys whose hash output is a chosen value
+        k ^= k >> 16
+        k = (k * pow(2057, -1, 1 << 32)) & 0xFFFFFFFF
+        k ^= k >> 4; k ^= k >> 8; k ^= k >> 16
+        k = (k * pow(5, -1, 1 << 32)) & 0xFFFFFFFF
+        k ^= k >> 12; k ^= k >> 24
+        k = ((k + 1) * pow(32767, -1, 1 << 32)) & 0xFFFFFFFF
+        return k
+    feats = []
+    for target in (2 * M, 2 * M + 1, M, M - 1, M + 1, 0, 1):
+        key = inv_wang32(target)               # (f+1)*(j+1) == key for j = 0  ->  f = key - 1
+        f = (key - 1) & 0xFFFFFFFF
+        if f < 0xFFFFFFFF:
+            feats.append(f)
+    rows = []
+    ncols = 2 ** 32
+    for f in feats:
+        rows.append(csr_matrix(([1.0, 1.0], ([0, 0], sorted({f, 777}))), shape=(1, ncols)) if f != 777
+                    else csr_matrix(([1.0], ([0], [777])), shape=(1, ncols)))
+    X = vstack(rows).tocsr()
+    X.indices = X.indices.astype(np.int64)
+    with Fitted(cuda, X, number_of_hash_functions=64, minimal_blocks_in_common=1) as g, \
+            Fitted(oracle, X, number_of_hash_functions=64, minimal_blocks_in_common=1) as o:
+        sg, so = g.sig(), o.sig()
+        assert np.array_equal(sg, so)
+        assert sorted(so[:3, 0].tolist()) == [0, 0, 1]     # the engineered residues really occur
+        assert np.array_equal(cuda.collision_counts(g.h), oracle.collision_counts(o.h))
+
+
+def test_synthetic_clusters_fast_and_exact(cuda, oracle):
+    X = synth_csr(300, seed=5)
+    for fast in (True, False):
+        kw = dict(fast=fast, n_neighbors=25)
+        with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
+            assert np.array_equal(g.sig(), o.sig())
+            assert np.array_equal(cuda.collision_counts(g.h), oracle.collision_counts(o.h))
+            a, b = cuda.kneighbors(g.h, 25), oracle.kneighbors(o.h, 25)
+            assert_neighbours_equal_up_to_ties(*a, *b, 0 if fast else RTOL)
+            if fast:
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_excess_factor_and_absolute_numbers(cuda, oracle):
+    X = synth_csr(120, seed=6)
+    kw = dict(fast=False, excess_factor=3, minimal_blocks_in_common=40, n_neighbors=10)
+    with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
+        a, b = cuda.kneighbors(g.h, 10), oracle.kneighbors(o.h, 10)
+        assert_neighbours_equal_up_to_ties(*a, *b, RTOL)
+    kw = dict(fast=True, absolute_numbers=True, minimal_blocks_in_common=40)
+    with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
+        a, b = cuda.kneighbors(g.h, 10), oracle.kneighbors(o.h, 10)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_partial_fit_equals_fit(cuda, fixture20, golden20):
+    X = fixture20[0]
+    h = cuda.create(n_neighbors=20, fast=False, **REF_KWARGS)
+    for a, b, app in ((0, 7, False), (7, 15, True), (15, 20, True)):
+        cuda.fit_csr(h, X[a:b].indptr, X[a:b].indices, X[a:b].data.astype(np.float32), app)
+    assert cuda.n_fitted(h) == 20
+    assert np.array_equal(cuda.signatures(h, 800), golden20["sig32"])
+    idx, dist, nv = cuda.kneighbors(h, 20)
+    assert_neighbours_equal_up_to_ties(idx, dist, nv, golden20["idx_exact"], golden20["dist_exact"], golden20["nv_exact"], RTOL)
+    # refit replaces
+    cuda.fit_csr(h, X[:5].indptr, X[:5].indices, X[:5].data.astype(np.float32), False)
+    assert cuda.n_fitted(h) == 5 and np.array_equal(cuda.signatures(h, 800), golden20["sig32"][:5])
+    cuda.destroy(h)
+
+
+def test_minhash_class_runs_on_the_gpu(cuda, fixture20, golden20):
+    """The reference-facing Python class, unpatched: must be served by the CUDA library."""
+    from schicexplorer_b200 import MinHash
+    X = fixture20[0]
+    mh = MinHash(n_neighbors=20, number_of_hash_functions=800, number_of_cores=8, shingle_size=5, fast=True,
+                 maxFeatures=int(max(X.getnnz(1))), absolute_numbers=False, max_bin_size=100000,
+                 minimal_blocks_in_common=100, excess_factor=1, prune_inverse_index=False)
+    mh.fit(X)
+    assert mh._api.backend == "cuda"
+    assert np.array_equal(mh.signatures(), golden20["sig32"])
+    g = mh.kneighbors_graph(mode="distance")
+    assert g.shape == (20, 20) and np.array_equal(np.diff(g.indptr), golden20["nv_fast"])
+    assert mh._api.launch_count(mh._h) > 0
+    mh.close()
+
+
+def test_device_resident_entry_points(cuda, oracle):
+    import torch
+    X = synth_csr(200, seed=8)
+    dev = torch.device("cuda:0")
+    ip = torch.from_numpy(X.indptr.astype(np.int64)).to(dev)
+    ix = torch.from_numpy(X.indices.astype(np.int32)).to(dev)
+    dt = torch.from_numpy(X.data.astype(np.float32)).to(dev)
+    k = 16
+    with Fitted(oracle, X, fast=False, n_neighbors=k) as o:
+        h = cuda.create(n_neighbors=k, fast=False, device=0, **REF_KWARGS)
+        cuda.set_stream(h, torch.cuda.current_stream().cuda_stream)
+        cuda.fit_csr_device(h, X.shape[0], X.nnz, ip.data_ptr(), ix.data_ptr(), dt.data_ptr(), False)
+        idx = torch.empty((200, k), dtype=torch.int32, device=dev)
+        dist = torch.empty((200, k), dtype=torch.float32, device=dev)
+        nv = torch.empty(200, dtype=torch.int32, device=dev)
+        cuda.kneighbors_device(h, k, -1, idx.data_ptr(), dist.data_ptr(), nv.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(cuda.signatures(h, 800), o.sig())
+        b = oracle.kneighbors(o.h, k)
+        assert_neighbours_equal_up_to_ties(idx.cpu().numpy(), dist.cpu().numpy(), nv.cpu().numpy(), *b, RTOL)
+        ms = cuda.stage_ms(h)
+        assert ms["signatures"] > 0 and ms["collisions"] > 0 and ms["rerank"] > 0
+        cuda.destroy(h)
+
+
+def test_external_database_matches_local(cuda, oracle):
+    """Sharded query path on one GPU: two handles each hash half of the rows, the 'gathered'
+    signature matrix / CSR is handed back, each answers for its own rows."""
+    import torch
+    X = synth_csr(150, seed=9)
+    dev = torch.device("cuda:0")
+    k = 12
+    ip = torch.from_numpy(X.indptr.astype(np.int64)).to(dev)
+    ix = torch.from_numpy(X.indices.astype(np.int32)).to(dev)
+    dt = torch.from_numpy(X.data.astype(np.float32)).to(dev)
+    with Fitted(oracle, X, fast=False, n_neighbors=k) as o:
+        ref = oracle.kneighbors(o.h, k)
+    sig_all = torch.empty((150, 800), dtype=torch.int32, device=dev)
+    parts, handles = [(0, 70), (70, 150)], []
+    for a, b in parts:
+        h = cuda.create(n_neighbors=k, fast=False, device=0, **REF_KWARGS)
+        S = X[a:b]
+        cuda.fit_csr(h, S.indptr, S.indices, S.data.astype(np.float32), False)
+        p, n = cuda.signatures_device(h)
+        assert n == b - a
+        cuda.synchronize(h)
+        src = torch.from_numpy(cuda.signatures(h, 800).view(np.int32)).to(dev)
+        sig_all[a:b] = src
+        handles.append(h)
+    torch.cuda.synchronize()
+    for (a, b), h in zip(parts, handles):
+        cuda.set_database_device(h, 150, a, sig_all.data_ptr(), ip.data_ptr(), ix.data_ptr(), dt.data_ptr())
+        idx, dist, nv = cuda.kneighbors(h, k, n_rows=b - a)
+        assert_neighbours_equal_up_to_ties(idx, dist, nv, ref[0][a:b], ref[1][a:b], ref[2][a:b], RTOL)
+        cuda.destroy(h)
+
+
+def test_full_size_properties(cuda):
+    """Size-independent properties at BASELINE scale per cell (full-length rows, H=800): order
+    invariance, partial_fit == fit, idempotence, symmetry of counts, self collision = H."""
+    cfg = synth.SynthConfig(3, 256)
+    ip, ix, dt, _ = synth.generate_csr(cfg, 0, 256, workers=1)
+    X = synth.to_scipy(cfg, ip, ix, dt)
+    with Fitted(cuda, X, fast=True, n_neighbors=50) as g:
+        sig = g.sig()
+        cnt = cuda.collision_counts(g.h)
+        assert np.array_equal(cnt, cnt.T) and (np.diag(cnt) == 800).all()
+        assert sig.max() < 2147483647
+        # idempotence
+        cuda.fit_csr(g.h, X.indptr, X.indices, None, False)
+        assert np.array_equal(g.sig(), sig)
+        # permutation of the non-zeros inside rows
+        rng = np.random.default_rng(3)
+        perm = X.indices.copy()
+        for r in range(0, 256, 17):
+            a, b = X.indptr[r], X.indptr[r + 1]
+            perm[a:b] = rng.permutation(perm[a:b])
+        cuda.fit_csr(g.h, X.indptr, perm, None, False)
+        assert np.array_equal(g.sig(), sig)
+        # fit in two appends
+        cuda.fit_csr(g.h, X[:100].indptr, X[:100].indices, None, False)
+        cuda.fit_csr(g.h, X[100:].indptr, X[100:].indices, None, True)
+        assert np.array_equal(g.sig(), sig)
+        # signature of a row is the column-wise min of the signatures of any split of its features
+        r = 5
+        a, b = X.indptr[r], X.indptr[r + 1]
+        mid = (a + b) // 2
+        halves = csr_matrix((np.ones(b - a), X.indices[a:b], [0, mid - a, b - a]), shape=(2, X.shape[1]))
+        cuda.fit_csr(g.h, halves.indptr, halves.indices, None, False)
+        assert np.array_equal(g.sig().min(axis=0), sig[r])
+
+
+def test_error_codes(cuda):
+    from schicexplorer_b200._capi import SchicError
+    with pytest.raises(SchicError):
+        cuda.create(n_neighbors=5, number_of_hash_functions=70000)
+    h = cuda.create(n_neighbors=5)
+    with pytest.raises(SchicError) as e:
+        cuda.kneighbors(h, 5, n_rows=1)
+    assert e.value.status == -2
+    cuda.destroy(h)
