@@ -35,6 +35,11 @@ int schic_mh_kneighbors_device(schic_mh_handle* h, int32_t k, int32_t fast, int3
  * signature all-gather. */
 int schic_mh_signatures_device(schic_mh_handle* h, void** d_sig_out, int64_t* n_rows_out);
 
+/* Device addresses of the local CSR shard as the handle holds it (after a host or device fit):
+ * the send buffers of the CSR all-gather that the distributed exact rerank needs. */
+int schic_mh_csr_device(schic_mh_handle* h, const int64_t** d_indptr_out, const uint32_t** d_indices_out,
+                        const float** d_data_out, int64_t* nnz_out);
+
 /* Distributed query: use an external (all-gathered, borrowed) database of n_total rows; this
  * handle's local rows are database rows [row0, row0+n_local). d_sig_all uint32 [n_total, H];
  * the CSR of the whole database (d_indptr_all/d_indices_all/d_data_all) is needed only for the

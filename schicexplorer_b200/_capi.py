@@ -53,7 +53,7 @@ BASE_SYMBOLS = (
 )
 # symbols only the CUDA library exports (include/schic_mh_cuda.h)
 CUDA_SYMBOLS = (
-    "schic_mh_fit_csr_device", "schic_mh_kneighbors_device", "schic_mh_signatures_device",
+    "schic_mh_fit_csr_device", "schic_mh_kneighbors_device", "schic_mh_signatures_device", "schic_mh_csr_device",
     "schic_mh_set_database_device", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free",
@@ -97,6 +97,7 @@ class CApi:
             L.schic_mh_fit_csr_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _i32]
             L.schic_mh_kneighbors_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
             L.schic_mh_signatures_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_i64)]
+            L.schic_mh_csr_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]
             L.schic_mh_set_database_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp]
             L.schic_mh_set_stream.argtypes = [_vp, _vp]
             L.schic_mh_stage_ms.argtypes = [_vp, _vp, _i32]
@@ -205,6 +206,11 @@ class CApi:
         p, n = _vp(), _i64()
         self.check(self.lib.schic_mh_signatures_device(_vp(h), C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def csr_device(self, h):
+        a, b, c, n = _vp(), _vp(), _vp(), _i64()
+        self.check(self.lib.schic_mh_csr_device(_vp(h), C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return a.value, b.value, c.value, n.value
 
     def set_database_device(self, h, n_total, row0, d_sig, d_indptr=None, d_indices=None, d_data=None):
         self.check(self.lib.schic_mh_set_database_device(_vp(h), n_total, row0, _ptr(d_sig), _ptr(d_indptr),

@@ -488,6 +488,18 @@ int schic_mh_signatures_device(schic_mh_handle* h, void** d_sig_out, int64_t* n_
     return SCHIC_OK;
 }
 
+int schic_mh_csr_device(schic_mh_handle* h, const int64_t** d_indptr_out, const uint32_t** d_indices_out,
+                        const float** d_data_out, int64_t* nnz_out) {
+    ST_TRY(check(h));
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    if (!d_indptr_out || !d_indices_out || !d_data_out || !nnz_out) return fail(SCHIC_ERR_INVALID_ARG, "null argument");
+    *d_indptr_out = h->d_indptr();
+    *d_indices_out = h->d_feat();
+    *d_data_out = h->d_val();
+    *nnz_out = h->nnz;
+    return SCHIC_OK;
+}
+
 int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t row0, const uint32_t* d_sig_all,
                                  const int64_t* d_indptr_all, const uint32_t* d_indices_all, const float* d_data_all) {
     ST_TRY(check(h));

@@ -1,0 +1,158 @@
+"""Multi-GPU host layer: one process per GPU, cells sharded across ranks.
+
+SURVEY.md 8(e): rows (cells) are independent for K1, so each rank hashes its own shard; the one
+real exchange step is an all-gather of the signature matrix (uint32 [n/G, H] per rank) with NCCL
+over NVLink (``torch.distributed``), plus -- only for the exact rerank -- an all-gather of the CSR
+shards so that any candidate row is local. Each rank then answers the kNN queries of its own cells
+against the gathered database (K3 -> select -> K4). No reduction collective is needed.
+
+PyTorch is plumbing here (device buffers, process group, streams); all arithmetic is in the
+kernels behind the C ABI (include/schic_mh_cuda.h).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition_rows(n_rows: int, world: int) -> list:
+    """Contiguous, near-equal row blocks: rank r owns [bounds[r], bounds[r+1])."""
+    base, rem = divmod(n_rows, world)
+    bounds = [0]
+    for r in range(world):
+        bounds.append(bounds[-1] + base + (1 if r < rem else 0))
+    return bounds
+
+
+def partition_rows_by_nnz(indptr: np.ndarray, world: int) -> list:
+    """Contiguous row blocks balanced by non-zeros (prefix-sum split) to tame row-length skew."""
+    n = len(indptr) - 1
+    total = indptr[-1] - indptr[0]
+    bounds = [0]
+    for r in range(1, world):
+        target = indptr[0] + total * r // world
+        bounds.append(int(min(max(np.searchsorted(indptr, target, side="left"), bounds[-1]), n)))
+    bounds.append(n)
+    return bounds
+
+
+def _gather_padded(local: torch.Tensor, counts: list, group) -> torch.Tensor:
+    """All-gather of unequal first-dimension shards: pad to the largest, gather, compact."""
+    world = len(counts)
+    mx = max(counts)
+    tail = local.shape[1:]
+    if local.shape[0] < mx:
+        pad = torch.empty((mx,) + tuple(tail), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+        local = pad
+    if len(set(counts)) == 1:
+        out = torch.empty((world * mx,) + tuple(tail), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    buf = torch.empty((world, mx) + tuple(tail), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf.view((world * mx,) + tuple(tail)), local.contiguous(), group=group)
+    return torch.cat([buf[r, :counts[r]] for r in range(world)], dim=0)
+
+
+class ShardedMinHash:
+    """Cells [row0, row0 + n_local) of an n_total-cell data set live on this rank.
+
+    ``api`` is the CUDA C-ABI binding (or, in the CPU gloo tests, any object with the same
+    methods); tensors live on ``device``.
+    """
+
+    def __init__(self, api, n_total: int, row_bounds: list, device, group=None, **minhash_kwargs):
+        self.api, self.group, self.device = api, group, device
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_total = n_total
+        self.bounds = list(row_bounds)
+        self.row0, self.n_local = self.bounds[self.rank], self.bounds[self.rank + 1] - self.bounds[self.rank]
+        self.kw = dict(minhash_kwargs)
+        self.H = int(self.kw["number_of_hash_functions"])
+        self.fast = bool(self.kw.get("fast", True))
+        dev_index = device.index if device.type == "cuda" else -1
+        self.h = api.create(device=dev_index, **self.kw)
+        if device.type == "cuda":
+            api.set_stream(self.h, torch.cuda.current_stream(device).cuda_stream)
+        self._keep = {}
+
+    def close(self):
+        if self.h is not None:
+            self.api.destroy(self.h)
+            self.h = None
+
+    # -- step 1: hash the local shard (device-resident CSR) ---------------------------------
+    def fit_local(self, d_indptr: torch.Tensor, d_indices: torch.Tensor, d_data):
+        self._keep["csr"] = (d_indptr, d_indices, d_data)
+        nnz = int(d_indices.numel())
+        self.api.fit_csr_device(self.h, self.n_local, nnz, d_indptr.data_ptr(), d_indices.data_ptr(),
+                                None if d_data is None else d_data.data_ptr(), False)
+
+    def fit_local_host(self, indptr: np.ndarray, indices: np.ndarray, data):
+        """Same, from HOST buffers (pinned for full PCIe speed): the H2D copy is part of the call and
+        is overlapped with K1 chunk by chunk inside the library."""
+        self.api.fit_csr(self.h, indptr, indices, data, False)
+        p_ip, p_ix, p_dt, nnz = self.api.csr_device(self.h)
+        d_ip = _wrap_device(p_ip, (self.n_local + 1,), "<i8", torch.int64, self.device)
+        d_ix = _wrap_device(p_ix, (nnz,), "<i4", torch.int32, self.device)
+        d_dt = None if not p_dt else _wrap_device(p_dt, (nnz,), "<f4", torch.float32, self.device)
+        self._keep["csr"] = (d_ip, d_ix, d_dt)
+
+    # -- step 2: the exchange ------------------------------------------------------------------
+    def gather(self):
+        """All-gather signatures (and the CSR shards when the exact rerank needs them) and hand
+        the gathered database back to the kernels."""
+        counts = [self.bounds[r + 1] - self.bounds[r] for r in range(self.world)]
+        ptr, n = self.api.signatures_device(self.h)
+        assert n == self.n_local
+        sig_local = _wrap_device(ptr, (self.n_local, self.H), "<i4", torch.int32, self.device)
+        if self.world == 1:
+            sig_all = sig_local
+        else:
+            sig_all = _gather_padded(sig_local, counts, self.group)
+        self._keep["sig_all"] = sig_all
+        ip_all = ix_all = dt_all = None
+        if not self.fast:
+            d_indptr, d_indices, d_data = self._keep["csr"]
+            if self.world == 1:
+                ip_all, ix_all, dt_all = d_indptr, d_indices, d_data
+            else:
+                nnz_local = torch.tensor([d_indices.numel()], dtype=torch.int64, device=self.device)
+                nnz_all = torch.empty(self.world, dtype=torch.int64, device=self.device)
+                dist.all_gather_into_tensor(nnz_all, nnz_local, group=self.group)
+                nnzs = [int(x) for x in nnz_all.tolist()]
+                ix_all = _gather_padded(d_indices, nnzs, self.group)
+                dt_all = _gather_padded(d_data, nnzs, self.group)
+                # row lengths -> global indptr
+                lens = (d_indptr[1:] - d_indptr[:-1]).contiguous()
+                lens_all = _gather_padded(lens, counts, self.group)
+                ip_all = torch.zeros(self.n_total + 1, dtype=torch.int64, device=self.device)
+                torch.cumsum(lens_all, 0, out=ip_all[1:])
+            self._keep["csr_all"] = (ip_all, ix_all, dt_all)
+        self.api.set_database_device(self.h, self.n_total, self.row0, sig_all.data_ptr(),
+                                     None if ip_all is None else ip_all.data_ptr(),
+                                     None if ix_all is None else ix_all.data_ptr(),
+                                     None if dt_all is None else dt_all.data_ptr())
+
+    # -- step 3: local queries -------------------------------------------------------------------
+    def kneighbors_local(self, k: int, out=None):
+        if out is None:
+            out = (torch.empty((self.n_local, k), dtype=torch.int32, device=self.device),
+                   torch.empty((self.n_local, k), dtype=torch.float32, device=self.device),
+                   torch.empty(self.n_local, dtype=torch.int32, device=self.device))
+        idx, dst, nv = out
+        self.api.kneighbors_device(self.h, k, -1, idx.data_ptr(), dst.data_ptr(), nv.data_ptr())
+        return out
+
+
+def _wrap_device(ptr: int, shape, typestr: str, dtype, device) -> torch.Tensor:
+    """Zero-copy torch view of a device buffer owned by the C library (uint32 is viewed as int32)."""
+    n = int(np.prod(shape))
+    if n == 0:
+        return torch.empty(shape, dtype=dtype, device=device)
+
+    class _Holder:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+    return torch.as_tensor(_Holder(), device=device).view(shape)
