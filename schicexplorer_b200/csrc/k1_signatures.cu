@@ -250,7 +250,7 @@ static int pick_R(int slabs) {
 }
 
 #ifndef K1_VARIANT
-#define K1_VARIANT 0
+#define K1_VARIANT 2
 #endif
 
 template <int V>

@@ -23,8 +23,10 @@
 namespace schic {
 
 constexpr int K4_THREADS = 256;
-constexpr int K4_SLOTS = 8192;            // hash table slots (64 KB: 4 B key + 4 B value)
-constexpr int K4_PART = 5120;             // query non-zeros per table fill (load factor 0.625)
+constexpr int K4_SLOTS = 8192;            // hash table slots (32 KB keys + 32 KB values)
+constexpr int K4_BUCKETS = K4_SLOTS / 4;  // a bucket = 4 consecutive keys = one LDS.128
+constexpr int K4_BUCKET_BITS = 11;
+constexpr int K4_PART = 2560;             // query non-zeros per table fill: load factor 0.31
 constexpr uint32_t K4_EMPTY = 0xFFFFFFFFu;
 
 __global__ void row_norms_kernel(const int64_t* __restrict__ indptr, const float* __restrict__ val, int64_t n_rows,
@@ -42,33 +44,27 @@ __global__ void row_norms_kernel(const int64_t* __restrict__ indptr, const float
     if (lane == 0) norm2[row] = acc;
 }
 
-__device__ __forceinline__ uint32_t k4_hash(uint32_t f) { return (f * 2654435761u) >> (32 - 13); }  // log2(8192)
+__device__ __forceinline__ uint32_t k4_bucket(uint32_t f) { return (f * 2654435761u) >> (32 - K4_BUCKET_BITS); }
 
-// first position in [b, e) whose feature is >= key; warp-cooperative 32-ary search, uniform result
-__device__ __forceinline__ int64_t warp_lower_bound(const uint32_t* __restrict__ feat, int64_t b, int64_t e,
-                                                    uint32_t key, int lane) {
-    while (e - b > 32) {
-        const int64_t step = (e - b + 31) / 32;            // 32 probes at b + (lane+1)*step - 1
-        int64_t p = b + (int64_t)(lane + 1) * step - 1;
-        const bool in = p < e;
-        const bool ge = in ? (__ldg(feat + p) >= key) : true;
-        const unsigned m = __ballot_sync(0xffffffffu, ge);  // first lane whose probe is >= key
-        if (m == 0u) return e;                               // every probe (incl. position e-1) is < key
-        const int first = __ffs(m) - 1;
-        const int64_t nb = b + (int64_t)first * step;
-        int64_t ne = b + (int64_t)(first + 1) * step - 1;    // probe position itself may be the answer
-        if (ne > e) ne = e;
-        // answer lies in [nb, ne]: everything before nb is < key, feat[ne] >= key (or ne == e)
-        b = nb;
-        e = ne;
+// first position in [b, e) whose feature is >= key (plain binary search, one thread)
+__device__ __forceinline__ int64_t lower_bound_feat(const uint32_t* __restrict__ feat, int64_t b, int64_t e, uint32_t key) {
+    while (b < e) {
+        const int64_t mid = (b + e) >> 1;
+        if (__ldg(feat + mid) < key) b = mid + 1; else e = mid;
     }
-    const int64_t p = b + lane;
-    const bool ge = p < e ? (__ldg(feat + p) >= key) : true;
-    const unsigned m = __ballot_sync(0xffffffffu, ge);
-    if (m == 0u) return e;
-    const int first = __ffs(m) - 1;
-    const int64_t r = b + first;
-    return r < e ? r : e;
+    return b;
+}
+
+// One probe of one element: fetch the 4 keys of bucket b, report hit slot / miss / "bucket full, go on".
+struct K4Probe { bool found; bool more; int slot; };
+__device__ __forceinline__ K4Probe k4_probe(const uint32_t* __restrict__ tkey, uint32_t b, uint32_t f) {
+    const uint4 k = *reinterpret_cast<const uint4*>(tkey + 4 * b);
+    K4Probe r;
+    const bool m0 = k.x == f, m1 = k.y == f, m2 = k.z == f, m3 = k.w == f;
+    r.found = m0 || m1 || m2 || m3;
+    r.slot = (int)(4 * b) + (m1 ? 1 : (m2 ? 2 : (m3 ? 3 : 0)));
+    r.more = !r.found && k.w != K4_EMPTY;    // slots fill in order, so a free last slot ends the search
+    return r;
 }
 
 __global__ void __launch_bounds__(K4_THREADS)
@@ -82,12 +78,14 @@ k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict_
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(tval + K4_SLOTS);   // [P]
     double* dot = reinterpret_cast<double*>(keys + P);                   // [kcand]
     int64_t* cursor = reinterpret_cast<int64_t*>(dot + kcand);           // [kcand] next unread y position
-    int32_t* cand = reinterpret_cast<int32_t*>(cursor + kcand);          // [kcand]
+    int64_t* slice_end = cursor + kcand;                                 // [kcand] end of this part's slice
+    int32_t* cand = reinterpret_cast<int32_t*>(slice_end + kcand);       // [kcand]
+    __shared__ int s_next;
 
     const int64_t q = blockIdx.x;
     const int64_t qrow = q_row0 + q;
     const int ncand = min(cand_nvalid[q], kcand);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
 
     for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
         const int32_t d = cand_idx[q * kcand + c];
@@ -103,36 +101,86 @@ k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict_
         const bool last = xt >= xe;
         const uint32_t hi = last ? 0u : __ldg(feat + xt);
         __syncthreads();   // previous part fully consumed (and cand/dot/cursor initialised)
-        for (int i = threadIdx.x; i < K4_SLOTS; i += blockDim.x) tkey[i] = K4_EMPTY;
+        for (int i = threadIdx.x; i < K4_SLOTS / 4; i += blockDim.x)
+            reinterpret_cast<uint4*>(tkey)[i] = make_uint4(K4_EMPTY, K4_EMPTY, K4_EMPTY, K4_EMPTY);
+        if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
+        // scatter this part of the query row: first free slot of the home bucket, else the next bucket
         for (int64_t i = xs + threadIdx.x; i < xt; i += blockDim.x) {
             const uint32_t f = __ldg(feat + i);
-            uint32_t h = k4_hash(f);
-            while (atomicCAS(&tkey[h], K4_EMPTY, f) != K4_EMPTY) h = (h + 1) & (K4_SLOTS - 1);
-            tval[h] = __ldg(val + i);
+            uint32_t slot = 4 * k4_bucket(f);
+            while (atomicCAS(&tkey[slot], K4_EMPTY, f) != K4_EMPTY) slot = (slot + 1) & (K4_SLOTS - 1);
+            tval[slot] = __ldg(val + i);
+        }
+        // where each candidate's slice for this feature range ends: one binary search per candidate,
+        // all candidates in parallel (their latency overlaps the scatter of the other warps)
+        for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
+            const int64_t ye = indptr[cand[c] + 1];
+            slice_end[c] = last ? ye : lower_bound_feat(feat, cursor[c], ye, hi);
         }
         __syncthreads();
-        for (int c = warp; c < ncand; c += n_warps) {
-            const int32_t d = cand[c];
+        // candidates are handed to warps dynamically (their slices differ in length)
+        for (;;) {
+            int c = 0;
+            if (lane == 0) c = atomicAdd(&s_next, 1);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= ncand) break;
             const int64_t ys = cursor[c];
-            const int64_t ye = indptr[d + 1];
-            const int64_t yt = last ? ye : warp_lower_bound(feat, ys, ye, hi, lane);
+            const int len = (int)(slice_end[c] - ys);
+            const uint32_t* __restrict__ yf = feat + ys;
+            const float* __restrict__ yvp = val + ys;
+            // Stream the slice, 4 independent elements per lane and iteration; the loads of the next
+            // iteration are issued before the current one is probed (register double buffering).
             double acc = 0.0;
-            for (int64_t i = ys + lane; i < yt; i += 32) {
-                const uint32_t f = __ldg(feat + i);
-                const float yv = __ldg(val + i);
-                uint32_t h = k4_hash(f);
-                uint32_t key = tkey[h];
-                while (key != K4_EMPTY) {
-                    if (key == f) { acc += (double)tval[h] * (double)yv; break; }
-                    h = (h + 1) & (K4_SLOTS - 1);
-                    key = tkey[h];
+            uint32_t fn[4];
+            float vn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = u * 32 + lane;
+                fn[u] = i < len ? __ldg(yf + i) : K4_EMPTY;
+                vn[u] = i < len ? __ldg(yvp + i) : 0.f;
+            }
+            for (int i0 = 0; i0 < len; i0 += 128) {
+                uint32_t f[4];
+                float yv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { f[u] = fn[u]; yv[u] = vn[u]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + 128 + u * 32 + lane;
+                    fn[u] = i < len ? __ldg(yf + i) : K4_EMPTY;
+                    vn[u] = i < len ? __ldg(yvp + i) : 0.f;
                 }
+                uint32_t b[4];
+                K4Probe pr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {       // first probes: 4 independent LDS.128 in flight
+                    b[u] = k4_bucket(f[u]);
+                    pr[u] = k4_probe(tkey, b[u], f[u]);
+                    if (f[u] == K4_EMPTY) { pr[u].found = false; pr[u].more = false; }
+                }
+                while (pr[0].more || pr[1].more || pr[2].more || pr[3].more) {   // rare: home bucket was full
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (pr[u].more) {
+                            b[u] = (b[u] + 1) & (K4_BUCKETS - 1);
+                            pr[u] = k4_probe(tkey, b[u], f[u]);
+                        }
+                    }
+                }
+                float prod[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) prod[u] = pr[u].found ? tval[pr[u].slot] * yv[u] : 0.f;
+                // products of fp32 counts are exact in fp32 for integer data; the sum is kept in fp64
+                acc += (double)prod[0] + (double)prod[1];
+                acc += (double)prod[2] + (double)prod[3];
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) { dot[c] += acc; cursor[c] = yt; }
+            if (lane == 0) dot[c] += acc;
         }
+        __syncthreads();
+        for (int c = threadIdx.x; c < ncand; c += blockDim.x) cursor[c] = slice_end[c];
     }
     __syncthreads();
 
@@ -181,7 +229,7 @@ int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* 
     (void)indptr0;
     if (nq <= 0) return 0;
     const int P = next_pow2(kcand);
-    const size_t smem = (size_t)K4_SLOTS * 8 + (size_t)P * 8 + (size_t)kcand * (8 + 8 + 4) + 16;
+    const size_t smem = (size_t)K4_SLOTS * 8 + (size_t)P * 8 + (size_t)kcand * (8 + 8 + 8 + 4) + 16;
     if (smem > 220 * 1024) return -1;   // caller reports SCHIC_ERR_UNSUPPORTED
     cudaFuncSetAttribute(k4_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k4_rerank_kernel<<<(unsigned)nq, K4_THREADS, smem, stream>>>(d_indptr, d_feat, d_val, d_norm2, q_row0, d_cand_idx,
