@@ -1,0 +1,56 @@
+"""Turn ncu outputs (brought back in gpurun_out/) into the small text summaries kept under profiles/.
+
+  python tools/summarize_ncu.py launches gpurun_out/launches.csv         > profiles/rNN_launches.md
+  python tools/summarize_ncu.py full gpurun_out/prof.ncu-rep             > profiles/rNN_ncu_full.md
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+FULL_METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.sum",
+    "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+]
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        name = r[ki].split("(")[0].replace("void ", "")
+        v = float(r[vi].replace(",", ""))
+        v = {"ns": v / 1e6, "us": v / 1e3, "usecond": v / 1e3, "nsecond": v / 1e6}.get(r[ui], v)
+        agg.setdefault(name, []).append(v)
+    tot = sum(sum(v) for v in agg.values())
+    print("| kernel | launches | total ms | avg ms | share of GPU time |")
+    print("|---|---:|---:|---:|---:|")
+    for k, v in agg.items():
+        print(f"| `{k}` | {len(v)} | {sum(v):.3f} | {sum(v) / len(v):.3f} | {100 * sum(v) / tot:.1f} % |")
+    print(f"\nsum of kernel time: {tot:.3f} ms (ncu per-launch times are serialised and cold-cache: compare shares)")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        print(f"\n### `{r[idx['Kernel Name']][:110]}`\n")
+        print("| metric | value | unit |")
+        print("|---|---:|---|")
+        for m in FULL_METRICS:
+            if m in idx:
+                print(f"| {m} | {r[idx[m]]} | {units[idx[m]]} |")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
