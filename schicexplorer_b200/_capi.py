@@ -237,7 +237,7 @@ class CApi:
         """INT32 issue-rate micro-benchmark (Tint-op/s per SASS opcode) -- the roofline denominator."""
         out = np.zeros(12, dtype=np.float64)
         self.check(self.lib.schic_int32_peak(device, iters, _ptr(out)))
-        names = ("lop3", "imad", "mix_lop3_imad", "sm_mhz", "shf", "imad_hi", "vimnmx", "vimnmx3", "iadd")
+        names = ("lop3", "imad", "mix_lop3_imad", "sm_mhz", "shf", "imad_hi", "vimnmx", "vimnmx3", "iadd", "imad_wide")
         return dict(zip(names, out.tolist()))
 
     def k1_variant_ms(self, variant, n_rows, nnz, d_indptr, d_indices, n_hash, d_sig, reps=3) -> float:

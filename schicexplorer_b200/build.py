@@ -13,7 +13,11 @@ OUT = os.path.join(CSRC, "libschic_mh.so")
 SOURCES = ["capi.cu", "k1_signatures.cu", "k3_collisions.cu", "k3_select.cu", "k4_rerank.cu", "k5_graph.cu",
            "int_peak.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-DK1_ALL_VARIANTS"]
+              "-Xcompiler", "-fPIC"]
+# SCHIC_K1_ALL_VARIANTS=1 also compiles the 20 instruction-selection variants of K1 that
+# tools/k1_variants.py times (experiment only; the product uses K1_VARIANT in k1_signatures.cu)
+if os.environ.get("SCHIC_K1_ALL_VARIANTS") == "1":
+    NVCC_FLAGS.append("-DK1_ALL_VARIANTS")
 
 
 def _stale(target: str, deps) -> bool:

@@ -8,7 +8,7 @@
 
 namespace schic {
 
-enum PeakOp { OP_LOP3 = 0, OP_IMAD = 1, OP_MIX = 2, OP_SHF = 3, OP_IMADHI = 4, OP_MIN = 5, OP_MIN3 = 6, OP_ADD = 7 };
+enum PeakOp { OP_LOP3 = 0, OP_IMAD = 1, OP_MIX = 2, OP_SHF = 3, OP_IMADHI = 4, OP_MIN = 5, OP_MIN3 = 6, OP_ADD = 7, OP_WIDE = 8 };
 
 template <int OP>
 __device__ __forceinline__ void one_op(uint32_t& x, uint32_t y, uint32_t z, int chain) {
@@ -24,6 +24,8 @@ __device__ __forceinline__ void one_op(uint32_t& x, uint32_t y, uint32_t z, int 
         asm volatile("min.u32 %0, %0, %1;" : "+r"(x) : "r"(y));
     } else if (OP == OP_MIN3) {
         asm volatile("{ .reg .u32 t; min.u32 t, %1, %2; min.u32 %0, %0, t; }" : "+r"(x) : "r"(y), "r"(z));
+    } else if (OP == OP_WIDE) {
+        asm volatile("{ .reg .u64 w; .reg .u32 lo; mul.wide.u32 w, %0, %1; mov.b64 {lo, %0}, w; }" : "+r"(x) : "r"(y));
     } else {
         asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(y));
     }
@@ -84,7 +86,7 @@ static double run_one(int iters, uint32_t* d_out, unsigned long long* d_clk, cud
 }
 
 // out: [0] LOP3, [1] IMAD, [2] 1:1 LOP3+IMAD mix, [3] SM MHz during the mix, [4] SHF, [5] IMAD.HI,
-//      [6] VIMNMX (2-input), [7] VIMNMX3 (counted as one op), [8] IADD  -- all in Tint-op/s
+//      [6] VIMNMX (2-input), [7] VIMNMX3 (counted as one op), [8] IADD, [9] IMAD.WIDE -- all in Tint-op/s
 int run_int32_peak(int iters, double* out, cudaStream_t stream) {
     uint32_t* d_out = nullptr;
     unsigned long long* d_clk = nullptr;
@@ -98,6 +100,7 @@ int run_int32_peak(int iters, double* out, cudaStream_t stream) {
     out[6] = run_one<OP_MIN>(iters, d_out, d_clk, stream, nullptr);
     out[7] = run_one<OP_MIN3>(iters, d_out, d_clk, stream, nullptr);
     out[8] = run_one<OP_ADD>(iters, d_out, d_clk, stream, nullptr);
+    out[9] = run_one<OP_WIDE>(iters, d_out, d_clk, stream, nullptr);
     cudaFree(d_out);
     cudaFree(d_clk);
     return cudaGetLastError() == cudaSuccess ? 18 : -1;

@@ -64,6 +64,7 @@ __device__ __noinline__ uint32_t exact_segment_min(const uint32_t* __restrict__ 
 //   bit 0     the "+2" is issued as IMAD (FMA pipe) instead of VIADD (ALU pipe)
 //   bit 1     features are consumed in pairs so both running minima use the 3-input VIMNMX3
 //   bits 2-3  number (0..3) of the three ">> s" done as IMAD.HI (FMA pipe) instead of SHF (ALU pipe)
+//   bit 4     the final ">> 16" comes from IMAD.WIDE (FMA pipe) + a masking LOP3
 template <int V>
 __device__ __forceinline__ uint32_t shr_v(uint32_t x, int s, int which) {
     if (which < ((V >> 2) & 3)) {
@@ -81,7 +82,15 @@ __device__ __forceinline__ uint32_t kprime(uint32_t a, uint32_t one) {
     const uint32_t c = b * 5u;
     const uint32_t d = c ^ shr_v<V>(c, 4, 1);
     const uint32_t e = d * 2057u;
-    const uint32_t k = e ^ shr_v<V>(e, 16, 0);
+    uint32_t k;
+    if (V & 16) {
+        // (e >> 16) from the FMA pipe: the high word of d * (2057 << 16) holds bits 16..47 of d*2057,
+        // whose low 16 bits are e >> 16; one LOP3 masks and xors.
+        const unsigned long long wide = (unsigned long long)d * (unsigned long long)(2057u << 16);
+        k = e ^ ((uint32_t)(wide >> 32) & 0xFFFFu);
+    } else {
+        k = e ^ shr_v<V>(e, 16, 0);
+    }
     if (V & 1) {
         uint32_t kp;
         asm("mad.lo.u32 %0, %1, %2, 2;" : "=r"(kp) : "r"(k), "r"(one));
@@ -293,6 +302,7 @@ int launch_signatures32_variant(int variant, const int64_t* d_indptr, const uint
 #define K1_V(VV) case VV: k1_dispatch<VV>(5, grid, block, stream, d_indptr, d_feat, n_rows, nnz, indptr0, H, (slabs + 4) / 5, d_sig); break;
         K1_V(0) K1_V(1) K1_V(2) K1_V(3) K1_V(4) K1_V(5) K1_V(6) K1_V(7)
         K1_V(8) K1_V(9) K1_V(10) K1_V(11) K1_V(12) K1_V(13) K1_V(14) K1_V(15)
+        K1_V(16) K1_V(17) K1_V(18) K1_V(19)
 #undef K1_V
         default: return -1;
     }

@@ -152,6 +152,10 @@ def _wrap_device(ptr: int, shape, typestr: str, dtype, device) -> torch.Tensor:
     n = int(np.prod(shape))
     if n == 0:
         return torch.empty(shape, dtype=dtype, device=device)
+    if device.type == "cpu":   # CPU tests (gloo): the "device" buffers are host memory
+        import ctypes
+        buf = (ctypes.c_char * (n * np.dtype(typestr).itemsize)).from_address(ptr)
+        return torch.from_numpy(np.frombuffer(buf, dtype=np.dtype(typestr), count=n)).view(shape)
 
     class _Holder:
         __cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}

@@ -1,0 +1,145 @@
+"""CPU suite: the multi-process host logic (row partition, padded all-gather + compaction, global
+indptr rebuild, per-rank query ranges) under torch.distributed gloo, world_size 2 and 3. The
+device-pointer C ABI is emulated over host memory with the CPU oracle + numpy as the compute back end
+(test infrastructure), so shard-and-gather must reproduce the single-process oracle exactly."""
+import ctypes
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import REF_KWARGS
+from schicexplorer_b200 import synth
+from schicexplorer_b200.dist import ShardedMinHash, partition_rows, partition_rows_by_nnz
+
+
+def _np_at(ptr, n, dtype):
+    buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+class HostEmulatedDeviceApi:
+    """Same method names as the CUDA binding's device-pointer calls; pointers are host addresses."""
+
+    def __init__(self, oracle):
+        self.o = oracle
+        self.state = {}
+
+    def create(self, device=-1, **kw):
+        h = self.o.create(**kw)
+        self.state[h] = dict(kw=kw)
+        return h
+
+    def destroy(self, h):
+        self.o.destroy(h)
+
+    def set_stream(self, h, s):
+        pass
+
+    def fit_csr_device(self, h, n_rows, nnz, p_ip, p_ix, p_dt, append):
+        ip = _np_at(p_ip, n_rows + 1, np.int64).copy()
+        ix = _np_at(p_ix, nnz, np.uint32).copy()
+        dt = None if p_dt is None else _np_at(p_dt, nnz, np.float32).copy()
+        self.o.fit_csr(h, ip, ix, dt, append)
+        st = self.state[h]
+        st["sig"] = self.o.signatures(h, st["kw"]["number_of_hash_functions"])
+        st["n"] = n_rows
+
+    def signatures_device(self, h):
+        s = self.state[h]["sig"]
+        return s.ctypes.data, s.shape[0]
+
+    def set_database_device(self, h, n_total, row0, p_sig, p_ip, p_ix, p_dt):
+        st = self.state[h]
+        H = st["kw"]["number_of_hash_functions"]
+        st["db"] = dict(n=n_total, row0=row0, sig=_np_at(p_sig, n_total * H, np.uint32).reshape(n_total, H).copy())
+        if p_ip is not None:
+            ip = _np_at(p_ip, n_total + 1, np.int64).copy()
+            st["db"].update(ip=ip, ix=_np_at(p_ix, int(ip[-1]), np.uint32).copy(),
+                            dt=_np_at(p_dt, int(ip[-1]), np.float32).copy())
+
+    def kneighbors_device(self, h, k, fast, p_idx, p_dist, p_nv):
+        # the gathered database is re-fitted into a scratch oracle handle; this rank keeps its own rows
+        st = self.state[h]
+        db, kw = st["db"], st["kw"]
+        g = self.o.create(**kw)
+        if "ip" in db:
+            self.o.fit_csr(g, db["ip"], db["ix"], db["dt"], False)
+            assert np.array_equal(self.o.signatures(g, kw["number_of_hash_functions"]), db["sig"])
+        else:
+            pytest.skip("fast path without CSR is exercised through signatures only")
+        idx, dst, nv = self.o.kneighbors(g, k, fast)
+        self.o.destroy(g)
+        a, b = db["row0"], db["row0"] + st["n"]
+        _np_at(p_idx, st["n"] * k, np.int32)[:] = idx[a:b].ravel()
+        _np_at(p_dist, st["n"] * k, np.float32)[:] = dst[a:b].ravel()
+        _np_at(p_nv, st["n"], np.int32)[:] = nv[a:b]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, k, by_nnz, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle_api
+        cfg = synth.small_config(n, config_id=21, median_nnz=400, min_nnz=30, max_nnz=1500)
+        ip, ix, dt, _ = synth.generate_csr(cfg, workers=1)
+        bounds = partition_rows_by_nnz(ip, world) if by_nnz else partition_rows(n, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        kw = dict(REF_KWARGS, n_neighbors=k, fast=False, number_of_hash_functions=128, minimal_blocks_in_common=10)
+        api = HostEmulatedDeviceApi(oracle_api())
+        dev = torch.device("cpu")
+        sh = ShardedMinHash(api, n, bounds, dev, **kw)
+        a, b = int(ip[lo]), int(ip[hi])
+        t_ip = torch.from_numpy((ip[lo:hi + 1] - ip[lo]).copy())
+        t_ix = torch.from_numpy(ix[a:b].view(np.int32).copy())
+        t_dt = torch.from_numpy(dt[a:b].copy())
+        sh.fit_local(t_ip, t_ix, t_dt)
+        sh.gather()
+        idx, dst, nv = sh.kneighbors_local(k)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), idx=idx.numpy(), dist=dst.numpy(), nv=nv.numpy(),
+                 lo=lo, hi=hi, sig_all=sh._keep["sig_all"].numpy().view(np.uint32))
+        sh.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,by_nnz", [(2, False), (3, True)])
+def test_shard_and_gather_equals_single_process(oracle, tmp_path, world, by_nnz):
+    n, k = 45, 6
+    mp.spawn(_worker, args=(world, _free_port(), n, k, by_nnz, str(tmp_path)), nprocs=world, join=True)
+    cfg = synth.small_config(n, config_id=21, median_nnz=400, min_nnz=30, max_nnz=1500)
+    ip, ix, dt, _ = synth.generate_csr(cfg, workers=1)
+    kw = dict(REF_KWARGS, n_neighbors=k, fast=False, number_of_hash_functions=128, minimal_blocks_in_common=10)
+    h = oracle.create(**kw)
+    oracle.fit_csr(h, ip, ix, dt, False)
+    ref_sig = oracle.signatures(h, 128)
+    ridx, rdist, rnv = oracle.kneighbors(h, k)
+    oracle.destroy(h)
+    covered = 0
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        lo, hi = int(z["lo"]), int(z["hi"])
+        assert np.array_equal(z["sig_all"], ref_sig)               # every rank holds the whole database
+        assert np.array_equal(z["idx"], ridx[lo:hi]) and np.array_equal(z["nv"], rnv[lo:hi])
+        assert np.array_equal(z["dist"], rdist[lo:hi])
+        covered += hi - lo
+    assert covered == n
+
+
+def test_partitions():
+    assert partition_rows(10, 4) == [0, 3, 6, 8, 10]
+    ip = np.concatenate([[0], np.cumsum([100, 1, 1, 1, 1, 100, 1, 1])])
+    b = partition_rows_by_nnz(ip, 2)
+    assert b[0] == 0 and b[-1] == 8 and all(x <= y for x, y in zip(b, b[1:]))
+    loads = [ip[b[i + 1]] - ip[b[i]] for i in range(2)]
+    assert max(loads) <= 110

@@ -282,3 +282,20 @@ def test_error_codes(cuda):
         cuda.kneighbors(h, 5, n_rows=1)
     assert e.value.status == -2
     cuda.destroy(h)
+
+
+def test_multi_gpu_shard_and_gather_is_identical():
+    """NCCL path: needs >= 2 GPUs on the box (skipped on a 1-GPU box; tools/verify_multi_gpu.py is the
+    same check run by hand under torchrun, and tests/test_distributed.py covers the host logic on gloo)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.join(os.path.dirname(__file__), "..")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577",
+                        os.path.join(root, "tools", "verify_multi_gpu.py")], capture_output=True, text=True, timeout=600)
+    assert "MULTI_GPU_PARITY_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

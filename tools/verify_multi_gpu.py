@@ -1,0 +1,66 @@
+"""Multi-GPU parity check (run under torchrun on N >= 2 GPUs of one box):
+sharded build (NCCL all-gather of signatures and CSR shards) == single-GPU build, bit for bit on
+indices / counts, and identical fp32 distances (same kernels, same summation order per pair).
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/verify_multi_gpu.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from schicexplorer_b200 import _capi, synth  # noqa: E402
+from schicexplorer_b200.dist import ShardedMinHash, partition_rows_by_nnz  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    api = _capi.cuda_api()
+    n, k = int(os.environ.get("VERIFY_CELLS", "900")), 20
+    cfg = synth.small_config(n, config_id=31)
+    ip, ix, dt, _ = synth.generate_csr(cfg, workers=1)
+    ok = True
+    for fast in (True, False):
+        kw = dict(n_neighbors=k, number_of_hash_functions=800, fast=fast, minimal_blocks_in_common=100,
+                  excess_factor=1, max_bin_size=100000)
+        bounds = partition_rows_by_nnz(ip, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        a, b = int(ip[lo]), int(ip[hi])
+        sh = ShardedMinHash(api, n, bounds, dev, **kw)
+        sh.fit_local(torch.from_numpy((ip[lo:hi + 1] - ip[lo]).copy()).to(dev),
+                     torch.from_numpy(ix[a:b].view(np.int32).copy()).to(dev),
+                     None if fast else torch.from_numpy(dt[a:b].copy()).to(dev))
+        sh.gather()
+        idx, dst, nv = sh.kneighbors_local(k)
+        torch.cuda.synchronize()
+        # single-GPU reference on every rank (same library, local database)
+        h = api.create(device=local, **kw)
+        api.fit_csr(h, ip, ix, None if fast else dt, False)
+        ridx, rdst, rnv = api.kneighbors(h, k)
+        rsig = api.signatures(h, 800)
+        api.destroy(h)
+        same = (np.array_equal(idx.cpu().numpy(), ridx[lo:hi]) and np.array_equal(nv.cpu().numpy(), rnv[lo:hi])
+                and np.array_equal(dst.cpu().numpy(), rdst[lo:hi])
+                and np.array_equal(sh._keep["sig_all"].cpu().numpy().view(np.uint32), rsig))
+        flag = torch.tensor([int(same)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = ok and bool(flag.item())
+        if rank == 0:
+            print(f"fast={fast}: world={world} rows/rank={[bounds[i+1]-bounds[i] for i in range(world)]} identical={bool(flag.item())}")
+        sh.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_PARITY_OK" if ok else "MULTI_GPU_PARITY_FAILED")
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
