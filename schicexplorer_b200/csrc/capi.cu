@@ -87,6 +87,7 @@ struct schic_mh_handle {
 
     // scratch of kneighbors
     DevBuf<uint16_t> counts; DevBuf<int32_t> cand_idx, cand_cnt, cand_nv;
+    DevBuf<uint32_t> sig_masked;   // database signatures with oversized buckets blanked (K2)
     DevBuf<int32_t> out_idx, out_nv; DevBuf<float> out_dist;
     DevBuf<int64_t> g_indptr; DevBuf<int32_t> g_indices; DevBuf<float> g_data;
 
@@ -168,6 +169,14 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
     return 0;
 }
 
+int prune_buckets(schic_mh_handle* h, const uint32_t* db_sig, int64_t ndb) {
+    const int H = h->p.number_of_hash_functions;
+    ST_TRY(h->sig_masked.reserve(ndb * (int64_t)H, 0, h->stream));
+    add_launches(h, schic::launch_bucket_mask(db_sig, ndb, H, h->p.max_bin_size, h->sig_masked.p, h->stream));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
 int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const float* val, int64_t rows) {
     if (h->norm_of == (const void*)indptr && h->norm_rows == rows) return 0;
     ST_TRY(h->norm2.reserve(rows, 0, h->stream));
@@ -192,8 +201,6 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
     const int64_t* db_indptr = h->ext ? h->db_indptr : h->d_indptr();
     const uint32_t* db_feat = h->ext ? h->db_feat : h->d_feat();
     const float* db_val = h->ext ? h->db_val : h->d_val();
-    if (ndb >= h->p.max_bin_size)
-        return fail(SCHIC_ERR_UNSUPPORTED, "n_fitted >= max_bin_size: bucket pruning is not built yet");
     if (k > ndb) k = (int)ndb;   // cannot have more neighbours than fitted rows; outputs keep stride k
     const int64_t kc64 = fast ? (int64_t)k : std::min<int64_t>((int64_t)k * std::max(1, h->p.excess_factor), ndb);
     const int kcand = (int)kc64;
@@ -203,6 +210,13 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
     }
     reset_stage(h, {ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H});
     cudaStream_t s = h->stream;
+    const uint32_t* q_sig = h->sig.p;
+    if (ndb >= h->p.max_bin_size) {   // rule 5: blank the members of buckets with >= max_bin_size cells
+        StageTimer t(h, ST_COLL, s);
+        ST_TRY(prune_buckets(h, db_sig, ndb));
+        db_sig = h->sig_masked.p;
+        q_sig = h->sig_masked.p + row0 * (int64_t)H;
+    }
 
     ST_TRY(h->cand_idx.reserve(nq * kcand, 0, s));
     ST_TRY(h->cand_cnt.reserve(nq * kcand, 0, s));
@@ -223,7 +237,7 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
         const int64_t q1 = std::min(nq, q0 + qb);
         {
             StageTimer t(h, ST_COLL, s);
-            add_launches(h, schic::launch_collision_counts(h->sig.p + q0 * (int64_t)H, q1 - q0, db_sig, ndb, H,
+            add_launches(h, schic::launch_collision_counts(q_sig + q0 * (int64_t)H, q1 - q0, db_sig, ndb, H,
                                                           h->counts.p, ld, s));
         }
         {
@@ -520,13 +534,17 @@ int schic_mh_collision_counts(schic_mh_handle* h, int64_t row0, int64_t row1, ui
     const int H = h->p.number_of_hash_functions;
     const int64_t ndb = h->ext ? h->db_n : h->n;
     const uint32_t* db_sig = h->ext ? h->db_sig : h->sig.p;
-    if (ndb >= h->p.max_bin_size)
-        return fail(SCHIC_ERR_UNSUPPORTED, "n_fitted >= max_bin_size: bucket pruning is not built yet");
+    const uint32_t* q_sig = h->sig.p;
+    if (ndb >= h->p.max_bin_size) {
+        ST_TRY(prune_buckets(h, db_sig, ndb));
+        db_sig = h->sig_masked.p;
+        q_sig = h->sig_masked.p + (h->ext ? h->db_row0 : 0) * (int64_t)H;
+    }
     const int64_t ld = (ndb + 7) & ~(int64_t)7;
     const int64_t nq = row1 - row0;
     if (nq == 0) return SCHIC_OK;
     ST_TRY(h->counts.reserve(nq * ld, 0, h->stream));
-    add_launches(h, schic::launch_collision_counts(h->sig.p + row0 * (int64_t)H, nq, db_sig, ndb, H, h->counts.p, ld, h->stream));
+    add_launches(h, schic::launch_collision_counts(q_sig + row0 * (int64_t)H, nq, db_sig, ndb, H, h->counts.p, ld, h->stream));
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpy2DAsync(out, (size_t)ndb * 2, h->counts.p, (size_t)ld * 2, (size_t)ndb * 2, (size_t)nq,
                              cudaMemcpyDeviceToHost, h->stream));

@@ -24,6 +24,11 @@ int launch_signatures64(const int64_t* d_indptr, const uint32_t* d_feat_lo, cons
                         int64_t n_rows, int64_t nnz, int64_t indptr0, int H, uint32_t* d_sig,
                         cudaStream_t stream);
 
+// ---- K2: max_bin_size bucket pruning (k2_buckets.cu) ------------------------------------------
+// out[c][j] = sig[c][j] unless its bucket {d : sig[d][j] == sig[c][j]} has >= max_bin_size members, then 0.
+int launch_bucket_mask(const uint32_t* d_sig, int64_t n, int H, int64_t max_bin_size, uint32_t* d_out,
+                       cudaStream_t stream);
+
 // ---- K3: collision counts (k3_collisions.cu) ---------------------------------------------
 // cnt[q][d] = #{j : sigQ[q][j] == sigD[d][j], value admissible}; uint16 row major [nq, ld_out].
 int launch_collision_counts(const uint32_t* d_sig_q, int64_t nq, const uint32_t* d_sig_db, int64_t ndb,

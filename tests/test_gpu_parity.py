@@ -299,3 +299,23 @@ def test_multi_gpu_shard_and_gather_is_identical():
                         "--master-addr", "127.0.0.1", "--master-port", "29577",
                         os.path.join(root, "tools", "verify_multi_gpu.py")], capture_output=True, text=True, timeout=600)
     assert "MULTI_GPU_PARITY_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_max_bin_size_bucket_pruning(cuda, oracle):
+    """SURVEY 8(c) rule 5: buckets with >= max_bin_size members are ignored (K2)."""
+    X = synth_csr(1, median_nnz=300, min_nnz=100, max_nnz=600)
+    Xr = vstack([X] * 6).tocsr()
+    for mbs, expect in ((5, 0), (6, 0), (7, 32)):
+        with Fitted(cuda, Xr, number_of_hash_functions=32, minimal_blocks_in_common=1, max_bin_size=mbs) as g:
+            assert (cuda.collision_counts(g.h) == expect).all()
+    # the --saveMemory branch of the reference does not pass max_bin_size (upstream default 50):
+    # with a few hundred clustered cells many buckets are larger than that
+    Xs = synth_csr(260, seed=13)
+    for fast in (True, False):
+        kw = dict(fast=fast, n_neighbors=15, max_bin_size=50, minimal_blocks_in_common=20)
+        with Fitted(cuda, Xs, **kw) as g, Fitted(oracle, Xs, **kw) as o:
+            cg, co = cuda.collision_counts(g.h), oracle.collision_counts(o.h)
+            assert np.array_equal(cg, co)
+            assert (np.diag(co) < 800).any()          # pruning really happened
+            a, b = cuda.kneighbors(g.h, 15), oracle.kneighbors(o.h, 15)
+            assert_neighbours_equal_up_to_ties(*a, *b, 0 if fast else RTOL)
