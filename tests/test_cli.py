@@ -1,0 +1,74 @@
+"""CPU suite: the scHicClusterMinHash command line (same flags as the reference) end to end, with the
+CPU oracle injected as the C-ABI back end. Re-expresses the assertions of the reference's
+schicexplorer/test/test_scHicClusterMinHash.py:35-216 -- cell order of the output file and exactly
+3 distinct labels -- on the same 20 cells."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from schicexplorer_b200 import MinHash, scHicClusterMinHash
+
+MATRIX = os.path.join(GOLDEN, "fixture20.npz")
+
+
+@pytest.fixture(autouse=True)
+def oracle_backed(oracle, monkeypatch):
+    monkeypatch.setattr(MinHash, "_api_factory", staticmethod(lambda: oracle))
+
+
+def check_output(path, names, n_clusters=3):
+    rows = [l.split(" ") for l in open(path).read().strip().split("\n")]
+    assert [r[0] for r in rows] == names                       # row order = cell_name_list order
+    assert len({r[1] for r in rows}) == n_clusters             # "exactly 3 distinct labels"
+
+
+def run(tmp_path, extra, method="kmeans"):
+    out = str(tmp_path / "clusters.txt")
+    args = f"--matrix {MATRIX} --numberOfClusters 3 --clusterMethod {method} --outFileName {out} -t 3 -nh 800 " \
+           f"--createScatterPlot {tmp_path / 'plot.png'} {extra}".split()
+    scHicClusterMinHash.main(args)
+    return out
+
+
+@pytest.mark.parametrize("method,extra", [
+    ("kmeans", "-dim_pca 100"), ("agglomerative_ward", "--noPCA"), ("agglomerative_complete", "--noPCA"),
+    ("agglomerative_average", "--noPCA"), ("agglomerative_single", "--noPCA"), ("birch", "-dim_pca 50"),
+    ("spectral", ""), ("spectral", "--chromosomes chr1 chr2"), ("kmeans", "-em"), ("spectral", "-em"),
+    ("kmeans", "--saveMemory"), ("agglomerative_ward", "--saveMemory --noPCA"), ("spectral", "--saveMemory -em"),
+])
+def test_cli_reference_cases(tmp_path, fixture20, method, extra):
+    out = run(tmp_path, extra, method)
+    check_output(out, fixture20[1])
+
+
+def test_flag_contract():
+    p = scHicClusterMinHash.parse_arguments()
+    a = p.parse_args("-m x.scool -o out.txt".split())
+    # defaults of the reference (scHicClusterMinHash.py:47-240)
+    assert a.numberOfClusters == 12 and a.clusterMethod == "spectral" and a.numberOfHashFunctions == 4000
+    assert a.numberOfNearestNeighbors is None and a.shareOfMatrixToBeTransferred == 0.25 and a.threads == 8
+    assert a.dimensionsPCA == 100 and a.dpi == 300 and a.createScatterPlot == "scatterPlot.eps"
+    assert a.umap_n_neighbors == 30 and a.umap_metric == "canberra" and a.umap_min_dist == 0.3
+    # the -em polarity trap: store_false, so the default True means fast=True
+    assert a.euclideanModeMinHash is True
+    assert p.parse_args("-m x -o y -em".split()).euclideanModeMinHash is False
+    b = p.parse_args("-m x -o y -c 7 -cm birch -ic -sirm raw.npz -nh 1200 -k 50 -s 0.5 -sm --noPCA --noUMAP "
+                     "-dim_pca 20 -d 5000000 --chromosomes chr1 chr2 -av 1 -lt t.tex --runInHyperoptMode -t 4".split())
+    assert b.numberOfClusters == 7 and b.intraChromosomalContactsOnly and b.saveMemory and b.distance == 5e6
+    assert b.chromosomes == ["chr1", "chr2"] and b.numberOfNearestNeighbors == 50
+    with pytest.raises(SystemExit) as e:
+        p.parse_args(["--help"])
+    assert e.value.code == 0
+    with pytest.raises(SystemExit) as e:
+        p.parse_args(["--version"])
+    assert e.value.code == 0
+
+
+def test_save_intermediate_raw_matrix(tmp_path, fixture20):
+    from scipy.sparse import load_npz
+    raw = str(tmp_path / "raw.npz")
+    run(tmp_path, f"--noPCA -sirm {raw}", "agglomerative_ward")
+    X = load_npz(raw)
+    assert X.shape == fixture20[0].shape and X.nnz == fixture20[0].nnz
