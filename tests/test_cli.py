@@ -72,3 +72,16 @@ def test_save_intermediate_raw_matrix(tmp_path, fixture20):
     run(tmp_path, f"--noPCA -sirm {raw}", "agglomerative_ward")
     X = load_npz(raw)
     assert X.shape == fixture20[0].shape and X.nnz == fixture20[0].nnz
+
+
+@pytest.mark.parametrize("fname,prefix", [("test_matrix.scool", "/cells/"), ("test_matrix_old.scool", "/")])
+def test_cli_on_real_scool(tmp_path, fname, prefix):
+    """The reference's tests pass `--matrix test-data/test_matrix.scool`
+    (test_scHicClusterMinHash.py:66-74); same file here, read without cooler/h5py."""
+    out = str(tmp_path / "clusters.txt")
+    args = f"--matrix {os.path.join(GOLDEN, fname)} --numberOfClusters 3 --clusterMethod kmeans --outFileName {out} " \
+           f"-t 3 -nh 800 -dim_pca 100 --createScatterPlot {tmp_path / 'plot.png'}".split()
+    scHicClusterMinHash.main(args)
+    rows = [l.split(" ") for l in open(out).read().strip().split("\n")]
+    assert len(rows) == 20 and all(r[0].startswith(prefix) for r in rows)
+    assert len({r[1] for r in rows}) == 3
