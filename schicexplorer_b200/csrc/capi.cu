@@ -6,6 +6,7 @@
 // path in this file: without a usable GPU every entry point fails with SCHIC_ERR_NO_DEVICE.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -77,7 +78,10 @@ struct schic_mh_handle {
     DevBuf<int64_t> indptr; DevBuf<uint32_t> feat; DevBuf<uint32_t> feat_hi; DevBuf<float> val;
     bool have_val = false, have_hi = false;
     DevBuf<uint32_t> sig;
+    DevBuf<unsigned char> k1_scratch;    // work-item list of the filtered K1 kernel
     DevBuf<double> norm2; int64_t norm_rows = 0; const void* norm_of = nullptr;
+    DevBuf<uint32_t> win_dir, max_feat; int n_windows = 0;   // window directory of the windowed rerank (0: hash kernel)
+    int window_mode = 32;
 
     // external database (distributed query)
     bool ext = false;
@@ -158,11 +162,23 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
     const int H = h->p.number_of_hash_functions;
     uint32_t* sig = h->sig.p + r0 * (int64_t)H;
     int nl;
-    if (h->p.hash_width == 64)
+    const char* k1_mode = getenv("SCHIC_K1_MODE");      // "chunk": the unfiltered fixed-chunk kernel (experiments, tests)
+    if (h->p.hash_width == 64) {
         nl = schic::launch_signatures64(h->d_indptr() + r0, h->d_feat(), h->have_hi ? h->feat_hi.p : nullptr,
                                         r1 - r0, pos1 - pos0, pos0, H, sig, s);
-    else
+    } else if (k1_mode && strcmp(k1_mode, "chunk") == 0) {
         nl = schic::launch_signatures32(h->d_indptr() + r0, h->d_feat(), r1 - r0, pos1 - pos0, pos0, H, sig, s);
+    } else {
+        // the scratch of an earlier chunk may still be read by its kernel: same stream, so reuse is ordered,
+        // but growing would free it -- size it for the worst case of this call up front
+        const size_t need = schic::k1f_scratch_bytes(r1 - r0, pos1 - pos0);
+        if ((int64_t)need > h->k1_scratch.cap) {
+            CU_TRY(cudaStreamSynchronize(s));
+            ST_TRY(h->k1_scratch.reserve((int64_t)need, 0, s));
+        }
+        nl = schic::launch_signatures32_filter(h->d_indptr() + r0, h->d_feat(), r1 - r0, pos1 - pos0, H, sig,
+                                               h->k1_scratch.p, s);
+    }
     if (nl < 0) return fail(SCHIC_ERR_CUDA, "K1 launch failed");
     add_launches(h, nl);
     CU_TRY(cudaGetLastError());
@@ -177,11 +193,35 @@ int prune_buckets(schic_mh_handle* h, const uint32_t* db_sig, int64_t ndb) {
     return 0;
 }
 
-int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const float* val, int64_t rows) {
+// Per-database preparation of the exact rerank, cached until the next fit: fp64 row norms and, when the
+// feature space spans at most kMaxWindows windows, the window directory of the windowed kernel.
+// SCHIC_K4_MODE=hash forces the hash-table kernel (tests compare the two).
+int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const uint32_t* feat, const float* val, int64_t rows) {
     if (h->norm_of == (const void*)indptr && h->norm_rows == rows) return 0;
-    ST_TRY(h->norm2.reserve(rows, 0, h->stream));
-    add_launches(h, schic::launch_row_norms(indptr, val, rows, 0, h->norm2.p, h->stream));
+    constexpr int kMaxWindows = 1024;
+    cudaStream_t s = h->stream;
+    ST_TRY(h->norm2.reserve(rows, 0, s));
+    add_launches(h, schic::launch_row_norms(indptr, val, rows, 0, h->norm2.p, s));
     CU_TRY(cudaGetLastError());
+    h->n_windows = 0;
+    const char* mode = getenv("SCHIC_K4_MODE");
+    h->window_mode = (mode && strcmp(mode, "window64") == 0) ? 64 : 32;
+    if (!(mode && strcmp(mode, "hash") == 0)) {
+        ST_TRY(h->max_feat.reserve(1, 0, s));
+        const int nl = schic::launch_row_max_feature(indptr, feat, rows, h->max_feat.p, s);
+        if (nl < 0) return fail(SCHIC_ERR_CUDA, "max-feature launch failed");
+        add_launches(h, nl);
+        uint32_t mx = 0;
+        CU_TRY(cudaMemcpyAsync(&mx, h->max_feat.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        const int nw = schic::rerank_window_count(mx);
+        if (nw <= kMaxWindows) {
+            ST_TRY(h->win_dir.reserve(rows * (int64_t)(nw + 1), 0, s));
+            add_launches(h, schic::launch_row_window_dir(indptr, feat, rows, nw, h->win_dir.p, s));
+            CU_TRY(cudaGetLastError());
+            h->n_windows = nw;
+        }
+    }
     h->norm_of = indptr;
     h->norm_rows = rows;
     return 0;
@@ -230,7 +270,18 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
 
     // query blocking: the uint16 count matrix is produced and consumed in row blocks of <= 2 GiB
     const int64_t ld = (ndb + 7) & ~(int64_t)7;
-    int64_t qb = std::max<int64_t>(128, ((int64_t)1 << 30) / ld);
+    // budget: a quarter of the free HBM, at least 2 GiB, at most 32 GiB (the all-rows-in-one-block case also
+    // lets K3 use the symmetry of the counts)
+    int64_t budget_elems = (int64_t)1 << 30;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+            budget_elems = std::max<int64_t>(budget_elems, std::min<int64_t>((int64_t)(free_b / 4) / 2, (int64_t)1 << 34));
+        else
+            cudaGetLastError();
+        budget_elems = std::max<int64_t>(budget_elems, h->counts.cap);   // never shrink below what is already held
+    }
+    int64_t qb = std::max<int64_t>(128, budget_elems / ld);
     qb = std::min<int64_t>((qb / 128) * 128, (nq + 127) / 128 * 128);
     ST_TRY(h->counts.reserve(qb * ld, 0, s));
     for (int64_t q0 = 0; q0 < nq; q0 += qb) {
@@ -256,8 +307,10 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
                                                    h->p.absolute_numbers, d_idx, d_dist, d_nv, s));
     } else {
         StageTimer t(h, ST_RERANK, s);
-        ST_TRY(ensure_norms(h, db_indptr, db_val, ndb));
-        const int nl = schic::launch_rerank(db_indptr, db_feat, db_val, 0, h->norm2.p, row0, nq, h->cand_idx.p,
+        ST_TRY(ensure_norms(h, db_indptr, db_feat, db_val, ndb));
+        const int nl = schic::launch_rerank(db_indptr, db_feat, db_val, 0, h->norm2.p,
+                                            h->n_windows > 0 ? h->win_dir.p : nullptr, h->n_windows, h->window_mode, row0, nq,
+                                            h->cand_idx.p,
                                             h->cand_nv.p, kcand, k, d_idx, d_dist, d_nv, s);
         if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k * excess_factor too large for the in-shared-memory rerank");
         add_launches(h, nl);
@@ -663,17 +716,22 @@ int schic_k1_variant_ms(int32_t variant, int64_t n_rows, int64_t nnz, const int6
     cudaEvent_t e0, e1;
     CU_TRY(cudaEventCreate(&e0));
     CU_TRY(cudaEventCreate(&e1));
-    if (schic::launch_signatures32_variant(variant, d_indptr, d_indices, n_rows, nnz, pos0, n_hash, d_sig, nullptr) < 0)
-        return fail(SCHIC_ERR_UNSUPPORTED, "variant not compiled in");
+    void* scratch = nullptr;
+    if (variant >= 100) CU_TRY(cudaMalloc(&scratch, schic::k1f_scratch_bytes(n_rows, nnz)));
+    auto launch = [&]() {
+        return variant >= 100 ? schic::launch_signatures32_filter(d_indptr, d_indices, n_rows, nnz, n_hash, d_sig, scratch, nullptr)
+                              : schic::launch_signatures32_variant(variant, d_indptr, d_indices, n_rows, nnz, pos0, n_hash, d_sig, nullptr);
+    };
+    if (launch() < 0) return fail(SCHIC_ERR_UNSUPPORTED, "variant not compiled in");
     CU_TRY(cudaEventRecord(e0, nullptr));
-    for (int r = 0; r < reps; ++r)
-        schic::launch_signatures32_variant(variant, d_indptr, d_indices, n_rows, nnz, pos0, n_hash, d_sig, nullptr);
+    for (int r = 0; r < reps; ++r) launch();
     CU_TRY(cudaEventRecord(e1, nullptr));
     CU_TRY(cudaEventSynchronize(e1));
     CU_TRY(cudaEventElapsedTime(ms_out, e0, e1));
     *ms_out /= (float)reps;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (scratch) cudaFree(scratch);
     CU_TRY(cudaGetLastError());
     return SCHIC_OK;
 }

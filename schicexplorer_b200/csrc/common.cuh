@@ -17,6 +17,11 @@ constexpr uint32_t kModulus = SCHIC_MH_MODULUS;  // 2^31 - 1; also the empty-row
 int launch_signatures32(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
                         int64_t indptr0, int H, uint32_t* d_sig /* first row of this batch */,
                         cudaStream_t stream);
+// Filtered variant (whole rows per CTA, cheap "cannot be a new minimum" test per evaluation, exact path
+// only when it fails). d_scratch: k1f_scratch_bytes(n_rows, nnz) bytes of device memory.
+size_t k1f_scratch_bytes(int64_t n_rows, int64_t nnz);
+int launch_signatures32_filter(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
+                               int H, uint32_t* d_sig, void* d_scratch, cudaStream_t stream);
 // variant >= 0 selects an instruction-selection variant (only in builds with -DK1_ALL_VARIANTS).
 int launch_signatures32_variant(int variant, const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows,
                                 int64_t nnz, int64_t indptr0, int H, uint32_t* d_sig, cudaStream_t stream);
@@ -49,12 +54,20 @@ int launch_fast_distance(const int32_t* d_idx_in, const int32_t* d_cnt_in, const
 // norms2[r] = sum of squares of row r (fp64).
 int launch_row_norms(const int64_t* d_indptr, const float* d_val, int64_t n_rows, int64_t indptr0,
                      double* d_norm2, cudaStream_t stream);
+// Window directory of the windowed rerank kernel: largest feature id of the database (device
+// scalar), number of windows for it, and dir[row][0..n_windows] (uint32 offsets from the row start).
+int launch_row_max_feature(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, uint32_t* d_out_max,
+                           cudaStream_t stream);
+int rerank_window_count(uint32_t max_feature);
+int launch_row_window_dir(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int n_windows,
+                          uint32_t* d_dir, cudaStream_t stream);
 // For query q (database row q_row0+q) and each of its candidates: euclidean distance over the
 // union of supports; then order by (dist asc, idx asc), keep k. CSR arrays are the database's.
+// d_dir != nullptr selects the windowed kernel (needs the directory above), else the hash-table kernel.
 int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* d_val, int64_t indptr0,
-                  const double* d_norm2, int64_t q_row0, int64_t nq, const int32_t* d_cand_idx,
-                  const int32_t* d_cand_nvalid, int kcand, int k, int32_t* d_idx_out, float* d_dist_out,
-                  int32_t* d_nvalid_out, cudaStream_t stream);
+                  const double* d_norm2, const uint32_t* d_dir, int n_windows, int window_mode /* 32 | 64: entry width */,
+                  int64_t q_row0, int64_t nq, const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int kcand, int k,
+                  int32_t* d_idx_out, float* d_dist_out, int32_t* d_nvalid_out, cudaStream_t stream);
 
 // ---- K5: graph emit (k5_graph.cu) ---------------------------------------------------------
 // CSR of the kNN graph: indptr = exclusive scan of n_valid, rows sorted by column.

@@ -214,6 +214,225 @@ k1_signatures32_kernel(const int64_t* __restrict__ indptr, const uint32_t* __res
     }
 }
 
+// ---- filtered variant ---------------------------------------------------------------------------
+// The kernel above evaluates the full hash + both running minima for every (feature, hash function):
+// 7 ALU-pipe ops per evaluation, and ncu shows the ALU pipe 98 % busy. But after m features of a row
+// the probability that the next one lowers a given minimum is only ~1/m, so almost every evaluation
+// only has to prove "not smaller than the current minimum". The last mix step is
+//     k6 = k5 ^ (k5 >> 16),   v = k6 mod (2^31 - 1)   with   k5 = d * 2057,
+// and bits 30..16 of k6 equal bits 30..16 of k5: a 15-bit prefix of v (up to the +1 carry of the
+// modulo fold) is known one xor-shift and the whole modulo earlier. With
+//     t = d * 4114 + 0x20000  (mod 2^32)          -- one IMAD: 2*k5, prefix moved up by one step
+// v < best implies t <= thr(best) = ((best >> 16) + 2) * 2^17 - 1 (the +0x20000 makes the three
+// residue-wrapping inputs, prefix 0x7FFF, land on t < 2^17 so they always pass; proof in DESIGN.md).
+// Fast path per evaluation: 3 IMAD (FMA pipe) + 2 x (SHF + LOP3) + 1 compare = 5 ALU-pipe ops instead
+// of 7; only when some lane passes the filter (true new minima: ~32 ln(m) per warp and hash register
+// over a row, plus 2^-14 false positives) the warp takes an exact slow path for that pair of features.
+// To make the minima long-lived a CTA owns a whole row (or an up-to-K1F_PART slice of a long row),
+// streaming it through a shared-memory tile; work items are sorted by length (longest first) by a
+// tiny single-CTA kernel so the tail of the grid is made of short items.
+constexpr int K1F_TILE = 2048;
+constexpr int K1F_PART = 16384;
+constexpr int K1F_BINS = 64;
+
+struct K1Item { int64_t begin; int32_t len; int32_t row; };
+
+// items[]: every row cut into ceil(len / K1F_PART) equal parts, ordered by part length, longest first
+// (counting sort on 64 length bins; order inside a bin is arbitrary, the result does not depend on it).
+__global__ void __launch_bounds__(1024)
+k1f_build_items_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, K1Item* __restrict__ items,
+                       int* __restrict__ n_items) {
+    __shared__ int hist[K1F_BINS];
+    __shared__ int cursor[K1F_BINS];
+    for (int i = threadIdx.x; i < K1F_BINS; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    auto split = [](int64_t len, int& nparts, int& plen, int& bin) {
+        nparts = (int)((len + K1F_PART - 1) / K1F_PART);
+        plen = nparts ? (int)((len + nparts - 1) / nparts) : 0;
+        bin = K1F_BINS - 1 - (int)(((int64_t)plen * (K1F_BINS - 1)) / K1F_PART);    // long parts -> low bins
+    };
+    for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+        int np, pl, b;
+        split(indptr[r + 1] - indptr[r], np, pl, b);
+        if (np) atomicAdd(&hist[b], np);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < K1F_BINS; ++b) { cursor[b] = acc; acc += hist[b]; }
+        *n_items = acc;
+    }
+    __syncthreads();
+    for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+        int np, pl, b;
+        const int64_t beg = indptr[r], len = indptr[r + 1] - beg;
+        split(len, np, pl, b);
+        if (!np) continue;
+        const int pos = atomicAdd(&cursor[b], np);
+        for (int p = 0; p < np; ++p) {
+            const int64_t o = (int64_t)p * pl;
+            K1Item it;
+            it.begin = beg + o;
+            it.len = (int)min((int64_t)pl, len - o);
+            it.row = (int)r;
+            items[pos + p] = it;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t k1f_filter_key(uint32_t a) {
+    const uint32_t b = a ^ (a >> 12);
+    const uint32_t c = b * 5u;
+    const uint32_t d = c ^ (c >> 4);
+    return d * 4114u + 0x20000u;
+}
+
+__device__ __forceinline__ uint32_t k1f_threshold(uint32_t best) {
+    const uint32_t hb = best >> 16;
+    return hb >= 0x7FFEu ? 0xFFFFFFFFu : ((hb + 2u) << 17) - 1u;
+}
+
+__device__ __forceinline__ void k1f_exact_update(uint32_t a, uint32_t& best, uint32_t& thr) {
+    const uint32_t k6 = mix_from_a(a);
+    uint32_t v = (k6 & kModulus) + (k6 >> 31);     // k6 mod (2^31 - 1): fold the top bit, then one subtract
+    v = v >= kModulus ? v - kModulus : v;
+    if (v < best) { best = v; thr = k1f_threshold(v); }
+}
+
+// Exact (mod, then min) over a whole item for one hash constant, features read straight from global
+// memory (all lanes the same address): only used when the speculative start threshold was too low
+// for some lane (probability ~e^-11 per lane and hash function).
+__device__ __noinline__ uint32_t k1f_exact_item_min(const uint32_t* __restrict__ src, int len, uint32_t c) {
+    uint32_t best = kModulus;
+    for (int i = 0; i < len; ++i) {
+        const uint32_t k6 = mix_from_a((__ldg(src + i) + 1u) * c - 1u);
+        uint32_t v = (k6 & kModulus) + (k6 >> 31);
+        v = v >= kModulus ? v - kModulus : v;
+        best = v < best ? v : best;
+    }
+    return best;
+}
+
+// grid = (item upper bound, unit groups); block = 32 * warps, one unit (R*32 hash functions) per warp.
+// Per lane and hash register r: best[r] (exact running minimum), thr[r] (filter threshold), mn[r]
+// (running minimum of the filter keys since the last exact step). The inner loop only feeds mn[r]
+// (one 3-input min per two evaluations); after every 4 features one compare per r decides whether
+// the exact path has to look at those 4 features.
+// The start threshold is speculative: thr0 ~ 2^32 * 12 / len, i.e. the filter assumes the final
+// minimum is below the level ~12 of the len features reach. The assumption is verified at the end
+// (thr(best) <= thr0 proves that nothing that was skipped could have been smaller); where it fails
+// the lane's minimum is recomputed exactly. This removes the ~ln(len) early updates per minimum.
+template <int R>
+__global__ void __launch_bounds__(32 * K1_MAX_WARPS)
+k1_filter_kernel(const K1Item* __restrict__ items, const int* __restrict__ n_items, const uint32_t* __restrict__ feat,
+                 int H, int units, uint32_t* __restrict__ sig) {
+    __shared__ __align__(16) uint32_t tile[K1F_TILE];
+    if ((int)blockIdx.x >= *n_items) return;
+    const K1Item it = items[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const int unit = blockIdx.y * n_warps + warp;
+    const bool active = unit < units;
+    const int j0 = unit * R * 32 + lane;
+
+    const uint32_t thr0 = it.len <= 12 ? 0xFFFFFFFFu
+                                       : (uint32_t)min((unsigned long long)0xFFFFFFFFu, (12ull << 32) / (unsigned)it.len);
+    uint32_t c[R], best[R], thr[R], mn[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        c[r] = 32767u * (uint32_t)(j0 + 32 * r + 1);     // a = (f+1)(j+1)*32767 - 1 = (f+1)*c - 1
+        best[r] = kModulus;
+        thr[r] = thr0;
+        mn[r] = 0xFFFFFFFFu;
+    }
+    const uint32_t* __restrict__ src = feat + it.begin;
+    for (int t0 = 0; t0 < it.len; t0 += K1F_TILE) {
+        const int tlen = min(K1F_TILE, it.len - t0);
+        const int tlen4 = (tlen + 3) & ~3;               // padded with copies of the last feature (min is idempotent)
+        __syncthreads();
+        for (int i = threadIdx.x; i < tlen4; i += blockDim.x) tile[i] = __ldg(src + t0 + min(i, tlen - 1)) + 1u;
+        __syncthreads();
+        if (!active) continue;
+        for (int i = 0; i < tlen4; i += 4) {
+            const uint4 f4 = *reinterpret_cast<const uint4*>(tile + i);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t t0k = k1f_filter_key(f4.x * c[r] - 1u), t1k = k1f_filter_key(f4.y * c[r] - 1u);
+                const uint32_t t2k = k1f_filter_key(f4.z * c[r] - 1u), t3k = k1f_filter_key(f4.w * c[r] - 1u);
+                mn[r] = min(mn[r], min(t0k, t1k));
+                mn[r] = min(mn[r], min(t2k, t3k));
+            }
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) any = any || (mn[r] <= thr[r]);
+            if (any) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (mn[r] <= thr[r]) {
+                        k1f_exact_update(f4.x * c[r] - 1u, best[r], thr[r]);
+                        k1f_exact_update(f4.y * c[r] - 1u, best[r], thr[r]);
+                        k1f_exact_update(f4.z * c[r] - 1u, best[r], thr[r]);
+                        k1f_exact_update(f4.w * c[r] - 1u, best[r], thr[r]);
+                        mn[r] = 0xFFFFFFFFu;
+                    }
+                }
+            }
+        }
+    }
+    if (active) {
+        uint32_t* __restrict__ sig_row = sig + (int64_t)it.row * H;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int j = j0 + 32 * r;
+            // the speculation holds iff everything skipped under thr0 is provably >= best
+            if (k1f_threshold(best[r]) > thr0) best[r] = k1f_exact_item_min(src, it.len, c[r]);
+            if (j < H) atomicMin(sig_row + j, best[r]);
+        }
+    }
+}
+
+int64_t k1f_item_capacity(int64_t n_rows, int64_t nnz) { return n_rows + nnz / K1F_PART + 1; }
+
+// scratch: K1Item[k1f_item_capacity] followed by one int (16-byte aligned)
+size_t k1f_scratch_bytes(int64_t n_rows, int64_t nnz) {
+    return (size_t)k1f_item_capacity(n_rows, nnz) * sizeof(K1Item) + 16;
+}
+
+static int pick_R_filter(int slabs) {
+    int best = 5, best_waste = 1 << 30;
+    for (int R = 6; R >= 4; --R) {
+        const int waste = ((slabs + R - 1) / R) * R - slabs;
+        if (waste < best_waste) { best_waste = waste; best = R; }
+    }
+    return best;
+}
+
+int launch_signatures32_filter(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
+                               int H, uint32_t* d_sig, void* d_scratch, cudaStream_t stream) {
+    if (n_rows <= 0) return 0;
+    const int64_t total = n_rows * (int64_t)H;
+    const int64_t want = (total + 1023) / 1024;
+    fill_u32_kernel<<<(int)(want < 148 * 8 ? want : 148 * 8), 256, 0, stream>>>(d_sig, total, kModulus);
+    if (nnz <= 0) return 1;
+    const int64_t cap = k1f_item_capacity(n_rows, nnz);
+    K1Item* items = reinterpret_cast<K1Item*>(d_scratch);
+    int* n_items = reinterpret_cast<int*>(items + cap);
+    k1f_build_items_kernel<<<1, 1024, 0, stream>>>(d_indptr, n_rows, items, n_items);
+    const int slabs = (H + 31) / 32;
+    const int R = pick_R_filter(slabs);
+    const int units = (slabs + R - 1) / R;
+    int n_warps = units < K1_MAX_WARPS ? units : K1_MAX_WARPS;
+    for (int w = K1_MAX_WARPS; w >= 4; --w)
+        if (units % w == 0) { n_warps = w; break; }
+    const dim3 grid((unsigned)cap, (unsigned)((units + n_warps - 1) / n_warps));
+    const dim3 block(32 * n_warps);
+    switch (R) {
+        case 4: k1_filter_kernel<4><<<grid, block, 0, stream>>>(items, n_items, d_feat, H, units, d_sig); break;
+        case 5: k1_filter_kernel<5><<<grid, block, 0, stream>>>(items, n_items, d_feat, H, units, d_sig); break;
+        default: k1_filter_kernel<6><<<grid, block, 0, stream>>>(items, n_items, d_feat, H, units, d_sig); break;
+    }
+    return 3;
+}
+
 // ---- width 64 (alternative HashSpec): the same formula in uint64 before the modulo --------
 __device__ __forceinline__ uint32_t hash64_dev(uint64_t f1, uint32_t jp1) {
     uint64_t k = f1 * (uint64_t)jp1;

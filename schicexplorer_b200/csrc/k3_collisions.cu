@@ -21,12 +21,16 @@ constexpr int K3_JB = 32;         // hash functions per staging step
 constexpr int K3_LD = K3_TILE + 4;  // padded leading dimension (keeps 16-byte alignment)
 constexpr int K3_THREADS = 256;
 
+// SYM: queries == database (same matrix, all rows in one launch). Counts are symmetric, so only tiles on
+// or above the diagonal are computed and each off-diagonal tile is also stored transposed: half the compares.
+template <bool SYM>
 __global__ void __launch_bounds__(K3_THREADS, 2)
 k3_collision_kernel(const uint32_t* __restrict__ sig_q, int64_t nq, const uint32_t* __restrict__ sig_d,
                     int64_t nd, int H, uint16_t* __restrict__ cnt, int64_t ld_out) {
     __shared__ __align__(16) uint32_t Qs[K3_JB][K3_LD];
     __shared__ __align__(16) uint32_t Ds[K3_JB][K3_LD];
 
+    if (SYM && blockIdx.x < blockIdx.y) return;
     const int64_t q0 = (int64_t)blockIdx.y * K3_TILE;
     const int64_t d0 = (int64_t)blockIdx.x * K3_TILE;
     const int tx = threadIdx.x & 15;   // 8 database columns tx*8..
@@ -100,13 +104,38 @@ k3_collision_kernel(const uint32_t* __restrict__ sig_q, int64_t nq, const uint32
                 if (d0 + tx * 8 + b < nd) dst[b] = (uint16_t)acc[a][b];
         }
     }
+    if (SYM && blockIdx.x > blockIdx.y) {
+        // mirrored tile: row d0 + tx*8 + b, columns q0 + ty*8 .. +7 (16 bytes; 16 threads of equal tx cover 256 B)
+        const bool tvec_ok = ((ld_out & 7) == 0) && ((((uintptr_t)cnt) & 15) == 0) && (q0 + ty * 8 + 8 <= nq);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int64_t d = d0 + tx * 8 + b;
+            if (d >= nd) continue;
+            uint16_t* dst = cnt + d * ld_out + q0 + ty * 8;
+            if (tvec_ok) {
+                uint4 o;
+                o.x = (uint32_t)acc[0][b] | ((uint32_t)acc[1][b] << 16);
+                o.y = (uint32_t)acc[2][b] | ((uint32_t)acc[3][b] << 16);
+                o.z = (uint32_t)acc[4][b] | ((uint32_t)acc[5][b] << 16);
+                o.w = (uint32_t)acc[6][b] | ((uint32_t)acc[7][b] << 16);
+                *reinterpret_cast<uint4*>(dst) = o;
+            } else {
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+                    if (q0 + ty * 8 + a < nq) dst[a] = (uint16_t)acc[a][b];
+            }
+        }
+    }
 }
 
 int launch_collision_counts(const uint32_t* d_sig_q, int64_t nq, const uint32_t* d_sig_db, int64_t ndb,
                             int H, uint16_t* d_cnt, int64_t ld_out, cudaStream_t stream) {
     if (nq <= 0 || ndb <= 0) return 0;
     dim3 grid((unsigned)((ndb + K3_TILE - 1) / K3_TILE), (unsigned)((nq + K3_TILE - 1) / K3_TILE));
-    k3_collision_kernel<<<grid, K3_THREADS, 0, stream>>>(d_sig_q, nq, d_sig_db, ndb, H, d_cnt, ld_out);
+    if (d_sig_q == d_sig_db && nq == ndb)
+        k3_collision_kernel<true><<<grid, K3_THREADS, 0, stream>>>(d_sig_q, nq, d_sig_db, ndb, H, d_cnt, ld_out);
+    else
+        k3_collision_kernel<false><<<grid, K3_THREADS, 0, stream>>>(d_sig_q, nq, d_sig_db, ndb, H, d_cnt, ld_out);
     return 1;
 }
 

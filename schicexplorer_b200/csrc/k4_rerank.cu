@@ -108,6 +108,7 @@ k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict_
         // scatter this part of the query row: first free slot of the home bucket, else the next bucket
         for (int64_t i = xs + threadIdx.x; i < xt; i += blockDim.x) {
             const uint32_t f = __ldg(feat + i);
+            if (f == K4_EMPTY) continue;     // the one id that equals the empty marker: added out of band below
             uint32_t slot = 4 * k4_bucket(f);
             while (atomicCAS(&tkey[slot], K4_EMPTY, f) != K4_EMPTY) slot = (slot + 1) & (K4_SLOTS - 1);
             tval[slot] = __ldg(val + i);
@@ -186,6 +187,239 @@ k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict_
 
     // distances -> packed keys -> sort by (distance asc, index asc)
     const double nq2 = norm2[qrow];
+    const bool x_has_max = xe > xb && __ldg(feat + xe - 1) == K4_EMPTY;
+    for (int c = threadIdx.x; c < P; c += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (c < ncand) {
+            const int32_t d = cand[c];
+            double xy = dot[c];
+            // id 2^32-1 doubles as the table's empty marker and is skipped by the table; rows are sorted, so
+            // it can only be the last non-zero of a row: its product is added here
+            if (x_has_max) {
+                const int64_t yb = indptr[d], ye = indptr[d + 1];
+                if (ye > yb && __ldg(feat + ye - 1) == K4_EMPTY)
+                    xy += (double)__ldg(val + xe - 1) * (double)__ldg(val + ye - 1);
+            }
+            double d2 = nq2 + norm2[d] - 2.0 * xy;
+            if (d2 < 0.0 || (int64_t)d == qrow) d2 = 0.0;
+            const float dist = (float)sqrt(d2);
+            key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)(uint32_t)d;
+        }
+        keys[c] = key;
+    }
+    bitonic_sort_shared(keys, P);
+    const int nv = min(ncand, k);
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        int32_t oi = -1;
+        float od = __int_as_float(0x7f800000);
+        if (t < nv) {
+            const unsigned long long key = keys[t];
+            oi = (int32_t)(uint32_t)(key & 0xFFFFFFFFull);
+            od = __uint_as_float((uint32_t)(key >> 32));
+        }
+        idx_out[q * k + t] = oi;
+        dist_out[q * k + t] = od;
+    }
+    if (threadIdx.x == 0) nvalid_out[q] = nv;
+}
+
+
+// =================================================================================================
+// Windowed variant (default when the feature space is small enough, i.e. every Hi-C resolution the
+// CLI is used at): the hash probe above costs ~45 issued instructions per candidate non-zero (two
+// LDS.128 probe rounds, 8 compares, selects) and the kernel sits on the ALU pipe, not on HBM. Here the
+// feature axis is cut into fixed windows of 2^18 ids; for one window the query row becomes a
+// direct-addressed table in shared memory -- one 32-bit entry per 16 feature ids holding a 16-bit
+// presence mask and the rank of the entry's first key -- so a probe is one LDS, a bit test, a POPC and
+// one LDS of the value: ~15 instructions, no probe sequence, no 128-bit bank conflicts.
+// A per-row "window directory" (offset of each window's first non-zero, built once per fit by
+// row_window_dir_kernel) replaces the per-candidate binary searches: a candidate's slice for window w
+// is [dir[w], dir[w+1]). Non-zeros of a candidate that fall in windows where the query row is empty
+// are never read.
+// =================================================================================================
+constexpr int K4W_THREADS = 512;
+constexpr int K4W_WIN_BITS = 18;                        // feature ids per window
+constexpr int K4W_WORDS = 1 << (K4W_WIN_BITS - 4);      // table entries (64 KB)
+constexpr int K4W_KCAP = 4096;                          // query non-zeros per table fill (values: 16 KB)
+constexpr int K4W_UNROLL = 8;                           // candidate non-zeros per lane and iteration
+
+__global__ void row_max_feature_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat,
+                                       int64_t n_rows, uint32_t* __restrict__ out_max) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t m = 0;
+    if (row < n_rows) {
+        const int64_t b = indptr[row], e = indptr[row + 1];
+        if (e > b) m = __ldg(feat + e - 1);    // rows are sorted: the last id is the largest
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out_max, m);
+}
+
+// dir[row][w] = offset (relative to the row start) of the first non-zero with (id >> WIN_BITS) >= w,
+// w = 0..n_windows (dir[row][n_windows] = row length). One warp per row; every entry is written once.
+__global__ void row_window_dir_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat,
+                                      int64_t n_rows, int n_windows, uint32_t* __restrict__ dir) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    const int64_t b = indptr[row], e = indptr[row + 1];
+    uint32_t* __restrict__ d = dir + row * (int64_t)(n_windows + 1);
+    for (int64_t i = b + lane; i < e; i += 32) {
+        const int w = (int)(__ldg(feat + i) >> K4W_WIN_BITS);
+        const int wp = i == b ? -1 : (int)(__ldg(feat + i - 1) >> K4W_WIN_BITS);
+        for (int x = wp + 1; x <= w; ++x) d[x] = (uint32_t)(i - b);
+    }
+    const int wl = e > b ? (int)(__ldg(feat + e - 1) >> K4W_WIN_BITS) : -1;
+    for (int x = wl + 1 + lane; x <= n_windows; x += 32) d[x] = (uint32_t)(e - b);
+}
+
+// Table entry layouts (E64 = false / true), both 4 feature ids per byte of shared memory:
+//   32-bit entry per 16 ids: presence mask in the low half, rank of the entry's first key in the high half;
+//   64-bit entry per 32 ids: {presence mask, BYTE offset of the first key's value} -- one LDS.64, and the
+//   value address is a single LEA (rank * 4 + offset).
+template <bool E64>
+__device__ __forceinline__ float k4w_probe(const uint32_t* __restrict__ tab, const float* __restrict__ tval, uint32_t t,
+                                           float yv, float acc) {
+    if (E64) {
+        const uint2 e = reinterpret_cast<const uint2*>(tab)[t >> 5];
+        const uint32_t m = 1u << (t & 31u);
+        const uint32_t off = e.y + 4u * (uint32_t)__popc(e.x & (m - 1u));
+        const float tv = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(tval) + off);
+        return (e.x & m) ? fmaf(tv, yv, acc) : acc;
+    } else {
+        const uint32_t e = tab[t >> 4];
+        const uint32_t m = 1u << (t & 15u);
+        const uint32_t idx = (e >> 16) + __popc(e & (m - 1u));
+        const float tv = tval[idx];                     // always in bounds (tval is padded by 32)
+        return (e & m) ? fmaf(tv, yv, acc) : acc;
+    }
+}
+
+template <bool E64>
+__global__ void __launch_bounds__(K4W_THREADS, 2)
+k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat,
+                        const float* __restrict__ val, const double* __restrict__ norm2,
+                        const uint32_t* __restrict__ dir, int n_windows, int64_t q_row0,
+                        const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_nvalid, int kcand, int P,
+                        int k, int32_t* __restrict__ idx_out, float* __restrict__ dist_out,
+                        int32_t* __restrict__ nvalid_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* tab = reinterpret_cast<uint32_t*>(smem_raw);                      // [K4W_WORDS]
+    float* tval = reinterpret_cast<float*>(tab + K4W_WORDS);                    // [K4W_KCAP + 32]
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(tval + K4W_KCAP + 32);   // [P]
+    double* dot = reinterpret_cast<double*>(keys + P);                          // [kcand]
+    int64_t* sl_pos = reinterpret_cast<int64_t*>(dot + kcand);                  // [kcand] slice start (absolute)
+    int64_t* cbeg = sl_pos + kcand;                                             // [kcand] row start of the candidate
+    int32_t* sl_len = reinterpret_cast<int32_t*>(cbeg + kcand);                 // [kcand]
+    int32_t* cand = sl_len + kcand;                                             // [kcand]
+    uint32_t* qdir = reinterpret_cast<uint32_t*>(cand + kcand);                 // [n_windows + 1]
+    __shared__ int s_next;
+
+    const int64_t q = blockIdx.x;
+    const int64_t qrow = q_row0 + q;
+    const int ncand = min(cand_nvalid[q], kcand);
+    const int lane = threadIdx.x & 31;
+    const int64_t nw1 = (int64_t)n_windows + 1;
+
+    for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
+        const int32_t d = cand_idx[q * kcand + c];
+        cand[c] = d;
+        cbeg[c] = indptr[d];
+        dot[c] = 0.0;
+    }
+    for (int w = threadIdx.x; w <= n_windows; w += blockDim.x) qdir[w] = dir[qrow * nw1 + w];
+    for (int i = threadIdx.x; i < K4W_KCAP + 32; i += blockDim.x) tval[i] = 0.f;
+    const int64_t xb = indptr[qrow];
+    __syncthreads();
+
+    for (int w = 0; w < n_windows; ++w) {
+        const uint32_t k0 = qdir[w], k1 = qdir[w + 1];
+        if (k1 == k0) continue;                          // the query row is empty in this window
+        const uint32_t lo = (uint32_t)w << K4W_WIN_BITS;
+        for (uint32_t i0 = k0; i0 < k1; i0 += K4W_KCAP) {    // more than KCAP keys in one window: sub-parts
+            const uint32_t i1 = min(i0 + (uint32_t)K4W_KCAP, k1);
+            const bool first = i0 == k0, last = i1 == k1;
+            __syncthreads();                             // previous part fully consumed
+            for (int i = threadIdx.x; i < K4W_WORDS / 4; i += blockDim.x)
+                reinterpret_cast<uint4*>(tab)[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (threadIdx.x == 0) s_next = 0;
+            // candidate slices of this part: straight from the window directory; a binary search only
+            // at the inner borders of sub-parts
+            const uint32_t f_lo = first ? 0u : __ldg(feat + xb + i0);
+            const uint32_t f_hi = last ? 0u : __ldg(feat + xb + i1);
+            for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
+                const int64_t d = cand[c];
+                const int64_t cb = cbeg[c];
+                const uint32_t* __restrict__ dc = dir + d * nw1;
+                const int64_t wb = cb + __ldg(dc + w), we = cb + __ldg(dc + w + 1);
+                const int64_t ys = first ? wb : lower_bound_feat(feat, wb, we, f_lo);
+                const int64_t ye = last ? we : lower_bound_feat(feat, wb, we, f_hi);
+                sl_pos[c] = ys;
+                sl_len[c] = (int)(ye - ys);
+            }
+            __syncthreads();
+            for (uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+                const uint32_t t = __ldg(feat + xb + i) - lo;
+                const uint32_t tp = i == i0 ? 0xFFFFFFFFu : __ldg(feat + xb + i - 1) - lo;
+                if (E64) {
+                    const uint32_t word = t >> 5;
+                    atomicOr(&tab[2 * word], 1u << (t & 31u));
+                    if (i == i0 || (tp >> 5) != word) tab[2 * word + 1] = (i - i0) * 4u;   // sole writer of this half
+                } else {
+                    const uint32_t word = t >> 4;
+                    uint32_t add = 1u << (t & 15u);
+                    if (i == i0 || (tp >> 4) != word) add |= (i - i0) << 16;
+                    atomicOr(&tab[word], add);
+                }
+                tval[i - i0] = __ldg(val + xb + i);
+            }
+            __syncthreads();
+            for (;;) {                                   // candidates are handed to warps dynamically
+                int c = 0;
+                if (lane == 0) c = atomicAdd(&s_next, 1);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= ncand) break;
+                const int len = sl_len[c];
+                if (len <= 0) continue;
+                const uint32_t* __restrict__ yf = feat + sl_pos[c] + lane;
+                const float* __restrict__ yvp = val + sl_pos[c] + lane;
+                double acc = 0.0;
+                int i0b = 0;
+                for (; i0b + 32 * K4W_UNROLL <= len; i0b += 32 * K4W_UNROLL) {     // full blocks: no guards
+                    uint32_t f[K4W_UNROLL];
+                    float yv[K4W_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < K4W_UNROLL; ++u) { f[u] = __ldg(yf + i0b + 32 * u); yv[u] = __ldg(yvp + i0b + 32 * u); }
+                    float a32 = 0.f;                     // exact for integer counts: 8 products < 2^24
+#pragma unroll
+                    for (int u = 0; u < K4W_UNROLL; ++u) a32 = k4w_probe<E64>(tab, tval, f[u] - lo, yv[u], a32);
+                    acc += (double)a32;
+                }
+                if (i0b < len) {                         // guarded tail block
+                    uint32_t f[K4W_UNROLL];
+                    float yv[K4W_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < K4W_UNROLL; ++u) {
+                        const bool ok = i0b + 32 * u + lane < len;
+                        f[u] = ok ? __ldg(yf + i0b + 32 * u) : lo;
+                        yv[u] = ok ? __ldg(yvp + i0b + 32 * u) : 0.f;
+                    }
+                    float a32 = 0.f;
+#pragma unroll
+                    for (int u = 0; u < K4W_UNROLL; ++u) a32 = k4w_probe<E64>(tab, tval, f[u] - lo, yv[u], a32);
+                    acc += (double)a32;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) dot[c] += acc;
+            }
+        }
+    }
+    __syncthreads();
+
+    // distances -> packed keys -> sort by (distance asc, index asc)
+    const double nq2 = norm2[qrow];
     for (int c = threadIdx.x; c < P; c += blockDim.x) {
         unsigned long long key = ~0ull;
         if (c < ncand) {
@@ -213,6 +447,24 @@ k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict_
     if (threadIdx.x == 0) nvalid_out[q] = nv;
 }
 
+int launch_row_max_feature(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, uint32_t* d_out_max,
+                           cudaStream_t stream) {
+    if (cudaMemsetAsync(d_out_max, 0, sizeof(uint32_t), stream) != cudaSuccess) return -1;
+    if (n_rows <= 0) return 0;
+    row_max_feature_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, stream>>>(d_indptr, d_feat, n_rows, d_out_max);
+    return 1;
+}
+
+int rerank_window_count(uint32_t max_feature) { return (int)(max_feature >> K4W_WIN_BITS) + 1; }
+
+int launch_row_window_dir(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int n_windows,
+                          uint32_t* d_dir, cudaStream_t stream) {
+    if (n_rows <= 0) return 0;
+    const int64_t threads = n_rows * 32;
+    row_window_dir_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_indptr, d_feat, n_rows, n_windows, d_dir);
+    return 1;
+}
+
 int launch_row_norms(const int64_t* d_indptr, const float* d_val, int64_t n_rows, int64_t indptr0,
                      double* d_norm2, cudaStream_t stream) {
     (void)indptr0;
@@ -223,12 +475,24 @@ int launch_row_norms(const int64_t* d_indptr, const float* d_val, int64_t n_rows
 }
 
 int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* d_val, int64_t indptr0,
-                  const double* d_norm2, int64_t q_row0, int64_t nq, const int32_t* d_cand_idx,
-                  const int32_t* d_cand_nvalid, int kcand, int k, int32_t* d_idx_out, float* d_dist_out,
-                  int32_t* d_nvalid_out, cudaStream_t stream) {
+                  const double* d_norm2, const uint32_t* d_dir, int n_windows, int window_mode, int64_t q_row0,
+                  int64_t nq, const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int kcand, int k,
+                  int32_t* d_idx_out, float* d_dist_out, int32_t* d_nvalid_out, cudaStream_t stream) {
     (void)indptr0;
     if (nq <= 0) return 0;
     const int P = next_pow2(kcand);
+    if (d_dir && n_windows > 0) {
+        const size_t smem = (size_t)K4W_WORDS * 4 + (size_t)(K4W_KCAP + 32) * 4 + (size_t)P * 8 +
+                            (size_t)kcand * (8 + 8 + 8 + 4 + 4) + (size_t)(n_windows + 1) * 4 + 16;
+        if (smem <= 220 * 1024) {
+            auto kern = window_mode == 64 ? k4_rerank_window_kernel<true> : k4_rerank_window_kernel<false>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<(unsigned)nq, K4W_THREADS, smem, stream>>>(d_indptr, d_feat, d_val, d_norm2, d_dir, n_windows, q_row0,
+                                                              d_cand_idx, d_cand_nvalid, kcand, P, k, d_idx_out, d_dist_out,
+                                                              d_nvalid_out);
+            return 1;
+        }
+    }
     const size_t smem = (size_t)K4_SLOTS * 8 + (size_t)P * 8 + (size_t)kcand * (8 + 8 + 8 + 4) + 16;
     if (smem > 220 * 1024) return -1;   // caller reports SCHIC_ERR_UNSUPPORTED
     cudaFuncSetAttribute(k4_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -319,3 +319,76 @@ def test_max_bin_size_bucket_pruning(cuda, oracle):
             assert (np.diag(co) < 800).any()          # pruning really happened
             a, b = cuda.kneighbors(g.h, 15), oracle.kneighbors(o.h, 15)
             assert_neighbours_equal_up_to_ties(*a, *b, 0 if fast else RTOL)
+
+
+@pytest.mark.parametrize("mode", ["hash", "window", "window64"])
+def test_rerank_kernel_variants(cuda, oracle, monkeypatch, mode):
+    """K4 has two implementations (hash table / windowed direct table, the latter with 32- or 64-bit
+    entries); SCHIC_K4_MODE selects one. All must agree with the oracle, including on rows that
+    (a) hold more than one table fill (> 4096 non-zeros) inside ONE window, (b) are empty / tiny,
+    (c) use ids near 2^32 (too many windows: the library must fall back to the hash kernel)."""
+    monkeypatch.setenv("SCHIC_K4_MODE", mode)
+    rng = np.random.default_rng(17)
+    # (a)+(b): 60 rows drawn from a 2^18-wide id range starting mid-window, 5000..12000 non-zeros each
+    ncols = 1 << 23
+    base = (5 << 18) + 1000
+    rows, cols, vals = [], [], []
+    pool = rng.choice(200000, size=40000, replace=False) + base
+    for r in range(60):
+        m = int(rng.integers(5000, 12000))
+        c = np.sort(rng.choice(pool, size=m, replace=False))
+        extra = np.sort(rng.choice(ncols, size=300, replace=False))      # a few ids in other windows
+        c = np.unique(np.concatenate([c, extra]))
+        rows.append(np.full(len(c), r)); cols.append(c); vals.append(rng.integers(1, 50, size=len(c)).astype(np.float64))
+    X = csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(60, ncols))
+    empty = csr_matrix((1, ncols))
+    one = csr_matrix(([3.0], ([0], [base + 7])), shape=(1, ncols))
+    X = vstack([empty, X[:30], one, X[30:], empty]).tocsr()
+    kw = dict(fast=False, n_neighbors=20, number_of_hash_functions=256, minimal_blocks_in_common=1)
+    with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
+        a, b = cuda.kneighbors(g.h, 20), oracle.kneighbors(o.h, 20)
+        assert_neighbours_equal_up_to_ties(*a, *b, RTOL)
+    # realistic clustered cells, k*excess_factor candidates
+    Xs = synth_csr(200, seed=21)
+    kw = dict(fast=False, n_neighbors=15, excess_factor=2, minimal_blocks_in_common=30)
+    with Fitted(cuda, Xs, **kw) as g, Fitted(oracle, Xs, **kw) as o:
+        a, b = cuda.kneighbors(g.h, 15), oracle.kneighbors(o.h, 15)
+        assert_neighbours_equal_up_to_ties(*a, *b, RTOL)
+    # (c) ids spread over the whole 32-bit range
+    ncols = 2 ** 32
+    rows, cols = [], []
+    shared = np.sort(rng.choice(ncols - 1, size=3000, replace=False))
+    for r in range(24):
+        c = np.unique(np.concatenate([rng.choice(shared, size=2000, replace=False),
+                                      rng.choice(ncols - 1, size=500, replace=False), [ncols - 1]]))
+        rows.append(np.full(len(c), r)); cols.append(c)
+    cc = np.concatenate(cols)
+    Xw = csr_matrix((rng.integers(1, 9, size=len(cc)).astype(np.float64), (np.concatenate(rows), cc)), shape=(24, ncols))
+    Xw.indices = Xw.indices.astype(np.int64)
+    kw = dict(fast=False, n_neighbors=8, number_of_hash_functions=128, minimal_blocks_in_common=1)
+    with Fitted(cuda, Xw, **kw) as g, Fitted(oracle, Xw, **kw) as o:
+        a, b = cuda.kneighbors(g.h, 8), oracle.kneighbors(o.h, 8)
+        assert_neighbours_equal_up_to_ties(*a, *b, RTOL)
+
+
+def test_k1_filtered_equals_chunked_kernel(cuda, oracle, monkeypatch):
+    """K1 has two implementations: the filtered whole-row kernel (default) and the unfiltered fixed-chunk
+    kernel (SCHIC_K1_MODE=chunk). Both must be bit-identical to the oracle on rows of every length class:
+    empty, 1..13 non-zeros (no speculation), a few hundred, > 16384 (split into parts), > 2048 (several tiles)."""
+    rng = np.random.default_rng(23)
+    ncols = 2744 * 2744
+    lens = [0, 1, 2, 3, 4, 5, 11, 12, 13, 14, 63, 64, 65, 500, 2047, 2048, 2049, 4100, 16383, 16384, 16385, 40000, 0, 70001]
+    rows, cols = [], []
+    for r, m in enumerate(lens):
+        c = np.sort(rng.choice(ncols, size=m, replace=False))
+        rows.append(np.full(m, r)); cols.append(c)
+    cc = np.concatenate(cols)
+    X = csr_matrix((np.ones(len(cc)), (np.concatenate(rows), cc)), shape=(len(lens), ncols))
+    for H in (800, 1200, 96):
+        kw = dict(number_of_hash_functions=H, minimal_blocks_in_common=1)
+        with Fitted(oracle, X, **kw) as o:
+            want = o.sig()
+        for mode in ("filter", "chunk"):
+            monkeypatch.setenv("SCHIC_K1_MODE", mode)
+            with Fitted(cuda, X, **kw) as g:
+                assert np.array_equal(g.sig(), want), (H, mode)
