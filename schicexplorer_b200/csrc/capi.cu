@@ -162,7 +162,9 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
     const int H = h->p.number_of_hash_functions;
     uint32_t* sig = h->sig.p + r0 * (int64_t)H;
     int nl;
-    const char* k1_mode = getenv("SCHIC_K1_MODE");      // "chunk": the unfiltered fixed-chunk kernel (experiments, tests)
+    // SCHIC_K1_MODE (experiments, tests): "chunk" = the unfiltered fixed-chunk kernel, "direct" = the filtered
+    // kernel without the shared-memory tile; default = filtered kernel with tile (the fastest measured)
+    const char* k1_mode = getenv("SCHIC_K1_MODE");
     if (h->p.hash_width == 64) {
         nl = schic::launch_signatures64(h->d_indptr() + r0, h->d_feat(), h->have_hi ? h->feat_hi.p : nullptr,
                                         r1 - r0, pos1 - pos0, pos0, H, sig, s);
@@ -177,7 +179,7 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
             ST_TRY(h->k1_scratch.reserve((int64_t)need, 0, s));
         }
         nl = schic::launch_signatures32_filter(h->d_indptr() + r0, h->d_feat(), r1 - r0, pos1 - pos0, H, sig,
-                                               h->k1_scratch.p, s);
+                                               h->k1_scratch.p, (k1_mode && strcmp(k1_mode, "direct") == 0) ? 1 : 0, s);
     }
     if (nl < 0) return fail(SCHIC_ERR_CUDA, "K1 launch failed");
     add_launches(h, nl);
@@ -469,11 +471,13 @@ int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, 
 
     // Upload the feature ids in row-aligned chunks on the copy stream; K1 for chunk i runs on the
     // compute stream while chunk i+1 is still in flight.
-    const int64_t kChunkNnz = (int64_t)8 << 20;
+    // A small first chunk (8 M non-zeros, ~0.6 ms of PCIe) lets K1 start early; later chunks are 32 M so that
+    // every K1 launch still holds several waves of row work items.
     cudaEvent_t sig0 = get_event(h);
     bool sig_started = false;
     int64_t c0 = 0;
     while (c0 < n_rows) {
+        const int64_t kChunkNnz = (int64_t)(c0 == 0 ? 8 : 32) << 20;
         int64_t c1 = c0 + 1;
         while (c1 < n_rows && (ip[c1 + 1] - ip[c0]) <= kChunkNnz) ++c1;
         const int64_t a = ip[c0] - pos0, b = ip[c1] - pos0;
@@ -719,7 +723,7 @@ int schic_k1_variant_ms(int32_t variant, int64_t n_rows, int64_t nnz, const int6
     void* scratch = nullptr;
     if (variant >= 100) CU_TRY(cudaMalloc(&scratch, schic::k1f_scratch_bytes(n_rows, nnz)));
     auto launch = [&]() {
-        return variant >= 100 ? schic::launch_signatures32_filter(d_indptr, d_indices, n_rows, nnz, n_hash, d_sig, scratch, nullptr)
+        return variant >= 100 ? schic::launch_signatures32_filter(d_indptr, d_indices, n_rows, nnz, n_hash, d_sig, scratch, variant == 101 ? 1 : 0, nullptr)
                               : schic::launch_signatures32_variant(variant, d_indptr, d_indices, n_rows, nnz, pos0, n_hash, d_sig, nullptr);
     };
     if (launch() < 0) return fail(SCHIC_ERR_UNSUPPORTED, "variant not compiled in");

@@ -21,7 +21,8 @@ int launch_signatures32(const int64_t* d_indptr, const uint32_t* d_feat, int64_t
 // only when it fails). d_scratch: k1f_scratch_bytes(n_rows, nnz) bytes of device memory.
 size_t k1f_scratch_bytes(int64_t n_rows, int64_t nnz);
 int launch_signatures32_filter(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
-                               int H, uint32_t* d_sig, void* d_scratch, cudaStream_t stream);
+                               int H, uint32_t* d_sig, void* d_scratch, int direct /* 1: no shared-memory tile */,
+                               cudaStream_t stream);
 // variant >= 0 selects an instruction-selection variant (only in builds with -DK1_ALL_VARIANTS).
 int launch_signatures32_variant(int variant, const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows,
                                 int64_t nnz, int64_t indptr0, int H, uint32_t* d_sig, cudaStream_t stream);

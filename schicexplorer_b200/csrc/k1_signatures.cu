@@ -322,11 +322,52 @@ __device__ __noinline__ uint32_t k1f_exact_item_min(const uint32_t* __restrict__
 // minimum is below the level ~12 of the len features reach. The assumption is verified at the end
 // (thr(best) <= thr0 proves that nothing that was skipped could have been smaller); where it fails
 // the lane's minimum is recomputed exactly. This removes the ~ln(len) early updates per minimum.
+// One group of 4 features for all R hash registers of the lane: feed the filter minima, then (rarely)
+// the exact path. fp1[] = feature id + 1.
 template <int R>
+__device__ __forceinline__ void k1f_step4(const uint32_t (&fp1)[4], const uint32_t (&c)[R], uint32_t (&best)[R],
+                                          uint32_t (&thr)[R], uint32_t (&mn)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t t0k = k1f_filter_key(fp1[0] * c[r] - 1u), t1k = k1f_filter_key(fp1[1] * c[r] - 1u);
+        const uint32_t t2k = k1f_filter_key(fp1[2] * c[r] - 1u), t3k = k1f_filter_key(fp1[3] * c[r] - 1u);
+        mn[r] = min(mn[r], min(t0k, t1k));
+        mn[r] = min(mn[r], min(t2k, t3k));
+    }
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) any = any || (mn[r] <= thr[r]);
+    if (any) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (mn[r] <= thr[r]) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) k1f_exact_update(fp1[u] * c[r] - 1u, best[r], thr[r]);
+                mn[r] = 0xFFFFFFFFu;
+            }
+        }
+    }
+}
+
+// grid = (item upper bound, unit groups); block = 32 * warps, one unit (R*32 hash functions) per warp.
+// Per lane and hash register r: best[r] (exact running minimum), thr[r] (filter threshold), mn[r]
+// (running minimum of the filter keys since the last exact step). The inner loop only feeds mn[r]
+// (one 3-input min per two evaluations); after every 4 features one compare per r decides whether
+// the exact path has to look at those 4 features.
+// The start threshold is speculative: thr0 ~ 2^32 * 12 / len, i.e. the filter assumes the final
+// minimum is below the level ~12 of the len features reach. The assumption is verified at the end
+// (thr(best) <= thr0 proves that nothing that was skipped could have been smaller); where it fails
+// the lane's minimum is recomputed exactly. This removes the ~ln(len) early updates per minimum.
+// DIRECT = false: the CTA stages 2048-feature tiles in shared memory (two barriers per tile).
+// DIRECT = true : no shared memory and no barriers -- every warp reads the features itself with
+//                 warp-uniform loads (one L1 line serves 32 features of all warps of the CTA), one
+//                 group of 4 prefetched into registers while the previous one is hashed.
+template <int R, bool DIRECT>
 __global__ void __launch_bounds__(32 * K1_MAX_WARPS)
 k1_filter_kernel(const K1Item* __restrict__ items, const int* __restrict__ n_items, const uint32_t* __restrict__ feat,
-                 int H, int units, uint32_t* __restrict__ sig) {
-    __shared__ __align__(16) uint32_t tile[K1F_TILE];
+                 int H, int units, uint32_t one /* = 1 at run time: keeps the "+1" an IMAD on the FMA pipe */,
+                 uint32_t* __restrict__ sig) {
+    __shared__ __align__(16) uint32_t tile[DIRECT ? 4 : K1F_TILE];
     if ((int)blockIdx.x >= *n_items) return;
     const K1Item it = items[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
@@ -345,36 +386,42 @@ k1_filter_kernel(const K1Item* __restrict__ items, const int* __restrict__ n_ite
         mn[r] = 0xFFFFFFFFu;
     }
     const uint32_t* __restrict__ src = feat + it.begin;
-    for (int t0 = 0; t0 < it.len; t0 += K1F_TILE) {
-        const int tlen = min(K1F_TILE, it.len - t0);
-        const int tlen4 = (tlen + 3) & ~3;               // padded with copies of the last feature (min is idempotent)
-        __syncthreads();
-        for (int i = threadIdx.x; i < tlen4; i += blockDim.x) tile[i] = __ldg(src + t0 + min(i, tlen - 1)) + 1u;
-        __syncthreads();
-        if (!active) continue;
-        for (int i = 0; i < tlen4; i += 4) {
-            const uint4 f4 = *reinterpret_cast<const uint4*>(tile + i);
+    if (DIRECT) {
+        if (!active) return;
+        const int n4 = it.len & ~3;
+        uint32_t nxt[4] = {0u, 0u, 0u, 0u};
+        if (n4 > 0) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t t0k = k1f_filter_key(f4.x * c[r] - 1u), t1k = k1f_filter_key(f4.y * c[r] - 1u);
-                const uint32_t t2k = k1f_filter_key(f4.z * c[r] - 1u), t3k = k1f_filter_key(f4.w * c[r] - 1u);
-                mn[r] = min(mn[r], min(t0k, t1k));
-                mn[r] = min(mn[r], min(t2k, t3k));
+            for (int u = 0; u < 4; ++u) nxt[u] = __ldg(src + u);
+        }
+        for (int i = 0; i < n4; i += 4) {
+            uint32_t cur[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) asm("mad.lo.u32 %0, %1, %2, 1;" : "=r"(cur[u]) : "r"(nxt[u]), "r"(one));
+            if (i + 8 <= n4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) nxt[u] = __ldg(src + i + 4 + u);
             }
-            bool any = false;
+            k1f_step4<R>(cur, c, best, thr, mn);
+        }
+        if (n4 < it.len) {                                // 1..3 left: pad with copies of the last feature
+            uint32_t cur[4];
 #pragma unroll
-            for (int r = 0; r < R; ++r) any = any || (mn[r] <= thr[r]);
-            if (any) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (mn[r] <= thr[r]) {
-                        k1f_exact_update(f4.x * c[r] - 1u, best[r], thr[r]);
-                        k1f_exact_update(f4.y * c[r] - 1u, best[r], thr[r]);
-                        k1f_exact_update(f4.z * c[r] - 1u, best[r], thr[r]);
-                        k1f_exact_update(f4.w * c[r] - 1u, best[r], thr[r]);
-                        mn[r] = 0xFFFFFFFFu;
-                    }
-                }
+            for (int u = 0; u < 4; ++u) cur[u] = __ldg(src + min(n4 + u, it.len - 1)) + 1u;
+            k1f_step4<R>(cur, c, best, thr, mn);
+        }
+    } else {
+        for (int t0 = 0; t0 < it.len; t0 += K1F_TILE) {
+            const int tlen = min(K1F_TILE, it.len - t0);
+            const int tlen4 = (tlen + 3) & ~3;           // padded with copies of the last feature (min is idempotent)
+            __syncthreads();
+            for (int i = threadIdx.x; i < tlen4; i += blockDim.x) tile[i] = __ldg(src + t0 + min(i, tlen - 1)) + 1u;
+            __syncthreads();
+            if (!active) continue;
+            for (int i = 0; i < tlen4; i += 4) {
+                const uint4 f4 = *reinterpret_cast<const uint4*>(tile + i);
+                const uint32_t cur[4] = {f4.x, f4.y, f4.z, f4.w};
+                k1f_step4<R>(cur, c, best, thr, mn);
             }
         }
     }
@@ -407,7 +454,7 @@ static int pick_R_filter(int slabs) {
 }
 
 int launch_signatures32_filter(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
-                               int H, uint32_t* d_sig, void* d_scratch, cudaStream_t stream) {
+                               int H, uint32_t* d_sig, void* d_scratch, int direct, cudaStream_t stream) {
     if (n_rows <= 0) return 0;
     const int64_t total = n_rows * (int64_t)H;
     const int64_t want = (total + 1023) / 1024;
@@ -425,11 +472,17 @@ int launch_signatures32_filter(const int64_t* d_indptr, const uint32_t* d_feat, 
         if (units % w == 0) { n_warps = w; break; }
     const dim3 grid((unsigned)cap, (unsigned)((units + n_warps - 1) / n_warps));
     const dim3 block(32 * n_warps);
+#define K1F_LAUNCH(RR)                                                                                       \
+    do {                                                                                                     \
+        if (direct) k1_filter_kernel<RR, true><<<grid, block, 0, stream>>>(items, n_items, d_feat, H, units, 1u, d_sig);  \
+        else k1_filter_kernel<RR, false><<<grid, block, 0, stream>>>(items, n_items, d_feat, H, units, 1u, d_sig);        \
+    } while (0)
     switch (R) {
-        case 4: k1_filter_kernel<4><<<grid, block, 0, stream>>>(items, n_items, d_feat, H, units, d_sig); break;
-        case 5: k1_filter_kernel<5><<<grid, block, 0, stream>>>(items, n_items, d_feat, H, units, d_sig); break;
-        default: k1_filter_kernel<6><<<grid, block, 0, stream>>>(items, n_items, d_feat, H, units, d_sig); break;
+        case 4: K1F_LAUNCH(4); break;
+        case 5: K1F_LAUNCH(5); break;
+        default: K1F_LAUNCH(6); break;
     }
+#undef K1F_LAUNCH
     return 3;
 }
 

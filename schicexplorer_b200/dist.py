@@ -77,6 +77,8 @@ class ShardedMinHash:
         if device.type == "cuda":
             api.set_stream(self.h, torch.cuda.current_stream(device).cuda_stream)
         self._keep = {}
+        self._side = None
+        self._csr_event = None
 
     def close(self):
         if self.h is not None:
@@ -86,6 +88,7 @@ class ShardedMinHash:
     # -- step 1: hash the local shard (device-resident CSR) ---------------------------------
     def fit_local(self, d_indptr: torch.Tensor, d_indices: torch.Tensor, d_data):
         self._keep["csr"] = (d_indptr, d_indices, d_data)
+        self._start_csr_gather()
         nnz = int(d_indices.numel())
         self.api.fit_csr_device(self.h, self.n_local, nnz, d_indptr.data_ptr(), d_indices.data_ptr(),
                                 None if d_data is None else d_data.data_ptr(), False)
@@ -99,8 +102,42 @@ class ShardedMinHash:
         d_ix = _wrap_device(p_ix, (nnz,), "<i4", torch.int32, self.device)
         d_dt = None if not p_dt else _wrap_device(p_dt, (nnz,), "<f4", torch.float32, self.device)
         self._keep["csr"] = (d_ip, d_ix, d_dt)
+        self._start_csr_gather()
 
     # -- step 2: the exchange ------------------------------------------------------------------
+    def _gather_csr(self):
+        """All-gather of the CSR shards (only the exact rerank reads other ranks' rows)."""
+        counts = [self.bounds[r + 1] - self.bounds[r] for r in range(self.world)]
+        d_indptr, d_indices, d_data = self._keep["csr"]
+        nnz_local = torch.tensor([d_indices.numel()], dtype=torch.int64, device=self.device)
+        nnz_all = torch.empty(self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(nnz_all, nnz_local, group=self.group)
+        nnzs = [int(x) for x in nnz_all.tolist()]
+        ix_all = _gather_padded(d_indices, nnzs, self.group)
+        dt_all = _gather_padded(d_data, nnzs, self.group)
+        # row lengths -> global indptr
+        lens = (d_indptr[1:] - d_indptr[:-1]).contiguous()
+        lens_all = _gather_padded(lens, counts, self.group)
+        ip_all = torch.zeros(self.n_total + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(lens_all, 0, out=ip_all[1:])
+        return ip_all, ix_all, dt_all
+
+    def _start_csr_gather(self):
+        """The CSR exchange does not depend on the signatures: on a GPU it is issued on a side stream
+        *before* K1 so that the NVLink transfer (1.15 GB at S10) runs underneath the hashing."""
+        self._keep.pop("csr_all", None)
+        self._csr_event = None
+        if self.fast or self.world == 1 or self.device.type != "cuda":
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        main = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(main)           # the previous build no longer reads the old gathered CSR
+        with torch.cuda.stream(self._side):
+            self._keep["csr_all"] = self._gather_csr()
+            self._csr_event = torch.cuda.Event()
+            self._csr_event.record(self._side)
+
     def gather(self):
         """All-gather signatures (and the CSR shards when the exact rerank needs them) and hand
         the gathered database back to the kernels."""
@@ -115,21 +152,13 @@ class ShardedMinHash:
         self._keep["sig_all"] = sig_all
         ip_all = ix_all = dt_all = None
         if not self.fast:
-            d_indptr, d_indices, d_data = self._keep["csr"]
             if self.world == 1:
-                ip_all, ix_all, dt_all = d_indptr, d_indices, d_data
+                ip_all, ix_all, dt_all = self._keep["csr"]
+            elif "csr_all" in self._keep:
+                torch.cuda.current_stream(self.device).wait_event(self._csr_event)
+                ip_all, ix_all, dt_all = self._keep["csr_all"]
             else:
-                nnz_local = torch.tensor([d_indices.numel()], dtype=torch.int64, device=self.device)
-                nnz_all = torch.empty(self.world, dtype=torch.int64, device=self.device)
-                dist.all_gather_into_tensor(nnz_all, nnz_local, group=self.group)
-                nnzs = [int(x) for x in nnz_all.tolist()]
-                ix_all = _gather_padded(d_indices, nnzs, self.group)
-                dt_all = _gather_padded(d_data, nnzs, self.group)
-                # row lengths -> global indptr
-                lens = (d_indptr[1:] - d_indptr[:-1]).contiguous()
-                lens_all = _gather_padded(lens, counts, self.group)
-                ip_all = torch.zeros(self.n_total + 1, dtype=torch.int64, device=self.device)
-                torch.cumsum(lens_all, 0, out=ip_all[1:])
+                ip_all, ix_all, dt_all = self._gather_csr()
             self._keep["csr_all"] = (ip_all, ix_all, dt_all)
         self.api.set_database_device(self.h, self.n_total, self.row0, sig_all.data_ptr(),
                                      None if ip_all is None else ip_all.data_ptr(),

@@ -388,7 +388,7 @@ def test_k1_filtered_equals_chunked_kernel(cuda, oracle, monkeypatch):
         kw = dict(number_of_hash_functions=H, minimal_blocks_in_common=1)
         with Fitted(oracle, X, **kw) as o:
             want = o.sig()
-        for mode in ("filter", "chunk"):
+        for mode in ("tile", "direct", "chunk"):
             monkeypatch.setenv("SCHIC_K1_MODE", mode)
             with Fitted(cuda, X, **kw) as g:
                 assert np.array_equal(g.sig(), want), (H, mode)
