@@ -78,7 +78,10 @@ struct schic_mh_handle {
     DevBuf<int64_t> indptr; DevBuf<uint32_t> feat; DevBuf<uint32_t> feat_hi; DevBuf<float> val;
     bool have_val = false, have_hi = false;
     DevBuf<uint32_t> sig;
-    DevBuf<unsigned char> k1_scratch;    // work-item list of the filtered K1 kernel
+    DevBuf<unsigned char> k1_scratch;    // work-item list of the filtered / table K1 kernels
+    // shared-table K1 (k1_table.cu): per-id presence bytes and slots, hit entries, {entries used, overflow, max id}
+    DevBuf<unsigned char> k1t_present; DevBuf<unsigned long long> k1t_slot; DevBuf<uint16_t> k1t_entries;
+    DevBuf<uint32_t> k1t_counters;
     DevBuf<double> norm2; int64_t norm_rows = 0; const void* norm_of = nullptr;
     DevBuf<uint32_t> win_dir, max_feat; int n_windows = 0;   // window directory of the windowed rerank (0: hash kernel)
     int window_mode = 32;
@@ -158,28 +161,72 @@ int check(const schic_mh_handle* h) {
 void add_launches(schic_mh_handle* h, int n) { if (n > 0) h->launches += n; }
 
 // K1 on rows [r0, r1) of the handle's CSR (positions are absolute in the device arrays).
+// SCHIC_K1_MODE (experiments, tests): "chunk" = the unfiltered fixed-chunk kernel, "tile" / "direct" = the
+// filtered per-cell kernel with / without the shared-memory tile, "table" = force the shared-table path;
+// default: shared table when the batch re-uses feature ids enough (k1t_applicable), else filtered "tile".
+enum K1Mode { K1_AUTO = 0, K1_CHUNK, K1_TILE, K1_DIRECT, K1_TABLE };
+K1Mode k1_mode_from_env() {
+    const char* m = getenv("SCHIC_K1_MODE");
+    if (!m) return K1_AUTO;
+    if (strcmp(m, "chunk") == 0) return K1_CHUNK;
+    if (strcmp(m, "tile") == 0) return K1_TILE;
+    if (strcmp(m, "direct") == 0) return K1_DIRECT;
+    if (strcmp(m, "table") == 0) return K1_TABLE;
+    return K1_AUTO;
+}
+
+// cheap test before anything touches the device: could this batch qualify for the shared-table path at all?
+bool k1_table_candidate(const schic_mh_handle* h, int64_t n_rows, int64_t nnz) {
+    if (h->p.hash_width != 32) return false;
+    const K1Mode m = k1_mode_from_env();
+    if (m == K1_TABLE) return n_rows > 0 && nnz > 0;
+    if (m != K1_AUTO) return false;
+    const int H = h->p.number_of_hash_functions;
+    return n_rows > 0 && nnz >= ((int64_t)1 << 21) && 2.0 * ((double)nnz / (double)n_rows) / (double)H >= 4.0;
+}
+
+// K1 on rows [r0, r1) of the handle's CSR (positions are absolute in the device arrays).
 int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t pos1, cudaStream_t s) {
     const int H = h->p.number_of_hash_functions;
     uint32_t* sig = h->sig.p + r0 * (int64_t)H;
-    int nl;
-    // SCHIC_K1_MODE (experiments, tests): "chunk" = the unfiltered fixed-chunk kernel, "direct" = the filtered
-    // kernel without the shared-memory tile; default = filtered kernel with tile (the fastest measured)
-    const char* k1_mode = getenv("SCHIC_K1_MODE");
+    const int64_t n_rows = r1 - r0, nnz = pos1 - pos0;
+    const K1Mode mode = k1_mode_from_env();
+    int nl = -1;
     if (h->p.hash_width == 64) {
         nl = schic::launch_signatures64(h->d_indptr() + r0, h->d_feat(), h->have_hi ? h->feat_hi.p : nullptr,
-                                        r1 - r0, pos1 - pos0, pos0, H, sig, s);
-    } else if (k1_mode && strcmp(k1_mode, "chunk") == 0) {
-        nl = schic::launch_signatures32(h->d_indptr() + r0, h->d_feat(), r1 - r0, pos1 - pos0, pos0, H, sig, s);
+                                        n_rows, nnz, pos0, H, sig, s);
+    } else if (mode == K1_CHUNK) {
+        nl = schic::launch_signatures32(h->d_indptr() + r0, h->d_feat(), n_rows, nnz, pos0, H, sig, s);
     } else {
-        // the scratch of an earlier chunk may still be read by its kernel: same stream, so reuse is ordered,
-        // but growing would free it -- size it for the worst case of this call up front
-        const size_t need = schic::k1f_scratch_bytes(r1 - r0, pos1 - pos0);
-        if ((int64_t)need > h->k1_scratch.cap) {
+        if (k1_table_candidate(h, n_rows, nnz)) {
+            // largest id of the batch decides (8-byte read back: one stream synchronisation per batch)
+            ST_TRY(h->k1t_counters.reserve(4, 0, s));
+            add_launches(h, schic::launch_max_id(h->d_feat() + pos0, nnz, h->k1t_counters.p + 2, s));
+            uint32_t max_id = 0;
+            CU_TRY(cudaMemcpyAsync(&max_id, h->k1t_counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             CU_TRY(cudaStreamSynchronize(s));
-            ST_TRY(h->k1_scratch.reserve((int64_t)need, 0, s));
+            if (mode == K1_TABLE ? (max_id < 134217728u && H <= 65535) : schic::k1t_applicable(n_rows, nnz, max_id, H)) {
+                const size_t ecap = schic::k1t_entries_capacity(nnz, max_id);
+                ST_TRY(h->k1t_present.reserve((int64_t)max_id + 1, 0, s));
+                ST_TRY(h->k1t_slot.reserve((int64_t)max_id + 1, 0, s));
+                ST_TRY(h->k1t_entries.reserve((int64_t)ecap, 0, s));
+                ST_TRY(h->k1_scratch.reserve((int64_t)schic::k1t_items_bytes(n_rows, nnz), 0, s));
+                nl = schic::launch_signatures32_table(h->d_indptr() + r0, h->d_feat(), n_rows, nnz, pos0, max_id, H, sig,
+                                                      h->k1t_present.p, reinterpret_cast<uint2*>(h->k1t_slot.p),
+                                                      h->k1t_entries.p, ecap, h->k1t_counters.p, h->k1_scratch.p, s);
+            }
         }
-        nl = schic::launch_signatures32_filter(h->d_indptr() + r0, h->d_feat(), r1 - r0, pos1 - pos0, H, sig,
-                                               h->k1_scratch.p, (k1_mode && strcmp(k1_mode, "direct") == 0) ? 1 : 0, s);
+        if (nl < 0) {
+            // the scratch of an earlier chunk may still be read by its kernel: same stream, so reuse is ordered,
+            // but growing would free it -- synchronise before that
+            const size_t need = schic::k1f_scratch_bytes(n_rows, nnz);
+            if ((int64_t)need > h->k1_scratch.cap) {
+                CU_TRY(cudaStreamSynchronize(s));
+                ST_TRY(h->k1_scratch.reserve((int64_t)need, 0, s));
+            }
+            nl = schic::launch_signatures32_filter(h->d_indptr() + r0, h->d_feat(), n_rows, nnz, H, sig, h->k1_scratch.p,
+                                                   mode == K1_DIRECT ? 1 : 0, s);
+        }
     }
     if (nl < 0) return fail(SCHIC_ERR_CUDA, "K1 launch failed");
     add_launches(h, nl);
@@ -476,8 +523,11 @@ int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, 
     cudaEvent_t sig0 = get_event(h);
     bool sig_started = false;
     int64_t c0 = 0;
+    // (a batch that may take the shared-table K1 path is hashed in one piece after its last chunk has landed:
+    // the table is built from all of its feature ids)
+    const bool whole_batch = k1_table_candidate(h, n_rows, nnz);
     while (c0 < n_rows) {
-        const int64_t kChunkNnz = (int64_t)(c0 == 0 ? 8 : 32) << 20;
+        const int64_t kChunkNnz = whole_batch ? INT64_MAX : (int64_t)(c0 == 0 ? 8 : 32) << 20;
         int64_t c1 = c0 + 1;
         while (c1 < n_rows && (ip[c1 + 1] - ip[c0]) <= kChunkNnz) ++c1;
         const int64_t a = ip[c0] - pos0, b = ip[c1] - pos0;
@@ -721,8 +771,26 @@ int schic_k1_variant_ms(int32_t variant, int64_t n_rows, int64_t nnz, const int6
     CU_TRY(cudaEventCreate(&e0));
     CU_TRY(cudaEventCreate(&e1));
     void* scratch = nullptr;
-    if (variant >= 100) CU_TRY(cudaMalloc(&scratch, schic::k1f_scratch_bytes(n_rows, nnz)));
+    unsigned char* present = nullptr; uint2* slot = nullptr; uint16_t* entries = nullptr; uint32_t* counters = nullptr;
+    uint32_t max_id = 0;
+    size_t ecap = 0;
+    if (variant >= 200) {          // shared-table path
+        CU_TRY(cudaMalloc(&counters, 4 * sizeof(uint32_t)));
+        schic::launch_max_id(d_indices + pos0, nnz, counters + 2, nullptr);
+        CU_TRY(cudaMemcpy(&max_id, counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (max_id >= 134217728u) return fail(SCHIC_ERR_UNSUPPORTED, "id range too large for the table path");
+        ecap = schic::k1t_entries_capacity(nnz, max_id);
+        CU_TRY(cudaMalloc(&present, (size_t)max_id + 1));
+        CU_TRY(cudaMalloc(&slot, ((size_t)max_id + 1) * sizeof(uint2)));
+        CU_TRY(cudaMalloc(&entries, ecap * sizeof(uint16_t)));
+        CU_TRY(cudaMalloc(&scratch, schic::k1t_items_bytes(n_rows, nnz)));
+    } else if (variant >= 100) {
+        CU_TRY(cudaMalloc(&scratch, schic::k1f_scratch_bytes(n_rows, nnz)));
+    }
     auto launch = [&]() {
+        if (variant >= 200)
+            return schic::launch_signatures32_table(d_indptr, d_indices, n_rows, nnz, pos0, max_id, n_hash, d_sig, present,
+                                                    slot, entries, ecap, counters, scratch, nullptr);
         return variant >= 100 ? schic::launch_signatures32_filter(d_indptr, d_indices, n_rows, nnz, n_hash, d_sig, scratch, variant == 101 ? 1 : 0, nullptr)
                               : schic::launch_signatures32_variant(variant, d_indptr, d_indices, n_rows, nnz, pos0, n_hash, d_sig, nullptr);
     };
@@ -735,7 +803,16 @@ int schic_k1_variant_ms(int32_t variant, int64_t n_rows, int64_t nnz, const int6
     *ms_out /= (float)reps;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (variant >= 200) {
+        uint32_t c2[2] = {0, 0};
+        cudaMemcpy(c2, counters, sizeof(c2), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[k1 table] max_id %u entries %u of %zu overflow %u\n", max_id, c2[0], ecap, c2[1]);
+    }
     if (scratch) cudaFree(scratch);
+    if (present) cudaFree(present);
+    if (slot) cudaFree(slot);
+    if (entries) cudaFree(entries);
+    if (counters) cudaFree(counters);
     CU_TRY(cudaGetLastError());
     return SCHIC_OK;
 }

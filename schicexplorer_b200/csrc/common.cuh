@@ -23,6 +23,15 @@ size_t k1f_scratch_bytes(int64_t n_rows, int64_t nnz);
 int launch_signatures32_filter(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
                                int H, uint32_t* d_sig, void* d_scratch, int direct /* 1: no shared-memory tile */,
                                cudaStream_t stream);
+// Shared-table variant (k1_table.cu): every (feature id, hash function) is evaluated once for the whole batch.
+bool k1t_applicable(int64_t n_rows, int64_t nnz, uint32_t max_id, int H);
+size_t k1t_entries_capacity(int64_t nnz, uint32_t max_id);
+size_t k1t_items_bytes(int64_t n_rows, int64_t nnz);
+int launch_max_id(const uint32_t* d_feat, int64_t nnz, uint32_t* d_out_max, cudaStream_t stream);
+int launch_signatures32_table(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
+                              int64_t indptr0, uint32_t max_id, int H, uint32_t* d_sig, uint8_t* d_present,
+                              uint2* d_slot, uint16_t* d_entries, size_t entries_cap, uint32_t* d_counters,
+                              void* d_items, cudaStream_t stream);
 // variant >= 0 selects an instruction-selection variant (only in builds with -DK1_ALL_VARIANTS).
 int launch_signatures32_variant(int variant, const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows,
                                 int64_t nnz, int64_t indptr0, int H, uint32_t* d_sig, cudaStream_t stream);

@@ -237,7 +237,7 @@ k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict_
 // is [dir[w], dir[w+1]). Non-zeros of a candidate that fall in windows where the query row is empty
 // are never read.
 // =================================================================================================
-constexpr int K4W_THREADS = 512;
+constexpr int K4W_THREADS = 384;
 constexpr int K4W_WIN_BITS = 18;                        // feature ids per window
 constexpr int K4W_WORDS = 1 << (K4W_WIN_BITS - 4);      // table entries (64 KB)
 constexpr int K4W_KCAP = 4096;                          // query non-zeros per table fill (values: 16 KB)
@@ -330,6 +330,8 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
     }
     for (int w = threadIdx.x; w <= n_windows; w += blockDim.x) qdir[w] = dir[qrow * nw1 + w];
     for (int i = threadIdx.x; i < K4W_KCAP + 32; i += blockDim.x) tval[i] = 0.f;
+    for (int i = threadIdx.x; i < K4W_WORDS / 4; i += blockDim.x)
+        reinterpret_cast<uint4*>(tab)[i] = make_uint4(0u, 0u, 0u, 0u);
     const int64_t xb = indptr[qrow];
     __syncthreads();
 
@@ -340,9 +342,7 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
         for (uint32_t i0 = k0; i0 < k1; i0 += K4W_KCAP) {    // more than KCAP keys in one window: sub-parts
             const uint32_t i1 = min(i0 + (uint32_t)K4W_KCAP, k1);
             const bool first = i0 == k0, last = i1 == k1;
-            __syncthreads();                             // previous part fully consumed
-            for (int i = threadIdx.x; i < K4W_WORDS / 4; i += blockDim.x)
-                reinterpret_cast<uint4*>(tab)[i] = make_uint4(0u, 0u, 0u, 0u);
+            // (the previous part was fully consumed before its un-build below, so the slice arrays are free)
             if (threadIdx.x == 0) s_next = 0;
             // candidate slices of this part: straight from the window directory; a binary search only
             // at the inner borders of sub-parts
@@ -358,7 +358,7 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
                 sl_pos[c] = ys;
                 sl_len[c] = (int)(ye - ys);
             }
-            __syncthreads();
+            __syncthreads();                             // table un-built by everyone, slices visible
             for (uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
                 const uint32_t t = __ldg(feat + xb + i) - lo;
                 const uint32_t tp = i == i0 ? 0xFFFFFFFFu : __ldg(feat + xb + i - 1) - lo;
@@ -375,44 +375,97 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
                 tval[i - i0] = __ldg(val + xb + i);
             }
             __syncthreads();
-            for (;;) {                                   // candidates are handed to warps dynamically
-                int c = 0;
-                if (lane == 0) c = atomicAdd(&s_next, 1);
-                c = __shfl_sync(0xffffffffu, c, 0);
-                if (c >= ncand) break;
-                const int len = sl_len[c];
-                if (len <= 0) continue;
-                const uint32_t* __restrict__ yf = feat + sl_pos[c] + lane;
-                const float* __restrict__ yvp = val + sl_pos[c] + lane;
+            {   // pull what the NEXT part's set-up will read (query keys/values, the candidates' directory
+                // entries) into L2 now, so that the two set-up phases do not sit on DRAM latency
+                uint32_t nk0 = 0, nk1 = 0;
+                int nwin = w;
+                if (!last) {
+                    nk0 = i1; nk1 = min(i1 + (uint32_t)K4W_KCAP, k1);
+                } else {
+                    nwin = w + 1;
+                    while (nwin < n_windows && qdir[nwin + 1] == qdir[nwin]) ++nwin;
+                    if (nwin < n_windows) { nk0 = qdir[nwin]; nk1 = min(qdir[nwin + 1], nk0 + (uint32_t)K4W_KCAP); }
+                }
+                if (nk1 > nk0) {
+                    const uint32_t pi = nk0 + 32u * threadIdx.x;
+                    if (pi < nk1 + 32u) {
+                        const int64_t at = xb + min(pi, nk1 - 1u);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(feat + at));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(val + at));
+                    }
+                    for (int c = threadIdx.x; c < ncand; c += blockDim.x)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(dir + (int64_t)cand[c] * nw1 + nwin));
+                }
+            }
+            // Streaming: every warp walks a flattened sequence of (candidate, 256-non-zero block) pairs --
+            // candidates are handed out dynamically -- with the loads of the next block (also across a
+            // candidate boundary) in flight while the current one is probed.
+            {
+                constexpr int BLK = 32 * K4W_UNROLL;
+                auto fetch = [&]() {                     // next candidate with a non-empty slice, or ncand
+                    int c;
+                    do {
+                        c = 0;
+                        if (lane == 0) c = atomicAdd(&s_next, 1);
+                        c = __shfl_sync(0xffffffffu, c, 0);
+                    } while (c < ncand && sl_len[c] <= 0);
+                    return c;
+                };
+                uint32_t fn[K4W_UNROLL];
+                float vn[K4W_UNROLL];
+                auto load = [&](const uint32_t* __restrict__ yf, const float* __restrict__ yvp, int off, int len) {
+                    if (off + BLK <= len) {              // warp-uniform: full block, no guards
+#pragma unroll
+                        for (int u = 0; u < K4W_UNROLL; ++u) { fn[u] = __ldg(yf + off + 32 * u); vn[u] = __ldg(yvp + off + 32 * u); }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < K4W_UNROLL; ++u) {
+                            const bool ok = off + 32 * u + lane < len;
+                            fn[u] = ok ? __ldg(yf + off + 32 * u) : lo;      // t = 0 with value 0: contributes nothing
+                            vn[u] = ok ? __ldg(yvp + off + 32 * u) : 0.f;
+                        }
+                    }
+                };
+                int c = fetch();
+                int off = 0, len = 0;
+                const uint32_t* __restrict__ yf = feat;
+                const float* __restrict__ yvp = val;
+                if (c < ncand) {
+                    len = sl_len[c]; yf = feat + sl_pos[c] + lane; yvp = val + sl_pos[c] + lane;
+                    load(yf, yvp, 0, len);
+                }
                 double acc = 0.0;
-                int i0b = 0;
-                for (; i0b + 32 * K4W_UNROLL <= len; i0b += 32 * K4W_UNROLL) {     // full blocks: no guards
+                while (c < ncand) {
                     uint32_t f[K4W_UNROLL];
                     float yv[K4W_UNROLL];
 #pragma unroll
-                    for (int u = 0; u < K4W_UNROLL; ++u) { f[u] = __ldg(yf + i0b + 32 * u); yv[u] = __ldg(yvp + i0b + 32 * u); }
+                    for (int u = 0; u < K4W_UNROLL; ++u) { f[u] = fn[u]; yv[u] = vn[u]; }
+                    const int cur = c;
+                    off += BLK;
+                    const bool done = off >= len;        // last block of the current candidate
+                    if (done) {
+                        c = fetch();
+                        off = 0;
+                        if (c < ncand) { len = sl_len[c]; yf = feat + sl_pos[c] + lane; yvp = val + sl_pos[c] + lane; }
+                    }
+                    if (c < ncand) load(yf, yvp, off, len);
                     float a32 = 0.f;                     // exact for integer counts: 8 products < 2^24
 #pragma unroll
                     for (int u = 0; u < K4W_UNROLL; ++u) a32 = k4w_probe<E64>(tab, tval, f[u] - lo, yv[u], a32);
                     acc += (double)a32;
-                }
-                if (i0b < len) {                         // guarded tail block
-                    uint32_t f[K4W_UNROLL];
-                    float yv[K4W_UNROLL];
+                    if (done) {
 #pragma unroll
-                    for (int u = 0; u < K4W_UNROLL; ++u) {
-                        const bool ok = i0b + 32 * u + lane < len;
-                        f[u] = ok ? __ldg(yf + i0b + 32 * u) : lo;
-                        yv[u] = ok ? __ldg(yvp + i0b + 32 * u) : 0.f;
+                        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                        if (lane == 0) dot[cur] += acc;
+                        acc = 0.0;
                     }
-                    float a32 = 0.f;
-#pragma unroll
-                    for (int u = 0; u < K4W_UNROLL; ++u) a32 = k4w_probe<E64>(tab, tval, f[u] - lo, yv[u], a32);
-                    acc += (double)a32;
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0) dot[c] += acc;
+            }
+            // sparse clear: zero exactly the entries this part set (the table is all zero between parts)
+            __syncthreads();
+            for (uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+                const uint32_t t = __ldg(feat + xb + i) - lo;
+                if (E64) { tab[2 * (t >> 5)] = 0u; tab[2 * (t >> 5) + 1] = 0u; } else { tab[t >> 4] = 0u; }
             }
         }
     }

@@ -388,7 +388,27 @@ def test_k1_filtered_equals_chunked_kernel(cuda, oracle, monkeypatch):
         kw = dict(number_of_hash_functions=H, minimal_blocks_in_common=1)
         with Fitted(oracle, X, **kw) as o:
             want = o.sig()
-        for mode in ("tile", "direct", "chunk"):
+        for mode in ("tile", "direct", "chunk", "table"):
             monkeypatch.setenv("SCHIC_K1_MODE", mode)
             with Fitted(cuda, X, **kw) as g:
                 assert np.array_equal(g.sig(), want), (H, mode)
+
+
+@pytest.mark.parametrize("H", [800, 4000, 33])
+def test_k1_shared_table_path(cuda, oracle, monkeypatch, H):
+    """The shared-table K1 (every (id, hash function) evaluated once per batch, per-cell lookup, exact fallback)
+    on clustered cells that really share ids, forced on (the automatic choice needs >= 2M non-zeros): signatures
+    and collision counts bit-identical to the oracle; also through partial_fit (a table per appended batch)."""
+    monkeypatch.setenv("SCHIC_K1_MODE", "table")
+    X = synth_csr(160, seed=29)
+    empty = csr_matrix((1, X.shape[1]))
+    Xe = vstack([X[:50], empty, X[50:]]).tocsr()
+    kw = dict(number_of_hash_functions=H, minimal_blocks_in_common=1)
+    with Fitted(oracle, Xe, **kw) as o:
+        want, want_cnt = o.sig(), oracle.collision_counts(o.h)
+    with Fitted(cuda, Xe, **kw) as g:
+        assert np.array_equal(g.sig(), want)
+        assert np.array_equal(cuda.collision_counts(g.h), want_cnt)
+        cuda.fit_csr(g.h, Xe[:70].indptr, Xe[:70].indices, None, False)
+        cuda.fit_csr(g.h, Xe[70:].indptr, Xe[70:].indices, None, True)
+        assert np.array_equal(g.sig(), want)

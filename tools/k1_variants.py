@@ -26,7 +26,7 @@ if __name__ == "__main__":
     nnz = int(ip[-1])
     res = {}
     ref = None
-    for v in [-1, 100, 101]:
+    for v in [-1, 100, 200]:
         ms = api.k1_variant_ms(v, n, nnz, d_ip.data_ptr(), d_ix.data_ptr(), H, d_sig.data_ptr(), reps=3)
         sig = d_sig.cpu().numpy()
         if ref is None:
