@@ -20,6 +20,13 @@ extern "C" {
 /* Number of visible CUDA devices (0 and SCHIC_OK when there is no driver/GPU). */
 int schic_device_count(int32_t* n_out);
 
+/* schic_mh_fit_csr (host CSR in) that returns as soon as the uploads and K1 are queued instead of when the
+ * last byte has crossed PCIe: the value array is only read by the exact rerank, so collision counting can
+ * start while it is still in flight. The caller keeps indptr / indices / data alive and unchanged until
+ * schic_mh_synchronize(), a kneighbors call that returns host results, or the next fit on the handle. */
+int schic_mh_fit_csr_async(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
+                           int32_t index_bits, const float* data, int32_t append);
+
 /* MinHash.fit on a CSR shard already in HBM. The arrays are BORROWED (not copied) and must stay
  * valid until the next fit or destroy. d_indptr [n_rows+1] int64 (absolute positions into
  * d_indices/d_data), d_indices uint32, d_data float32 (may be NULL when fast=1). append must be 0. */

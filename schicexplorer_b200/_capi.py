@@ -53,7 +53,7 @@ BASE_SYMBOLS = (
 )
 # symbols only the CUDA library exports (include/schic_mh_cuda.h)
 CUDA_SYMBOLS = (
-    "schic_mh_fit_csr_device", "schic_mh_kneighbors_device", "schic_mh_signatures_device", "schic_mh_csr_device",
+    "schic_mh_fit_csr_async", "schic_mh_fit_csr_device", "schic_mh_kneighbors_device", "schic_mh_signatures_device", "schic_mh_csr_device",
     "schic_mh_set_database_device", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free",
@@ -94,6 +94,7 @@ class CApi:
         self.backend = L.schic_mh_backend().decode()
         self.is_cuda = self.backend == "cuda"
         if self.is_cuda:
+            L.schic_mh_fit_csr_async.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32]
             L.schic_mh_fit_csr_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _i32]
             L.schic_mh_kneighbors_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
             L.schic_mh_signatures_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_i64)]
@@ -147,7 +148,16 @@ class CApi:
         if h:
             self.lib.schic_mh_destroy(_vp(h))
 
-    def fit_csr(self, h, indptr, indices, data, append: bool):
+    def fit_csr(self, h, indptr, indices, data, append: bool, async_upload: bool = False):
+        """``async_upload`` (CUDA back end only): return once the uploads and K1 are queued; the caller keeps the
+        three arrays alive until the next synchronising call (include/schic_mh_cuda.h). The arrays must then
+        already have the wire dtypes (int64 / uint32|uint64 / float32, C contiguous) so no temporary is made."""
+        if async_upload:
+            ok = (indptr.dtype == np.int64 and indptr.flags.c_contiguous and indices.flags.c_contiguous and
+                  indices.dtype.itemsize in (4, 8) and
+                  (data is None or (data.dtype == np.float32 and data.flags.c_contiguous)))
+            if not ok:
+                raise ValueError("async_upload needs int64 indptr, 32/64-bit indices and float32 data, C contiguous")
         indptr = np.ascontiguousarray(indptr, dtype=np.int64)
         if indices.dtype.itemsize == 8:
             indices = np.ascontiguousarray(indices).view(np.uint64)
@@ -157,8 +167,8 @@ class CApi:
             bits = 32
         if data is not None:
             data = np.ascontiguousarray(data, dtype=np.float32)
-        self.check(self.lib.schic_mh_fit_csr(_vp(h), len(indptr) - 1, _ptr(indptr), _ptr(indices), bits,
-                                             _ptr(data), int(append)))
+        fn = self.lib.schic_mh_fit_csr_async if async_upload else self.lib.schic_mh_fit_csr
+        self.check(fn(_vp(h), len(indptr) - 1, _ptr(indptr), _ptr(indices), bits, _ptr(data), int(append)))
 
     def n_fitted(self, h) -> int:
         n = _i64()

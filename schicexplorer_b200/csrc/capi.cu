@@ -82,6 +82,8 @@ struct schic_mh_handle {
     // shared-table K1 (k1_table.cu): per-id presence bytes and slots, hit entries, {entries used, overflow, max id}
     DevBuf<unsigned char> k1t_present; DevBuf<unsigned long long> k1t_slot; DevBuf<uint16_t> k1t_entries;
     DevBuf<uint32_t> k1t_counters;
+    std::vector<uint32_t> host_lo, host_hi;   // split 64-bit ids of the last fit (must outlive an async upload)
+    int64_t count_budget = 0;                 // elements of the uint16 count matrix we allow ourselves (cached)
     DevBuf<double> norm2; int64_t norm_rows = 0; const void* norm_of = nullptr;
     DevBuf<uint32_t> win_dir, max_feat; int n_windows = 0;   // window directory of the windowed rerank (0: hash kernel)
     int window_mode = 32;
@@ -103,6 +105,7 @@ struct schic_mh_handle {
     std::vector<cudaEvent_t> pool;      // every event ever created (owned)
     std::vector<cudaEvent_t> free_ev;   // recycled
     std::vector<cudaEvent_t> misc_ev;   // ordering events of the current fit (not stage timers)
+    cudaEvent_t val_done = nullptr;     // pending async value upload (member of misc_ev)
 
     const int64_t* d_indptr() const { return borrowed ? b_indptr : indptr.p; }
     const uint32_t* d_feat() const { return borrowed ? b_feat : feat.p; }
@@ -249,6 +252,7 @@ int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const uint32_t* feat
     if (h->norm_of == (const void*)indptr && h->norm_rows == rows) return 0;
     constexpr int kMaxWindows = 1024;
     cudaStream_t s = h->stream;
+    if (h->val_done) CU_TRY(cudaStreamWaitEvent(s, h->val_done, 0));   // async fit: the values may still be in flight
     ST_TRY(h->norm2.reserve(rows, 0, s));
     add_launches(h, schic::launch_row_norms(indptr, val, rows, 0, h->norm2.p, s));
     CU_TRY(cudaGetLastError());
@@ -321,15 +325,15 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
     const int64_t ld = (ndb + 7) & ~(int64_t)7;
     // budget: a quarter of the free HBM, at least 2 GiB, at most 32 GiB (the all-rows-in-one-block case also
     // lets K3 use the symmetry of the counts)
-    int64_t budget_elems = (int64_t)1 << 30;
-    {
+    if (h->count_budget == 0) {
         size_t free_b = 0, total_b = 0;
+        h->count_budget = (int64_t)1 << 30;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
-            budget_elems = std::max<int64_t>(budget_elems, std::min<int64_t>((int64_t)(free_b / 4) / 2, (int64_t)1 << 34));
+            h->count_budget = std::max<int64_t>(h->count_budget, std::min<int64_t>((int64_t)(free_b / 4) / 2, (int64_t)1 << 34));
         else
             cudaGetLastError();
-        budget_elems = std::max<int64_t>(budget_elems, h->counts.cap);   // never shrink below what is already held
     }
+    const int64_t budget_elems = std::max<int64_t>(h->count_budget, h->counts.cap);   // never below what is already held
     int64_t qb = std::max<int64_t>(128, budget_elems / ld);
     qb = std::min<int64_t>((qb / 128) * 128, (nq + 127) / 128 * 128);
     ST_TRY(h->counts.reserve(qb * ld, 0, s));
@@ -451,8 +455,8 @@ int schic_mh_synchronize(schic_mh_handle* h) {
     return SCHIC_OK;
 }
 
-int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
-                     int32_t index_bits, const float* data, int32_t append) {
+static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
+                        int32_t index_bits, const float* data, int32_t append, bool async_upload) {
     ST_TRY(check(h));
     if (n_rows < 0 || !indptr) return fail(SCHIC_ERR_INVALID_ARG, "bad CSR arguments");
     if (index_bits != 32 && index_bits != 64) return fail(SCHIC_ERR_INVALID_ARG, "index_bits must be 32 or 64");
@@ -463,6 +467,7 @@ int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, 
         if (indptr[r + 1] < indptr[r]) return fail(SCHIC_ERR_INVALID_ARG, "indptr not monotone");
     ST_TRY(use_device(h));
     if (h->borrowed && append) return fail(SCHIC_ERR_UNSUPPORTED, "cannot append to a borrowed device CSR");
+    CU_TRY(cudaStreamSynchronize(h->copy_stream));   // an earlier async upload may still use the buffers / host vectors
     if (!append || h->borrowed) {
         CU_TRY(cudaStreamSynchronize(h->stream));
         h->n = 0; h->nnz = 0; h->borrowed = false; h->have_val = false; h->have_hi = false;
@@ -471,6 +476,7 @@ int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, 
     reset_stage(h, {ST_H2D, ST_SIG});
     for (cudaEvent_t e : h->misc_ev) h->free_ev.push_back(e);
     h->misc_ev.clear();
+    h->val_done = nullptr;
     h->norm_of = nullptr;
     const int H = h->p.number_of_hash_functions;
     const int64_t r0 = h->n, pos0 = h->nnz;
@@ -490,7 +496,8 @@ int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, 
     for (int64_t r = 0; r <= n_rows; ++r) ip[r] = pos0 + (indptr[r] - indptr[0]);
     // 32-bit feature ids (width 32 hashes (uint32)(f+1), so truncation is exact there)
     const uint32_t* f32 = nullptr;
-    std::vector<uint32_t> lo, hi;
+    std::vector<uint32_t>& lo = h->host_lo;
+    std::vector<uint32_t>& hi = h->host_hi;
     if (index_bits == 32) {
         f32 = (const uint32_t*)indices + indptr[0];
     } else {
@@ -521,7 +528,7 @@ int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, 
     // A small first chunk (8 M non-zeros, ~0.6 ms of PCIe) lets K1 start early; later chunks are 32 M so that
     // every K1 launch still holds several waves of row work items.
     cudaEvent_t sig0 = get_event(h);
-    bool sig_started = false;
+    bool sig_started = false, val_enqueued = false;
     int64_t c0 = 0;
     // (a batch that may take the shared-table K1 path is hashed in one piece after its last chunk has landed:
     // the table is built from all of its feature ids)
@@ -539,6 +546,12 @@ int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, 
         cudaEvent_t ready = get_misc_event(h);
         if (!ready) return fail(SCHIC_ERR_CUDA, "cudaEventCreate failed");
         CU_TRY(cudaEventRecord(ready, cs));
+        if (c1 == n_rows && want_val && nnz > 0) {
+            // the values follow the last feature chunk at once, so the copy engine stays busy while K1 runs
+            // (and while the host may block on K1's id-range read-back)
+            CU_TRY(cudaMemcpyAsync(h->val.p + pos0, data + indptr[0], (size_t)nnz * 4, cudaMemcpyHostToDevice, cs));
+            val_enqueued = true;
+        }
         CU_TRY(cudaStreamWaitEvent(s, ready, 0));
         if (!sig_started && sig0) { cudaEventRecord(sig0, s); sig_started = true; }
         ST_TRY(hash_rows(h, r0 + c0, r0 + c1, ip[c0], ip[c1], s));
@@ -546,7 +559,7 @@ int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, 
     }
     cudaEvent_t sig1 = get_event(h);
     if (sig_started && sig1) { cudaEventRecord(sig1, s); h->ev[ST_SIG].push_back({sig0, sig1}); }
-    if (want_val && nnz > 0)
+    if (want_val && nnz > 0 && !val_enqueued)
         CU_TRY(cudaMemcpyAsync(h->val.p + pos0, data + indptr[0], (size_t)nnz * 4, cudaMemcpyHostToDevice, cs));
     if (up0 && up1) { cudaEventRecord(up1, cs); h->ev[ST_H2D].push_back({up0, up1}); }
     // the host vectors (lo/hi) and the caller's arrays must outlive the copies; later stages use
@@ -554,9 +567,23 @@ int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, 
     cudaEvent_t done = get_misc_event(h);
     if (!done) return fail(SCHIC_ERR_CUDA, "cudaEventCreate failed");
     CU_TRY(cudaEventRecord(done, cs));
-    CU_TRY(cudaStreamWaitEvent(s, done, 0));
-    CU_TRY(cudaStreamSynchronize(cs));
+    if (async_upload) {
+        h->val_done = done;                   // the rerank preparation waits for it (ensure_norms)
+    } else {
+        CU_TRY(cudaStreamWaitEvent(s, done, 0));
+        CU_TRY(cudaStreamSynchronize(cs));
+    }
     return SCHIC_OK;
+}
+
+int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
+                     int32_t index_bits, const float* data, int32_t append) {
+    return fit_csr_impl(h, n_rows, indptr, indices, index_bits, data, append, false);
+}
+
+int schic_mh_fit_csr_async(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
+                           int32_t index_bits, const float* data, int32_t append) {
+    return fit_csr_impl(h, n_rows, indptr, indices, index_bits, data, append, true);
 }
 
 int schic_mh_fit_csr_device(schic_mh_handle* h, int64_t n_rows, int64_t nnz, const int64_t* d_indptr,

@@ -66,7 +66,10 @@ __global__ void k1t_max_id_kernel(const uint32_t* __restrict__ feat, int64_t nnz
 // ---- 1. mark ---------------------------------------------------------------------------------------
 __global__ void k1t_mark_kernel(const uint32_t* __restrict__ feat, int64_t nnz, uint8_t* __restrict__ present) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) present[__ldg(feat + i)] = 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const uint32_t f = __ldg(feat + i);
+        if (!present[f]) present[f] = 1;         // ids repeat ~40x: after the first touch this is a read that hits in L2
+    }
 }
 
 // ---- 2. build --------------------------------------------------------------------------------------
@@ -226,7 +229,9 @@ k1t_lookup_kernel(const K1TItem* __restrict__ items, const int* __restrict__ n_i
 }
 
 // ---- 4. fallback -------------------------------------------------------------------------------------
-// One CTA per row: hash functions whose signature entry is still the sentinel are recomputed exactly, lane <-> j.
+// One CTA per row: hash functions whose signature entry is still the sentinel are recomputed exactly. A warp
+// takes one such j at a time and spreads the row's non-zeros over its lanes (coalesced loads, shuffle min):
+// the common case is a long row with one or two failures, which a lane-per-j loop would walk serially.
 __global__ void __launch_bounds__(128)
 k1t_fallback_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat, int H,
                     uint32_t* __restrict__ sig) {
@@ -243,13 +248,22 @@ k1t_fallback_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restri
     __syncthreads();
     const int n = s_n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    for (int base = warp * 32; base < n; base += n_warps * 32) {
-        const bool ok = base + lane < n;
-        const uint32_t j = ok ? fj[base + lane] : fj[base];
+    const int len = (int)(e - b);
+    const uint32_t* __restrict__ src = feat + b;
+    for (int t = warp; t < n; t += n_warps) {
+        const uint32_t j = fj[t];
         const uint32_t c = 32767u * (j + 1u);
         uint32_t best = kModulus;
-        for (int64_t i = b; i < e; ++i) best = min(best, k1t_value(__ldg(feat + i) + 1u, c));
-        if (ok) sig_row[j] = best;
+        int i = lane;
+        for (; i + 96 < len; i += 128) {         // 4 independent loads per lane in flight
+            const uint32_t f0 = __ldg(src + i), f1 = __ldg(src + i + 32), f2 = __ldg(src + i + 64), f3 = __ldg(src + i + 96);
+            best = min(best, min(k1t_value(f0 + 1u, c), k1t_value(f1 + 1u, c)));
+            best = min(best, min(k1t_value(f2 + 1u, c), k1t_value(f3 + 1u, c)));
+        }
+        for (; i < len; i += 32) best = min(best, k1t_value(__ldg(src + i) + 1u, c));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (lane == 0) sig_row[j] = best;
     }
 }
 

@@ -257,21 +257,21 @@ __global__ void row_max_feature_kernel(const int64_t* __restrict__ indptr, const
 }
 
 // dir[row][w] = offset (relative to the row start) of the first non-zero with (id >> WIN_BITS) >= w,
-// w = 0..n_windows (dir[row][n_windows] = row length). One warp per row; every entry is written once.
-__global__ void row_window_dir_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat,
-                                      int64_t n_rows, int n_windows, uint32_t* __restrict__ dir) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// w = 0..n_windows (dir[row][n_windows] = row length). One 128-thread CTA per row; every entry is written once.
+__global__ void __launch_bounds__(128)
+row_window_dir_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat,
+                      int64_t n_rows, int n_windows, uint32_t* __restrict__ dir) {
+    const int64_t row = blockIdx.x;
     if (row >= n_rows) return;
     const int64_t b = indptr[row], e = indptr[row + 1];
     uint32_t* __restrict__ d = dir + row * (int64_t)(n_windows + 1);
-    for (int64_t i = b + lane; i < e; i += 32) {
+    for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
         const int w = (int)(__ldg(feat + i) >> K4W_WIN_BITS);
         const int wp = i == b ? -1 : (int)(__ldg(feat + i - 1) >> K4W_WIN_BITS);
         for (int x = wp + 1; x <= w; ++x) d[x] = (uint32_t)(i - b);
     }
     const int wl = e > b ? (int)(__ldg(feat + e - 1) >> K4W_WIN_BITS) : -1;
-    for (int x = wl + 1 + lane; x <= n_windows; x += 32) d[x] = (uint32_t)(e - b);
+    for (int x = wl + 1 + threadIdx.x; x <= n_windows; x += blockDim.x) d[x] = (uint32_t)(e - b);
 }
 
 // Table entry layouts (E64 = false / true), both 4 feature ids per byte of shared memory:
@@ -441,6 +441,7 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
 #pragma unroll
                     for (int u = 0; u < K4W_UNROLL; ++u) { f[u] = fn[u]; yv[u] = vn[u]; }
                     const int cur = c;
+                    const int fill = len - off;          // non-zeros in the current block (may exceed BLK)
                     off += BLK;
                     const bool done = off >= len;        // last block of the current candidate
                     if (done) {
@@ -450,8 +451,17 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
                     }
                     if (c < ncand) load(yf, yvp, off, len);
                     float a32 = 0.f;                     // exact for integer counts: 8 products < 2^24
+                    // short last blocks (slices average ~1.7 blocks) skip the probe groups that are all padding
 #pragma unroll
-                    for (int u = 0; u < K4W_UNROLL; ++u) a32 = k4w_probe<E64>(tab, tval, f[u] - lo, yv[u], a32);
+                    for (int u = 0; u < 2; ++u) a32 = k4w_probe<E64>(tab, tval, f[u] - lo, yv[u], a32);
+                    if (fill > 64) {
+#pragma unroll
+                        for (int u = 2; u < 4; ++u) a32 = k4w_probe<E64>(tab, tval, f[u] - lo, yv[u], a32);
+                    }
+                    if (fill > 128) {
+#pragma unroll
+                        for (int u = 4; u < K4W_UNROLL; ++u) a32 = k4w_probe<E64>(tab, tval, f[u] - lo, yv[u], a32);
+                    }
                     acc += (double)a32;
                     if (done) {
 #pragma unroll
@@ -513,8 +523,7 @@ int rerank_window_count(uint32_t max_feature) { return (int)(max_feature >> K4W_
 int launch_row_window_dir(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int n_windows,
                           uint32_t* d_dir, cudaStream_t stream) {
     if (n_rows <= 0) return 0;
-    const int64_t threads = n_rows * 32;
-    row_window_dir_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_indptr, d_feat, n_rows, n_windows, d_dir);
+    row_window_dir_kernel<<<(unsigned)n_rows, 128, 0, stream>>>(d_indptr, d_feat, n_rows, n_windows, d_dir);
     return 1;
 }
 

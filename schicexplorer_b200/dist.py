@@ -93,15 +93,23 @@ class ShardedMinHash:
         self.api.fit_csr_device(self.h, self.n_local, nnz, d_indptr.data_ptr(), d_indices.data_ptr(),
                                 None if d_data is None else d_data.data_ptr(), False)
 
-    def fit_local_host(self, indptr: np.ndarray, indices: np.ndarray, data):
+    def fit_local_host(self, indptr: np.ndarray, indices: np.ndarray, data, async_upload: bool = False):
         """Same, from HOST buffers (pinned for full PCIe speed): the H2D copy is part of the call and
-        is overlapped with K1 chunk by chunk inside the library."""
-        self.api.fit_csr(self.h, indptr, indices, data, False)
+        is overlapped with K1 inside the library. ``async_upload``: do not wait for the value array to
+        land (only the exact rerank reads it) -- the caller keeps the buffers alive until the step's
+        results have been read back."""
+        if async_upload:
+            self._keep["host_csr"] = (indptr, indices, data)
+            self.api.fit_csr(self.h, indptr, indices, data, False, async_upload=True)
+        else:
+            self.api.fit_csr(self.h, indptr, indices, data, False)
         p_ip, p_ix, p_dt, nnz = self.api.csr_device(self.h)
         d_ip = _wrap_device(p_ip, (self.n_local + 1,), "<i8", torch.int64, self.device)
         d_ix = _wrap_device(p_ix, (nnz,), "<i4", torch.int32, self.device)
         d_dt = None if not p_dt else _wrap_device(p_dt, (nnz,), "<f4", torch.float32, self.device)
         self._keep["csr"] = (d_ip, d_ix, d_dt)
+        if async_upload and self.world > 1 and not self.fast:
+            self.api.synchronize(self.h)       # the CSR exchange reads the value array: it must have landed
         self._start_csr_gather()
 
     # -- step 2: the exchange ------------------------------------------------------------------

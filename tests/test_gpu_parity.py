@@ -412,3 +412,30 @@ def test_k1_shared_table_path(cuda, oracle, monkeypatch, H):
         cuda.fit_csr(g.h, Xe[:70].indptr, Xe[:70].indices, None, False)
         cuda.fit_csr(g.h, Xe[70:].indptr, Xe[70:].indices, None, True)
         assert np.array_equal(g.sig(), want)
+
+
+def test_async_host_fit(cuda, oracle):
+    """schic_mh_fit_csr_async: returns before the value array has landed; results identical to the blocking call."""
+    X = synth_csr(220, seed=33)
+    k = 14
+    ip = X.indptr.astype(np.int64)
+    ix = np.ascontiguousarray(X.indices.astype(np.uint32))
+    dt = np.ascontiguousarray(X.data.astype(np.float32))
+    with Fitted(oracle, X, fast=False, n_neighbors=k) as o:
+        want = oracle.kneighbors(o.h, k)
+        want_sig = o.sig()
+    h = cuda.create(n_neighbors=k, fast=False, **REF_KWARGS)
+    for _ in range(2):                                   # second round: refit while nothing is pending
+        cuda.fit_csr(h, ip, ix, dt, False, async_upload=True)
+        got = cuda.kneighbors(h, k)
+        assert_neighbours_equal_up_to_ties(*got, *want, RTOL)
+        assert np.array_equal(cuda.signatures(h, 800), want_sig)
+    # async append
+    cuda.fit_csr(h, ip[:101], ix[:ip[100]], dt[:ip[100]], False, async_upload=True)
+    ip2 = ip[100:] - ip[100]
+    cuda.fit_csr(h, ip2, ix[ip[100]:], dt[ip[100]:], True, async_upload=True)
+    got = cuda.kneighbors(h, k)
+    assert_neighbours_equal_up_to_ties(*got, *want, RTOL)
+    with pytest.raises(ValueError):
+        cuda.fit_csr(h, X.indptr, X.indices, X.data, False, async_upload=True)   # int32 indptr / float64 data
+    cuda.destroy(h)
