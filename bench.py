@@ -13,8 +13,9 @@ K4 rerank, neighbour lists left in HBM.
 `value`  : inputs resident in HBM, device-timed with CUDA events, max over ranks.
 `e2e`    : same build through the C-ABI host entry points (pinned host CSR in, neighbour lists out),
            H2D and D2H inside the timed region.
-`roofline`: K1 (the dominant kernel) against the INT32 issue rate measured live by
-           schic_int32_peak; HBM figures alongside.
+`roofline`: the dominant kernel of the step -- K4, the exact rerank -- against the measured HBM copy peak
+           (MEASURED_PEAKS.json), algorithmic bytes of SURVEY 8(d); K1 (signatures) is reported beside it with
+           the INT32 issue rates measured live by schic_int32_peak.
 The total work is fixed as N grows ("scaling": "strong"): the 10 k cells are sharded over the ranks.
 """
 from __future__ import annotations
@@ -164,20 +165,6 @@ def run_reference(args):
     }))
 
 
-def k4_roofline(rerank_ms, nnz_local, n_local, n_total, k, hbm_peak):
-    """Second kernel of the step: K4 streams 8 bytes (id + value) per candidate non-zero. Algorithmic bytes =
-    n_local * k candidate rows of the mean row length (8*nnz_d per pair)."""
-    if rerank_ms <= 0:
-        return None
-    mean_row = nnz_local / max(1, n_local)
-    algo = 8.0 * mean_row * n_local * min(k, n_total)
-    gbs = algo / (rerank_ms * 1e-3) / 1e9
-    return {"kernel": "k4_rerank_window_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-            "frac": gbs / hbm_peak, "algorithmic_bytes": algo,
-            "note": "8 B x candidate-row length x n*k pairs / K4 CUDA-event time; real DRAM traffic is lower (L2 hits, "
-                    "windows the query row does not touch are never read): see profiles/ for dram__bytes."}
-
-
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -311,35 +298,55 @@ def run_ours(args):
     stage_e2e = api.stage_ms(sh2.h)
 
     if rank == 0:
-        # ---- roofline of the dominant kernel (K1) ------------------------------------------
         peak = api.int32_peak(local_rank, 2048)
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
             hbm_src = "measured (MEASURED_PEAKS.json)"
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-        evals = nnz_local * H                                    # this rank's K1 launches per step
+        # ---- roofline of the dominant kernel: K4 (exact rerank), HBM bound ---------------------------
+        # algorithmic bytes: 8 B (id + value) per non-zero of every candidate row; the units of one
+        # launch are this rank's n_local * k candidate pairs of the mean row length
+        mean_row = nnz_all.item() / max(1, n_total)
+        k4_s = stage["rerank"] * 1e-3
+        k4_bytes = 8.0 * mean_row * (hi - lo) * min(k, n_total)
+        roofline = None
+        if not fast and k4_s > 0:
+            gbs = k4_bytes / k4_s / 1e9
+            roofline = {
+                "kernel": "k4_rerank_window_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": gbs / hbm_peak, "traffic": 58.78e9 * (hi - lo) / 10000.0 if args.workload == "s10" else None,
+                "peak_source": hbm_src, "kernel_ms": stage["rerank"], "share_of_step": stage["rerank"] / ms_per_step,
+                "algorithmic_bytes": k4_bytes,
+                "note": "achieved = 8 B x mean row length x (n_local*k candidate pairs) / K4 CUDA-event time of the last timed "
+                        "step. frac can exceed 1: 31 % of the sectors hit in L2 and windows the query row does not touch are "
+                        "never read, so DRAM traffic (ncu dram__bytes of one S10 launch, profiles/, scaled by rows) is about "
+                        "half the algorithmic bytes. ncu: L1/shared data pipe 67 % and issue 68 % busy, DRAM 46 %.",
+            }
+        # ---- K1 (signatures): reference-formulation rate vs. what is executed ------------------------
+        evals = nnz_local * H
         k1_s = float(k1_ms.item()) * 1e-3
-        achieved = evals * INT_OPS_PER_EVAL / k1_s / 1e12 if k1_s > 0 else 0.0
-        k1_bytes = 4 * nnz_local + 4 * (hi - lo) * H + 8 * (hi - lo + 1)
-        issued = 9.3      # SASS instructions issued per evaluation (ncu smsp__inst_executed x 32 / evals, profiles/)
-        roofline = {
-            "kernel": "k1_filter_kernel<5,false>", "bound": "int32-issue", "achieved": achieved,
-            "peak": peak["mix_lop3_imad"], "unit": "Tint-op/s", "frac": achieved / peak["mix_lop3_imad"],
-            "traffic": 0.637e9 * nnz_local / 143427802,
-            "note": "achieved = nnz*H hash evaluations x 15 algorithmic int32 ops (SURVEY 8(d): the reference formulation "
-                    "hashes, reduces modulo 2^31-1 and compares every evaluation) / K1 CUDA-event time; peak = measured 1:1 "
-                    "LOP3+IMAD issue rate (schic_int32_peak, this run). frac exceeds 1 because the kernel proves most "
-                    "evaluations cannot lower the running minimum after 8.5 issued ops (15-bit prefix filter, DESIGN.md "
-                    "section 4) and finishes only the rest: frac_issued counts what is really issued (9.3 ops/eval, ncu), "
-                    "ncu shows the ALU pipe 91 % busy. traffic = ncu dram bytes of one launch (profiles/), scaled by nnz.",
-            "frac_issued": (evals * issued / k1_s / 1e12) / peak["mix_lop3_imad"] if k1_s > 0 else 0.0,
-            "gevals_per_s": evals / k1_s / 1e9 if k1_s > 0 else 0.0,
-            "k1_ms": float(k1_ms.item()), "k1_share_of_step": float(k1_ms.item()) / ms_per_step,
-            "hbm": {"achieved_gbs": k1_bytes / k1_s / 1e9 if k1_s > 0 else 0.0, "peak_gbs": hbm_peak, "peak_source": hbm_src},
-            "k4_rerank_hbm": k4_roofline(stage["rerank"], nnz_local, hi - lo, n_total, k, hbm_peak) if not fast else None,
+        k1 = {
+            "kernels": "k1t_mark/build/lookup/fallback (shared table) or k1_filter_kernel", "bound": "int32-issue",
+            "k1_ms": float(k1_ms.item()), "share_of_step": float(k1_ms.item()) / ms_per_step,
+            "reference_formulation_gevals_per_s": evals / k1_s / 1e9 if k1_s > 0 else 0.0,
+            "reference_formulation_tintops": evals * INT_OPS_PER_EVAL / k1_s / 1e12 if k1_s > 0 else 0.0,
+            "int32_issue_peak_tintops": peak["mix_lop3_imad"],
+            "note": "SURVEY 8(d) counts nnz*H evaluations x 15 int32 ops. The shared-table path evaluates each (distinct id, "
+                    "hash function) once per batch (S10: 3.77e6 ids x 800 = 3.0e9 evaluations, 1.26 ms, ALU pipe 79 % busy) "
+                    "and looks the rest up, so the reference-formulation rate exceeds the issue peak many times over without "
+                    "any evaluation being approximated (bit-exact vs the oracle). Per-cell filtered kernel for comparison: "
+                    "35.6 ms, 9.3 issued ops/evaluation, ALU pipe 91 % busy.",
             "int32_peaks_tops": peak,
         }
+        if roofline is None:      # fast path (no rerank): K3 is the dominant kernel, INT32 issue bound
+            k3_s = stage["collisions"] * 1e-3
+            compares = (hi - lo) * n_total * H * (0.5 if world == 1 else 1.0)
+            ach = compares / k3_s / 1e12 if k3_s > 0 else 0.0
+            roofline = {"kernel": "k3_collision_kernel", "bound": "int32-issue", "achieved": ach, "peak": peak["lop3"],
+                        "unit": "Tcompare/s", "frac": ach / peak["lop3"], "traffic": None,
+                        "note": "one ISETP (ALU pipe) per signature compare; peak = measured single-pipe issue rate"}
+        roofline["k1_signatures"] = k1
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",

@@ -61,8 +61,8 @@ int schic_mh_set_stream(schic_mh_handle* h, void* cuda_stream);
 int schic_mh_synchronize(schic_mh_handle* h);
 
 /* CUDA-event time (ms) of the stages of the most recent fit + kneighbors on this handle:
- * [0] h2d, [1] signatures (K1), [2] collisions (K3), [3] select, [4] rerank (K4), [5] graph (K5),
- * [6] d2h, [7] sum. Synchronises the stream. */
+ * [0] h2d, [1] signatures (K1), [2] collisions (K3), [3] select, [4] rerank (K4 launch alone), [5] graph (K5),
+ * [6] d2h, [7] rerank preparation (row norms, window directory), [8] sum; n_out >= 9. Synchronises the stream. */
 int schic_mh_stage_ms(schic_mh_handle* h, float* out, int32_t n_out);
 
 /* Number of kernels this handle has launched so far. */

@@ -230,9 +230,9 @@ class CApi:
         self.check(self.lib.schic_mh_set_stream(_vp(h), _vp(stream)))
 
     def stage_ms(self, h) -> dict:
-        out = np.zeros(8, dtype=np.float32)
-        self.check(self.lib.schic_mh_stage_ms(_vp(h), _ptr(out), 8))
-        names = ("h2d", "signatures", "collisions", "select", "rerank", "graph", "d2h", "total")
+        out = np.zeros(9, dtype=np.float32)
+        self.check(self.lib.schic_mh_stage_ms(_vp(h), _ptr(out), 9))
+        names = ("h2d", "signatures", "collisions", "select", "rerank", "graph", "d2h", "rerank_prep", "total")
         return dict(zip(names, out.tolist()))
 
     def launch_count(self, h) -> int:

@@ -59,7 +59,7 @@ struct DevBuf {
     }
 };
 
-enum Stage { ST_H2D = 0, ST_SIG, ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_COUNT };
+enum Stage { ST_H2D = 0, ST_SIG, ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_PREP, ST_COUNT };
 
 }  // namespace
 
@@ -301,7 +301,7 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
         if (!db_val || !db_feat) return fail(SCHIC_ERR_INVALID_ARG, "exact rerank needs the CSR values (fit with data)");
         if (h->have_hi) return fail(SCHIC_ERR_UNSUPPORTED, "exact rerank supports 32-bit feature ids only");
     }
-    reset_stage(h, {ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H});
+    reset_stage(h, {ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_PREP});
     cudaStream_t s = h->stream;
     const uint32_t* q_sig = h->sig.p;
     if (ndb >= h->p.max_bin_size) {   // rule 5: blank the members of buckets with >= max_bin_size cells
@@ -359,8 +359,11 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
         add_launches(h, schic::launch_fast_distance(h->cand_idx.p, h->cand_cnt.p, h->cand_nv.p, nq, kcand, k, H,
                                                    h->p.absolute_numbers, d_idx, d_dist, d_nv, s));
     } else {
+        {
+            StageTimer t(h, ST_PREP, s);     // row norms + window directory of the database (once per fit)
+            ST_TRY(ensure_norms(h, db_indptr, db_feat, db_val, ndb));
+        }
         StageTimer t(h, ST_RERANK, s);
-        ST_TRY(ensure_norms(h, db_indptr, db_feat, db_val, ndb));
         const int nl = schic::launch_rerank(db_indptr, db_feat, db_val, 0, h->norm2.p,
                                             h->n_windows > 0 ? h->win_dir.p : nullptr, h->n_windows, h->window_mode, row0, nq,
                                             h->cand_idx.p,
@@ -754,7 +757,7 @@ int schic_mh_kneighbors_graph(schic_mh_handle* h, int32_t k, int32_t fast, int64
 
 int schic_mh_stage_ms(schic_mh_handle* h, float* out, int32_t n_out) {
     ST_TRY(check(h));
-    if (!out || n_out < ST_COUNT + 1) return fail(SCHIC_ERR_INVALID_ARG, "out must hold 8 floats");
+    if (!out || n_out < ST_COUNT + 1) return fail(SCHIC_ERR_INVALID_ARG, "out must hold 9 floats");
     ST_TRY(use_device(h));
     CU_TRY(cudaStreamSynchronize(h->stream));
     CU_TRY(cudaStreamSynchronize(h->copy_stream));
