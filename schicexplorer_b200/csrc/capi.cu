@@ -95,7 +95,7 @@ struct schic_mh_handle {
     const uint32_t* db_feat = nullptr; const float* db_val = nullptr;
 
     // scratch of kneighbors
-    DevBuf<uint16_t> counts; DevBuf<int32_t> cand_idx, cand_cnt, cand_nv;
+    DevBuf<uint16_t> counts; DevBuf<int32_t> cand_idx, cand_cnt, cand_nv, sel_flags;
     DevBuf<uint32_t> sig_masked;   // database signatures with oversized buckets blanked (K2)
     DevBuf<int32_t> out_idx, out_nv; DevBuf<float> out_dist;
     DevBuf<int64_t> g_indptr; DevBuf<int32_t> g_indices; DevBuf<float> g_data;
@@ -180,7 +180,7 @@ K1Mode k1_mode_from_env() {
 
 // cheap test before anything touches the device: could this batch qualify for the shared-table path at all?
 bool k1_table_candidate(const schic_mh_handle* h, int64_t n_rows, int64_t nnz) {
-    if (h->p.hash_width != 32) return false;
+    if (h->p.hash_width == 64 && h->have_hi) return false;      // ids >= 2^32: far beyond the per-id arrays
     const K1Mode m = k1_mode_from_env();
     if (m == K1_TABLE) return n_rows > 0 && nnz > 0;
     if (m != K1_AUTO) return false;
@@ -195,10 +195,7 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
     const int64_t n_rows = r1 - r0, nnz = pos1 - pos0;
     const K1Mode mode = k1_mode_from_env();
     int nl = -1;
-    if (h->p.hash_width == 64) {
-        nl = schic::launch_signatures64(h->d_indptr() + r0, h->d_feat(), h->have_hi ? h->feat_hi.p : nullptr,
-                                        n_rows, nnz, pos0, H, sig, s);
-    } else if (mode == K1_CHUNK) {
+    if (mode == K1_CHUNK && h->p.hash_width == 32) {
         nl = schic::launch_signatures32(h->d_indptr() + r0, h->d_feat(), n_rows, nnz, pos0, H, sig, s);
     } else {
         if (k1_table_candidate(h, n_rows, nnz)) {
@@ -214,12 +211,15 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
                 ST_TRY(h->k1t_slot.reserve((int64_t)max_id + 1, 0, s));
                 ST_TRY(h->k1t_entries.reserve((int64_t)ecap, 0, s));
                 ST_TRY(h->k1_scratch.reserve((int64_t)schic::k1t_items_bytes(n_rows, nnz), 0, s));
-                nl = schic::launch_signatures32_table(h->d_indptr() + r0, h->d_feat(), n_rows, nnz, pos0, max_id, H, sig,
+                nl = schic::launch_signatures_table(h->p.hash_width, h->d_indptr() + r0, h->d_feat(), n_rows, nnz, pos0, max_id, H, sig,
                                                       h->k1t_present.p, reinterpret_cast<uint2*>(h->k1t_slot.p),
                                                       h->k1t_entries.p, ecap, h->k1t_counters.p, h->k1_scratch.p, s);
             }
         }
-        if (nl < 0) {
+        if (nl < 0 && h->p.hash_width == 64) {
+            nl = schic::launch_signatures64(h->d_indptr() + r0, h->d_feat(), h->have_hi ? h->feat_hi.p : nullptr,
+                                            n_rows, nnz, pos0, H, sig, s);
+        } else if (nl < 0) {
             // the scratch of an earlier chunk may still be read by its kernel: same stream, so reuse is ordered,
             // but growing would free it -- synchronise before that
             const size_t need = schic::k1f_scratch_bytes(n_rows, nnz);
@@ -314,6 +314,7 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
     ST_TRY(h->cand_idx.reserve(nq * kcand, 0, s));
     ST_TRY(h->cand_cnt.reserve(nq * kcand, 0, s));
     ST_TRY(h->cand_nv.reserve(nq, 0, s));
+    ST_TRY(h->sel_flags.reserve(nq, 0, s));
     if (!d_idx) {
         ST_TRY(h->out_idx.reserve(nq * k, 0, s));
         ST_TRY(h->out_dist.reserve(nq * k, 0, s));
@@ -348,7 +349,7 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
             StageTimer t(h, ST_SELECT, s);
             const int nl = schic::launch_select_topk(h->counts.p, q1 - q0, ndb, ld, H, h->p.minimal_blocks_in_common,
                                                      kcand, h->cand_idx.p + q0 * kcand, h->cand_cnt.p + q0 * kcand,
-                                                     h->cand_nv.p + q0, s);
+                                                     h->cand_nv.p + q0, h->sel_flags.p, s);
             if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k * excess_factor too large for the in-shared-memory select");
             add_launches(h, nl);
         }
@@ -819,7 +820,7 @@ int schic_k1_variant_ms(int32_t variant, int64_t n_rows, int64_t nnz, const int6
     }
     auto launch = [&]() {
         if (variant >= 200)
-            return schic::launch_signatures32_table(d_indptr, d_indices, n_rows, nnz, pos0, max_id, n_hash, d_sig, present,
+            return schic::launch_signatures_table(32, d_indptr, d_indices, n_rows, nnz, pos0, max_id, n_hash, d_sig, present,
                                                     slot, entries, ecap, counters, scratch, nullptr);
         return variant >= 100 ? schic::launch_signatures32_filter(d_indptr, d_indices, n_rows, nnz, n_hash, d_sig, scratch, variant == 101 ? 1 : 0, nullptr)
                               : schic::launch_signatures32_variant(variant, d_indptr, d_indices, n_rows, nnz, pos0, n_hash, d_sig, nullptr);

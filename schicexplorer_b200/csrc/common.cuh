@@ -28,7 +28,7 @@ bool k1t_applicable(int64_t n_rows, int64_t nnz, uint32_t max_id, int H);
 size_t k1t_entries_capacity(int64_t nnz, uint32_t max_id);
 size_t k1t_items_bytes(int64_t n_rows, int64_t nnz);
 int launch_max_id(const uint32_t* d_feat, int64_t nnz, uint32_t* d_out_max, cudaStream_t stream);
-int launch_signatures32_table(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
+int launch_signatures_table(int width /* 32 | 64: HashSpec */, const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
                               int64_t indptr0, uint32_t max_id, int H, uint32_t* d_sig, uint8_t* d_present,
                               uint2* d_slot, uint16_t* d_entries, size_t entries_cap, uint32_t* d_counters,
                               void* d_items, cudaStream_t stream);
@@ -52,9 +52,12 @@ int launch_collision_counts(const uint32_t* d_sig_q, int64_t nq, const uint32_t*
 // ---- K3b: threshold + top-k select + fast distance (k3_select.cu) --------------------------
 // For each query row: candidates with cnt >= min_blocks (and > 0), ordered by (cnt desc, idx asc),
 // first kcand kept. Writes idx [nq,kcand] (-1 padded), cnt [nq,kcand], n_valid [nq].
+// d_row_flags: device int [nq] scratch or nullptr. Non-null lets the launcher use the single-histogram kernel
+// (H <= 4095); rows it cannot finish (more ties at the threshold than its buffer holds) are flagged there and
+// redone by the two-level radix kernel in the same call.
 int launch_select_topk(const uint16_t* d_cnt, int64_t nq, int64_t ndb, int64_t ld_cnt, int H,
                        int min_blocks, int kcand, int32_t* d_idx, int32_t* d_cntsel, int32_t* d_nvalid,
-                       cudaStream_t stream);
+                       int* d_row_flags, cudaStream_t stream);
 // dist = absolute ? cnt : 1 - cnt/H (fp32), first k of kcand columns; pads +inf / -1.
 int launch_fast_distance(const int32_t* d_idx_in, const int32_t* d_cnt_in, const int32_t* d_nvalid_in,
                          int64_t nq, int kcand, int k, int H, int absolute, int32_t* d_idx_out,

@@ -41,6 +41,24 @@ __device__ __forceinline__ uint32_t k1t_value(uint32_t fp1, uint32_t c) {
     const uint32_t v = (k6 & kModulus) + (k6 >> 31);
     return v >= kModulus ? v - kModulus : v;
 }
+// width-64 HashSpec: the same formula in uint64 before the modulo (ids < 2^27 here, so f+1 has no high word)
+__device__ __forceinline__ uint32_t k1t_value64(uint32_t fp1, uint32_t jp1) {
+    uint64_t k = (uint64_t)fp1 * (uint64_t)jp1;
+    k = ~k + (k << 15);
+    k ^= k >> 12;
+    k += k << 2;
+    k ^= k >> 4;
+    k *= 2057ull;
+    k ^= k >> 16;
+    uint64_t s = (k & kModulus) + ((k >> 31) & kModulus) + (k >> 62);    // fold 31-bit limbs (2^31 == 1 mod M)
+    s = (s & kModulus) + (s >> 31);
+    const uint32_t v = (uint32_t)s;
+    return v >= kModulus ? v - kModulus : v;
+}
+template <bool W64>
+__device__ __forceinline__ uint32_t k1t_value_w(uint32_t fp1, uint32_t j) {
+    return W64 ? k1t_value64(fp1, j + 1u) : k1t_value(fp1, 32767u * (j + 1u));
+}
 // 15-bit prefix filter key (see k1_signatures.cu): v < best  =>  key <= threshold(best)
 __device__ __forceinline__ uint32_t k1t_key(uint32_t a) {
     const uint32_t b = a ^ (a >> 12);
@@ -74,7 +92,7 @@ __global__ void k1t_mark_kernel(const uint32_t* __restrict__ feat, int64_t nnz, 
 
 // ---- 2. build --------------------------------------------------------------------------------------
 // counters[0] = entries used, counters[1] = overflow flag (hit list or entry buffer too small)
-template <int R>
+template <int R, bool W64>
 __global__ void __launch_bounds__(32 * K1T_MAX_WARPS)
 k1t_build_kernel(const uint8_t* __restrict__ present, uint32_t n_ids, int H, int units, uint32_t T, uint32_t thrT,
                  uint2* __restrict__ slot, uint16_t* __restrict__ entries, uint32_t entries_cap,
@@ -105,6 +123,20 @@ k1t_build_kernel(const uint8_t* __restrict__ present, uint32_t n_ids, int H, int
             uint32_t c[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) c[r] = 32767u * (uint32_t)(j0 + 32 * r + 1);
+            if (W64) {                                              // no prefix filter for the 64-bit mix: plain evaluate + test
+                for (int i = 0; i < np; ++i) {
+                    const uint32_t li = plist[i];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int j = j0 + 32 * r;
+                        if (j < H && k1t_value64(f0 + li + 1u, (uint32_t)j + 1u) < T) {
+                            const int pos = atomicAdd(&s_nhit, 1);
+                            if (pos < K1T_HITCAP) hit[pos] = (li << 16) | (uint32_t)j;
+                        }
+                    }
+                }
+                continue;
+            }
             for (int i = 0; i < np4; i += 4) {
                 const uint4 l4 = *reinterpret_cast<const uint4*>(plist + i);
                 const uint32_t li[4] = {l4.x, l4.y, l4.z, l4.w};
@@ -201,6 +233,7 @@ k1t_items_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, K1TItem* __
     if (threadIdx.x == 0) *n_items = s_n;
 }
 
+template <bool W64>
 __global__ void __launch_bounds__(256)
 k1t_lookup_kernel(const K1TItem* __restrict__ items, const int* __restrict__ n_items, const uint32_t* __restrict__ feat,
                   const uint2* __restrict__ slot, const uint16_t* __restrict__ entries, const uint32_t* __restrict__ counters,
@@ -217,7 +250,7 @@ k1t_lookup_kernel(const K1TItem* __restrict__ items, const int* __restrict__ n_i
         const uint2 s = __ldg(slot + f);
         for (uint32_t e = 0; e < s.y; ++e) {
             const uint32_t j = __ldg(entries + s.x + e);
-            atomicMin(&sig_s[j], k1t_value(f + 1u, 32767u * (j + 1u)));
+            atomicMin(&sig_s[j], k1t_value_w<W64>(f + 1u, j));
         }
     }
     __syncthreads();
@@ -232,6 +265,7 @@ k1t_lookup_kernel(const K1TItem* __restrict__ items, const int* __restrict__ n_i
 // One CTA per row: hash functions whose signature entry is still the sentinel are recomputed exactly. A warp
 // takes one such j at a time and spreads the row's non-zeros over its lanes (coalesced loads, shuffle min):
 // the common case is a long row with one or two failures, which a lane-per-j loop would walk serially.
+template <bool W64>
 __global__ void __launch_bounds__(128)
 k1t_fallback_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat, int H,
                     uint32_t* __restrict__ sig) {
@@ -252,15 +286,14 @@ k1t_fallback_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restri
     const uint32_t* __restrict__ src = feat + b;
     for (int t = warp; t < n; t += n_warps) {
         const uint32_t j = fj[t];
-        const uint32_t c = 32767u * (j + 1u);
         uint32_t best = kModulus;
         int i = lane;
         for (; i + 96 < len; i += 128) {         // 4 independent loads per lane in flight
             const uint32_t f0 = __ldg(src + i), f1 = __ldg(src + i + 32), f2 = __ldg(src + i + 64), f3 = __ldg(src + i + 96);
-            best = min(best, min(k1t_value(f0 + 1u, c), k1t_value(f1 + 1u, c)));
-            best = min(best, min(k1t_value(f2 + 1u, c), k1t_value(f3 + 1u, c)));
+            best = min(best, min(k1t_value_w<W64>(f0 + 1u, j), k1t_value_w<W64>(f1 + 1u, j)));
+            best = min(best, min(k1t_value_w<W64>(f2 + 1u, j), k1t_value_w<W64>(f3 + 1u, j)));
         }
-        for (; i < len; i += 32) best = min(best, k1t_value(__ldg(src + i) + 1u, c));
+        for (; i < len; i += 32) best = min(best, k1t_value_w<W64>(__ldg(src + i) + 1u, j));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
         if (lane == 0) sig_row[j] = best;
@@ -309,7 +342,7 @@ static int pick_R_table(int slabs) {
 
 // d_present [max_id+1] bytes, d_slot [max_id+1], d_entries [entries_cap], d_counters [2] uint32, d_items/d_n_items:
 // k1t_item_capacity entries + 1 int.
-int launch_signatures32_table(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
+int launch_signatures_table(int width, const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
                               int64_t indptr0, uint32_t max_id, int H, uint32_t* d_sig, uint8_t* d_present,
                               uint2* d_slot, uint16_t* d_entries, size_t entries_cap, uint32_t* d_counters,
                               void* d_items, cudaStream_t stream) {
@@ -335,7 +368,15 @@ int launch_signatures32_table(const int64_t* d_indptr, const uint32_t* d_feat, i
     for (int w = K1T_MAX_WARPS; w >= 4; --w)
         if (units % w == 0) { n_warps = w; break; }
     const unsigned build_grid = (n_ids + K1T_IDS - 1) / K1T_IDS;
-#define K1T_BUILD(RR) k1t_build_kernel<RR><<<build_grid, 32 * n_warps, 0, stream>>>(d_present, n_ids, H, units, T, thrT, d_slot, d_entries, (uint32_t)entries_cap, d_counters)
+#define K1T_BUILD(RR)                                                                                                  \
+    do {                                                                                                               \
+        if (width == 64)                                                                                               \
+            k1t_build_kernel<RR, true><<<build_grid, 32 * n_warps, 0, stream>>>(d_present, n_ids, H, units, T, thrT,    \
+                                                                                d_slot, d_entries, (uint32_t)entries_cap, d_counters); \
+        else                                                                                                           \
+            k1t_build_kernel<RR, false><<<build_grid, 32 * n_warps, 0, stream>>>(d_present, n_ids, H, units, T, thrT,   \
+                                                                                 d_slot, d_entries, (uint32_t)entries_cap, d_counters); \
+    } while (0)
     switch (R) {
         case 4: K1T_BUILD(4); break;
         case 5: K1T_BUILD(5); break;
@@ -347,10 +388,17 @@ int launch_signatures32_table(const int64_t* d_indptr, const uint32_t* d_feat, i
     K1TItem* items = reinterpret_cast<K1TItem*>(d_items);
     int* n_items = reinterpret_cast<int*>(items + cap);
     k1t_items_kernel<<<1, 1024, 0, stream>>>(d_indptr, n_rows, items, n_items); ++nl;
-    cudaFuncSetAttribute(k1t_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H * 4);
-    k1t_lookup_kernel<<<(unsigned)cap, 256, (size_t)H * 4, stream>>>(items, n_items, d_feat, d_slot, d_entries, d_counters, H, d_sig); ++nl;
-    cudaFuncSetAttribute(k1t_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H * 2);
-    k1t_fallback_kernel<<<(unsigned)n_rows, 128, (size_t)H * 2, stream>>>(d_indptr, d_feat, H, d_sig); ++nl;
+    if (width == 64) {
+        cudaFuncSetAttribute(k1t_lookup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H * 4);
+        k1t_lookup_kernel<true><<<(unsigned)cap, 256, (size_t)H * 4, stream>>>(items, n_items, d_feat, d_slot, d_entries, d_counters, H, d_sig); ++nl;
+        cudaFuncSetAttribute(k1t_fallback_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H * 2);
+        k1t_fallback_kernel<true><<<(unsigned)n_rows, 128, (size_t)H * 2, stream>>>(d_indptr, d_feat, H, d_sig); ++nl;
+    } else {
+        cudaFuncSetAttribute(k1t_lookup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H * 4);
+        k1t_lookup_kernel<false><<<(unsigned)cap, 256, (size_t)H * 4, stream>>>(items, n_items, d_feat, d_slot, d_entries, d_counters, H, d_sig); ++nl;
+        cudaFuncSetAttribute(k1t_fallback_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H * 2);
+        k1t_fallback_kernel<false><<<(unsigned)n_rows, 128, (size_t)H * 2, stream>>>(d_indptr, d_feat, H, d_sig); ++nl;
+    }
     return nl;
 }
 

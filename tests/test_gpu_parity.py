@@ -394,8 +394,9 @@ def test_k1_filtered_equals_chunked_kernel(cuda, oracle, monkeypatch):
                 assert np.array_equal(g.sig(), want), (H, mode)
 
 
+@pytest.mark.parametrize("width", [32, 64])
 @pytest.mark.parametrize("H", [800, 4000, 33])
-def test_k1_shared_table_path(cuda, oracle, monkeypatch, H):
+def test_k1_shared_table_path(cuda, oracle, monkeypatch, H, width):
     """The shared-table K1 (every (id, hash function) evaluated once per batch, per-cell lookup, exact fallback)
     on clustered cells that really share ids, forced on (the automatic choice needs >= 2M non-zeros): signatures
     and collision counts bit-identical to the oracle; also through partial_fit (a table per appended batch)."""
@@ -403,7 +404,7 @@ def test_k1_shared_table_path(cuda, oracle, monkeypatch, H):
     X = synth_csr(160, seed=29)
     empty = csr_matrix((1, X.shape[1]))
     Xe = vstack([X[:50], empty, X[50:]]).tocsr()
-    kw = dict(number_of_hash_functions=H, minimal_blocks_in_common=1)
+    kw = dict(number_of_hash_functions=H, minimal_blocks_in_common=1, hash_width=width)
     with Fitted(oracle, Xe, **kw) as o:
         want, want_cnt = o.sig(), oracle.collision_counts(o.h)
     with Fitted(cuda, Xe, **kw) as g:
@@ -439,3 +440,21 @@ def test_async_host_fit(cuda, oracle):
     with pytest.raises(ValueError):
         cuda.fit_csr(h, X.indptr, X.indices, X.data, False, async_upload=True)   # int32 indptr / float64 data
     cuda.destroy(h)
+
+
+def test_select_ties_and_overflow_fallback(cuda, oracle):
+    """Top-k select: ties at the threshold must keep the lowest indices. 2500 copies of three different rows give
+    every query > 2048 candidates with the same count (the single-histogram kernel's tie buffer overflows, the
+    radix kernel redoes those rows); n is not a multiple of 8 (row padding of the count matrix)."""
+    base = synth_csr(3, median_nnz=600, min_nnz=300, max_nnz=900)
+    reps = [base[i % 3] for i in range(7501)]
+    X = vstack(reps).tocsr()
+    kw = dict(number_of_hash_functions=64, minimal_blocks_in_common=1, n_neighbors=30)
+    with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
+        a, b = cuda.kneighbors(g.h, 30), oracle.kneighbors(o.h, 30)
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # moderate ties (fit the buffer): 40 copies
+    X = vstack([base[i % 3] for i in range(121)] + [synth_csr(50, seed=41, median_nnz=600, min_nnz=300, max_nnz=900)]).tocsr()
+    with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
+        a, b = cuda.kneighbors(g.h, 30), oracle.kneighbors(o.h, 30)
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
