@@ -69,7 +69,8 @@ int schic_mh_stage_ms(schic_mh_handle* h, float* out, int32_t n_out);
 int schic_mh_launch_count(schic_mh_handle* h, int64_t* n_out);
 
 /* INT32 issue-rate micro-benchmark, Tint-op/s: out[0] LOP3, [1] IMAD, [2] 1:1 mix, [3] SM MHz,
- * [4] SHF, [5] IMAD.HI, [6] VIMNMX, [7] VIMNMX3, [8] IADD; out must hold 12 doubles. */
+ * [4] SHF, [5] IMAD.HI, [6] VIMNMX, [7] VIMNMX3, [8] IADD, [9] IMAD.WIDE, [10] HSET2, [11] HADD2,
+ * [12] 1:1 HSET2+HADD2, [13] ISETP + predicated FADD pairs; out must hold 16 doubles. */
 int schic_int32_peak(int32_t device, int32_t iters, double* out);
 
 /* Experiment hook: K1 with instruction-selection variant v on device-resident CSR; elapsed ms. */

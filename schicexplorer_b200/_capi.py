@@ -15,7 +15,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-CUDA_LIB_PATH = os.path.join(_HERE, "csrc", "libschic_mh.so")
+# SCHIC_CUDA_LIB: experiment builds of the same library (tools/); the product always loads the in-tree default
+CUDA_LIB_PATH = os.environ.get("SCHIC_CUDA_LIB") or os.path.join(_HERE, "csrc", "libschic_mh.so")
 
 
 class SchicError(RuntimeError):
@@ -245,9 +246,10 @@ class CApi:
 
     def int32_peak(self, device: int = -1, iters: int = 4096) -> dict:
         """INT32 issue-rate micro-benchmark (Tint-op/s per SASS opcode) -- the roofline denominator."""
-        out = np.zeros(12, dtype=np.float64)
+        out = np.zeros(16, dtype=np.float64)
         self.check(self.lib.schic_int32_peak(device, iters, _ptr(out)))
-        names = ("lop3", "imad", "mix_lop3_imad", "sm_mhz", "shf", "imad_hi", "vimnmx", "vimnmx3", "iadd", "imad_wide")
+        names = ("lop3", "imad", "mix_lop3_imad", "sm_mhz", "shf", "imad_hi", "vimnmx", "vimnmx3", "iadd", "imad_wide",
+                 "hset2", "hadd2", "mix_hset2_hadd2", "isetp_fadd_pair")
         return dict(zip(names, out.tolist()))
 
     def k1_variant_ms(self, variant, n_rows, nnz, d_indptr, d_indices, n_hash, d_sig, reps=3) -> float:

@@ -788,7 +788,7 @@ int schic_int32_peak(int32_t device, int32_t iters, double* out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SCHIC_ERR_NO_DEVICE, "no CUDA device"); }
     if (device >= 0) CU_TRY(cudaSetDevice(device));
-    for (int i = 0; i < 12; ++i) out[i] = 0.0;
+    for (int i = 0; i < 16; ++i) out[i] = 0.0;
     if (schic::run_int32_peak(iters < 64 ? 64 : iters, out, nullptr) < 0) return fail(SCHIC_ERR_CUDA, "int32 peak kernel failed");
     return SCHIC_OK;
 }

@@ -8,7 +8,8 @@
 
 namespace schic {
 
-enum PeakOp { OP_LOP3 = 0, OP_IMAD = 1, OP_MIX = 2, OP_SHF = 3, OP_IMADHI = 4, OP_MIN = 5, OP_MIN3 = 6, OP_ADD = 7, OP_WIDE = 8 };
+enum PeakOp { OP_LOP3 = 0, OP_IMAD = 1, OP_MIX = 2, OP_SHF = 3, OP_IMADHI = 4, OP_MIN = 5, OP_MIN3 = 6, OP_ADD = 7, OP_WIDE = 8,
+              OP_HSET2 = 9, OP_HADD2 = 10, OP_MIXH = 11, OP_MIXSETP = 12 };
 
 template <int OP>
 __device__ __forceinline__ void one_op(uint32_t& x, uint32_t y, uint32_t z, int chain) {
@@ -24,6 +25,15 @@ __device__ __forceinline__ void one_op(uint32_t& x, uint32_t y, uint32_t z, int 
         asm volatile("min.u32 %0, %0, %1;" : "+r"(x) : "r"(y));
     } else if (OP == OP_MIN3) {
         asm volatile("{ .reg .u32 t; min.u32 t, %1, %2; min.u32 %0, %0, t; }" : "+r"(x) : "r"(y), "r"(z));
+    } else if (OP == OP_HSET2 || (OP == OP_MIXH && (chain & 1) == 0)) {
+        // packed fp16 compare producing 1.0h / 0.0h per half (K3 experiment: two 16-bit compares per instruction)
+        asm volatile("set.eq.f16x2.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y));
+    } else if (OP == OP_HADD2 || OP == OP_MIXH) {
+        asm volatile("add.f16x2 %0, %0, %1;" : "+r"(x) : "r"(z));
+    } else if (OP == OP_MIXSETP) {
+        // the current K3 inner pair: compare on the ALU pipe, predicated fp32 add on the FMA pipe
+        asm volatile("{ .reg .pred p; .reg .f32 t; setp.eq.u32 p, %1, %2; mov.b32 t, %0; @p add.f32 t, t, 0f3F800000; mov.b32 %0, t; }"
+                     : "+r"(x) : "r"(y), "r"(z + chain));
     } else if (OP == OP_WIDE) {
         asm volatile("{ .reg .u64 w; .reg .u32 lo; mul.wide.u32 w, %0, %1; mov.b64 {lo, %0}, w; }" : "+r"(x) : "r"(y));
     } else {
@@ -86,7 +96,8 @@ static double run_one(int iters, uint32_t* d_out, unsigned long long* d_clk, cud
 }
 
 // out: [0] LOP3, [1] IMAD, [2] 1:1 LOP3+IMAD mix, [3] SM MHz during the mix, [4] SHF, [5] IMAD.HI,
-//      [6] VIMNMX (2-input), [7] VIMNMX3 (counted as one op), [8] IADD, [9] IMAD.WIDE -- all in Tint-op/s
+//      [6] VIMNMX (2-input), [7] VIMNMX3 (counted as one op), [8] IADD, [9] IMAD.WIDE, [10] HSET2, [11] HADD2,
+//      [12] 1:1 HSET2+HADD2, [13] ISETP + predicated FADD pairs (counted as one op per pair) -- all in T instr-lanes/s
 int run_int32_peak(int iters, double* out, cudaStream_t stream) {
     uint32_t* d_out = nullptr;
     unsigned long long* d_clk = nullptr;
@@ -101,6 +112,10 @@ int run_int32_peak(int iters, double* out, cudaStream_t stream) {
     out[7] = run_one<OP_MIN3>(iters, d_out, d_clk, stream, nullptr);
     out[8] = run_one<OP_ADD>(iters, d_out, d_clk, stream, nullptr);
     out[9] = run_one<OP_WIDE>(iters, d_out, d_clk, stream, nullptr);
+    out[10] = run_one<OP_HSET2>(iters, d_out, d_clk, stream, nullptr);
+    out[11] = run_one<OP_HADD2>(iters, d_out, d_clk, stream, nullptr);
+    out[12] = run_one<OP_MIXH>(iters, d_out, d_clk, stream, nullptr);
+    out[13] = run_one<OP_MIXSETP>(iters, d_out, d_clk, stream, nullptr);
     cudaFree(d_out);
     cudaFree(d_clk);
     return cudaGetLastError() == cudaSuccess ? 18 : -1;

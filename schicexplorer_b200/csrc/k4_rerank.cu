@@ -237,11 +237,17 @@ k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict_
 // is [dir[w], dir[w+1]). Non-zeros of a candidate that fall in windows where the query row is empty
 // are never read.
 // =================================================================================================
-constexpr int K4W_THREADS = 384;
+#ifndef K4W_THREADS_DEF
+#define K4W_THREADS_DEF 512
+#endif
+#ifndef K4W_UNROLL_DEF
+#define K4W_UNROLL_DEF 8
+#endif
+constexpr int K4W_THREADS = K4W_THREADS_DEF;
 constexpr int K4W_WIN_BITS = 18;                        // feature ids per window
 constexpr int K4W_WORDS = 1 << (K4W_WIN_BITS - 4);      // table entries (64 KB)
 constexpr int K4W_KCAP = 4096;                          // query non-zeros per table fill (values: 16 KB)
-constexpr int K4W_UNROLL = 8;                           // candidate non-zeros per lane and iteration
+constexpr int K4W_UNROLL = K4W_UNROLL_DEF;              // candidate non-zeros per lane and iteration
 
 __global__ void row_max_feature_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat,
                                        int64_t n_rows, uint32_t* __restrict__ out_max) {
@@ -451,16 +457,13 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
                     }
                     if (c < ncand) load(yf, yvp, off, len);
                     float a32 = 0.f;                     // exact for integer counts: 8 products < 2^24
-                    // short last blocks (slices average ~1.7 blocks) skip the probe groups that are all padding
+                    // short last blocks (slices average ~1.7 blocks) skip the probe pairs that are all padding
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) a32 = k4w_probe<E64>(tab, tval, f[u] - lo, yv[u], a32);
-                    if (fill > 64) {
-#pragma unroll
-                        for (int u = 2; u < 4; ++u) a32 = k4w_probe<E64>(tab, tval, f[u] - lo, yv[u], a32);
-                    }
-                    if (fill > 128) {
-#pragma unroll
-                        for (int u = 4; u < K4W_UNROLL; ++u) a32 = k4w_probe<E64>(tab, tval, f[u] - lo, yv[u], a32);
+                    for (int g = 0; g < K4W_UNROLL / 2; ++g) {
+                        if (g == 0 || fill > 64 * g) {
+                            a32 = k4w_probe<E64>(tab, tval, f[2 * g] - lo, yv[2 * g], a32);
+                            a32 = k4w_probe<E64>(tab, tval, f[2 * g + 1] - lo, yv[2 * g + 1], a32);
+                        }
                     }
                     acc += (double)a32;
                     if (done) {

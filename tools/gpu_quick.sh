@@ -1,6 +1,6 @@
-set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/q_pytest.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/q_pytest.log
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/q_bench.json 2> gpurun_out/q_bench.err; echo "rc=$?"; python -c "
-import json; b=json.load(open('gpurun_out/q_bench.json')); print(b['value'], b['ms_per_step'], b['stage_ms']); print(b['e2e']['value'], b['e2e']['ms_per_step'])"
-timeout 1500 python bench.py --workload s50 --steps 2 --warmup 3 --no-cpu-baseline --skip-e2e > gpurun_out/s50_bench.json 2> gpurun_out/s50_bench.err; echo "rc=$?"; cat gpurun_out/s50_bench.json
+for v in default 384_4 512_4 512_8; do
+  if [ $v = default ]; then unset SCHIC_CUDA_LIB; else export SCHIC_CUDA_LIB=$PWD/schicexplorer_b200/csrc/build/var/libschic_k4_$v.so; fi
+  timeout 300 python bench.py --steps 4 --warmup 3 --skip-e2e --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; b=json.loads(sys.stdin.read()); print('$v', b['ms_per_step'], b['stage_ms']['rerank'])"
+done
