@@ -97,6 +97,7 @@ struct schic_mh_handle {
     // scratch of kneighbors
     DevBuf<uint16_t> counts; DevBuf<int32_t> cand_idx, cand_cnt, cand_nv, sel_flags;
     DevBuf<uint32_t> sig_masked;   // database signatures with oversized buckets blanked (K2)
+    DevBuf<uint32_t> k3h_table; DevBuf<uint16_t> sig16;   // packed K3: renaming tables, renamed signatures
     DevBuf<int32_t> out_idx, out_nv; DevBuf<float> out_dist;
     DevBuf<int64_t> g_indptr; DevBuf<int32_t> g_indices; DevBuf<float> g_data;
 
@@ -280,6 +281,20 @@ int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const uint32_t* feat
     return 0;
 }
 
+// Packed K3 (two hash functions per compare): rename the database signatures to 16-bit ids. Returns 1 when the
+// packed kernels can be used (h->sig16 filled), 0 when not applicable; SCHIC_K3_MODE=plain forces 0.
+int prepare_packed_counts(schic_mh_handle* h, const uint32_t* db_sig, int64_t ndb) {
+    const int H = h->p.number_of_hash_functions;
+    const char* mode = getenv("SCHIC_K3_MODE");
+    if ((mode && strcmp(mode, "plain") == 0) || !schic::k3h_applicable(ndb, H)) return 0;
+    ST_TRY(h->k3h_table.reserve((int64_t)schic::k3h_table_elems(ndb, H), 0, h->stream));
+    ST_TRY(h->sig16.reserve(ndb * (int64_t)schic::k3h_padded_hashes(H), 0, h->stream));
+    const int nl = schic::launch_rename_signatures(db_sig, ndb, H, h->k3h_table.p, h->sig16.p, h->stream);
+    if (nl < 0) return fail(SCHIC_ERR_CUDA, "signature renaming launch failed");
+    add_launches(h, nl);
+    return 1;
+}
+
 // The whole query side on device. Results land in h->out_idx / out_dist / out_nv ([n, k]) unless
 // caller-provided device outputs are given.
 int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx, float* d_dist, int32_t* d_nv) {
@@ -338,12 +353,23 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
     int64_t qb = std::max<int64_t>(128, budget_elems / ld);
     qb = std::min<int64_t>((qb / 128) * 128, (nq + 127) / 128 * 128);
     ST_TRY(h->counts.reserve(qb * ld, 0, s));
+    int packed = 0;
+    {
+        StageTimer t(h, ST_COLL, s);
+        packed = prepare_packed_counts(h, db_sig, ndb);
+        if (packed < 0) return packed;
+    }
+    const int64_t Hp = schic::k3h_padded_hashes(H);
     for (int64_t q0 = 0; q0 < nq; q0 += qb) {
         const int64_t q1 = std::min(nq, q0 + qb);
         {
             StageTimer t(h, ST_COLL, s);
-            add_launches(h, schic::launch_collision_counts(q_sig + q0 * (int64_t)H, q1 - q0, db_sig, ndb, H,
-                                                          h->counts.p, ld, s));
+            if (packed)
+                add_launches(h, schic::launch_collision_counts_packed(h->sig16.p + (row0 + q0) * Hp, q1 - q0,
+                                                                     h->sig16.p, ndb, H, h->counts.p, ld, s));
+            else
+                add_launches(h, schic::launch_collision_counts(q_sig + q0 * (int64_t)H, q1 - q0, db_sig, ndb, H,
+                                                              h->counts.p, ld, s));
         }
         {
             StageTimer t(h, ST_SELECT, s);
@@ -682,7 +708,16 @@ int schic_mh_collision_counts(schic_mh_handle* h, int64_t row0, int64_t row1, ui
     const int64_t nq = row1 - row0;
     if (nq == 0) return SCHIC_OK;
     ST_TRY(h->counts.reserve(nq * ld, 0, h->stream));
-    add_launches(h, schic::launch_collision_counts(q_sig + row0 * (int64_t)H, nq, db_sig, ndb, H, h->counts.p, ld, h->stream));
+    const int packed = prepare_packed_counts(h, db_sig, ndb);
+    if (packed < 0) return packed;
+    if (packed) {
+        const int64_t Hp = schic::k3h_padded_hashes(H);
+        const int64_t first = (h->ext ? h->db_row0 : 0) + row0;     // the query rows are database rows
+        add_launches(h, schic::launch_collision_counts_packed(h->sig16.p + first * Hp, nq, h->sig16.p, ndb, H,
+                                                             h->counts.p, ld, h->stream));
+    } else {
+        add_launches(h, schic::launch_collision_counts(q_sig + row0 * (int64_t)H, nq, db_sig, ndb, H, h->counts.p, ld, h->stream));
+    }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpy2DAsync(out, (size_t)ndb * 2, h->counts.p, (size_t)ld * 2, (size_t)ndb * 2, (size_t)nq,
                              cudaMemcpyDeviceToHost, h->stream));

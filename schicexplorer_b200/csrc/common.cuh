@@ -49,6 +49,16 @@ int launch_bucket_mask(const uint32_t* d_sig, int64_t n, int H, int64_t max_bin_
 int launch_collision_counts(const uint32_t* d_sig_q, int64_t nq, const uint32_t* d_sig_db, int64_t ndb,
                             int H, uint16_t* d_cnt, int64_t ld_out, cudaStream_t stream);
 
+// Packed variant: signatures renamed per hash function to 16-bit ids stored as normal fp16 bit patterns; one
+// HSET2 + HADD2 pair handles two hash functions. Same counts, bit for bit. H <= 4094, ndb <= 57 344.
+bool k3h_applicable(int64_t ndb, int H);
+int k3h_padded_hashes(int H);
+size_t k3h_table_elems(int64_t ndb, int H);
+int launch_rename_signatures(const uint32_t* d_sig_db, int64_t ndb, int H, uint32_t* d_table, uint16_t* d_sig16,
+                             cudaStream_t stream);
+int launch_collision_counts_packed(const uint16_t* d_q16, int64_t nq, const uint16_t* d_d16, int64_t ndb, int H,
+                                   uint16_t* d_cnt, int64_t ld_out, cudaStream_t stream);
+
 // ---- K3b: threshold + top-k select + fast distance (k3_select.cu) --------------------------
 // For each query row: candidates with cnt >= min_blocks (and > 0), ordered by (cnt desc, idx asc),
 // first kcand kept. Writes idx [nq,kcand] (-1 padded), cnt [nq,kcand], n_valid [nq].

@@ -12,6 +12,8 @@
 // in shared memory so every operand fetch is a conflict-free LDS.128. Non-admissible values
 // (0, the sentinel M, padding) are rewritten while staging to two patterns that can never be
 // equal, so the inner loop has no validity test.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace schic {
@@ -136,6 +138,187 @@ int launch_collision_counts(const uint32_t* d_sig_q, int64_t nq, const uint32_t*
         k3_collision_kernel<true><<<grid, K3_THREADS, 0, stream>>>(d_sig_q, nq, d_sig_db, ndb, H, d_cnt, ld_out);
     else
         k3_collision_kernel<false><<<grid, K3_THREADS, 0, stream>>>(d_sig_q, nq, d_sig_db, ndb, H, d_cnt, ld_out);
+    return 1;
+}
+
+
+
+// =================================================================================================
+// Packed variant: two hash functions per compare instruction.
+//
+// The kernel above spends one ISETP (ALU pipe) + one FADD (FMA pipe) per signature compare; the ALU pipe
+// is its roof (64 compares / clk / SM). Equality does not need the 31-bit values, only "same value in
+// the same column": per hash function the values of the fitted cells are renamed to 16-bit ids through
+// an open-addressing table in global memory (id = slot index, so equal values <-> equal ids, exactly),
+// and the ids are written as *fp16 bit patterns of normal numbers* (never zero, never NaN), two hash
+// functions per 32-bit word. Then one HSET2.BF.EQ compares two hash functions at once (1.0h / 0.0h per
+// half) and one HADD2 accumulates both counts in a half2 register (exact: counts <= H/2 <= 2047).
+// Inadmissible values (0, M), padding rows and the padding column of an odd H are NaN: never equal.
+// Limits: H <= 4094 (fp16 count range), n <= K3H_MAX_ROWS (ids fit 61 440 normal fp16 patterns).
+// =================================================================================================
+constexpr int K3H_MAX_IDS = 61440;          // finite, non-zero, normal fp16 bit patterns: 2 * 30 * 1024
+constexpr int K3H_MAX_ROWS = 57344;         // load factor of the renaming table stays <= 0.94 in the worst case
+constexpr uint16_t K3H_NAN = 0x7E00u;
+
+__host__ __device__ inline int k3h_table_capacity(int64_t n) {
+    int64_t c = (n * 5) / 2 + 1024;
+    return (int)(c > K3H_MAX_IDS ? K3H_MAX_IDS : c);
+}
+
+// table: [H][cap] uint32, zero-initialised (0 is inadmissible, so it can mean "empty")
+__global__ void __launch_bounds__(256)
+k3h_rename_kernel(const uint32_t* __restrict__ sig, int64_t n, int H, int Hp, int cap, uint32_t* __restrict__ table,
+                  uint16_t* __restrict__ sig16) {
+    const int64_t total = n * (int64_t)Hp;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t row = e / Hp;
+        const int j = (int)(e - row * Hp);
+        uint16_t out = K3H_NAN;
+        if (j < H) {
+            const uint32_t v = __ldg(sig + row * (int64_t)H + j);
+            if (v != 0u && v != kModulus) {
+                uint32_t* __restrict__ t = table + (int64_t)j * cap;
+                uint32_t slot = (uint32_t)(((uint64_t)(v * 2654435761u) * (uint64_t)cap) >> 32);
+                for (;;) {
+                    const uint32_t old = atomicCAS(t + slot, 0u, v);
+                    if (old == 0u || old == v) break;
+                    slot = slot + 1u == (uint32_t)cap ? 0u : slot + 1u;
+                }
+                out = slot < 30720u ? (uint16_t)(0x0400u + slot) : (uint16_t)(0x8400u + (slot - 30720u));
+            }
+        }
+        sig16[e] = out;
+    }
+}
+
+template <bool SYM>
+__global__ void __launch_bounds__(K3_THREADS, 2)
+k3h_collision_kernel(const uint32_t* __restrict__ q16, int64_t nq, const uint32_t* __restrict__ d16, int64_t nd, int Hw,
+                     uint16_t* __restrict__ cnt, int64_t ld_out) {
+    __shared__ __align__(16) uint32_t Qs[K3_JB][K3_LD];
+    __shared__ __align__(16) uint32_t Ds[K3_JB][K3_LD];
+
+    if (SYM && blockIdx.x < blockIdx.y) return;
+    const int64_t q0 = (int64_t)blockIdx.y * K3_TILE;
+    const int64_t d0 = (int64_t)blockIdx.x * K3_TILE;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint32_t NAN2 = 0x7E007E00u;
+
+    uint32_t acc[8][8];                         // half2 counters: even / odd hash functions
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0u;
+
+    for (int j0 = 0; j0 < Hw; j0 += K3_JB) {
+        const int j = j0 + lane;
+#pragma unroll 4
+        for (int r = warp; r < K3_TILE; r += K3_THREADS / 32) {
+            uint32_t vq = NAN2, vd = NAN2;
+            if (j < Hw) {
+                if (q0 + r < nq) vq = __ldg(q16 + (q0 + r) * (int64_t)Hw + j);
+                if (d0 + r < nd) vd = __ldg(d16 + (d0 + r) * (int64_t)Hw + j);
+            }
+            Qs[lane][r] = vq;
+            Ds[lane][r] = vd;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int jj = 0; jj < K3_JB; ++jj) {
+            const uint4 qa = *reinterpret_cast<const uint4*>(&Qs[jj][ty * 8]);
+            const uint4 qb = *reinterpret_cast<const uint4*>(&Qs[jj][ty * 8 + 4]);
+            const uint4 da = *reinterpret_cast<const uint4*>(&Ds[jj][tx * 8]);
+            const uint4 db = *reinterpret_cast<const uint4*>(&Ds[jj][tx * 8 + 4]);
+            const uint32_t q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+            const uint32_t d[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b)
+                    asm("{ .reg .b32 e; set.eq.f16x2.f16x2 e, %1, %2; add.f16x2 %0, %0, e; }"
+                        : "+r"(acc[a][b]) : "r"(q[a]), "r"(d[b]));
+        }
+        __syncthreads();
+    }
+
+    auto total = [](uint32_t h2) -> uint32_t {   // low half + high half, both exact small integers
+        const __half2 v = *reinterpret_cast<const __half2*>(&h2);
+        return (uint32_t)(__low2float(v) + __high2float(v));
+    };
+    const bool vec_ok = ((ld_out & 7) == 0) && ((((uintptr_t)cnt) & 15) == 0) && (d0 + tx * 8 + 8 <= nd);
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int64_t q = q0 + ty * 8 + a;
+        if (q >= nq) continue;
+        uint16_t* dst = cnt + q * ld_out + d0 + tx * 8;
+        if (vec_ok) {
+            uint4 o;
+            o.x = total(acc[a][0]) | (total(acc[a][1]) << 16);
+            o.y = total(acc[a][2]) | (total(acc[a][3]) << 16);
+            o.z = total(acc[a][4]) | (total(acc[a][5]) << 16);
+            o.w = total(acc[a][6]) | (total(acc[a][7]) << 16);
+            *reinterpret_cast<uint4*>(dst) = o;
+        } else {
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+                if (d0 + tx * 8 + b < nd) dst[b] = (uint16_t)total(acc[a][b]);
+        }
+    }
+    if (SYM && blockIdx.x > blockIdx.y) {
+        const bool tvec_ok = ((ld_out & 7) == 0) && ((((uintptr_t)cnt) & 15) == 0) && (q0 + ty * 8 + 8 <= nq);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int64_t d = d0 + tx * 8 + b;
+            if (d >= nd) continue;
+            uint16_t* dst = cnt + d * ld_out + q0 + ty * 8;
+            if (tvec_ok) {
+                uint4 o;
+                o.x = total(acc[0][b]) | (total(acc[1][b]) << 16);
+                o.y = total(acc[2][b]) | (total(acc[3][b]) << 16);
+                o.z = total(acc[4][b]) | (total(acc[5][b]) << 16);
+                o.w = total(acc[6][b]) | (total(acc[7][b]) << 16);
+                *reinterpret_cast<uint4*>(dst) = o;
+            } else {
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+                    if (q0 + ty * 8 + a < nq) dst[a] = (uint16_t)total(acc[a][b]);
+            }
+        }
+    }
+}
+
+bool k3h_applicable(int64_t ndb, int H) { return H <= 4094 && ndb <= K3H_MAX_ROWS && ndb > 0; }
+int k3h_padded_hashes(int H) { return (H + 1) & ~1; }
+size_t k3h_table_elems(int64_t ndb, int H) { return (size_t)H * (size_t)k3h_table_capacity(ndb); }
+
+// d_table: k3h_table_elems uint32 (zeroed here), d_sig16: ndb * k3h_padded_hashes(H) uint16
+int launch_rename_signatures(const uint32_t* d_sig_db, int64_t ndb, int H, uint32_t* d_table, uint16_t* d_sig16,
+                             cudaStream_t stream) {
+    if (ndb <= 0) return 0;
+    const int cap = k3h_table_capacity(ndb);
+    const int Hp = k3h_padded_hashes(H);
+    if (cudaMemsetAsync(d_table, 0, (size_t)H * cap * sizeof(uint32_t), stream) != cudaSuccess) return -1;
+    const int64_t total = ndb * (int64_t)Hp;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k3h_rename_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_sig_db, ndb, H, Hp, cap, d_table, d_sig16);
+    return 1;
+}
+
+// q16 / d16: renamed signatures (rows of Hp uint16) of the query rows / of the database
+int launch_collision_counts_packed(const uint16_t* d_q16, int64_t nq, const uint16_t* d_d16, int64_t ndb, int H,
+                                   uint16_t* d_cnt, int64_t ld_out, cudaStream_t stream) {
+    if (nq <= 0 || ndb <= 0) return 0;
+    const int Hw = k3h_padded_hashes(H) / 2;
+    dim3 grid((unsigned)((ndb + K3_TILE - 1) / K3_TILE), (unsigned)((nq + K3_TILE - 1) / K3_TILE));
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(d_q16);
+    const uint32_t* d = reinterpret_cast<const uint32_t*>(d_d16);
+    if (d_q16 == d_d16 && nq == ndb)
+        k3h_collision_kernel<true><<<grid, K3_THREADS, 0, stream>>>(q, nq, d, ndb, Hw, d_cnt, ld_out);
+    else
+        k3h_collision_kernel<false><<<grid, K3_THREADS, 0, stream>>>(q, nq, d, ndb, Hw, d_cnt, ld_out);
     return 1;
 }
 

@@ -458,3 +458,23 @@ def test_select_ties_and_overflow_fallback(cuda, oracle):
     with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
         a, b = cuda.kneighbors(g.h, 30), oracle.kneighbors(o.h, 30)
         assert np.array_equal(a[2], b[2]) and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("H", [800, 801, 4094, 7])
+def test_k3_packed_equals_plain(cuda, oracle, monkeypatch, H):
+    """K3 has two implementations: 32-bit compares and the packed one (values renamed per hash function to 16-bit
+    ids in fp16 patterns, two hash functions per compare). Counts must be identical, including inadmissible
+    values (empty rows -> sentinel M), odd H (padding column) and a partial row range."""
+    X = synth_csr(300, seed=37)
+    empty = csr_matrix((1, X.shape[1]))
+    Xe = vstack([X[:100], empty, X[100:], empty]).tocsr()
+    kw = dict(number_of_hash_functions=H, minimal_blocks_in_common=1)
+    with Fitted(oracle, Xe, **kw) as o:
+        want = oracle.collision_counts(o.h)
+    got = {}
+    for mode in ("plain", "packed"):
+        monkeypatch.setenv("SCHIC_K3_MODE", mode)
+        with Fitted(cuda, Xe, **kw) as g:
+            got[mode] = cuda.collision_counts(g.h)
+            assert np.array_equal(cuda.collision_counts(g.h, 37, 203), want[37:203]), mode
+        assert np.array_equal(got[mode], want), mode
