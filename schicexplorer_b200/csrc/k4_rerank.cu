@@ -228,7 +228,7 @@ k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict_
 // Windowed variant (default when the feature space is small enough, i.e. every Hi-C resolution the
 // CLI is used at): the hash probe above costs ~45 issued instructions per candidate non-zero (two
 // LDS.128 probe rounds, 8 compares, selects) and the kernel sits on the ALU pipe, not on HBM. Here the
-// feature axis is cut into fixed windows of 2^18 ids; for one window the query row becomes a
+// feature axis is cut into fixed windows of 2^19 ids; for one window the query row becomes a
 // direct-addressed table in shared memory -- one 32-bit entry per 16 feature ids holding a 16-bit
 // presence mask and the rank of the entry's first key -- so a probe is one LDS, a bit test, a POPC and
 // one LDS of the value: ~15 instructions, no probe sequence, no 128-bit bank conflicts.
@@ -238,14 +238,20 @@ k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict_
 // are never read.
 // =================================================================================================
 #ifndef K4W_THREADS_DEF
-#define K4W_THREADS_DEF 512
+#define K4W_THREADS_DEF 1024
 #endif
 #ifndef K4W_UNROLL_DEF
 #define K4W_UNROLL_DEF 8
 #endif
 constexpr int K4W_THREADS = K4W_THREADS_DEF;
-constexpr int K4W_WIN_BITS = 18;                        // feature ids per window
-constexpr int K4W_WORDS = 1 << (K4W_WIN_BITS - 4);      // table entries (64 KB)
+#ifndef K4W_WIN_BITS_DEF
+#define K4W_WIN_BITS_DEF 19
+#endif
+#ifndef K4W_CTAS_DEF
+#define K4W_CTAS_DEF 1
+#endif
+constexpr int K4W_WIN_BITS = K4W_WIN_BITS_DEF;          // feature ids per window
+constexpr int K4W_WORDS = 1 << (K4W_WIN_BITS - 4);      // table entries (128 KB: one CTA per SM)
 constexpr int K4W_KCAP = 4096;                          // query non-zeros per table fill (values: 16 KB)
 constexpr int K4W_UNROLL = K4W_UNROLL_DEF;              // candidate non-zeros per lane and iteration
 
@@ -303,7 +309,7 @@ __device__ __forceinline__ float k4w_probe(const uint32_t* __restrict__ tab, con
 }
 
 template <bool E64>
-__global__ void __launch_bounds__(K4W_THREADS, 2)
+__global__ void __launch_bounds__(K4W_THREADS, K4W_CTAS_DEF)
 k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat,
                         const float* __restrict__ val, const double* __restrict__ norm2,
                         const uint32_t* __restrict__ dir, int n_windows, int64_t q_row0,
