@@ -200,7 +200,16 @@ def run_ours(args):
     d_ip = torch.from_numpy(ip).to(dev)
     d_ix = torch.from_numpy(ix.view(np.int32)).to(dev)
     d_dt = None if fast else torch.from_numpy(dt).to(dev)
-    sh = ShardedMinHash(api, n_total, bounds, dev, **kw)
+    # what a caller knows about its input before the first build: the matrix has nbins^2 columns, and how many
+    # non-zeros every rank's shard holds (metadata of the row partition, exchanged once)
+    n_features = cfg.chroms.nbins ** 2
+    if world > 1:
+        t_nnz = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(t_nnz, torch.tensor([nnz_local], dtype=torch.int64, device=dev))
+        shard_nnz = [int(x) for x in t_nnz.tolist()]
+    else:
+        shard_nnz = [nnz_local]
+    sh = ShardedMinHash(api, n_total, bounds, dev, n_features=n_features, shard_nnz=shard_nnz, **kw)
     out = (torch.empty((hi - lo, k), dtype=torch.int32, device=dev),
            torch.empty((hi - lo, k), dtype=torch.float32, device=dev),
            torch.empty(hi - lo, dtype=torch.int32, device=dev))
@@ -263,7 +272,7 @@ def run_ours(args):
     h_idx = torch.empty((hi - lo, k), dtype=torch.int32).pin_memory()
     h_dst = torch.empty((hi - lo, k), dtype=torch.float32).pin_memory()
     h_nv = torch.empty(hi - lo, dtype=torch.int32).pin_memory()
-    sh2 = ShardedMinHash(api, n_total, bounds, dev, **kw)
+    sh2 = ShardedMinHash(api, n_total, bounds, dev, n_features=n_features, shard_nnz=shard_nnz, **kw)
 
     host_ms = {"fit_csr": 0.0, "gather": 0.0, "kneighbors": 0.0, "d2h_sync": 0.0}
 

@@ -60,6 +60,13 @@ int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t ro
 int schic_mh_set_stream(schic_mh_handle* h, void* cuda_stream);
 int schic_mh_synchronize(schic_mh_handle* h);
 
+/* Optional hint: every feature id handed to fit is < n_features (the column count of the CSR matrix,
+ * nbins^2 in the reference, utilities.py:131). With it the library sizes its per-id tables and the rerank's window
+ * directory without reading the largest id back from the device, i.e. fit/kneighbors enqueue without a host
+ * synchronisation. An id >= n_features is a caller error: it is detected on the device, never written out of
+ * bounds, and reported by the next synchronising call (SCHIC_ERR_INVALID_ARG). 0 clears the hint. */
+int schic_mh_set_feature_range(schic_mh_handle* h, uint64_t n_features);
+
 /* CUDA-event time (ms) of the stages of the most recent fit + kneighbors on this handle:
  * [0] h2d, [1] signatures (K1), [2] collisions (K3), [3] select, [4] rerank (K4 launch alone), [5] graph (K5),
  * [6] d2h, [7] rerank preparation (row norms, window directory), [8] sum; n_out >= 9. Synchronises the stream. */

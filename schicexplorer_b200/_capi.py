@@ -54,7 +54,7 @@ BASE_SYMBOLS = (
 )
 # symbols only the CUDA library exports (include/schic_mh_cuda.h)
 CUDA_SYMBOLS = (
-    "schic_mh_fit_csr_async", "schic_mh_fit_csr_device", "schic_mh_kneighbors_device", "schic_mh_signatures_device", "schic_mh_csr_device",
+    "schic_mh_fit_csr_async", "schic_mh_set_feature_range", "schic_mh_fit_csr_device", "schic_mh_kneighbors_device", "schic_mh_signatures_device", "schic_mh_csr_device",
     "schic_mh_set_database_device", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free",
@@ -96,6 +96,7 @@ class CApi:
         self.is_cuda = self.backend == "cuda"
         if self.is_cuda:
             L.schic_mh_fit_csr_async.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32]
+            L.schic_mh_set_feature_range.argtypes = [_vp, C.c_uint64]
             L.schic_mh_fit_csr_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _i32]
             L.schic_mh_kneighbors_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
             L.schic_mh_signatures_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_i64)]
@@ -226,6 +227,13 @@ class CApi:
     def set_database_device(self, h, n_total, row0, d_sig, d_indptr=None, d_indices=None, d_data=None):
         self.check(self.lib.schic_mh_set_database_device(_vp(h), n_total, row0, _ptr(d_sig), _ptr(d_indptr),
                                                          _ptr(d_indices), _ptr(d_data)))
+
+    def set_feature_range(self, h, n_features: int):
+        """Hint (CUDA back end): every feature id is < n_features (the CSR's column count); lets fit / kneighbors
+        enqueue without reading the largest id back. No-op on back ends without the entry point."""
+        fn = getattr(self.lib, "schic_mh_set_feature_range", None)
+        if fn is not None and self.backend == "cuda":
+            self.check(fn(_vp(h), int(n_features)))
 
     def set_stream(self, h, stream: int):
         self.check(self.lib.schic_mh_set_stream(_vp(h), _vp(stream)))

@@ -84,6 +84,7 @@ struct schic_mh_handle {
     DevBuf<uint32_t> k1t_counters;
     std::vector<uint32_t> host_lo, host_hi;   // split 64-bit ids of the last fit (must outlive an async upload)
     int64_t count_budget = 0;                 // elements of the uint16 count matrix we allow ourselves (cached)
+    uint64_t feature_range = 0;               // caller's hint: all ids < feature_range (0: unknown, read the maximum back)
     DevBuf<double> norm2; int64_t norm_rows = 0; const void* norm_of = nullptr;
     DevBuf<uint32_t> win_dir, max_feat; int n_windows = 0;   // window directory of the windowed rerank (0: hash kernel)
     int window_mode = 32;
@@ -179,6 +180,27 @@ K1Mode k1_mode_from_env() {
     return K1_AUTO;
 }
 
+// {entries used, table overflow, max id scratch, id-beyond-range flag (sticky)}
+int ensure_counters(schic_mh_handle* h) {
+    if (h->k1t_counters.cap >= 4) return 0;
+    ST_TRY(h->k1t_counters.reserve(4, 0, h->stream));
+    CU_TRY(cudaMemsetAsync(h->k1t_counters.p, 0, 4 * sizeof(uint32_t), h->stream));
+    return 0;
+}
+
+// After a host synchronisation: did a kernel see an id beyond the caller's feature-range hint?
+int check_range_flag(schic_mh_handle* h) {
+    if (h->feature_range == 0 || h->k1t_counters.cap < 4) return 0;
+    uint32_t flag = 0;
+    CU_TRY(cudaMemcpyAsync(&flag, h->k1t_counters.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (flag) {
+        CU_TRY(cudaMemsetAsync(h->k1t_counters.p + 3, 0, sizeof(uint32_t), h->stream));
+        return fail(SCHIC_ERR_INVALID_ARG, "a feature id is >= the range declared with schic_mh_set_feature_range");
+    }
+    return 0;
+}
+
 // cheap test before anything touches the device: could this batch qualify for the shared-table path at all?
 bool k1_table_candidate(const schic_mh_handle* h, int64_t n_rows, int64_t nnz) {
     if (h->p.hash_width == 64 && h->have_hi) return false;      // ids >= 2^32: far beyond the per-id arrays
@@ -200,12 +222,17 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
         nl = schic::launch_signatures32(h->d_indptr() + r0, h->d_feat(), n_rows, nnz, pos0, H, sig, s);
     } else {
         if (k1_table_candidate(h, n_rows, nnz)) {
-            // largest id of the batch decides (8-byte read back: one stream synchronisation per batch)
-            ST_TRY(h->k1t_counters.reserve(4, 0, s));
-            add_launches(h, schic::launch_max_id(h->d_feat() + pos0, nnz, h->k1t_counters.p + 2, s));
+            // the id range decides: from the caller's hint, else the largest id of the batch is read back
+            // (4 bytes, one stream synchronisation per batch)
+            ST_TRY(ensure_counters(h));
             uint32_t max_id = 0;
-            CU_TRY(cudaMemcpyAsync(&max_id, h->k1t_counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            CU_TRY(cudaStreamSynchronize(s));
+            if (h->feature_range > 0 && h->feature_range <= 0xFFFFFFFFull) {
+                max_id = (uint32_t)(h->feature_range - 1);
+            } else {
+                add_launches(h, schic::launch_max_id(h->d_feat() + pos0, nnz, h->k1t_counters.p + 2, s));
+                CU_TRY(cudaMemcpyAsync(&max_id, h->k1t_counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+                CU_TRY(cudaStreamSynchronize(s));
+            }
             if (mode == K1_TABLE ? (max_id < 134217728u && H <= 65535) : schic::k1t_applicable(n_rows, nnz, max_id, H)) {
                 const size_t ecap = schic::k1t_entries_capacity(nnz, max_id);
                 ST_TRY(h->k1t_present.reserve((int64_t)max_id + 1, 0, s));
@@ -261,13 +288,17 @@ int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const uint32_t* feat
     const char* mode = getenv("SCHIC_K4_MODE");
     h->window_mode = (mode && strcmp(mode, "window64") == 0) ? 64 : 32;
     if (!(mode && strcmp(mode, "hash") == 0)) {
-        ST_TRY(h->max_feat.reserve(1, 0, s));
-        const int nl = schic::launch_row_max_feature(indptr, feat, rows, h->max_feat.p, s);
-        if (nl < 0) return fail(SCHIC_ERR_CUDA, "max-feature launch failed");
-        add_launches(h, nl);
         uint32_t mx = 0;
-        CU_TRY(cudaMemcpyAsync(&mx, h->max_feat.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaStreamSynchronize(s));
+        if (h->feature_range > 0 && h->feature_range <= 0xFFFFFFFFull) {
+            mx = (uint32_t)(h->feature_range - 1);
+        } else {
+            ST_TRY(h->max_feat.reserve(1, 0, s));
+            const int nl = schic::launch_row_max_feature(indptr, feat, rows, h->max_feat.p, s);
+            if (nl < 0) return fail(SCHIC_ERR_CUDA, "max-feature launch failed");
+            add_launches(h, nl);
+            CU_TRY(cudaMemcpyAsync(&mx, h->max_feat.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaStreamSynchronize(s));
+        }
         const int nw = schic::rerank_window_count(mx);
         if (nw <= kMaxWindows) {
             ST_TRY(h->win_dir.reserve(rows * (int64_t)(nw + 1), 0, s));
@@ -482,6 +513,13 @@ int schic_mh_synchronize(schic_mh_handle* h) {
     ST_TRY(use_device(h));
     CU_TRY(cudaStreamSynchronize(h->stream));
     CU_TRY(cudaStreamSynchronize(h->copy_stream));
+    return check_range_flag(h);
+}
+
+int schic_mh_set_feature_range(schic_mh_handle* h, uint64_t n_features) {
+    ST_TRY(check(h));
+    h->feature_range = n_features;
+    h->norm_of = nullptr;      // the window directory depends on it
     return SCHIC_OK;
 }
 
@@ -654,7 +692,7 @@ int schic_mh_signatures(schic_mh_handle* h, uint32_t* out) {
     ST_TRY(use_device(h));
     CU_TRY(cudaMemcpyAsync(out, h->sig.p, (size_t)h->n * h->p.number_of_hash_functions * 4, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
-    return SCHIC_OK;
+    return check_range_flag(h);
 }
 
 int schic_mh_signatures_device(schic_mh_handle* h, void** d_sig_out, int64_t* n_rows_out) {
@@ -754,7 +792,7 @@ int schic_mh_kneighbors(schic_mh_handle* h, int32_t k, int32_t fast, int32_t* id
         if (n_valid) CU_TRY(cudaMemcpyAsync(n_valid, h->out_nv.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     }
     CU_TRY(cudaStreamSynchronize(h->stream));
-    return SCHIC_OK;
+    return check_range_flag(h);
 }
 
 int schic_mh_kneighbors_graph(schic_mh_handle* h, int32_t k, int32_t fast, int64_t* indptr, int32_t* indices, float* data) {
@@ -788,7 +826,7 @@ int schic_mh_kneighbors_graph(schic_mh_handle* h, int32_t k, int32_t fast, int64
         }
     }
     CU_TRY(cudaStreamSynchronize(s));
-    return SCHIC_OK;
+    return check_range_flag(h);
 }
 
 int schic_mh_stage_ms(schic_mh_handle* h, float* out, int32_t n_out) {
@@ -842,6 +880,7 @@ int schic_k1_variant_ms(int32_t variant, int64_t n_rows, int64_t nnz, const int6
     size_t ecap = 0;
     if (variant >= 200) {          // shared-table path
         CU_TRY(cudaMalloc(&counters, 4 * sizeof(uint32_t)));
+        CU_TRY(cudaMemset(counters, 0, 4 * sizeof(uint32_t)));
         schic::launch_max_id(d_indices + pos0, nnz, counters + 2, nullptr);
         CU_TRY(cudaMemcpy(&max_id, counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         if (max_id >= 134217728u) return fail(SCHIC_ERR_UNSUPPORTED, "id range too large for the table path");

@@ -82,10 +82,13 @@ __global__ void k1t_max_id_kernel(const uint32_t* __restrict__ feat, int64_t nnz
 }
 
 // ---- 1. mark ---------------------------------------------------------------------------------------
-__global__ void k1t_mark_kernel(const uint32_t* __restrict__ feat, int64_t nnz, uint8_t* __restrict__ present) {
+// counters[3] != 0 afterwards: some id was >= n_ids (only possible when n_ids comes from the caller's hint)
+__global__ void k1t_mark_kernel(const uint32_t* __restrict__ feat, int64_t nnz, uint32_t n_ids,
+                                uint8_t* __restrict__ present, uint32_t* __restrict__ counters) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
         const uint32_t f = __ldg(feat + i);
+        if (f >= n_ids) { counters[3] = 1u; continue; }
         if (!present[f]) present[f] = 1;         // ids repeat ~40x: after the first touch this is a read that hits in L2
     }
 }
@@ -240,7 +243,7 @@ k1t_lookup_kernel(const K1TItem* __restrict__ items, const int* __restrict__ n_i
                   int H, uint32_t* __restrict__ sig) {
     extern __shared__ uint32_t sig_s[];          // [H]
     if ((int)blockIdx.x >= *n_items) return;
-    if (counters[1] != 0u) return;               // table overflow: slots are incomplete -> everything goes to step 4
+    if (counters[1] != 0u || counters[3] != 0u) return;   // table overflow / id beyond the table: everything goes to step 4
     const K1TItem it = items[blockIdx.x];
     for (int j = threadIdx.x; j < H; j += blockDim.x) sig_s[j] = kModulus;
     __syncthreads();
@@ -340,7 +343,8 @@ static int pick_R_table(int slabs) {
     return best;
 }
 
-// d_present [max_id+1] bytes, d_slot [max_id+1], d_entries [entries_cap], d_counters [2] uint32, d_items/d_n_items:
+// d_present [max_id+1] bytes, d_slot [max_id+1], d_entries [entries_cap], d_counters [4] uint32 ([3]: id >= max_id+1
+// seen, sticky), d_items/d_n_items:
 // k1t_item_capacity entries + 1 int.
 int launch_signatures_table(int width, const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
                               int64_t indptr0, uint32_t max_id, int H, uint32_t* d_sig, uint8_t* d_present,
@@ -359,8 +363,8 @@ int launch_signatures_table(int width, const int64_t* d_indptr, const uint32_t* 
     int nl = 0;
     k1t_fill_kernel<<<148 * 8, 256, 0, stream>>>(d_sig, n_rows * (int64_t)H, kModulus); ++nl;
     cudaMemsetAsync(d_present, 0, (size_t)n_ids, stream);
-    cudaMemsetAsync(d_counters, 0, 2 * sizeof(uint32_t), stream);
-    k1t_mark_kernel<<<148 * 8, 256, 0, stream>>>(d_feat + indptr0, nnz, d_present); ++nl;
+    cudaMemsetAsync(d_counters, 0, 2 * sizeof(uint32_t), stream);      // [3] (range violation) is sticky: cleared by the owner
+    k1t_mark_kernel<<<148 * 8, 256, 0, stream>>>(d_feat + indptr0, nnz, n_ids, d_present, d_counters); ++nl;
     const int slabs = (H + 31) / 32;
     const int R = pick_R_table(slabs);
     const int units = (slabs + R - 1) / R;

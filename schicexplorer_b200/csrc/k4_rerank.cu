@@ -277,12 +277,14 @@ row_window_dir_kernel(const int64_t* __restrict__ indptr, const uint32_t* __rest
     if (row >= n_rows) return;
     const int64_t b = indptr[row], e = indptr[row + 1];
     uint32_t* __restrict__ d = dir + row * (int64_t)(n_windows + 1);
+    // (ids beyond the last window -- only possible with a wrong feature-range hint, reported elsewhere -- are
+    // clamped to window n_windows, which no slice covers: memory safe)
     for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
-        const int w = (int)(__ldg(feat + i) >> K4W_WIN_BITS);
-        const int wp = i == b ? -1 : (int)(__ldg(feat + i - 1) >> K4W_WIN_BITS);
+        const int w = min((int)(__ldg(feat + i) >> K4W_WIN_BITS), n_windows);
+        const int wp = i == b ? -1 : min((int)(__ldg(feat + i - 1) >> K4W_WIN_BITS), n_windows);
         for (int x = wp + 1; x <= w; ++x) d[x] = (uint32_t)(i - b);
     }
-    const int wl = e > b ? (int)(__ldg(feat + e - 1) >> K4W_WIN_BITS) : -1;
+    const int wl = e > b ? min((int)(__ldg(feat + e - 1) >> K4W_WIN_BITS), n_windows) : -1;
     for (int x = wl + 1 + threadIdx.x; x <= n_windows; x += blockDim.x) d[x] = (uint32_t)(e - b);
 }
 

@@ -62,7 +62,8 @@ class ShardedMinHash:
     methods); tensors live on ``device``.
     """
 
-    def __init__(self, api, n_total: int, row_bounds: list, device, group=None, **minhash_kwargs):
+    def __init__(self, api, n_total: int, row_bounds: list, device, group=None, n_features=None, shard_nnz=None,
+                 **minhash_kwargs):
         self.api, self.group, self.device = api, group, device
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -76,6 +77,11 @@ class ShardedMinHash:
         self.h = api.create(device=dev_index, **self.kw)
         if device.type == "cuda":
             api.set_stream(self.h, torch.cuda.current_stream(device).cuda_stream)
+        # optional knowledge of the caller that removes host synchronisations from every build: the column count
+        # of the matrix (ids < n_features) and the non-zeros of every rank's shard (sizes of the CSR exchange)
+        if n_features is not None and hasattr(api, "set_feature_range"):
+            api.set_feature_range(self.h, int(n_features))
+        self.shard_nnz = None if shard_nnz is None else [int(x) for x in shard_nnz]
         self._keep = {}
         self._side = None
         self._csr_event = None
@@ -117,10 +123,14 @@ class ShardedMinHash:
         """All-gather of the CSR shards (only the exact rerank reads other ranks' rows)."""
         counts = [self.bounds[r + 1] - self.bounds[r] for r in range(self.world)]
         d_indptr, d_indices, d_data = self._keep["csr"]
-        nnz_local = torch.tensor([d_indices.numel()], dtype=torch.int64, device=self.device)
-        nnz_all = torch.empty(self.world, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(nnz_all, nnz_local, group=self.group)
-        nnzs = [int(x) for x in nnz_all.tolist()]
+        if self.shard_nnz is not None:
+            nnzs = self.shard_nnz
+            assert nnzs[self.rank] == d_indices.numel(), "shard_nnz does not match the local shard"
+        else:
+            nnz_local = torch.tensor([d_indices.numel()], dtype=torch.int64, device=self.device)
+            nnz_all = torch.empty(self.world, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(nnz_all, nnz_local, group=self.group)
+            nnzs = [int(x) for x in nnz_all.tolist()]
         ix_all = _gather_padded(d_indices, nnzs, self.group)
         dt_all = _gather_padded(d_data, nnzs, self.group)
         # row lengths -> global indptr

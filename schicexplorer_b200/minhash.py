@@ -107,6 +107,7 @@ class MinHash:
             indices = indices.astype(np.int64, copy=False)
         elif indices.dtype.itemsize != 4:
             indices = indices.astype(np.uint32)
+        api.set_feature_range(h, X.shape[1])      # ids are column indices of X: all < X.shape[1]
         api.fit_csr(h, X.indptr, indices, data, append)
         self._n_features = X.shape[1]
         return self

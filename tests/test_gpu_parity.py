@@ -478,3 +478,29 @@ def test_k3_packed_equals_plain(cuda, oracle, monkeypatch, H):
             got[mode] = cuda.collision_counts(g.h)
             assert np.array_equal(cuda.collision_counts(g.h, 37, 203), want[37:203]), mode
         assert np.array_equal(got[mode], want), mode
+
+
+def test_feature_range_hint(cuda, oracle, monkeypatch):
+    """schic_mh_set_feature_range: with the hint nothing is read back during fit / kneighbors and the results are the
+    same; an id beyond the declared range is detected on the device and reported (never written out of bounds)."""
+    from schicexplorer_b200._capi import SchicError
+    monkeypatch.setenv("SCHIC_K1_MODE", "table")
+    X = synth_csr(150, seed=43)
+    k = 12
+    with Fitted(oracle, X, fast=False, n_neighbors=k) as o:
+        want, want_sig = oracle.kneighbors(o.h, k), o.sig()
+    h = cuda.create(n_neighbors=k, fast=False, **REF_KWARGS)
+    cuda.set_feature_range(h, X.shape[1])
+    cuda.fit_csr(h, X.indptr, X.indices, X.data.astype(np.float32), False)
+    assert np.array_equal(cuda.signatures(h, 800), want_sig)
+    assert_neighbours_equal_up_to_ties(*cuda.kneighbors(h, k), *want, RTOL)
+    # declared range too small: reported, results of this handle are not to be used
+    cuda.set_feature_range(h, int(X.indices.max()) - 5)
+    cuda.fit_csr(h, X.indptr, X.indices, X.data.astype(np.float32), False)
+    with pytest.raises(SchicError):
+        cuda.signatures(h, 800)
+    # cleared again: back to the measured range
+    cuda.set_feature_range(h, 0)
+    cuda.fit_csr(h, X.indptr, X.indices, X.data.astype(np.float32), False)
+    assert np.array_equal(cuda.signatures(h, 800), want_sig)
+    cuda.destroy(h)
