@@ -55,6 +55,65 @@ def _gather_padded(local: torch.Tensor, counts: list, group) -> torch.Tensor:
     return torch.cat([buf[r, :counts[r]] for r in range(world)], dim=0)
 
 
+class PeerExchange:
+    """CSR exchange over NVLink peer memory instead of an NCCL all-gather (experimental, opt-in: see the note in
+    ShardedMinHash.__init__ -- correct, but slower than NCCL where legacy CUDA IPC mappings do not get NVLink DMA).
+
+    Every rank owns two sets (double buffering) of *global* CSR arrays (ids, values: the concatenation of all
+    shards, no padding) and shares them with its peers through CUDA IPC once. Per build a rank copies its shard
+    straight into all peers' arrays at its global offset -- plain device-to-device copies over NVLink / NVSwitch,
+    executed by the copy engines, so they neither take SMs from K1 / K3 nor need a compaction pass -- and a
+    one-element all-reduce on the same stream serves as the completion barrier (it can only finish once every rank
+    has issued it behind its own copies). Buffer set i % 2 is written in build i; a rank can start build i + 2
+    only after the barrier of build i + 1, i.e. after every peer has finished reading set i % 2.
+    """
+
+    def __init__(self, device, group, shard_nnz, value_dtype=torch.float32):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.device, self.group = device, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.nnz = [int(x) for x in shard_nnz]
+        self.off = [0]
+        for x in self.nnz:
+            self.off.append(self.off[-1] + x)
+        total = self.off[-1]
+        self.ix = [torch.empty(total, dtype=torch.int32, device=device) for _ in range(2)]
+        self.dt = [torch.empty(total, dtype=value_dtype, device=device) for _ in range(2)]
+        mine = [(reduce_tensor(a), reduce_tensor(b)) for a, b in zip(self.ix, self.dt)]
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self.peer_ix = [[None] * self.world for _ in range(2)]
+        self.peer_dt = [[None] * self.world for _ in range(2)]
+        for p in range(self.world):
+            for b in range(2):
+                if p == self.rank:
+                    self.peer_ix[b][p], self.peer_dt[b][p] = self.ix[b], self.dt[b]
+                else:
+                    (f1, a1), (f2, a2) = everyone[p][b]
+                    self.peer_ix[b][p], self.peer_dt[b][p] = f1(*a1), f2(*a2)
+        self.stream = torch.cuda.Stream(device)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.turn = 0
+        dist.barrier(group=group)
+
+    def exchange(self, local_ix: torch.Tensor, local_dt: torch.Tensor):
+        """Issue the copies behind everything already queued on the current stream. Returns (ids, values, event)."""
+        b = self.turn
+        self.turn ^= 1
+        lo, n = self.off[self.rank], self.nnz[self.rank]
+        assert local_ix.numel() == n
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            for step in range(self.world):                   # start with the next rank: spreads the load over the links
+                p = (self.rank + 1 + step) % self.world
+                self.peer_ix[b][p][lo:lo + n].copy_(local_ix, non_blocking=True)
+                self.peer_dt[b][p][lo:lo + n].copy_(local_dt, non_blocking=True)
+            dist.all_reduce(self.flag, group=self.group)     # completion barrier
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return self.ix[b], self.dt[b], ev
+
+
 class ShardedMinHash:
     """Cells [row0, row0 + n_local) of an n_total-cell data set live on this rank.
 
@@ -82,6 +141,25 @@ class ShardedMinHash:
         if n_features is not None and hasattr(api, "set_feature_range"):
             api.set_feature_range(self.h, int(n_features))
         self.shard_nnz = None if shard_nnz is None else [int(x) for x in shard_nnz]
+        # The CSR exchange gets its own communicator: collectives of one NCCL communicator run in issue order on one
+        # internal stream, so on the default group the (small, urgent) signature all-gather would queue behind the
+        # 1 GB CSR all-gather that was issued before K1 and K3 could not start until it had finished.
+        self._csr_group = None
+        self._peer = None
+        if self.world > 1 and not self.fast and device.type == "cuda" and group is None:
+            self._csr_group = dist.new_group(backend="nccl")
+            # SCHIC_CSR_EXCHANGE=p2p: copies into peer memory mapped through CUDA IPC instead of the NCCL all-gather
+            # (needs the shard sizes). Opt-in: on this pool's boxes a copy into legacy-IPC-mapped peer memory runs
+            # at 25 GB/s (tools/p2p_probe.py; same-process P2P: 735 GB/s, NCCL all-gather: 237 GB/s busbw at 2 ranks),
+            # so the NCCL path stays the default.
+            import os
+            if self.shard_nnz is not None and os.environ.get("SCHIC_CSR_EXCHANGE", "nccl") == "p2p":
+                try:
+                    self._peer = PeerExchange(device, self._csr_group, self.shard_nnz)
+                except Exception as e:       # no IPC / peer access on this box: the NCCL path still works
+                    import warnings
+                    warnings.warn(f"peer-memory CSR exchange unavailable ({e}); using the NCCL all-gather")
+                    self._peer = None
         self._keep = {}
         self._side = None
         self._csr_event = None
@@ -123,21 +201,28 @@ class ShardedMinHash:
         """All-gather of the CSR shards (only the exact rerank reads other ranks' rows)."""
         counts = [self.bounds[r + 1] - self.bounds[r] for r in range(self.world)]
         d_indptr, d_indices, d_data = self._keep["csr"]
+        group = self._csr_group if self._csr_group is not None else self.group
         if self.shard_nnz is not None:
             nnzs = self.shard_nnz
             assert nnzs[self.rank] == d_indices.numel(), "shard_nnz does not match the local shard"
         else:
             nnz_local = torch.tensor([d_indices.numel()], dtype=torch.int64, device=self.device)
             nnz_all = torch.empty(self.world, dtype=torch.int64, device=self.device)
-            dist.all_gather_into_tensor(nnz_all, nnz_local, group=self.group)
+            dist.all_gather_into_tensor(nnz_all, nnz_local, group=group)
             nnzs = [int(x) for x in nnz_all.tolist()]
-        ix_all = _gather_padded(d_indices, nnzs, self.group)
-        dt_all = _gather_padded(d_data, nnzs, self.group)
+        ev = None
+        if self._peer is not None:
+            ix_all, dt_all, ev = self._peer.exchange(d_indices, d_data)
+        else:
+            ix_all = _gather_padded(d_indices, nnzs, group)
+            dt_all = _gather_padded(d_data, nnzs, group)
         # row lengths -> global indptr
         lens = (d_indptr[1:] - d_indptr[:-1]).contiguous()
-        lens_all = _gather_padded(lens, counts, self.group)
+        lens_all = _gather_padded(lens, counts, group)
         ip_all = torch.zeros(self.n_total + 1, dtype=torch.int64, device=self.device)
         torch.cumsum(lens_all, 0, out=ip_all[1:])
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
         return ip_all, ix_all, dt_all
 
     def _start_csr_gather(self):

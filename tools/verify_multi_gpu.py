@@ -27,13 +27,23 @@ def main():
     cfg = synth.small_config(n, config_id=31)
     ip, ix, dt, _ = synth.generate_csr(cfg, workers=1)
     ok = True
-    for fast in (True, False):
+    # (fast, exchange): signatures only / exact rerank with the NCCL all-gather of the CSR shards / exact rerank with
+    # the peer-memory exchange (two builds in a row: both buffer sets of the double buffering are used)
+    for fast, exchange in ((True, "nccl"), (False, "nccl"), (False, "p2p"), (False, "p2p")):
+        os.environ["SCHIC_CSR_EXCHANGE"] = exchange
         kw = dict(n_neighbors=k, number_of_hash_functions=800, fast=fast, minimal_blocks_in_common=100,
                   excess_factor=1, max_bin_size=100000)
         bounds = partition_rows_by_nnz(ip, world)
         lo, hi = bounds[rank], bounds[rank + 1]
         a, b = int(ip[lo]), int(ip[hi])
-        sh = ShardedMinHash(api, n, bounds, dev, **kw)
+        shard_nnz = [int(ip[bounds[r + 1]] - ip[bounds[r]]) for r in range(world)]
+        if exchange == "p2p" and "sh_p2p" in globals():
+            sh = globals()["sh_p2p"]                     # second build on the same object
+        else:
+            sh = ShardedMinHash(api, n, bounds, dev, n_features=cfg.chroms.nbins ** 2, shard_nnz=shard_nnz, **kw)
+            if exchange == "p2p":
+                globals()["sh_p2p"] = sh
+                assert sh._peer is not None, "peer-memory exchange was not set up"
         sh.fit_local(torch.from_numpy((ip[lo:hi + 1] - ip[lo]).copy()).to(dev),
                      torch.from_numpy(ix[a:b].view(np.int32).copy()).to(dev),
                      None if fast else torch.from_numpy(dt[a:b].copy()).to(dev))
@@ -53,8 +63,11 @@ def main():
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         ok = ok and bool(flag.item())
         if rank == 0:
-            print(f"fast={fast}: world={world} rows/rank={[bounds[i+1]-bounds[i] for i in range(world)]} identical={bool(flag.item())}")
-        sh.close()
+            print(f"fast={fast} exchange={exchange}: world={world} rows/rank={[bounds[i+1]-bounds[i] for i in range(world)]} identical={bool(flag.item())}")
+        if sh is not globals().get("sh_p2p"):
+            sh.close()
+    if "sh_p2p" in globals():
+        globals()["sh_p2p"].close()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
