@@ -171,7 +171,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from schicexplorer_b200 import _capi, synth
+    from schicexplorer_b200 import MinHash, _capi, synth
     from schicexplorer_b200.dist import ShardedMinHash, partition_rows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -268,7 +268,10 @@ def run_ours(args):
     p_ix = api.pinned_empty(ix.shape, np.uint32); p_ix[:] = ix
     p_dt = None
     if not fast:
-        p_dt = api.pinned_empty(dt.shape, np.float32); p_dt[:] = dt
+        # the values are integer contact counts: they cross the C ABI as the host class sends them
+        # (MinHash._wire_values: uint8 / uint16 when the data allows, else float32)
+        wire = MinHash._wire_values(dt)
+        p_dt = api.pinned_empty(wire.shape, wire.dtype); p_dt[:] = wire
     h_idx = torch.empty((hi - lo, k), dtype=torch.int32).pin_memory()
     h_dst = torch.empty((hi - lo, k), dtype=torch.float32).pin_memory()
     h_nv = torch.empty(hi - lo, dtype=torch.int32).pin_memory()
@@ -302,7 +305,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n_total / float(e2e_s.item())
-    h2d = ip.nbytes + ix.nbytes + (0 if fast else dt.nbytes)
+    h2d = ip.nbytes + ix.nbytes + (0 if fast else p_dt.nbytes)
     d2h = h_idx.numel() * 4 + h_dst.numel() * 4 + h_nv.numel() * 4
     stage_e2e = api.stage_ms(sh2.h)
 

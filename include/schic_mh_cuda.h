@@ -60,6 +60,13 @@ int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t ro
 int schic_mh_set_stream(schic_mh_handle* h, void* cuda_stream);
 int schic_mh_synchronize(schic_mh_handle* h);
 
+/* schic_mh_fit_csr with the values given as unsigned integer counts (count_bits = 8 or 16) instead of float32:
+ * Hi-C values are contact counts, and narrow counts halve or quarter the PCIe bytes of the value array; they are
+ * widened to float32 on the device, everything downstream is unchanged. async_upload as schic_mh_fit_csr_async. */
+int schic_mh_fit_csr_counts(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
+                            int32_t index_bits, const void* counts, int32_t count_bits, int32_t append,
+                            int32_t async_upload);
+
 /* Optional hint: every feature id handed to fit is < n_features (the column count of the CSR matrix,
  * nbins^2 in the reference, utilities.py:131). With it the library sizes its per-id tables and the rerank's window
  * directory without reading the largest id back from the device, i.e. fit/kneighbors enqueue without a host

@@ -54,7 +54,7 @@ BASE_SYMBOLS = (
 )
 # symbols only the CUDA library exports (include/schic_mh_cuda.h)
 CUDA_SYMBOLS = (
-    "schic_mh_fit_csr_async", "schic_mh_set_feature_range", "schic_mh_fit_csr_device", "schic_mh_kneighbors_device", "schic_mh_signatures_device", "schic_mh_csr_device",
+    "schic_mh_fit_csr_async", "schic_mh_fit_csr_counts", "schic_mh_set_feature_range", "schic_mh_fit_csr_device", "schic_mh_kneighbors_device", "schic_mh_signatures_device", "schic_mh_csr_device",
     "schic_mh_set_database_device", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free",
@@ -97,6 +97,7 @@ class CApi:
         if self.is_cuda:
             L.schic_mh_fit_csr_async.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32]
             L.schic_mh_set_feature_range.argtypes = [_vp, C.c_uint64]
+            L.schic_mh_fit_csr_counts.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32]
             L.schic_mh_fit_csr_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _i32]
             L.schic_mh_kneighbors_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
             L.schic_mh_signatures_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_i64)]
@@ -157,7 +158,7 @@ class CApi:
         if async_upload:
             ok = (indptr.dtype == np.int64 and indptr.flags.c_contiguous and indices.flags.c_contiguous and
                   indices.dtype.itemsize in (4, 8) and
-                  (data is None or (data.dtype == np.float32 and data.flags.c_contiguous)))
+                  (data is None or (data.dtype in (np.float32, np.uint16, np.uint8) and data.flags.c_contiguous)))
             if not ok:
                 raise ValueError("async_upload needs int64 indptr, 32/64-bit indices and float32 data, C contiguous")
         indptr = np.ascontiguousarray(indptr, dtype=np.int64)
@@ -167,6 +168,12 @@ class CApi:
         else:
             indices = np.ascontiguousarray(indices).view(np.uint32)
             bits = 32
+        if data is not None and data.dtype in (np.uint8, np.uint16) and self.is_cuda:
+            # integer counts cross PCIe narrow and are widened on the device (include/schic_mh_cuda.h)
+            data = np.ascontiguousarray(data)
+            self.check(self.lib.schic_mh_fit_csr_counts(_vp(h), len(indptr) - 1, _ptr(indptr), _ptr(indices), bits,
+                                                        _ptr(data), data.dtype.itemsize * 8, int(append), int(async_upload)))
+            return
         if data is not None:
             data = np.ascontiguousarray(data, dtype=np.float32)
         fn = self.lib.schic_mh_fit_csr_async if async_upload else self.lib.schic_mh_fit_csr

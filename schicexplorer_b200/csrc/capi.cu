@@ -83,6 +83,7 @@ struct schic_mh_handle {
     DevBuf<unsigned char> k1t_present; DevBuf<unsigned long long> k1t_slot; DevBuf<uint16_t> k1t_entries;
     DevBuf<uint32_t> k1t_counters;
     std::vector<uint32_t> host_lo, host_hi;   // split 64-bit ids of the last fit (must outlive an async upload)
+    DevBuf<unsigned char> val_stage;          // narrow (uint16 / uint8) counts as uploaded, before widening
     int64_t count_budget = 0;                 // elements of the uint16 count matrix we allow ourselves (cached)
     uint64_t feature_range = 0;               // caller's hint: all ids < feature_range (0: unknown, read the maximum back)
     DevBuf<double> norm2; int64_t norm_rows = 0; const void* norm_of = nullptr;
@@ -523,8 +524,27 @@ int schic_mh_set_feature_range(schic_mh_handle* h, uint64_t n_features) {
     return SCHIC_OK;
 }
 
+// Values to the device on the copy stream: float32 as they are; uint16 / uint8 counts (a quarter to a half of the
+// PCIe bytes -- Hi-C values are integer counts) into a staging buffer, widened to float32 by a kernel behind them.
+static int upload_values(schic_mh_handle* h, const void* data, int32_t kind, size_t vbytes, int64_t first, int64_t pos0,
+                         int64_t nnz, cudaStream_t cs) {
+    const unsigned char* src = (const unsigned char*)data + (size_t)first * vbytes;
+    if (kind == 0) {
+        CU_TRY(cudaMemcpyAsync(h->val.p + pos0, src, (size_t)nnz * 4, cudaMemcpyHostToDevice, cs));
+        return 0;
+    }
+    ST_TRY(h->val_stage.reserve((int64_t)((size_t)nnz * vbytes), 0, cs));
+    CU_TRY(cudaMemcpyAsync(h->val_stage.p, src, (size_t)nnz * vbytes, cudaMemcpyHostToDevice, cs));
+    add_launches(h, schic::launch_widen_counts(h->val_stage.p, kind == 1 ? 16 : 8, nnz, h->val.p + pos0, cs));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// data_kind: 0 = float32 values, 1 = uint16 counts, 2 = uint8 counts (expanded to float32 on the device)
 static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
-                        int32_t index_bits, const float* data, int32_t append, bool async_upload) {
+                        int32_t index_bits, const void* data, int32_t data_kind, int32_t append, bool async_upload) {
+    if (data_kind < 0 || data_kind > 2) return fail(SCHIC_ERR_INVALID_ARG, "data_kind must be 0 (f32), 1 (u16) or 2 (u8)");
+    const size_t vbytes = data_kind == 0 ? 4 : (data_kind == 1 ? 2 : 1);
     ST_TRY(check(h));
     if (n_rows < 0 || !indptr) return fail(SCHIC_ERR_INVALID_ARG, "bad CSR arguments");
     if (index_bits != 32 && index_bits != 64) return fail(SCHIC_ERR_INVALID_ARG, "index_bits must be 32 or 64");
@@ -617,7 +637,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
         if (c1 == n_rows && want_val && nnz > 0) {
             // the values follow the last feature chunk at once, so the copy engine stays busy while K1 runs
             // (and while the host may block on K1's id-range read-back)
-            CU_TRY(cudaMemcpyAsync(h->val.p + pos0, data + indptr[0], (size_t)nnz * 4, cudaMemcpyHostToDevice, cs));
+            ST_TRY(upload_values(h, data, data_kind, vbytes, indptr[0], pos0, nnz, cs));
             val_enqueued = true;
         }
         CU_TRY(cudaStreamWaitEvent(s, ready, 0));
@@ -627,8 +647,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
     }
     cudaEvent_t sig1 = get_event(h);
     if (sig_started && sig1) { cudaEventRecord(sig1, s); h->ev[ST_SIG].push_back({sig0, sig1}); }
-    if (want_val && nnz > 0 && !val_enqueued)
-        CU_TRY(cudaMemcpyAsync(h->val.p + pos0, data + indptr[0], (size_t)nnz * 4, cudaMemcpyHostToDevice, cs));
+    if (want_val && nnz > 0 && !val_enqueued) ST_TRY(upload_values(h, data, data_kind, vbytes, indptr[0], pos0, nnz, cs));
     if (up0 && up1) { cudaEventRecord(up1, cs); h->ev[ST_H2D].push_back({up0, up1}); }
     // the host vectors (lo/hi) and the caller's arrays must outlive the copies; later stages use
     // the compute stream, so make it wait for the value upload as well
@@ -646,12 +665,19 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
 
 int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
                      int32_t index_bits, const float* data, int32_t append) {
-    return fit_csr_impl(h, n_rows, indptr, indices, index_bits, data, append, false);
+    return fit_csr_impl(h, n_rows, indptr, indices, index_bits, data, 0, append, false);
 }
 
 int schic_mh_fit_csr_async(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
                            int32_t index_bits, const float* data, int32_t append) {
-    return fit_csr_impl(h, n_rows, indptr, indices, index_bits, data, append, true);
+    return fit_csr_impl(h, n_rows, indptr, indices, index_bits, data, 0, append, true);
+}
+
+int schic_mh_fit_csr_counts(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
+                            int32_t index_bits, const void* counts, int32_t count_bits, int32_t append,
+                            int32_t async_upload) {
+    if (count_bits != 8 && count_bits != 16) return fail(SCHIC_ERR_INVALID_ARG, "count_bits must be 8 or 16");
+    return fit_csr_impl(h, n_rows, indptr, indices, index_bits, counts, count_bits == 16 ? 1 : 2, append, async_upload != 0);
 }
 
 int schic_mh_fit_csr_device(schic_mh_handle* h, int64_t n_rows, int64_t nnz, const int64_t* d_indptr,

@@ -77,6 +77,8 @@ int launch_fast_distance(const int32_t* d_idx_in, const int32_t* d_cnt_in, const
 // norms2[r] = sum of squares of row r (fp64).
 int launch_row_norms(const int64_t* d_indptr, const float* d_val, int64_t n_rows, int64_t indptr0,
                      double* d_norm2, cudaStream_t stream);
+// uint16 / uint8 counts -> float32 values (host uploads of integer counts cross PCIe narrow)
+int launch_widen_counts(const void* d_src, int bits, int64_t n, float* d_dst, cudaStream_t stream);
 // Window directory of the windowed rerank kernel: largest feature id of the database (device
 // scalar), number of windows for it, and dir[row][0..n_windows] (uint32 offsets from the row start).
 int launch_row_max_feature(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, uint32_t* d_out_max,

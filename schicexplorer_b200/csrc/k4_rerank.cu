@@ -44,6 +44,20 @@ __global__ void row_norms_kernel(const int64_t* __restrict__ indptr, const float
     if (lane == 0) norm2[row] = acc;
 }
 
+// uint16 / uint8 counts (as uploaded) -> float32 values
+template <typename T>
+__global__ void widen_counts_kernel(const T* __restrict__ src, int64_t n, float* __restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (float)src[i];
+}
+
+int launch_widen_counts(const void* d_src, int bits, int64_t n, float* d_dst, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    if (bits == 16) widen_counts_kernel<uint16_t><<<148 * 8, 256, 0, stream>>>((const uint16_t*)d_src, n, d_dst);
+    else widen_counts_kernel<uint8_t><<<148 * 8, 256, 0, stream>>>((const uint8_t*)d_src, n, d_dst);
+    return 1;
+}
+
 __device__ __forceinline__ uint32_t k4_bucket(uint32_t f) { return (f * 2654435761u) >> (32 - K4_BUCKET_BITS); }
 
 // first position in [b, e) whose feature is >= key (plain binary search, one thread)

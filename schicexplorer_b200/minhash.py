@@ -95,13 +95,26 @@ class MinHash:
             X = X.sorted_indices()
         return X
 
+    @staticmethod
+    def _wire_values(d: np.ndarray) -> np.ndarray:
+        """Values as they cross the C ABI: Hi-C values are integer contact counts, which go down as uint8 / uint16
+        (a quarter / half of the PCIe bytes; widened to float32 on the device, bit-identical results), anything
+        else as float32."""
+        if d.size and d.dtype.kind in "fiu":
+            lo, hi = d.min(), d.max()
+            if lo >= 0 and hi <= 65535:
+                narrow = d.astype(np.uint8 if hi <= 255 else np.uint16)
+                if d.dtype.kind in "iu" or np.array_equal(narrow, d):
+                    return narrow
+        return d.astype(np.float32, copy=False)
+
     def _fit(self, X, append: bool):
         X = self._as_csr(X)
         if append and self._n_features is not None and X.shape[1] != self._n_features:
             raise ValueError(f"partial_fit: X has {X.shape[1]} features, fitted data has {self._n_features}")
         api, h = self._ensure()
         # values are only needed by the exact rerank; ids above 2^32 go down as 64-bit
-        data = None if self.fast else X.data.astype(np.float32, copy=False)
+        data = None if self.fast else self._wire_values(X.data)
         indices = X.indices
         if X.shape[1] > 0xFFFFFFFF:
             indices = indices.astype(np.int64, copy=False)

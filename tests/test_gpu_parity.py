@@ -504,3 +504,34 @@ def test_feature_range_hint(cuda, oracle, monkeypatch):
     cuda.fit_csr(h, X.indptr, X.indices, X.data.astype(np.float32), False)
     assert np.array_equal(cuda.signatures(h, 800), want_sig)
     cuda.destroy(h)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_narrow_count_upload(cuda, oracle, dtype):
+    """schic_mh_fit_csr_counts: integer counts uploaded as uint8 / uint16 and widened on the device give exactly the
+    results of the float32 upload (blocking and async, append)."""
+    X = synth_csr(180, seed=47)
+    top = 255 if dtype == np.uint8 else 60000
+    X.data = np.minimum(X.data * (1 if dtype == np.uint8 else 97), top)
+    k = 10
+    ip, ix = X.indptr.astype(np.int64), np.ascontiguousarray(X.indices.astype(np.uint32))
+    f32, narrow = np.ascontiguousarray(X.data.astype(np.float32)), np.ascontiguousarray(X.data.astype(dtype))
+    with Fitted(oracle, X, fast=False, n_neighbors=k) as o:
+        want = oracle.kneighbors(o.h, k)
+    h = cuda.create(n_neighbors=k, fast=False, **REF_KWARGS)
+    cuda.fit_csr(h, ip, ix, f32, False)
+    ref = cuda.kneighbors(h, k)
+    for async_upload in (False, True):
+        cuda.fit_csr(h, ip, ix, narrow, False, async_upload=async_upload)
+        got = cuda.kneighbors(h, k)
+        assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+        assert_neighbours_equal_up_to_ties(*got, *want, RTOL)
+    cuda.fit_csr(h, ip[:91], ix[:ip[90]], narrow[:ip[90]], False)
+    cuda.fit_csr(h, ip[90:] - ip[90], ix[ip[90]:], narrow[ip[90]:], True)
+    got = cuda.kneighbors(h, k)
+    assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    cuda.destroy(h)
+    # the host class picks the narrow wire format on its own
+    from schicexplorer_b200 import MinHash
+    assert MinHash._wire_values(X.data).dtype == dtype
+    assert MinHash._wire_values(X.data + 0.5).dtype == np.float32
