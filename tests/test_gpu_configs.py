@@ -74,7 +74,8 @@ def test_config3_full_size(cuda, oracle, monkeypatch):
     """The configuration the metric is quoted on, at full size: 10 000 cells, H = 800, k = 100, exact rerank.
     * K1: the shared-table path (chosen automatically at this size) and the per-cell filtered kernel give the same
       signature matrix; 48 sampled rows equal the oracle's signatures of those rows.
-    * counts: symmetric, diagonal = number of admissible signature entries (checked on a 256-row block).
+    * counts: packed (fp16-id) and plain K3 agree on a 256-row block against all 10 000 columns; the block is
+      symmetric and its diagonal = number of admissible signature entries.
     * K4: windowed and hash-table kernels agree (indices identical, distances to 1e-6); every list starts with the
       query itself at distance 0 and is sorted; 32 sampled lists are recomputed directly from the sparse rows in
       float64 (1e-5 relative)."""
@@ -82,8 +83,9 @@ def test_config3_full_size(cuda, oracle, monkeypatch):
     n, H, k = 10_000, 800, 100
     rng = np.random.default_rng(5)
 
-    def build(k1_mode, k4_mode):
+    def build(k1_mode, k3_mode, k4_mode):
         monkeypatch.setenv("SCHIC_K1_MODE", k1_mode)
+        monkeypatch.setenv("SCHIC_K3_MODE", k3_mode)
         monkeypatch.setenv("SCHIC_K4_MODE", k4_mode)
         h = cuda.create(n_neighbors=k, fast=False, **REF_KWARGS)
         cuda.fit_csr(h, ip, ix, dt, False)
@@ -93,9 +95,9 @@ def test_config3_full_size(cuda, oracle, monkeypatch):
         cuda.destroy(h)
         return sig, res, cnt
 
-    sig_a, (idx_a, dist_a, nv_a), cnt_a = build("auto", "window")
-    sig_b, (idx_b, dist_b, nv_b), _ = build("tile", "hash")
-    assert np.array_equal(sig_a, sig_b)
+    sig_a, (idx_a, dist_a, nv_a), cnt_a = build("auto", "packed", "window")
+    sig_b, (idx_b, dist_b, nv_b), cnt_b = build("tile", "plain", "hash")
+    assert np.array_equal(sig_a, sig_b) and np.array_equal(cnt_a, cnt_b)
     assert np.array_equal(nv_a, nv_b) and np.array_equal(idx_a, idx_b)
     np.testing.assert_allclose(dist_a, dist_b, rtol=1e-6)
 
