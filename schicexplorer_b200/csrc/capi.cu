@@ -82,6 +82,7 @@ struct schic_mh_handle {
     // shared-table K1 (k1_table.cu): per-id presence bytes and slots, hit entries, {entries used, overflow, max id}
     DevBuf<unsigned char> k1t_present; DevBuf<unsigned long long> k1t_slot; DevBuf<uint16_t> k1t_entries;
     DevBuf<uint32_t> k1t_counters;
+    bool k1t_prebuilt = false;                // the table for this batch was built ahead of the upload (phase 1)
     std::vector<uint32_t> host_lo, host_hi;   // split 64-bit ids of the last fit (must outlive an async upload)
     DevBuf<unsigned char> val_stage;          // narrow (uint16 / uint8) counts as uploaded, before widening
     int64_t count_budget = 0;                 // elements of the uint16 count matrix we allow ourselves (cached)
@@ -242,7 +243,9 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
                 ST_TRY(h->k1_scratch.reserve((int64_t)schic::k1t_items_bytes(n_rows, nnz), 0, s));
                 nl = schic::launch_signatures_table(h->p.hash_width, h->d_indptr() + r0, h->d_feat(), n_rows, nnz, pos0, max_id, H, sig,
                                                       h->k1t_present.p, reinterpret_cast<uint2*>(h->k1t_slot.p),
-                                                      h->k1t_entries.p, ecap, h->k1t_counters.p, h->k1_scratch.p, s);
+                                                      h->k1t_entries.p, ecap, h->k1t_counters.p, h->k1_scratch.p,
+                                                      h->k1t_prebuilt ? 2 : 0, s);
+                h->k1t_prebuilt = false;      // valid for exactly this batch
             }
         }
         if (nl < 0 && h->p.hash_width == 64) {
@@ -621,6 +624,26 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
     // (a batch that may take the shared-table K1 path is hashed in one piece after its last chunk has landed:
     // the table is built from all of its feature ids)
     const bool whole_batch = k1_table_candidate(h, n_rows, nnz);
+    // With the caller's feature-range hint the table does not depend on the data at all (it is built for every id
+    // of the range): it is computed on the compute stream while the ids are still crossing PCIe, and the batch only
+    // needs the lookup + fallback once it has landed.
+    h->k1t_prebuilt = false;
+    if (whole_batch && k1_mode_from_env() == K1_AUTO && h->feature_range > 0 && h->feature_range <= 134217728ull &&
+        schic::k1t_applicable(n_rows, nnz, (uint32_t)(h->feature_range - 1), H)) {
+        const uint32_t max_id = (uint32_t)(h->feature_range - 1);
+        const size_t ecap = schic::k1t_entries_capacity(nnz, max_id);
+        ST_TRY(ensure_counters(h));
+        ST_TRY(h->k1t_present.reserve((int64_t)max_id + 1, 0, s));
+        ST_TRY(h->k1t_slot.reserve((int64_t)max_id + 1, 0, s));
+        ST_TRY(h->k1t_entries.reserve((int64_t)ecap, 0, s));
+        const int nl = schic::launch_signatures_table(h->p.hash_width, nullptr, nullptr, n_rows, nnz, 0, max_id, H, nullptr,
+                                                      h->k1t_present.p, reinterpret_cast<uint2*>(h->k1t_slot.p),
+                                                      h->k1t_entries.p, ecap, h->k1t_counters.p, nullptr, 1, s);
+        if (nl < 0) return fail(SCHIC_ERR_CUDA, "K1 table build failed");
+        add_launches(h, nl);
+        CU_TRY(cudaGetLastError());
+        h->k1t_prebuilt = true;
+    }
     while (c0 < n_rows) {
         const int64_t kChunkNnz = whole_batch ? INT64_MAX : (int64_t)(c0 == 0 ? 8 : 32) << 20;
         int64_t c1 = c0 + 1;
@@ -689,6 +712,7 @@ int schic_mh_fit_csr_device(schic_mh_handle* h, int64_t n_rows, int64_t nnz, con
     ST_TRY(use_device(h));
     reset_stage(h, {ST_H2D, ST_SIG});
     const int H = h->p.number_of_hash_functions;
+    h->k1t_prebuilt = false;
     h->borrowed = true; h->b_indptr = d_indptr; h->b_feat = d_indices; h->b_val = d_data;
     h->have_val = d_data != nullptr; h->have_hi = false;
     h->n = n_rows; h->nnz = nnz; h->norm_of = nullptr; h->ext = false;
@@ -921,7 +945,7 @@ int schic_k1_variant_ms(int32_t variant, int64_t n_rows, int64_t nnz, const int6
     auto launch = [&]() {
         if (variant >= 200)
             return schic::launch_signatures_table(32, d_indptr, d_indices, n_rows, nnz, pos0, max_id, n_hash, d_sig, present,
-                                                    slot, entries, ecap, counters, scratch, nullptr);
+                                                    slot, entries, ecap, counters, scratch, 0, nullptr);
         return variant >= 100 ? schic::launch_signatures32_filter(d_indptr, d_indices, n_rows, nnz, n_hash, d_sig, scratch, variant == 101 ? 1 : 0, nullptr)
                               : schic::launch_signatures32_variant(variant, d_indptr, d_indices, n_rows, nnz, pos0, n_hash, d_sig, nullptr);
     };

@@ -31,7 +31,7 @@ int launch_max_id(const uint32_t* d_feat, int64_t nnz, uint32_t* d_out_max, cuda
 int launch_signatures_table(int width /* 32 | 64: HashSpec */, const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
                               int64_t indptr0, uint32_t max_id, int H, uint32_t* d_sig, uint8_t* d_present,
                               uint2* d_slot, uint16_t* d_entries, size_t entries_cap, uint32_t* d_counters,
-                              void* d_items, cudaStream_t stream);
+                              void* d_items, int phase /* 0 all | 1 build for every id | 2 lookup */, cudaStream_t stream);
 // variant >= 0 selects an instruction-selection variant (only in builds with -DK1_ALL_VARIANTS).
 int launch_signatures32_variant(int variant, const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows,
                                 int64_t nnz, int64_t indptr0, int H, uint32_t* d_sig, cudaStream_t stream);

@@ -239,8 +239,8 @@ k1t_items_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, K1TItem* __
 template <bool W64>
 __global__ void __launch_bounds__(256)
 k1t_lookup_kernel(const K1TItem* __restrict__ items, const int* __restrict__ n_items, const uint32_t* __restrict__ feat,
-                  const uint2* __restrict__ slot, const uint16_t* __restrict__ entries, const uint32_t* __restrict__ counters,
-                  int H, uint32_t* __restrict__ sig) {
+                  const uint2* __restrict__ slot, const uint16_t* __restrict__ entries, uint32_t* __restrict__ counters,
+                  uint32_t n_ids, int H, uint32_t* __restrict__ sig) {
     extern __shared__ uint32_t sig_s[];          // [H]
     if ((int)blockIdx.x >= *n_items) return;
     if (counters[1] != 0u || counters[3] != 0u) return;   // table overflow / id beyond the table: everything goes to step 4
@@ -250,6 +250,7 @@ k1t_lookup_kernel(const K1TItem* __restrict__ items, const int* __restrict__ n_i
     const uint32_t* __restrict__ src = feat + it.begin;
     for (int i = threadIdx.x; i < it.len; i += blockDim.x) {
         const uint32_t f = __ldg(src + i);
+        if (f >= n_ids) { counters[3] = 1u; continue; }      // beyond the declared range: reported by the host
         const uint2 s = __ldg(slot + f);
         for (uint32_t e = 0; e < s.y; ++e) {
             const uint32_t j = __ldg(entries + s.x + e);
@@ -346,12 +347,18 @@ static int pick_R_table(int slabs) {
 // d_present [max_id+1] bytes, d_slot [max_id+1], d_entries [entries_cap], d_counters [4] uint32 ([3]: id >= max_id+1
 // seen, sticky), d_items/d_n_items:
 // k1t_item_capacity entries + 1 int.
+// phase 0: everything. phase 1: build the table only, for EVERY id <= max_id (no look at the data: it can run while
+// the ids are still being uploaded; needs only n_rows / nnz for the threshold). phase 2: lookup + fallback against
+// a table built by phase 1 with the same n_rows / nnz.
 int launch_signatures_table(int width, const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,
                               int64_t indptr0, uint32_t max_id, int H, uint32_t* d_sig, uint8_t* d_present,
                               uint2* d_slot, uint16_t* d_entries, size_t entries_cap, uint32_t* d_counters,
-                              void* d_items, cudaStream_t stream) {
+                              void* d_items, int phase, cudaStream_t stream) {
     if (n_rows <= 0) return 0;
-    if (nnz <= 0) { k1t_fill_kernel<<<148 * 8, 256, 0, stream>>>(d_sig, n_rows * (int64_t)H, kModulus); return 1; }
+    if (nnz <= 0) {
+        if (phase != 1) k1t_fill_kernel<<<148 * 8, 256, 0, stream>>>(d_sig, n_rows * (int64_t)H, kModulus);
+        return phase != 1 ? 1 : 0;
+    }
     const uint32_t n_ids = max_id + 1u;
     const double mean_row = (double)nnz / (double)n_rows;
     double tau = 2.0 * mean_row / (double)H;
@@ -361,11 +368,16 @@ int launch_signatures_table(int width, const int64_t* d_indptr, const uint32_t* 
     const uint32_t T = (uint32_t)Td;
     const uint32_t thrT = k1t_threshold(T);
     int nl = 0;
-    k1t_fill_kernel<<<148 * 8, 256, 0, stream>>>(d_sig, n_rows * (int64_t)H, kModulus); ++nl;
-    cudaMemsetAsync(d_present, 0, (size_t)n_ids, stream);
-    cudaMemsetAsync(d_counters, 0, 2 * sizeof(uint32_t), stream);      // [3] (range violation) is sticky: cleared by the owner
-    k1t_mark_kernel<<<148 * 8, 256, 0, stream>>>(d_feat + indptr0, nnz, n_ids, d_present, d_counters); ++nl;
+    if (phase != 1) { k1t_fill_kernel<<<148 * 8, 256, 0, stream>>>(d_sig, n_rows * (int64_t)H, kModulus); ++nl; }
     const int slabs = (H + 31) / 32;
+    if (phase != 2) {
+    if (phase == 1) {
+        cudaMemsetAsync(d_present, 1, (size_t)n_ids, stream);
+    } else {
+        cudaMemsetAsync(d_present, 0, (size_t)n_ids, stream);
+    }
+    cudaMemsetAsync(d_counters, 0, 2 * sizeof(uint32_t), stream);      // [3] (range violation) is sticky: cleared by the owner
+    if (phase == 0) { k1t_mark_kernel<<<148 * 8, 256, 0, stream>>>(d_feat + indptr0, nnz, n_ids, d_present, d_counters); ++nl; }
     const int R = pick_R_table(slabs);
     const int units = (slabs + R - 1) / R;
     int n_warps = units < K1T_MAX_WARPS ? units : K1T_MAX_WARPS;
@@ -388,18 +400,20 @@ int launch_signatures_table(int width, const int64_t* d_indptr, const uint32_t* 
     }
 #undef K1T_BUILD
     ++nl;
+    }
+    if (phase == 1) return nl;
     const int64_t cap = k1t_item_capacity(n_rows, nnz);
     K1TItem* items = reinterpret_cast<K1TItem*>(d_items);
     int* n_items = reinterpret_cast<int*>(items + cap);
     k1t_items_kernel<<<1, 1024, 0, stream>>>(d_indptr, n_rows, items, n_items); ++nl;
     if (width == 64) {
         cudaFuncSetAttribute(k1t_lookup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H * 4);
-        k1t_lookup_kernel<true><<<(unsigned)cap, 256, (size_t)H * 4, stream>>>(items, n_items, d_feat, d_slot, d_entries, d_counters, H, d_sig); ++nl;
+        k1t_lookup_kernel<true><<<(unsigned)cap, 256, (size_t)H * 4, stream>>>(items, n_items, d_feat, d_slot, d_entries, d_counters, n_ids, H, d_sig); ++nl;
         cudaFuncSetAttribute(k1t_fallback_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H * 2);
         k1t_fallback_kernel<true><<<(unsigned)n_rows, 128, (size_t)H * 2, stream>>>(d_indptr, d_feat, H, d_sig); ++nl;
     } else {
         cudaFuncSetAttribute(k1t_lookup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H * 4);
-        k1t_lookup_kernel<false><<<(unsigned)cap, 256, (size_t)H * 4, stream>>>(items, n_items, d_feat, d_slot, d_entries, d_counters, H, d_sig); ++nl;
+        k1t_lookup_kernel<false><<<(unsigned)cap, 256, (size_t)H * 4, stream>>>(items, n_items, d_feat, d_slot, d_entries, d_counters, n_ids, H, d_sig); ++nl;
         cudaFuncSetAttribute(k1t_fallback_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H * 2);
         k1t_fallback_kernel<false><<<(unsigned)n_rows, 128, (size_t)H * 2, stream>>>(d_indptr, d_feat, H, d_sig); ++nl;
     }

@@ -535,3 +535,31 @@ def test_narrow_count_upload(cuda, oracle, dtype):
     from schicexplorer_b200 import MinHash
     assert MinHash._wire_values(X.data).dtype == dtype
     assert MinHash._wire_values(X.data + 0.5).dtype == np.float32
+
+
+def test_table_prebuilt_during_upload(cuda, oracle):
+    """Host fit with the feature-range hint on a batch large enough for the automatic shared-table path: the table is
+    built for every id of the range before the ids have landed, the batch then only does lookup + fallback.
+    Signatures must equal the oracle's (sampled rows) and the data-dependent table path's (all rows)."""
+    cfg = synth.SynthConfig(7, 700)                      # 700 full-length cells: ~1e7 non-zeros, id range 7.5e6 > nnz/2 ...
+    ip, ix, dt, _ = synth.generate_csr(cfg, 0, 700, workers=8)
+    reps = 2                                             # ... so repeat the cells: 2e7 non-zeros, automatic table path
+    ipr = np.concatenate([[0]] + [ip[1:] + r * ip[-1] for r in range(reps)]).astype(np.int64)
+    ixr = np.ascontiguousarray(np.tile(ix, reps))
+    assert ipr[-1] >= 2 * cfg.chroms.nbins ** 2
+    kw = dict(REF_KWARGS)
+    h = cuda.create(n_neighbors=5, fast=True, **kw)
+    cuda.fit_csr(h, ipr, ixr, None, False)               # no hint: data-dependent table
+    sig_plain = cuda.signatures(h, 800)
+    cuda.set_feature_range(h, cfg.chroms.nbins ** 2)
+    cuda.fit_csr(h, ipr, ixr, None, False)               # hint: prebuilt full-range table
+    sig_pre = cuda.signatures(h, 800)
+    cuda.destroy(h)
+    assert np.array_equal(sig_plain, sig_pre) and np.array_equal(sig_pre[:700], sig_pre[700:])
+    rows = np.arange(0, 700, 29)
+    sub_ip = np.concatenate([[0], np.cumsum(ip[rows + 1] - ip[rows])]).astype(np.int64)
+    sub_ix = np.concatenate([ix[ip[r]:ip[r + 1]] for r in rows])
+    ho = oracle.create(n_neighbors=5, fast=True, **kw)
+    oracle.fit_csr(ho, sub_ip, sub_ix, None, False)
+    assert np.array_equal(oracle.signatures(ho, 800), sig_pre[rows])
+    oracle.destroy(ho)
