@@ -55,6 +55,13 @@ int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t ro
                                  const int64_t* d_indptr_all, const uint32_t* d_indices_all,
                                  const float* d_data_all);
 
+/* The CSR part of the database handed to schic_mh_set_database_device may still be in flight (e.g. an all-gather on
+ * another stream): `cuda_event` (a cudaEvent_t recorded behind that transfer; NULL = none) is waited for on the
+ * handle's stream right before the exact rerank touches the CSR arrays, so collision counting and the top-k select
+ * overlap the transfer. The signature part must be complete in stream order as usual. Cleared by the next
+ * schic_mh_set_database_device / fit. */
+int schic_mh_set_database_ready_event(schic_mh_handle* h, void* cuda_event);
+
 /* Run on the caller's stream (a cudaStream_t, e.g. torch's current stream) instead of the
  * handle's own. NULL selects the legacy default stream. */
 int schic_mh_set_stream(schic_mh_handle* h, void* cuda_stream);

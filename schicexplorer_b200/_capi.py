@@ -55,7 +55,7 @@ BASE_SYMBOLS = (
 # symbols only the CUDA library exports (include/schic_mh_cuda.h)
 CUDA_SYMBOLS = (
     "schic_mh_fit_csr_async", "schic_mh_fit_csr_counts", "schic_mh_set_feature_range", "schic_mh_fit_csr_device", "schic_mh_kneighbors_device", "schic_mh_signatures_device", "schic_mh_csr_device",
-    "schic_mh_set_database_device", "schic_mh_set_stream", "schic_mh_stage_ms",
+    "schic_mh_set_database_device", "schic_mh_set_database_ready_event", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free",
 )
@@ -97,6 +97,7 @@ class CApi:
         if self.is_cuda:
             L.schic_mh_fit_csr_async.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32]
             L.schic_mh_set_feature_range.argtypes = [_vp, C.c_uint64]
+            L.schic_mh_set_database_ready_event.argtypes = [_vp, _vp]
             L.schic_mh_fit_csr_counts.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32]
             L.schic_mh_fit_csr_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _i32]
             L.schic_mh_kneighbors_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
@@ -234,6 +235,11 @@ class CApi:
     def set_database_device(self, h, n_total, row0, d_sig, d_indptr=None, d_indices=None, d_data=None):
         self.check(self.lib.schic_mh_set_database_device(_vp(h), n_total, row0, _ptr(d_sig), _ptr(d_indptr),
                                                          _ptr(d_indices), _ptr(d_data)))
+
+    def set_database_ready_event(self, h, cuda_event: int):
+        """The CSR arrays given to set_database_device are complete once this cudaEvent_t has fired; the library waits
+        for it only before the exact rerank (CUDA back end)."""
+        self.check(self.lib.schic_mh_set_database_ready_event(_vp(h), _vp(cuda_event)))
 
     def set_feature_range(self, h, n_features: int):
         """Hint (CUDA back end): every feature id is < n_features (the CSR's column count); lets fit / kneighbors

@@ -96,6 +96,7 @@ struct schic_mh_handle {
     int64_t db_n = 0, db_row0 = 0;
     const uint32_t* db_sig = nullptr; const int64_t* db_indptr = nullptr;
     const uint32_t* db_feat = nullptr; const float* db_val = nullptr;
+    cudaEvent_t db_ready = nullptr;      // caller's event: the external CSR is complete once it has fired
 
     // scratch of kneighbors
     DevBuf<uint16_t> counts; DevBuf<int32_t> cand_idx, cand_cnt, cand_nv, sel_flags;
@@ -421,6 +422,7 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
         add_launches(h, schic::launch_fast_distance(h->cand_idx.p, h->cand_cnt.p, h->cand_nv.p, nq, kcand, k, H,
                                                    h->p.absolute_numbers, d_idx, d_dist, d_nv, s));
     } else {
+        if (h->ext && h->db_ready) CU_TRY(cudaStreamWaitEvent(s, h->db_ready, 0));   // external CSR still in flight?
         {
             StageTimer t(h, ST_PREP, s);     // row norms + window directory of the database (once per fit)
             ST_TRY(ensure_norms(h, db_indptr, db_feat, db_val, ndb));
@@ -562,7 +564,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
     if (!append || h->borrowed) {
         CU_TRY(cudaStreamSynchronize(h->stream));
         h->n = 0; h->nnz = 0; h->borrowed = false; h->have_val = false; h->have_hi = false;
-        h->norm_of = nullptr; h->ext = false;
+        h->norm_of = nullptr; h->ext = false; h->db_ready = nullptr;
     }
     reset_stage(h, {ST_H2D, ST_SIG});
     for (cudaEvent_t e : h->misc_ev) h->free_ev.push_back(e);
@@ -715,7 +717,7 @@ int schic_mh_fit_csr_device(schic_mh_handle* h, int64_t n_rows, int64_t nnz, con
     h->k1t_prebuilt = false;
     h->borrowed = true; h->b_indptr = d_indptr; h->b_feat = d_indices; h->b_val = d_data;
     h->have_val = d_data != nullptr; h->have_hi = false;
-    h->n = n_rows; h->nnz = nnz; h->norm_of = nullptr; h->ext = false;
+    h->n = n_rows; h->nnz = nnz; h->norm_of = nullptr; h->ext = false; h->db_ready = nullptr;
     ST_TRY(h->sig.reserve(n_rows * (int64_t)H, 0, h->stream));
     // indptr[0] of a borrowed CSR: read back one value (8 bytes) -- positions are absolute
     int64_t pos0 = 0;
@@ -769,12 +771,19 @@ int schic_mh_csr_device(schic_mh_handle* h, const int64_t** d_indptr_out, const 
 int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t row0, const uint32_t* d_sig_all,
                                  const int64_t* d_indptr_all, const uint32_t* d_indices_all, const float* d_data_all) {
     ST_TRY(check(h));
+    h->db_ready = nullptr;
     if (!d_sig_all) { h->ext = false; h->norm_of = nullptr; return SCHIC_OK; }
     if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "fit the local shard first");
     if (row0 < 0 || row0 + h->n > n_total) return fail(SCHIC_ERR_INVALID_ARG, "local rows do not fit in the database");
     h->ext = true; h->db_n = n_total; h->db_row0 = row0; h->db_sig = d_sig_all;
     h->db_indptr = d_indptr_all; h->db_feat = d_indices_all; h->db_val = d_data_all;
     h->norm_of = nullptr;
+    return SCHIC_OK;
+}
+
+int schic_mh_set_database_ready_event(schic_mh_handle* h, void* cuda_event) {
+    ST_TRY(check(h));
+    h->db_ready = (cudaEvent_t)cuda_event;
     return SCHIC_OK;
 }
 

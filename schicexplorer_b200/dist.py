@@ -254,12 +254,15 @@ class ShardedMinHash:
             sig_all = _gather_padded(sig_local, counts, self.group)
         self._keep["sig_all"] = sig_all
         ip_all = ix_all = dt_all = None
+        pending = None
         if not self.fast:
             if self.world == 1:
                 ip_all, ix_all, dt_all = self._keep["csr"]
             elif "csr_all" in self._keep:
-                torch.cuda.current_stream(self.device).wait_event(self._csr_event)
+                # the exchange may still be running: the library waits for its event right before the rerank,
+                # so K3 and the select (which only read signatures) overlap it
                 ip_all, ix_all, dt_all = self._keep["csr_all"]
+                pending = self._csr_event
             else:
                 ip_all, ix_all, dt_all = self._gather_csr()
             self._keep["csr_all"] = (ip_all, ix_all, dt_all)
@@ -267,6 +270,8 @@ class ShardedMinHash:
                                      None if ip_all is None else ip_all.data_ptr(),
                                      None if ix_all is None else ix_all.data_ptr(),
                                      None if dt_all is None else dt_all.data_ptr())
+        if pending is not None:
+            self.api.set_database_ready_event(self.h, pending.cuda_event)
 
     # -- step 3: local queries -------------------------------------------------------------------
     def kneighbors_local(self, k: int, out=None):
