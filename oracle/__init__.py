@@ -15,11 +15,19 @@ def build_oracle(force: bool = False) -> str:
     hdr = os.path.join(_HERE, "..", "include", "schic_mh.h")
     if (force or not os.path.exists(LIB_PATH)
             or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(SRC), os.path.getmtime(hdr))):
-        cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fopenmp", "-shared", "-fPIC",
-               "-o", LIB_PATH, SRC]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("oracle build failed:\n" + r.stderr)
+        # $CXX first, then the system g++ (an exotic $CXX may lack libgomp); last resort: no OpenMP (slower, same results)
+        attempts, errors = [], []
+        for cxx in dict.fromkeys([os.environ.get("CXX", "g++"), "g++"]):
+            attempts += [[cxx, "-fopenmp"], ]
+        attempts.append(["g++"])
+        for head in attempts:
+            cmd = [head[0], "-O3", "-std=c++17", *head[1:], "-shared", "-fPIC", "-o", LIB_PATH, SRC]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode == 0:
+                break
+            errors.append(" ".join(cmd) + "\n" + r.stderr)
+        else:
+            raise RuntimeError("oracle build failed:\n" + "\n".join(errors))
     return LIB_PATH
 
 
