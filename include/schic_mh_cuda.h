@@ -62,6 +62,21 @@ int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t ro
  * schic_mh_set_database_device / fit. */
 int schic_mh_set_database_ready_event(schic_mh_handle* h, void* cuda_event);
 
+/* Per-row preparation of the exact rerank (fp64 row norms, window directory), normally computed by the library for
+ * the whole database on first use. In a sharded run every rank can instead prepare its OWN rows and exchange the two
+ * small arrays:
+ *   schic_mh_rerank_windows      number of id windows for the range declared with schic_mh_set_feature_range
+ *                                (0: no hint, or the range needs the hash-table kernel -- then do not use the two below)
+ *   schic_mh_rerank_prep_rows    norms2[n_rows] (float64) and dir[n_rows, n_windows+1] (uint32) of the given CSR rows,
+ *                                queued on the handle's stream
+ *   schic_mh_set_database_prep_device   norms / directory of ALL database rows for the next kneighbors call on an
+ *                                external database (call after schic_mh_set_database_device, which clears them) */
+int schic_mh_rerank_windows(schic_mh_handle* h, int32_t* n_windows_out);
+int schic_mh_rerank_prep_rows(schic_mh_handle* h, int64_t n_rows, const int64_t* d_indptr, const uint32_t* d_indices,
+                              const float* d_data, int32_t n_windows, double* d_norm2_out, uint32_t* d_dir_out);
+int schic_mh_set_database_prep_device(schic_mh_handle* h, const double* d_norm2_all, const uint32_t* d_dir_all,
+                                      int32_t n_windows);
+
 /* Run on the caller's stream (a cudaStream_t, e.g. torch's current stream) instead of the
  * handle's own. NULL selects the legacy default stream. */
 int schic_mh_set_stream(schic_mh_handle* h, void* cuda_stream);

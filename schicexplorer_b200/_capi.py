@@ -55,7 +55,8 @@ BASE_SYMBOLS = (
 # symbols only the CUDA library exports (include/schic_mh_cuda.h)
 CUDA_SYMBOLS = (
     "schic_mh_fit_csr_async", "schic_mh_fit_csr_counts", "schic_mh_set_feature_range", "schic_mh_fit_csr_device", "schic_mh_kneighbors_device", "schic_mh_signatures_device", "schic_mh_csr_device",
-    "schic_mh_set_database_device", "schic_mh_set_database_ready_event", "schic_mh_set_stream", "schic_mh_stage_ms",
+    "schic_mh_set_database_device", "schic_mh_set_database_ready_event", "schic_mh_rerank_windows",
+    "schic_mh_rerank_prep_rows", "schic_mh_set_database_prep_device", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free",
 )
@@ -98,6 +99,9 @@ class CApi:
             L.schic_mh_fit_csr_async.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32]
             L.schic_mh_set_feature_range.argtypes = [_vp, C.c_uint64]
             L.schic_mh_set_database_ready_event.argtypes = [_vp, _vp]
+            L.schic_mh_rerank_windows.argtypes = [_vp, C.POINTER(_i32)]
+            L.schic_mh_rerank_prep_rows.argtypes = [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp]
+            L.schic_mh_set_database_prep_device.argtypes = [_vp, _vp, _vp, _i32]
             L.schic_mh_fit_csr_counts.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32]
             L.schic_mh_fit_csr_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _i32]
             L.schic_mh_kneighbors_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
@@ -240,6 +244,18 @@ class CApi:
         """The CSR arrays given to set_database_device are complete once this cudaEvent_t has fired; the library waits
         for it only before the exact rerank (CUDA back end)."""
         self.check(self.lib.schic_mh_set_database_ready_event(_vp(h), _vp(cuda_event)))
+
+    def rerank_windows(self, h) -> int:
+        n = _i32()
+        self.check(self.lib.schic_mh_rerank_windows(_vp(h), C.byref(n)))
+        return n.value
+
+    def rerank_prep_rows(self, h, n_rows, d_indptr, d_indices, d_data, n_windows, d_norm2_out, d_dir_out):
+        self.check(self.lib.schic_mh_rerank_prep_rows(_vp(h), n_rows, _ptr(d_indptr), _ptr(d_indices), _ptr(d_data),
+                                                      n_windows, _ptr(d_norm2_out), _ptr(d_dir_out)))
+
+    def set_database_prep_device(self, h, d_norm2_all, d_dir_all, n_windows):
+        self.check(self.lib.schic_mh_set_database_prep_device(_vp(h), _ptr(d_norm2_all), _ptr(d_dir_all), n_windows))
 
     def set_feature_range(self, h, n_features: int):
         """Hint (CUDA back end): every feature id is < n_features (the CSR's column count); lets fit / kneighbors

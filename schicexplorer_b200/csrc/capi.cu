@@ -97,6 +97,7 @@ struct schic_mh_handle {
     const uint32_t* db_sig = nullptr; const int64_t* db_indptr = nullptr;
     const uint32_t* db_feat = nullptr; const float* db_val = nullptr;
     cudaEvent_t db_ready = nullptr;      // caller's event: the external CSR is complete once it has fired
+    const double* ext_norm2 = nullptr; const uint32_t* ext_dir = nullptr; int ext_nw = 0;   // caller-provided rerank prep
 
     // scratch of kneighbors
     DevBuf<uint16_t> counts; DevBuf<int32_t> cand_idx, cand_cnt, cand_nv, sel_flags;
@@ -423,13 +424,15 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
                                                    h->p.absolute_numbers, d_idx, d_dist, d_nv, s));
     } else {
         if (h->ext && h->db_ready) CU_TRY(cudaStreamWaitEvent(s, h->db_ready, 0));   // external CSR still in flight?
-        {
+        const bool ext_prep = h->ext && h->ext_norm2 && h->ext_dir && h->ext_nw > 0;
+        if (!ext_prep) {
             StageTimer t(h, ST_PREP, s);     // row norms + window directory of the database (once per fit)
             ST_TRY(ensure_norms(h, db_indptr, db_feat, db_val, ndb));
         }
         StageTimer t(h, ST_RERANK, s);
-        const int nl = schic::launch_rerank(db_indptr, db_feat, db_val, 0, h->norm2.p,
-                                            h->n_windows > 0 ? h->win_dir.p : nullptr, h->n_windows, h->window_mode, row0, nq,
+        const int nl = schic::launch_rerank(db_indptr, db_feat, db_val, 0, ext_prep ? h->ext_norm2 : h->norm2.p,
+                                            ext_prep ? h->ext_dir : (h->n_windows > 0 ? h->win_dir.p : nullptr),
+                                            ext_prep ? h->ext_nw : h->n_windows, ext_prep ? 32 : h->window_mode, row0, nq,
                                             h->cand_idx.p,
                                             h->cand_nv.p, kcand, k, d_idx, d_dist, d_nv, s);
         if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k * excess_factor too large for the in-shared-memory rerank");
@@ -772,6 +775,7 @@ int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t ro
                                  const int64_t* d_indptr_all, const uint32_t* d_indices_all, const float* d_data_all) {
     ST_TRY(check(h));
     h->db_ready = nullptr;
+    h->ext_norm2 = nullptr; h->ext_dir = nullptr; h->ext_nw = 0;
     if (!d_sig_all) { h->ext = false; h->norm_of = nullptr; return SCHIC_OK; }
     if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "fit the local shard first");
     if (row0 < 0 || row0 + h->n > n_total) return fail(SCHIC_ERR_INVALID_ARG, "local rows do not fit in the database");
@@ -784,6 +788,38 @@ int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t ro
 int schic_mh_set_database_ready_event(schic_mh_handle* h, void* cuda_event) {
     ST_TRY(check(h));
     h->db_ready = (cudaEvent_t)cuda_event;
+    return SCHIC_OK;
+}
+
+int schic_mh_rerank_windows(schic_mh_handle* h, int32_t* n_windows_out) {
+    ST_TRY(check(h));
+    if (!n_windows_out) return fail(SCHIC_ERR_INVALID_ARG, "null argument");
+    *n_windows_out = 0;
+    const char* mode = getenv("SCHIC_K4_MODE");
+    if (mode && (strcmp(mode, "hash") == 0 || strcmp(mode, "window64") == 0)) return SCHIC_OK;
+    if (h->feature_range == 0 || h->feature_range > 0xFFFFFFFFull) return SCHIC_OK;
+    const int nw = schic::rerank_window_count((uint32_t)(h->feature_range - 1));
+    if (nw <= 1024) *n_windows_out = nw;
+    return SCHIC_OK;
+}
+
+int schic_mh_rerank_prep_rows(schic_mh_handle* h, int64_t n_rows, const int64_t* d_indptr, const uint32_t* d_indices,
+                              const float* d_data, int32_t n_windows, double* d_norm2_out, uint32_t* d_dir_out) {
+    ST_TRY(check(h));
+    if (n_rows < 0 || !d_indptr || !d_norm2_out || !d_dir_out || n_windows < 1) return fail(SCHIC_ERR_INVALID_ARG, "bad arguments");
+    if (n_rows > 0 && (!d_indices || !d_data)) return fail(SCHIC_ERR_INVALID_ARG, "the rerank preparation needs ids and values");
+    ST_TRY(use_device(h));
+    add_launches(h, schic::launch_row_norms(d_indptr, d_data, n_rows, 0, d_norm2_out, h->stream));
+    add_launches(h, schic::launch_row_window_dir(d_indptr, d_indices, n_rows, n_windows, d_dir_out, h->stream));
+    CU_TRY(cudaGetLastError());
+    return SCHIC_OK;
+}
+
+int schic_mh_set_database_prep_device(schic_mh_handle* h, const double* d_norm2_all, const uint32_t* d_dir_all,
+                                      int32_t n_windows) {
+    ST_TRY(check(h));
+    if (!h->ext) return fail(SCHIC_ERR_INVALID_ARG, "set the external database first");
+    h->ext_norm2 = d_norm2_all; h->ext_dir = d_dir_all; h->ext_nw = (d_norm2_all && d_dir_all) ? n_windows : 0;
     return SCHIC_OK;
 }
 

@@ -146,6 +146,12 @@ class ShardedMinHash:
         # 1 GB CSR all-gather that was issued before K1 and K3 could not start until it had finished.
         self._csr_group = None
         self._peer = None
+        # rerank preparation (row norms, window directory) on the rank that owns the rows, exchanged with the CSR:
+        # needs the feature-range hint (every rank must cut the id axis into the same windows)
+        self._nw = 0
+        if (self.world > 1 and not self.fast and device.type == "cuda" and n_features is not None
+                and hasattr(api, "rerank_windows")):
+            self._nw = api.rerank_windows(self.h)
         if self.world > 1 and not self.fast and device.type == "cuda" and group is None:
             self._csr_group = dist.new_group(backend="nccl")
             # SCHIC_CSR_EXCHANGE=p2p: copies into peer memory mapped through CUDA IPC instead of the NCCL all-gather
@@ -172,6 +178,13 @@ class ShardedMinHash:
     # -- step 1: hash the local shard (device-resident CSR) ---------------------------------
     def fit_local(self, d_indptr: torch.Tensor, d_indices: torch.Tensor, d_data):
         self._keep["csr"] = (d_indptr, d_indices, d_data)
+        self._keep.pop("prep_local", None)
+        if self._nw > 0:
+            norms = torch.empty(self.n_local, dtype=torch.float64, device=self.device)
+            wdir = torch.empty((self.n_local, self._nw + 1), dtype=torch.int32, device=self.device)
+            self.api.rerank_prep_rows(self.h, self.n_local, d_indptr.data_ptr(), d_indices.data_ptr(), d_data.data_ptr(),
+                                      self._nw, norms.data_ptr(), wdir.data_ptr())
+            self._keep["prep_local"] = (norms, wdir)
         self._start_csr_gather()
         nnz = int(d_indices.numel())
         self.api.fit_csr_device(self.h, self.n_local, nnz, d_indptr.data_ptr(), d_indices.data_ptr(),
@@ -192,6 +205,7 @@ class ShardedMinHash:
         d_ix = _wrap_device(p_ix, (nnz,), "<i4", torch.int32, self.device)
         d_dt = None if not p_dt else _wrap_device(p_dt, (nnz,), "<f4", torch.float32, self.device)
         self._keep["csr"] = (d_ip, d_ix, d_dt)
+        self._keep.pop("prep_local", None)
         if async_upload and self.world > 1 and not self.fast:
             self.api.synchronize(self.h)       # the CSR exchange reads the value array: it must have landed
         self._start_csr_gather()
@@ -223,6 +237,10 @@ class ShardedMinHash:
         torch.cumsum(lens_all, 0, out=ip_all[1:])
         if ev is not None:
             torch.cuda.current_stream(self.device).wait_event(ev)
+        self._keep.pop("prep_all", None)
+        if "prep_local" in self._keep:
+            norms, wdir = self._keep["prep_local"]
+            self._keep["prep_all"] = (_gather_padded(norms, counts, group), _gather_padded(wdir, counts, group))
         return ip_all, ix_all, dt_all
 
     def _start_csr_gather(self):
@@ -272,6 +290,9 @@ class ShardedMinHash:
                                      None if dt_all is None else dt_all.data_ptr())
         if pending is not None:
             self.api.set_database_ready_event(self.h, pending.cuda_event)
+        if not self.fast and self.world > 1 and "prep_all" in self._keep:
+            norms_all, dir_all = self._keep["prep_all"]
+            self.api.set_database_prep_device(self.h, norms_all.data_ptr(), dir_all.data_ptr(), self._nw)
 
     # -- step 3: local queries -------------------------------------------------------------------
     def kneighbors_local(self, k: int, out=None):
