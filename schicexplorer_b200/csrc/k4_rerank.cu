@@ -479,12 +479,17 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
                     }
                     if (c < ncand) load(yf, yvp, off, len);
                     float a32 = 0.f;                     // exact for integer counts: 8 products < 2^24
-                    // short last blocks (slices average ~1.7 blocks) skip the probe pairs that are all padding
+                    if (fill >= BLK) {                   // full block: all probes in one basic block (8 independent chains)
 #pragma unroll
-                    for (int g = 0; g < K4W_UNROLL / 2; ++g) {
-                        if (g == 0 || fill > 64 * g) {
-                            a32 = k4w_probe<E64>(tab, tval, f[2 * g] - lo, yv[2 * g], a32);
-                            a32 = k4w_probe<E64>(tab, tval, f[2 * g + 1] - lo, yv[2 * g + 1], a32);
+                        for (int u = 0; u < K4W_UNROLL; ++u) a32 = k4w_probe<E64>(tab, tval, f[u] - lo, yv[u], a32);
+                    } else {
+                        // short last blocks (slices average ~1.7 blocks) skip the probe pairs that are all padding
+#pragma unroll
+                        for (int g = 0; g < K4W_UNROLL / 2; ++g) {
+                            if (g == 0 || fill > 64 * g) {
+                                a32 = k4w_probe<E64>(tab, tval, f[2 * g] - lo, yv[2 * g], a32);
+                                a32 = k4w_probe<E64>(tab, tval, f[2 * g + 1] - lo, yv[2 * g + 1], a32);
+                            }
                         }
                     }
                     acc += (double)a32;

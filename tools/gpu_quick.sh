@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-timeout 300 python tools/sanitize_small.py > gpurun_out/san_plain.log 2>&1 && \
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 3 python tools/sanitize_small.py > gpurun_out/san_memcheck.log 2>&1
-echo "sanitizer rc=$?"; tail -3 gpurun_out/san_plain.log; grep -E "ERROR SUMMARY|Invalid|out of bounds|sanitize_small" gpurun_out/san_memcheck.log | head -20
+for v in 0 1; do
+  if [ $v = 1 ]; then export SCHIC_K4_VAL8=1; fi
+  timeout 300 python bench.py --steps 4 --warmup 3 --skip-e2e --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; b=json.loads(sys.stdin.read()); print('val8=$v', b['ms_per_step'], b['stage_ms']['rerank'], b['stage_ms']['rerank_prep'])"
+done
