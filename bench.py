@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cells", type=int, default=None, help="override the number of cells (debug)")
     ap.add_argument("--hashes", type=int, default=800)
     ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--hash-width", type=int, default=32, choices=[32, 64],
+                    help="HashSpec of SURVEY 8(c) rule 2: evaluate the mix in uint32 (default) or uint64 before the modulo")
     ap.add_argument("--fast", type=int, default=None, help="1: collision distances, 0: exact rerank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: device-resident leg alone")
@@ -62,7 +64,8 @@ def workload(args):
         cfg = synth.SynthConfig(**{**cfg.__dict__, "n_cells": args.cells})
     fast = args.fast if args.fast is not None else (0 if args.workload == "s10" else 1)
     kw = dict(n_neighbors=args.k, number_of_hash_functions=args.hashes, fast=bool(fast),
-              minimal_blocks_in_common=100, excess_factor=1, max_bin_size=100000, shingle_size=5)
+              minimal_blocks_in_common=100, excess_factor=1, max_bin_size=100000, shingle_size=5,
+              hash_width=args.hash_width)
     return cfg, kw
 
 
@@ -364,6 +367,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": args.workload, "n_cells": n_total, "n_hash": H, "k": k, "fast": int(fast),
+                       "hash_width": args.hash_width,
                        "nnz_total": int(nnz_all.item()), "sharding": f"cells/{world}",
                        "l2": "inputs (CSR %.2f GB/rank) larger than L2" % (h2d / 1e9)},
             "stage_ms": stage, "gpu_launches": int(n_launch.item()), "clocks": clocks,
