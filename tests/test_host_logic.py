@@ -133,3 +133,18 @@ def test_empty_cell_keeps_its_row(fixture20):
     empty = loader.CellPixels("/cells/empty", np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0))
     X, names = loader.cells_to_csr([cells[1], empty, cells[2]], chroms)
     assert X.shape[0] == 3 and X[1].nnz == 0 and names[1] == "/cells/empty"
+
+
+def test_wire_values_pick_the_narrowest_exact_format():
+    """MinHash._wire_values: integer contact counts cross the C ABI as uint8 / uint16, everything else as float32."""
+    from schicexplorer_b200 import MinHash
+    w = MinHash._wire_values
+    assert w(np.array([1.0, 2.0, 255.0])).dtype == np.uint8
+    assert w(np.array([1.0, 2.0, 256.0])).dtype == np.uint16
+    assert w(np.array([0, 7, 65535], dtype=np.int64)).dtype == np.uint16
+    assert w(np.array([1.0, 65536.0])).dtype == np.float32
+    assert w(np.array([1.0, 2.5])).dtype == np.float32
+    assert w(np.array([-1.0, 2.0])).dtype == np.float32
+    assert w(np.array([1.0, np.nan])).dtype == np.float32
+    assert w(np.array([], dtype=np.float64)).dtype == np.float32
+    assert np.array_equal(w(np.array([3.0, 4.0])), [3, 4])
