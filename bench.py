@@ -42,7 +42,7 @@ INT_OPS_PER_EVAL = 15      # algorithmic int32 ops per hash eval
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="s10", choices=["s10", "nagano", "s50", "sweep"])
