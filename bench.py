@@ -150,7 +150,8 @@ def run_reference(args):
     ora = oracle_api()
     cores = os.cpu_count() or 1
     ip, ix, dt, _ = synth.generate_csr(cfg)
-    m = pick_sample(ora, kw, args.k, ip, ix, dt, budget_s=25.0)
+    # the whole arm (warm-up + K steps) stays within a few minutes: ~150 s of CPU work in total
+    m = pick_sample(ora, kw, args.k, ip, ix, dt, budget_s=min(25.0, 150.0 / (args.steps + min(args.warmup, 1))))
     for _ in range(max(0, min(args.warmup, 1))):
         oracle_step(ora, kw, args.k, ip, ix, dt, m)
     times = [oracle_step(ora, kw, args.k, ip, ix, dt, m) for _ in range(args.steps)]
