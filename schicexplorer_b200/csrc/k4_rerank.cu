@@ -58,6 +58,39 @@ int launch_widen_counts(const void* d_src, int bits, int64_t n, float* d_dst, cu
     return 1;
 }
 
+// ||x - y||^2 of two sorted sparse rows by a plain two-pointer merge in fp64, term by term (the way the oracle and
+// the reference's CPU path do it). The kernels below use ||x||^2 + ||y||^2 - 2 x.y, which is exact for integer
+// counts but cancels for (near-)identical rows with non-integer values (fp32 products: absolute error ~1e-7 of the
+// norms); a pair whose distance comes out below 10 % of the norm scale is redone with this function by the thread
+// that owns it -- rare (duplicates, near-duplicates), and then identical rows give exactly 0.
+__device__ __noinline__ double exact_sqdist_merge(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat,
+                                                  const float* __restrict__ val, int64_t ra, int64_t rb) {
+    int64_t i = indptr[ra], j = indptr[rb];
+    const int64_t ie = indptr[ra + 1], je = indptr[rb + 1];
+    double acc = 0.0;
+    while (i < ie && j < je) {
+        const uint32_t fa = __ldg(feat + i), fb = __ldg(feat + j);
+        double t;
+        if (fa == fb) { t = (double)__ldg(val + i) - (double)__ldg(val + j); ++i; ++j; }
+        else if (fa < fb) { t = (double)__ldg(val + i); ++i; }
+        else { t = (double)__ldg(val + j); ++j; }
+        acc += t * t;
+    }
+    for (; i < ie; ++i) { const double t = (double)__ldg(val + i); acc += t * t; }
+    for (; j < je; ++j) { const double t = (double)__ldg(val + j); acc += t * t; }
+    return acc;
+}
+
+// d^2 from the norms and the dot product; pairs that cancel are redone exactly (see exact_sqdist_merge)
+__device__ __forceinline__ double k4_sqdist(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat,
+                                            const float* __restrict__ val, double nq2, double nd2, double xy,
+                                            int64_t qrow, int64_t d) {
+    if (d == qrow) return 0.0;
+    double d2 = nq2 + nd2 - 2.0 * xy;
+    if (d2 < 1e-2 * (nq2 + nd2)) d2 = exact_sqdist_merge(indptr, feat, val, qrow, d);
+    return d2 < 0.0 ? 0.0 : d2;
+}
+
 __device__ __forceinline__ uint32_t k4_bucket(uint32_t f) { return (f * 2654435761u) >> (32 - K4_BUCKET_BITS); }
 
 // first position in [b, e) whose feature is >= key (plain binary search, one thread)
@@ -214,8 +247,7 @@ k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict_
                 if (ye > yb && __ldg(feat + ye - 1) == K4_EMPTY)
                     xy += (double)__ldg(val + xe - 1) * (double)__ldg(val + ye - 1);
             }
-            double d2 = nq2 + norm2[d] - 2.0 * xy;
-            if (d2 < 0.0 || (int64_t)d == qrow) d2 = 0.0;
+            const double d2 = k4_sqdist(indptr, feat, val, nq2, norm2[d], xy, qrow, d);
             const float dist = (float)sqrt(d2);
             key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)(uint32_t)d;
         }
@@ -517,8 +549,7 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
         unsigned long long key = ~0ull;
         if (c < ncand) {
             const int32_t d = cand[c];
-            double d2 = nq2 + norm2[d] - 2.0 * dot[c];
-            if (d2 < 0.0 || (int64_t)d == qrow) d2 = 0.0;
+            const double d2 = k4_sqdist(indptr, feat, val, nq2, norm2[d], dot[c], qrow, d);
             const float dist = (float)sqrt(d2);
             key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)(uint32_t)d;
         }

@@ -1,0 +1,83 @@
+"""GPU suite (-m gpu): seeded random small cases, every kernel implementation against the oracle.
+
+Rows are drawn to hit the awkward spots: ids right at the borders of the rerank's 2^19-id windows and of the 16-id
+table entries, ids 0 and 2^32-1, empty / single-element rows, duplicated rows (ties everywhere), H not a multiple of
+32 or 2, k larger than the number of rows, thresholds that exclude everything. Bit-exact signatures, counts and
+neighbour indices; 1e-5 relative distances."""
+import os
+
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+
+from conftest import Fitted
+from test_gpu_parity import RTOL, assert_neighbours_equal_up_to_ties
+
+pytestmark = pytest.mark.gpu
+
+K1 = ["auto", "table", "tile", "direct", "chunk"]
+K3 = ["packed", "plain"]
+K4 = ["window", "hash"]
+
+
+def random_case(rng):
+    n = int(rng.integers(1, 48))
+    wide = rng.random() < 0.3                       # ids over the full 32-bit range (hash-table K4, filtered K1)
+    ncols = 2 ** 32 if wide else int(rng.choice([1 << 20, 2744 * 2744, (1 << 21) + 5]))
+    pool_size = int(rng.integers(8, 4000))
+    anchors = np.array([0, 15, 16, 17, (1 << 19) - 1, 1 << 19, (1 << 19) + 1, (1 << 20) - 1, ncols - 1, ncols - 2])
+    anchors = anchors[anchors < ncols]
+    pool = np.unique(np.concatenate([rng.integers(0, ncols, size=pool_size, dtype=np.uint64).astype(np.int64), anchors]))
+    rows, cols, vals = [], [], []
+    for r in range(n):
+        kind = rng.random()
+        if kind < 0.08:
+            continue                                # empty row
+        if kind < 0.16 and r > 0 and rows:          # duplicate of the previous non-empty row
+            m = rows[-1] == rows[-1][0]
+            rows.append(np.full(int(m.sum()), r)); cols.append(cols[-1].copy()); vals.append(vals[-1].copy())
+            continue
+        m = 1 if kind < 0.24 else int(rng.integers(1, min(len(pool), 6000) + 1))
+        c = np.sort(rng.choice(pool, size=m, replace=False))
+        rows.append(np.full(m, r)); cols.append(c)
+        vals.append(rng.integers(1, 300, size=m).astype(np.float64) if rng.random() < 0.7 else rng.random(m) * 9 + 0.1)
+    if not rows:
+        rows, cols, vals = [np.zeros(1, dtype=int)], [np.array([pool[0]])], [np.ones(1)]
+    X = csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, ncols))
+    X.sort_indices()
+    if wide:
+        X.indices = X.indices.astype(np.int64)
+    H = int(rng.choice([1, 2, 31, 33, 64, 96, 127, 255, 300]))
+    kw = dict(number_of_hash_functions=H, minimal_blocks_in_common=int(rng.choice([1, 1, 2, H // 2 + 1, H + 1])),
+              excess_factor=int(rng.choice([1, 1, 2, 5])), max_bin_size=int(rng.choice([100000, 100000, 3, n + 1])),
+              fast=bool(rng.random() < 0.4), n_neighbors=int(rng.integers(1, n + 6)))
+    return X, kw
+
+
+@pytest.mark.parametrize("seed", range(36))
+def test_random_case_all_implementations(cuda, oracle, monkeypatch, seed):
+    rng = np.random.default_rng(1000 + seed)
+    X, kw = random_case(rng)
+    k = kw["n_neighbors"]
+    with Fitted(oracle, X, **kw) as o:
+        want_sig, want_cnt = o.sig(), oracle.collision_counts(o.h)
+        want = oracle.kneighbors(o.h, k)
+        want_graph = oracle.kneighbors_graph(o.h, k)
+    modes = [(K1[seed % 5], K3[seed % 2], K4[(seed // 2) % 2]), ("auto", "packed", "window")]
+    for k1, k3, k4 in modes:
+        monkeypatch.setenv("SCHIC_K1_MODE", k1)
+        monkeypatch.setenv("SCHIC_K3_MODE", k3)
+        monkeypatch.setenv("SCHIC_K4_MODE", k4)
+        with Fitted(cuda, X, **kw) as g:
+            if seed % 3 == 0:
+                cuda.set_feature_range(g.h, X.shape[1])
+                data = None if kw["fast"] else X.data.astype(np.float32)
+                cuda.fit_csr(g.h, X.indptr, X.indices, data, False)
+            assert np.array_equal(g.sig(), want_sig), (k1, k3, k4)
+            assert np.array_equal(cuda.collision_counts(g.h), want_cnt), (k1, k3, k4)
+            got = cuda.kneighbors(g.h, k)
+            assert_neighbours_equal_up_to_ties(*got, *want, 0 if kw["fast"] else RTOL)
+            gi, gc, gd = cuda.kneighbors_graph(g.h, k)
+            assert np.array_equal(gi, want_graph[0])
+            if kw["fast"]:
+                assert np.array_equal(gc, want_graph[1]) and np.array_equal(gd, want_graph[2])
