@@ -54,7 +54,7 @@ def random_case(rng):
     return X, kw
 
 
-@pytest.mark.parametrize("seed", range(36))
+@pytest.mark.parametrize("seed", range(120))
 def test_random_case_all_implementations(cuda, oracle, monkeypatch, seed):
     rng = np.random.default_rng(1000 + seed)
     X, kw = random_case(rng)
@@ -69,10 +69,15 @@ def test_random_case_all_implementations(cuda, oracle, monkeypatch, seed):
         monkeypatch.setenv("SCHIC_K3_MODE", k3)
         monkeypatch.setenv("SCHIC_K4_MODE", k4)
         with Fitted(cuda, X, **kw) as g:
+            data = None if kw["fast"] else X.data.astype(np.float32)
             if seed % 3 == 0:
                 cuda.set_feature_range(g.h, X.shape[1])
-                data = None if kw["fast"] else X.data.astype(np.float32)
                 cuda.fit_csr(g.h, X.indptr, X.indices, data, False)
+            if seed % 4 == 1 and X.shape[0] > 1:            # the same rows through fit + partial_fit
+                cut = X.shape[0] // 2
+                a, b = X[:cut], X[cut:]
+                cuda.fit_csr(g.h, a.indptr, a.indices, None if kw["fast"] else a.data.astype(np.float32), False)
+                cuda.fit_csr(g.h, b.indptr, b.indices, None if kw["fast"] else b.data.astype(np.float32), True)
             assert np.array_equal(g.sig(), want_sig), (k1, k3, k4)
             assert np.array_equal(cuda.collision_counts(g.h), want_cnt), (k1, k3, k4)
             got = cuda.kneighbors(g.h, k)
