@@ -378,7 +378,9 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
     const int64_t ld = (ndb + 7) & ~(int64_t)7;
     // budget: a quarter of the free HBM, at least 2 GiB, at most 32 GiB (the all-rows-in-one-block case also
     // lets K3 use the symmetry of the counts)
-    if (h->count_budget == 0) {
+    if (const char* forced = getenv("SCHIC_COUNT_BUDGET")) {     // tests: force several query blocks on small inputs
+        h->count_budget = std::max<int64_t>(1, atoll(forced));
+    } else if (h->count_budget == 0) {
         size_t free_b = 0, total_b = 0;
         h->count_budget = (int64_t)1 << 30;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
@@ -386,7 +388,8 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
         else
             cudaGetLastError();
     }
-    const int64_t budget_elems = std::max<int64_t>(h->count_budget, h->counts.cap);   // never below what is already held
+    const int64_t budget_elems = getenv("SCHIC_COUNT_BUDGET") ? h->count_budget
+                                                              : std::max<int64_t>(h->count_budget, h->counts.cap);   // never below what is already held
     int64_t qb = std::max<int64_t>(128, budget_elems / ld);
     qb = std::min<int64_t>((qb / 128) * 128, (nq + 127) / 128 * 128);
     ST_TRY(h->counts.reserve(qb * ld, 0, s));
@@ -578,37 +581,49 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
     const int64_t r0 = h->n, pos0 = h->nnz;
     const bool want_val = data != nullptr;
     if (r0 > 0 && want_val != h->have_val) return fail(SCHIC_ERR_INVALID_ARG, "partial_fit must be consistent about data");
-    const bool want_hi = index_bits == 64 && h->p.hash_width == 64;
     cudaStream_t s = h->stream, cs = h->copy_stream;
 
-    ST_TRY(h->indptr.reserve(r0 + n_rows + 1, r0 + 1, s));
-    ST_TRY(h->feat.reserve(pos0 + nnz, pos0, s));
-    if (want_val) ST_TRY(h->val.reserve(pos0 + nnz, pos0, s));
-    if (want_hi) ST_TRY(h->feat_hi.reserve(pos0 + nnz, pos0, s));
-    ST_TRY(h->sig.reserve((r0 + n_rows) * (int64_t)H, r0 * (int64_t)H, s));
-
-    // rebased indptr (absolute positions in the device store)
-    std::vector<int64_t> ip(n_rows + 1);
-    for (int64_t r = 0; r <= n_rows; ++r) ip[r] = pos0 + (indptr[r] - indptr[0]);
-    // 32-bit feature ids (width 32 hashes (uint32)(f+1), so truncation is exact there)
+    // 32-bit feature ids (width 32 hashes (uint32)(f+1), so truncation is exact there); the width-64 hash also needs
+    // the high words, but only when some id really is >= 2^32 -- 64-bit arrays of small ids stay on the 32-bit paths
     const uint32_t* f32 = nullptr;
     std::vector<uint32_t>& lo = h->host_lo;
     std::vector<uint32_t>& hi = h->host_hi;
+    bool any_hi = false;
     if (index_bits == 32) {
         f32 = (const uint32_t*)indices + indptr[0];
     } else {
         const uint64_t* f64 = (const uint64_t*)indices + indptr[0];
         lo.resize(nnz);
-        if (want_hi) hi.resize(nnz);
-        bool any_hi = false;
         for (int64_t e = 0; e < nnz; ++e) {
             lo[e] = (uint32_t)f64[e];
-            if (want_hi) hi[e] = (uint32_t)(f64[e] >> 32);
             any_hi = any_hi || (f64[e] >> 32) != 0;
         }
         if (any_hi && !h->p.fast) return fail(SCHIC_ERR_UNSUPPORTED, "exact rerank supports feature ids < 2^32 only");
         f32 = lo.data();
     }
+    // high words are kept from the first batch that needs them on (earlier batches are back-filled with zeros)
+    const bool want_hi = h->p.hash_width == 64 && (any_hi || (r0 > 0 && h->have_hi));
+    if (want_hi) {
+        hi.assign(nnz, 0u);
+        if (any_hi) {
+            const uint64_t* f64 = (const uint64_t*)indices + indptr[0];
+            for (int64_t e = 0; e < nnz; ++e) hi[e] = (uint32_t)(f64[e] >> 32);
+        }
+    }
+
+    ST_TRY(h->indptr.reserve(r0 + n_rows + 1, r0 + 1, s));
+    ST_TRY(h->feat.reserve(pos0 + nnz, pos0, s));
+    if (want_val) ST_TRY(h->val.reserve(pos0 + nnz, pos0, s));
+    if (want_hi) {
+        const bool backfill = r0 > 0 && !h->have_hi;
+        ST_TRY(h->feat_hi.reserve(pos0 + nnz, backfill ? 0 : pos0, s));
+        if (backfill && pos0 > 0) CU_TRY(cudaMemsetAsync(h->feat_hi.p, 0, (size_t)pos0 * sizeof(uint32_t), s));
+    }
+    ST_TRY(h->sig.reserve((r0 + n_rows) * (int64_t)H, r0 * (int64_t)H, s));
+
+    // rebased indptr (absolute positions in the device store)
+    std::vector<int64_t> ip(n_rows + 1);
+    for (int64_t r = 0; r <= n_rows; ++r) ip[r] = pos0 + (indptr[r] - indptr[0]);
 
     cudaEvent_t up0 = get_event(h), up1 = get_event(h);
     if (up0) cudaEventRecord(up0, cs);

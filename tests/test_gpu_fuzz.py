@@ -50,7 +50,8 @@ def random_case(rng):
     H = int(rng.choice([1, 2, 31, 33, 64, 96, 127, 255, 300]))
     kw = dict(number_of_hash_functions=H, minimal_blocks_in_common=int(rng.choice([1, 1, 2, H // 2 + 1, H + 1])),
               excess_factor=int(rng.choice([1, 1, 2, 5])), max_bin_size=int(rng.choice([100000, 100000, 3, n + 1])),
-              fast=bool(rng.random() < 0.4), n_neighbors=int(rng.integers(1, n + 6)))
+              fast=bool(rng.random() < 0.4), n_neighbors=int(rng.integers(1, n + 6)),
+              hash_width=int(rng.choice([32, 32, 64])), absolute_numbers=bool(rng.random() < 0.2))
     return X, kw
 
 
@@ -86,3 +87,63 @@ def test_random_case_all_implementations(cuda, oracle, monkeypatch, seed):
             assert np.array_equal(gi, want_graph[0])
             if kw["fast"]:
                 assert np.array_equal(gc, want_graph[1]) and np.array_equal(gd, want_graph[2])
+
+
+@pytest.mark.parametrize("H", [4094, 4095, 4096, 5003])
+def test_hash_counts_around_the_packed_and_histogram_limits(cuda, oracle, H):
+    """H = 4094 is the last hash count of the packed K3 (fp16 counters), 4095 the last of the single-histogram select;
+    above them the 32-bit compare kernel and the two-level radix select take over."""
+    rng = np.random.default_rng(H)
+    X, kw = random_case(rng)
+    kw.update(number_of_hash_functions=H, minimal_blocks_in_common=1, hash_width=32, fast=True, max_bin_size=100000)
+    k = kw["n_neighbors"]
+    with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
+        assert np.array_equal(g.sig(), o.sig())
+        assert np.array_equal(cuda.collision_counts(g.h), oracle.collision_counts(o.h))
+        a, b = cuda.kneighbors(g.h, k), oracle.kneighbors(o.h, k)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("fast", [True, False])
+def test_several_query_blocks(cuda, oracle, monkeypatch, fast):
+    """The count matrix is produced in query blocks when it exceeds the memory budget (n beyond ~100 k cells); here the
+    budget is forced down so that 300 cells need three blocks: non-symmetric K3 per block, select / rerank offsets."""
+    from schicexplorer_b200 import synth
+    cfg = synth.small_config(300, config_id=51)
+    ip, ix, dt, _ = synth.generate_csr(cfg, workers=1)
+    X = synth.to_scipy(cfg, ip, ix, dt)
+    monkeypatch.setenv("SCHIC_COUNT_BUDGET", str(128 * 304))
+    kw = dict(fast=fast, n_neighbors=17, number_of_hash_functions=200, minimal_blocks_in_common=10)
+    with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
+        a, b = cuda.kneighbors(g.h, 17), oracle.kneighbors(o.h, 17)
+        assert_neighbours_equal_up_to_ties(*a, *b, 0 if fast else RTOL)
+        assert np.array_equal(cuda.collision_counts(g.h), oracle.collision_counts(o.h))
+
+
+@pytest.mark.parametrize("width", [32, 64])
+def test_ids_beyond_32_bits(cuda, oracle, width):
+    """Feature ids >= 2^32 (10 kb resolution: bins^2 ~ 7e10): the width-32 hash uses the low word, the width-64 hash
+    both words. Includes partial_fit where only the second batch has large ids (high words are back-filled)."""
+    rng = np.random.default_rng(width)
+    ncols = 1 << 40
+    small = np.unique(rng.integers(0, 1 << 31, size=400))
+    large = np.unique(rng.integers(1 << 32, ncols, size=400))
+    rows, cols = [], []
+    for r in range(30):
+        pool = small if r < 12 else np.concatenate([small, large])
+        c = np.sort(rng.choice(pool, size=int(rng.integers(1, 300)), replace=False))
+        rows.append(np.full(len(c), r)); cols.append(c)
+    X = csr_matrix((np.ones(sum(len(c) for c in cols)), (np.concatenate(rows), np.concatenate(cols))), shape=(30, ncols))
+    X.indices = X.indices.astype(np.int64)
+    X.indptr = X.indptr.astype(np.int64)
+    kw = dict(number_of_hash_functions=96, minimal_blocks_in_common=1, hash_width=width, fast=True, n_neighbors=9)
+    with Fitted(oracle, X, **kw) as o:
+        want_sig, want = o.sig(), oracle.kneighbors(o.h, 9)
+    with Fitted(cuda, X, **kw) as g:
+        assert np.array_equal(g.sig(), want_sig)
+        got = cuda.kneighbors(g.h, 9)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want))
+        a, b = X[:12], X[12:]
+        cuda.fit_csr(g.h, a.indptr, a.indices, None, False)          # small ids only
+        cuda.fit_csr(g.h, b.indptr, b.indices, None, True)           # large ids appear: back-fill
+        assert np.array_equal(g.sig(), want_sig)
