@@ -147,3 +147,57 @@ def test_ids_beyond_32_bits(cuda, oracle, width):
         cuda.fit_csr(g.h, a.indptr, a.indices, None, False)          # small ids only
         cuda.fit_csr(g.h, b.indptr, b.indices, None, True)           # large ids appear: back-fill
         assert np.array_equal(g.sig(), want_sig)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_sharded_query_path_on_one_gpu(cuda, oracle, seed):
+    """The multi-GPU query path emulated on one device: random contiguous shards, one handle per shard; the 'gathered'
+    database (signatures, CSR) is handed back to every handle together with the rerank preparation computed shard by
+    shard by its owner (schic_mh_rerank_prep_rows -> schic_mh_set_database_prep_device) and a ready event
+    (schic_mh_set_database_ready_event). Every shard must answer exactly like the single-handle build."""
+    import torch
+    from schicexplorer_b200 import synth
+    rng = np.random.default_rng(77 + seed)
+    n = int(rng.integers(60, 260))
+    cfg = synth.small_config(n, config_id=60 + seed)
+    ip, ix, dt, _ = synth.generate_csr(cfg, workers=1)
+    X = synth.to_scipy(cfg, ip, ix, dt)
+    dev = torch.device("cuda:0")
+    k, H = int(rng.integers(3, 30)), 160
+    kw = dict(n_neighbors=k, number_of_hash_functions=H, fast=False, minimal_blocks_in_common=20, excess_factor=int(rng.choice([1, 2])),
+              max_bin_size=100000)
+    with Fitted(oracle, X, **kw) as o:
+        ref = oracle.kneighbors(o.h, k)
+    cuts = sorted(set([0, n] + rng.integers(1, n, size=int(rng.integers(1, 4))).tolist()))
+    d_ip = torch.from_numpy(ip).to(dev)
+    d_ix = torch.from_numpy(ix.view(np.int32)).to(dev)
+    d_dt = torch.from_numpy(dt).to(dev)
+    sig_all = torch.empty((n, H), dtype=torch.int32, device=dev)
+    handles, nw = [], None
+    norms_all = torch.empty(n, dtype=torch.float64, device=dev)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        h = cuda.create(device=0, **kw)
+        cuda.set_stream(h, torch.cuda.current_stream().cuda_stream)
+        cuda.set_feature_range(h, X.shape[1])
+        sub_ip = (d_ip[a:b + 1] - d_ip[a]).contiguous()
+        lo, hi = int(ip[a]), int(ip[b])
+        cuda.fit_csr_device(h, b - a, hi - lo, sub_ip.data_ptr(), d_ix[lo:hi].data_ptr(), d_dt[lo:hi].data_ptr(), False)
+        p, cnt = cuda.signatures_device(h)
+        torch.cuda.synchronize()
+        sig_all[a:b] = torch.from_numpy(cuda.signatures(h, H).view(np.int32)).to(dev)
+        if nw is None:
+            nw = cuda.rerank_windows(h)
+            assert nw > 0
+            dir_all = torch.empty((n, nw + 1), dtype=torch.int32, device=dev)
+        cuda.rerank_prep_rows(h, b - a, sub_ip.data_ptr(), d_ix[lo:hi].data_ptr(), d_dt[lo:hi].data_ptr(), nw,
+                              norms_all[a:b].data_ptr(), dir_all[a:b].data_ptr())
+        handles.append((a, b, h, sub_ip))
+    ev = torch.cuda.Event()
+    ev.record()
+    for a, b, h, _ in handles:
+        cuda.set_database_device(h, n, a, sig_all.data_ptr(), d_ip.data_ptr(), d_ix.data_ptr(), d_dt.data_ptr())
+        cuda.set_database_ready_event(h, ev.cuda_event)
+        cuda.set_database_prep_device(h, norms_all.data_ptr(), dir_all.data_ptr(), nw)
+        idx, dist, nv = cuda.kneighbors(h, k, n_rows=b - a)
+        assert_neighbours_equal_up_to_ties(idx, dist, nv, ref[0][a:b], ref[1][a:b], ref[2][a:b], RTOL)
+        cuda.destroy(h)
