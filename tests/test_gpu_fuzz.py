@@ -201,3 +201,35 @@ def test_sharded_query_path_on_one_gpu(cuda, oracle, seed):
         idx, dist, nv = cuda.kneighbors(h, k, n_rows=b - a)
         assert_neighbours_equal_up_to_ties(idx, dist, nv, ref[0][a:b], ref[1][a:b], ref[2][a:b], RTOL)
         cuda.destroy(h)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_python_classes_chunked_fit(cuda, seed):
+    """The reference-facing classes: MinHashClustering.fit with a random pSaveMemory share (fit + partial_fit in
+    chunks, scHicClusterMinHash.py:350-353 / :406) gives the same kNN graph as one fit; values that are integer counts
+    and values that are not (different wire formats) both go through."""
+    from sklearn.cluster import KMeans
+    from schicexplorer_b200 import MinHash, MinHashClustering, synth
+    rng = np.random.default_rng(300 + seed)
+    n = int(rng.integers(24, 90))
+    cfg = synth.small_config(n, config_id=80 + seed)
+    ip, ix, dt, _ = synth.generate_csr(cfg, workers=1)
+    X = synth.to_scipy(cfg, ip, ix, dt)
+    if seed % 2:
+        X.data = X.data * 0.37 + 0.01                       # not integer: float32 wire format
+    fast = bool(seed % 3)
+    kw = dict(n_neighbors=int(rng.integers(2, n)), number_of_hash_functions=int(rng.choice([64, 200, 800])), fast=fast,
+              minimal_blocks_in_common=5, excess_factor=1, max_bin_size=100000, shingle_size=5, number_of_cores=2)
+    one = MinHash(**kw)
+    one.fit(X)
+    g1 = one.kneighbors_graph(mode="distance")
+    share = float(rng.choice([0.1, 0.25, 0.34, 0.5, 0.99]))
+    mhc = MinHashClustering(minHashObject=MinHash(**kw), clusteringObject=KMeans(n_clusters=2, n_init=2, random_state=0))
+    mhc.fit(X=X, pSaveMemory=share, pPca=False, pPcaDimensions=10, pUmap=False, pUmapDict={})
+    g2 = mhc._minHashObject.kneighbors_graph(mode="distance")
+    assert np.array_equal(g1.indptr, g2.indptr) and np.array_equal(g1.indices, g2.indices)
+    np.testing.assert_allclose(g1.data, g2.data, rtol=0 if fast else 1e-6)
+    assert len(mhc.predict(mhc._precomputed_graph)) == n
+    conn = one.kneighbors_graph(mode="connectivity")
+    assert np.array_equal(conn.indices, g1.indices) and (conn.data == 1).all()
+    one.close(); mhc._minHashObject.close()
