@@ -233,3 +233,34 @@ def test_python_classes_chunked_fit(cuda, seed):
     conn = one.kneighbors_graph(mode="connectivity")
     assert np.array_equal(conn.indices, g1.indices) and (conn.data == 1).all()
     one.close(); mhc._minHashObject.close()
+
+
+@pytest.mark.parametrize("H,hint", [(160, False), (160, True), (1500, True), (33, False)])
+def test_medium_batches_take_the_table_path_on_their_own(cuda, oracle, H, hint):
+    """Batches big enough (>= 2 M non-zeros, id range <= nnz / 2) choose the shared-table K1 without being told;
+    with the feature-range hint the host fit pre-builds the table for every id while the ids upload. H = 1500 with
+    6 000 non-zeros per row pushes tau down to 8 (more fallbacks), H = 33 is an odd padded unit."""
+    rng = np.random.default_rng(H + int(hint))
+    n, ncols = 420, 1 << 20
+    rows, cols = [], []
+    pool = rng.choice(ncols, size=60000, replace=False)
+    for r in range(n):
+        m = int(rng.integers(4000, 8000))
+        c = np.sort(rng.choice(pool, size=m, replace=False))
+        rows.append(np.full(m, r)); cols.append(c)
+    cc = np.concatenate(cols)
+    X = csr_matrix((np.ones(len(cc)), (np.concatenate(rows), cc)), shape=(n, ncols))
+    assert X.nnz >= (1 << 21) and ncols * 2 <= X.nnz
+    kw = dict(number_of_hash_functions=H, minimal_blocks_in_common=1, fast=True, n_neighbors=12)
+    with Fitted(oracle, X, **kw) as o:
+        want_sig = o.sig()
+        want = oracle.kneighbors(o.h, 12)
+    h = cuda.create(**{**kw, "max_bin_size": 100000})
+    if hint:
+        cuda.set_feature_range(h, ncols)
+    cuda.fit_csr(h, X.indptr, X.indices, None, False)
+    assert np.array_equal(cuda.signatures(h, H), want_sig)
+    got = cuda.kneighbors(h, 12)
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    assert cuda.launch_count(h) > 0
+    cuda.destroy(h)
