@@ -186,11 +186,7 @@ def run_ours(args):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         os.execv(sys.executable, cmd)
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    api = _capi.cuda_api()
+    # synthetic shard first (forks worker processes), CUDA / NCCL only afterwards
     cfg, kw = workload(args)
     n_total, H, k = cfg.n_cells, args.hashes, args.k
     bounds = partition_rows(n_total, world)
@@ -199,6 +195,11 @@ def run_ours(args):
     ip, ix, dt, _ = synth.generate_csr(cfg, lo, hi, workers=workers)
     nnz_local = int(ip[-1])
     fast = kw["fast"]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    api = _capi.cuda_api()
 
     # ---- device-resident inputs ("value") ------------------------------------------------
     d_ip = torch.from_numpy(ip).to(dev)
