@@ -224,6 +224,18 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
     int nl = -1;
     if (mode == K1_CHUNK && h->p.hash_width == 32) {
         nl = schic::launch_signatures32(h->d_indptr() + r0, h->d_feat(), n_rows, nnz, pos0, H, sig, s);
+    } else if (h->k1t_prebuilt) {
+        // the batch's table (every id of the hinted range) is already built: any row range of the batch only needs
+        // lookup + fallback, so the chunks are hashed as they land
+        const uint32_t max_id = (uint32_t)(h->feature_range - 1);
+        const size_t need = schic::k1t_items_bytes(n_rows, nnz);
+        if ((int64_t)need > h->k1_scratch.cap) {
+            CU_TRY(cudaStreamSynchronize(s));      // an earlier chunk's kernels may still read the old scratch
+            ST_TRY(h->k1_scratch.reserve((int64_t)need, 0, s));
+        }
+        nl = schic::launch_signatures_table(h->p.hash_width, h->d_indptr() + r0, h->d_feat(), n_rows, nnz, pos0, max_id, H, sig,
+                                            h->k1t_present.p, reinterpret_cast<uint2*>(h->k1t_slot.p), h->k1t_entries.p,
+                                            (size_t)h->k1t_entries.cap, h->k1t_counters.p, h->k1_scratch.p, 2, s);
     } else {
         if (k1_table_candidate(h, n_rows, nnz)) {
             // the id range decides: from the caller's hint, else the largest id of the batch is read back
@@ -245,9 +257,7 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
                 ST_TRY(h->k1_scratch.reserve((int64_t)schic::k1t_items_bytes(n_rows, nnz), 0, s));
                 nl = schic::launch_signatures_table(h->p.hash_width, h->d_indptr() + r0, h->d_feat(), n_rows, nnz, pos0, max_id, H, sig,
                                                       h->k1t_present.p, reinterpret_cast<uint2*>(h->k1t_slot.p),
-                                                      h->k1t_entries.p, ecap, h->k1t_counters.p, h->k1_scratch.p,
-                                                      h->k1t_prebuilt ? 2 : 0, s);
-                h->k1t_prebuilt = false;      // valid for exactly this batch
+                                                      h->k1t_entries.p, ecap, h->k1t_counters.p, h->k1_scratch.p, 0, s);
             }
         }
         if (nl < 0 && h->p.hash_width == 64) {
@@ -665,7 +675,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
         h->k1t_prebuilt = true;
     }
     while (c0 < n_rows) {
-        const int64_t kChunkNnz = whole_batch ? INT64_MAX : (int64_t)(c0 == 0 ? 8 : 32) << 20;
+        const int64_t kChunkNnz = (whole_batch && !h->k1t_prebuilt) ? INT64_MAX : (int64_t)(c0 == 0 ? 8 : 32) << 20;
         int64_t c1 = c0 + 1;
         while (c1 < n_rows && (ip[c1 + 1] - ip[c0]) <= kChunkNnz) ++c1;
         const int64_t a = ip[c0] - pos0, b = ip[c1] - pos0;
@@ -688,6 +698,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
         ST_TRY(hash_rows(h, r0 + c0, r0 + c1, ip[c0], ip[c1], s));
         c0 = c1;
     }
+    h->k1t_prebuilt = false;      // valid for exactly this batch
     cudaEvent_t sig1 = get_event(h);
     if (sig_started && sig1) { cudaEventRecord(sig1, s); h->ev[ST_SIG].push_back({sig0, sig1}); }
     if (want_val && nnz > 0 && !val_enqueued) ST_TRY(upload_values(h, data, data_kind, vbytes, indptr[0], pos0, nnz, cs));
