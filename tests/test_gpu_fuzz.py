@@ -264,3 +264,20 @@ def test_medium_batches_take_the_table_path_on_their_own(cuda, oracle, H, hint):
     assert all(np.array_equal(a, b) for a, b in zip(got, want))
     assert cuda.launch_count(h) > 0
     cuda.destroy(h)
+
+
+def test_more_rows_than_the_packed_k3_takes(cuda, oracle):
+    """n = 60 000 > 57 344: the 16-bit renaming does not apply, the 32-bit compare kernel (symmetric, one block) and the
+    uint64-key select path for large n must give the oracle's neighbours."""
+    rng = np.random.default_rng(60000)
+    n, ncols, m = 60000, 1 << 16, 24
+    protos = [np.sort(rng.choice(ncols, size=200, replace=False)) for _ in range(400)]
+    rows = np.repeat(np.arange(n), m)
+    cols = np.concatenate([np.sort(rng.choice(protos[r % 400], size=m, replace=False)) for r in range(n)])
+    X = csr_matrix((np.ones(n * m), (rows, cols)), shape=(n, ncols))
+    kw = dict(number_of_hash_functions=32, minimal_blocks_in_common=6, fast=True, n_neighbors=8, max_bin_size=100000)
+    with Fitted(oracle, X, **kw) as o:
+        want = oracle.kneighbors(o.h, 8)
+    with Fitted(cuda, X, **kw) as g:
+        got = cuda.kneighbors(g.h, 8)
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
