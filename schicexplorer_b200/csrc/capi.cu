@@ -102,7 +102,7 @@ struct schic_mh_handle {
     // scratch of kneighbors
     DevBuf<uint16_t> counts; DevBuf<int32_t> cand_idx, cand_cnt, cand_nv, sel_flags;
     DevBuf<uint32_t> sig_masked;   // database signatures with oversized buckets blanked (K2)
-    DevBuf<uint32_t> k3h_table; DevBuf<uint16_t> sig16;   // packed K3: renaming tables, renamed signatures
+    DevBuf<uint32_t> k3h_table, k3h_sizes; DevBuf<uint16_t> sig16;   // packed K3: renaming tables, bucket sizes, renamed signatures
     DevBuf<int32_t> out_idx, out_nv; DevBuf<float> out_dist;
     DevBuf<int64_t> g_indptr; DevBuf<int32_t> g_indices; DevBuf<float> g_data;
 
@@ -330,13 +330,21 @@ int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const uint32_t* feat
 
 // Packed K3 (two hash functions per compare): rename the database signatures to 16-bit ids. Returns 1 when the
 // packed kernels can be used (h->sig16 filled), 0 when not applicable; SCHIC_K3_MODE=plain forces 0.
+bool packed_counts_possible(const schic_mh_handle* h, int64_t ndb) {
+    const char* mode = getenv("SCHIC_K3_MODE");
+    return !(mode && strcmp(mode, "plain") == 0) && schic::k3h_applicable(ndb, h->p.number_of_hash_functions);
+}
+
+// db_sig: the UNPRUNED database signatures; buckets with >= max_bin_size members are blanked here when ndb reaches it
 int prepare_packed_counts(schic_mh_handle* h, const uint32_t* db_sig, int64_t ndb) {
     const int H = h->p.number_of_hash_functions;
-    const char* mode = getenv("SCHIC_K3_MODE");
-    if ((mode && strcmp(mode, "plain") == 0) || !schic::k3h_applicable(ndb, H)) return 0;
+    if (!packed_counts_possible(h, ndb)) return 0;
+    const bool prune = ndb >= h->p.max_bin_size;
     ST_TRY(h->k3h_table.reserve((int64_t)schic::k3h_table_elems(ndb, H), 0, h->stream));
+    if (prune) ST_TRY(h->k3h_sizes.reserve((int64_t)schic::k3h_table_elems(ndb, H), 0, h->stream));
     ST_TRY(h->sig16.reserve(ndb * (int64_t)schic::k3h_padded_hashes(H), 0, h->stream));
-    const int nl = schic::launch_rename_signatures(db_sig, ndb, H, h->k3h_table.p, h->sig16.p, h->stream);
+    const int nl = schic::launch_rename_signatures(db_sig, ndb, H, h->k3h_table.p, h->sig16.p,
+                                                   prune ? h->k3h_sizes.p : nullptr, prune ? h->p.max_bin_size : 0, h->stream);
     if (nl < 0) return fail(SCHIC_ERR_CUDA, "signature renaming launch failed");
     add_launches(h, nl);
     return 1;
@@ -366,7 +374,7 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
     reset_stage(h, {ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_PREP});
     cudaStream_t s = h->stream;
     const uint32_t* q_sig = h->sig.p;
-    if (ndb >= h->p.max_bin_size) {   // rule 5: blank the members of buckets with >= max_bin_size cells
+    if (ndb >= h->p.max_bin_size && !packed_counts_possible(h, ndb)) {   // rule 5 (the packed K3 prunes while renaming)
         StageTimer t(h, ST_COLL, s);
         ST_TRY(prune_buckets(h, db_sig, ndb));
         db_sig = h->sig_masked.p;
@@ -858,7 +866,7 @@ int schic_mh_collision_counts(schic_mh_handle* h, int64_t row0, int64_t row1, ui
     const int64_t ndb = h->ext ? h->db_n : h->n;
     const uint32_t* db_sig = h->ext ? h->db_sig : h->sig.p;
     const uint32_t* q_sig = h->sig.p;
-    if (ndb >= h->p.max_bin_size) {
+    if (ndb >= h->p.max_bin_size && !packed_counts_possible(h, ndb)) {
         ST_TRY(prune_buckets(h, db_sig, ndb));
         db_sig = h->sig_masked.p;
         q_sig = h->sig_masked.p + (h->ext ? h->db_row0 : 0) * (int64_t)H;

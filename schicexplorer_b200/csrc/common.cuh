@@ -55,7 +55,7 @@ bool k3h_applicable(int64_t ndb, int H);
 int k3h_padded_hashes(int H);
 size_t k3h_table_elems(int64_t ndb, int H);
 int launch_rename_signatures(const uint32_t* d_sig_db, int64_t ndb, int H, uint32_t* d_table, uint16_t* d_sig16,
-                             cudaStream_t stream);
+                             uint32_t* d_sizes /* nullable */, int64_t max_bin_size /* 0: no pruning */, cudaStream_t stream);
 int launch_collision_counts_packed(const uint16_t* d_q16, int64_t nq, const uint16_t* d_d16, int64_t ndb, int H,
                                    uint16_t* d_cnt, int64_t ld_out, cudaStream_t stream);
 

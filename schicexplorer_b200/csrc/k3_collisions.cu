@@ -168,7 +168,7 @@ __host__ __device__ inline int k3h_table_capacity(int64_t n) {
 // table: [H][cap] uint32, zero-initialised (0 is inadmissible, so it can mean "empty")
 __global__ void __launch_bounds__(256)
 k3h_rename_kernel(const uint32_t* __restrict__ sig, int64_t n, int H, int Hp, int cap, uint32_t* __restrict__ table,
-                  uint16_t* __restrict__ sig16) {
+                  uint32_t* __restrict__ sizes /* nullable: [H][cap] bucket sizes (zeroed) */, uint16_t* __restrict__ sig16) {
     const int64_t total = n * (int64_t)Hp;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -185,10 +185,27 @@ k3h_rename_kernel(const uint32_t* __restrict__ sig, int64_t n, int H, int Hp, in
                     if (old == 0u || old == v) break;
                     slot = slot + 1u == (uint32_t)cap ? 0u : slot + 1u;
                 }
+                if (sizes) atomicAdd(sizes + (int64_t)j * cap + slot, 1u);      // the slot IS the bucket of this value
                 out = slot < 30720u ? (uint16_t)(0x0400u + slot) : (uint16_t)(0x8400u + (slot - 30720u));
             }
         }
         sig16[e] = out;
+    }
+}
+
+// max_bin_size (SURVEY 8(c) rule 5): members of buckets with >= max_bin cells never collide -> NaN. The bucket sizes
+// come for free from the renaming (one counter per table slot): O(n H) instead of K2's all-pairs O(n^2 H).
+__global__ void __launch_bounds__(256)
+k3h_prune_kernel(uint16_t* __restrict__ sig16, int64_t n, int H, int Hp, int cap, const uint32_t* __restrict__ sizes,
+                 uint32_t max_bin) {
+    const int64_t total = n * (int64_t)Hp;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int j = (int)(e % Hp);
+        const uint32_t p = sig16[e];
+        if (j >= H || p == K3H_NAN) continue;
+        const uint32_t slot = p < 0x8000u ? p - 0x0400u : (p - 0x8400u) + 30720u;
+        if (__ldg(sizes + (int64_t)j * cap + slot) >= max_bin) sig16[e] = K3H_NAN;
     }
 }
 
@@ -293,18 +310,25 @@ bool k3h_applicable(int64_t ndb, int H) { return H <= 4094 && ndb <= K3H_MAX_ROW
 int k3h_padded_hashes(int H) { return (H + 1) & ~1; }
 size_t k3h_table_elems(int64_t ndb, int H) { return (size_t)H * (size_t)k3h_table_capacity(ndb); }
 
-// d_table: k3h_table_elems uint32 (zeroed here), d_sig16: ndb * k3h_padded_hashes(H) uint16
+// d_table: k3h_table_elems uint32 (zeroed here), d_sig16: ndb * k3h_padded_hashes(H) uint16.
+// max_bin_size > 0 with d_sizes (k3h_table_elems uint32, zeroed here): members of buckets with >= max_bin_size cells
+// are blanked (rule 5) -- replaces K2 on this path.
 int launch_rename_signatures(const uint32_t* d_sig_db, int64_t ndb, int H, uint32_t* d_table, uint16_t* d_sig16,
-                             cudaStream_t stream) {
+                             uint32_t* d_sizes, int64_t max_bin_size, cudaStream_t stream) {
     if (ndb <= 0) return 0;
     const int cap = k3h_table_capacity(ndb);
     const int Hp = k3h_padded_hashes(H);
+    const bool prune = d_sizes && max_bin_size > 0;
     if (cudaMemsetAsync(d_table, 0, (size_t)H * cap * sizeof(uint32_t), stream) != cudaSuccess) return -1;
+    if (prune && cudaMemsetAsync(d_sizes, 0, (size_t)H * cap * sizeof(uint32_t), stream) != cudaSuccess) return -1;
     const int64_t total = ndb * (int64_t)Hp;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    k3h_rename_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_sig_db, ndb, H, Hp, cap, d_table, d_sig16);
-    return 1;
+    k3h_rename_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_sig_db, ndb, H, Hp, cap, d_table, prune ? d_sizes : nullptr, d_sig16);
+    if (!prune) return 1;
+    const uint32_t mb = (uint32_t)(max_bin_size > 0xFFFFFFFFll ? 0xFFFFFFFFll : max_bin_size);
+    k3h_prune_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_sig16, ndb, H, Hp, cap, d_sizes, mb);
+    return 2;
 }
 
 // q16 / d16: renamed signatures (rows of Hp uint16) of the query rows / of the database
