@@ -102,6 +102,17 @@ int schic_mh_kneighbors(schic_mh_handle* h, int32_t k, int32_t fast,
 int schic_mh_kneighbors_graph(schic_mh_handle* h, int32_t k, int32_t fast,
                               int64_t* indptr, int32_t* indices, float* data);
 
+/* SURVEY 8(f)-3, the exact-kNN sibling: scHicCluster -drm knn (scHicCluster.py:179-180) runs sklearn
+ * NearestNeighbors(n_neighbors=k, algorithm='ball_tree').fit(X).kneighbors_graph(mode='distance'), which on a sparse
+ * X is brute-force euclidean kNN and leaves the query row itself out. Here: every fitted row is a candidate of every
+ * fitted row (handle fitted WITH data), order (distance asc, index asc), keep k.
+ *   include_self  0: sklearn's kneighbors_graph()/kneighbors() convention (query row dropped); 1: kept (distance 0)
+ *   outputs as schic_mh_kneighbors / schic_mh_kneighbors_graph */
+int schic_mh_kneighbors_exact(schic_mh_handle* h, int32_t k, int32_t include_self,
+                              int32_t* idx, float* dist, int32_t* n_valid);
+int schic_mh_kneighbors_exact_graph(schic_mh_handle* h, int32_t k, int32_t include_self,
+                                    int64_t* indptr, int32_t* indices, float* data);
+
 #ifdef __cplusplus
 }
 #endif

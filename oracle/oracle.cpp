@@ -344,15 +344,10 @@ int schic_mh_kneighbors(schic_mh_handle* h, int32_t k, int32_t fast, int32_t* id
     return SCHIC_OK;
 }
 
-int schic_mh_kneighbors_graph(schic_mh_handle* h, int32_t k, int32_t fast, int64_t* indptr, int32_t* indices, float* data) {
-    if (int e = check_handle(h)) return e;
-    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
-    if (k < 1 || !indptr || !indices || !data) return fail(SCHIC_ERR_INVALID_ARG, "bad kneighbors_graph arguments");
+// Rule 10: row c holds its neighbours sorted by column.
+static void lists_to_graph(const schic_mh_handle* h, int k, const std::vector<int32_t>& idx, const std::vector<float>& dist,
+                           const std::vector<int32_t>& nv, int64_t* indptr, int32_t* indices, float* data) {
     const int64_t n = h->n;
-    std::vector<int32_t> idx((size_t)n * k), nv(n);
-    std::vector<float> dist((size_t)n * k);
-    if (int e = schic_mh_kneighbors(h, k, fast, idx.data(), dist.data(), nv.data())) return e;
-    // Rule 10: row c holds its neighbours sorted by column.
     indptr[0] = 0;
     for (int64_t c = 0; c < n; ++c) indptr[c + 1] = indptr[c] + nv[c];
 #pragma omp parallel for schedule(static) num_threads(nthreads(h))
@@ -363,6 +358,62 @@ int schic_mh_kneighbors_graph(schic_mh_handle* h, int32_t k, int32_t fast, int64
         for (int t = 0; t < nv[c]; ++t) {
             indices[indptr[c] + t] = row[t].first;
             data[indptr[c] + t] = row[t].second;
+        }
+    }
+}
+
+int schic_mh_kneighbors_graph(schic_mh_handle* h, int32_t k, int32_t fast, int64_t* indptr, int32_t* indices, float* data) {
+    if (int e = check_handle(h)) return e;
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    if (k < 1 || !indptr || !indices || !data) return fail(SCHIC_ERR_INVALID_ARG, "bad kneighbors_graph arguments");
+    const int64_t n = h->n;
+    std::vector<int32_t> idx((size_t)n * k), nv(n);
+    std::vector<float> dist((size_t)n * k);
+    if (int e = schic_mh_kneighbors(h, k, fast, idx.data(), dist.data(), nv.data())) return e;
+    lists_to_graph(h, k, idx, dist, nv, indptr, indices, data);
+    return SCHIC_OK;
+}
+
+int schic_mh_kneighbors_exact(schic_mh_handle* h, int32_t k, int32_t include_self, int32_t* idx, float* dist, int32_t* n_valid);
+
+int schic_mh_kneighbors_exact_graph(schic_mh_handle* h, int32_t k, int32_t include_self, int64_t* indptr, int32_t* indices, float* data) {
+    if (int e = check_handle(h)) return e;
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    if (k < 1 || !indptr || !indices || !data) return fail(SCHIC_ERR_INVALID_ARG, "bad kneighbors_graph arguments");
+    const int64_t n = h->n;
+    std::vector<int32_t> idx((size_t)n * k), nv(n);
+    std::vector<float> dist((size_t)n * k);
+    if (int e = schic_mh_kneighbors_exact(h, k, include_self, idx.data(), dist.data(), nv.data())) return e;
+    lists_to_graph(h, k, idx, dist, nv, indptr, indices, data);
+    return SCHIC_OK;
+}
+
+// the exact-kNN sibling (scHicCluster.py:179-180 — sklearn NearestNeighbors(...).fit(X) followed by
+// kneighbors_graph(mode='distance'), which on sparse input is brute-force euclidean and leaves the query itself out).
+// Every fitted row is a candidate; order (dist asc, idx asc); keep k. include_self != 0 keeps the query row.
+int schic_mh_kneighbors_exact(schic_mh_handle* h, int32_t k, int32_t include_self, int32_t* idx, float* dist, int32_t* n_valid) {
+    if (int e = check_handle(h)) return e;
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    if (k < 1 || !idx || !dist) return fail(SCHIC_ERR_INVALID_ARG, "bad kneighbors arguments");
+    if (h->val.empty() && !h->idx.empty()) return fail(SCHIC_ERR_INVALID_ARG, "exact kNN needs the CSR values (fit with data)");
+    const int64_t n = h->n;
+#pragma omp parallel num_threads(nthreads(h))
+    {
+        std::vector<Cand> cand;
+#pragma omp for schedule(dynamic, 4)
+        for (int64_t c = 0; c < n; ++c) {
+            cand.clear();
+            for (int64_t d = 0; d < n; ++d)
+                if (include_self || d != c) cand.push_back({(int32_t)d, 0, euclid(h, c, d)});
+            std::sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) {
+                return a.dist != b.dist ? a.dist < b.dist : a.idx < b.idx;
+            });
+            if (cand.size() > (size_t)k) cand.resize(k);
+            for (int t = 0; t < k; ++t) {
+                if ((size_t)t < cand.size()) { idx[(size_t)c * k + t] = cand[t].idx; dist[(size_t)c * k + t] = cand[t].dist; }
+                else { idx[(size_t)c * k + t] = -1; dist[(size_t)c * k + t] = std::numeric_limits<float>::infinity(); }
+            }
+            if (n_valid) n_valid[c] = (int32_t)cand.size();
         }
     }
     return SCHIC_OK;

@@ -5,6 +5,7 @@ Public surface = the two classes scHiCExplorer imports from ``sparse_neighbors_s
 """
 from .minhash import MinHash
 from .clustering import MinHashClustering
+from .knn import NearestNeighbors
 
-__all__ = ["MinHash", "MinHashClustering"]
+__all__ = ["MinHash", "MinHashClustering", "NearestNeighbors"]
 __version__ = "0.1.0"

@@ -50,7 +50,7 @@ class Params(C.Structure):
 BASE_SYMBOLS = (
     "schic_mh_create", "schic_mh_destroy", "schic_mh_last_error", "schic_mh_backend",
     "schic_mh_fit_csr", "schic_mh_n_fitted", "schic_mh_signatures", "schic_mh_collision_counts",
-    "schic_mh_kneighbors", "schic_mh_kneighbors_graph",
+    "schic_mh_kneighbors", "schic_mh_kneighbors_graph", "schic_mh_kneighbors_exact", "schic_mh_kneighbors_exact_graph",
 )
 # symbols only the CUDA library exports (include/schic_mh_cuda.h)
 CUDA_SYMBOLS = (
@@ -58,7 +58,8 @@ CUDA_SYMBOLS = (
     "schic_mh_set_database_device", "schic_mh_set_database_ready_event", "schic_mh_rerank_windows",
     "schic_mh_rerank_prep_rows", "schic_mh_set_database_prep_device", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
-    "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free",
+    "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free", "schic_mh_kneighbors_exact_device",
+    "schic_mh_set_active_hashes",
 )
 
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
@@ -93,11 +94,15 @@ class CApi:
         L.schic_mh_collision_counts.argtypes = [_vp, _i64, _i64, _vp]
         L.schic_mh_kneighbors.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
         L.schic_mh_kneighbors_graph.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
+        L.schic_mh_kneighbors_exact.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
+        L.schic_mh_kneighbors_exact_graph.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
         self.backend = L.schic_mh_backend().decode()
         self.is_cuda = self.backend == "cuda"
         if self.is_cuda:
             L.schic_mh_fit_csr_async.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32]
             L.schic_mh_set_feature_range.argtypes = [_vp, C.c_uint64]
+            L.schic_mh_kneighbors_exact_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
+            L.schic_mh_set_active_hashes.argtypes = [_vp, _i32]
             L.schic_mh_set_database_ready_event.argtypes = [_vp, _vp]
             L.schic_mh_rerank_windows.argtypes = [_vp, C.POINTER(_i32)]
             L.schic_mh_rerank_prep_rows.argtypes = [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp]
@@ -218,7 +223,34 @@ class CApi:
         nnz = int(indptr[-1])
         return indptr, indices[:nnz], data[:nnz]
 
+    def kneighbors_exact(self, h, k: int, include_self: bool = False):
+        """Brute-force euclidean kNN over the fitted rows (scHicCluster -drm knn, scHicCluster.py:179-180)."""
+        n = self.n_fitted(h)
+        idx = np.empty((n, k), dtype=np.int32)
+        dist = np.empty((n, k), dtype=np.float32)
+        nv = np.empty(n, dtype=np.int32)
+        self.check(self.lib.schic_mh_kneighbors_exact(_vp(h), k, int(include_self), _ptr(idx), _ptr(dist), _ptr(nv)))
+        return idx, dist, nv
+
+    def kneighbors_exact_graph(self, h, k: int, include_self: bool = False):
+        n = self.n_fitted(h)
+        indptr = np.empty(n + 1, dtype=np.int64)
+        indices = np.empty(n * k, dtype=np.int32)
+        data = np.empty(n * k, dtype=np.float32)
+        self.check(self.lib.schic_mh_kneighbors_exact_graph(_vp(h), k, int(include_self), _ptr(indptr), _ptr(indices),
+                                                            _ptr(data)))
+        nnz = int(indptr[-1])
+        return indptr, indices[:nnz], data[:nnz]
+
     # -- include/schic_mh_cuda.h (device-pointer entry points) -------------------------------
+    def kneighbors_exact_device(self, h, k, include_self, d_idx, d_dist, d_nvalid):
+        self.check(self.lib.schic_mh_kneighbors_exact_device(_vp(h), k, int(include_self), _ptr(d_idx), _ptr(d_dist),
+                                                             _ptr(d_nvalid)))
+
+    def set_active_hashes(self, h, n_hashes: int):
+        """Query side uses the first n_hashes hash functions of the fitted signatures (hyperopt sweeps over -nh)."""
+        self.check(self.lib.schic_mh_set_active_hashes(_vp(h), int(n_hashes)))
+
     def fit_csr_device(self, h, n_rows, nnz, d_indptr, d_indices, d_data, append: bool):
         self.check(self.lib.schic_mh_fit_csr_device(_vp(h), n_rows, nnz, _ptr(d_indptr), _ptr(d_indices),
                                                     _ptr(d_data), int(append)))

@@ -78,6 +78,10 @@ struct schic_mh_handle {
     DevBuf<int64_t> indptr; DevBuf<uint32_t> feat; DevBuf<uint32_t> feat_hi; DevBuf<float> val;
     bool have_val = false, have_hi = false;
     DevBuf<uint32_t> sig;
+    // SURVEY 8(f)-4 (hyperopt sweeps over -nh): h_j depends only on j, so a prefix of the fitted signatures IS the
+    // signature matrix of a smaller hash count. While a prefix is active, sig holds the compacted [n, H_active] copy,
+    // sig_fit the fitted [n, H_fit] matrix, and p.number_of_hash_functions == H_active.
+    DevBuf<uint32_t> sig_fit; int H_fit = 0; bool sliced = false;
     DevBuf<unsigned char> k1_scratch;    // work-item list of the filtered / table K1 kernels
     // shared-table K1 (k1_table.cu): per-id presence bytes and slots, hit entries, {entries used, overflow, max id}
     DevBuf<unsigned char> k1t_present; DevBuf<unsigned long long> k1t_slot; DevBuf<uint16_t> k1t_entries;
@@ -100,7 +104,7 @@ struct schic_mh_handle {
     const double* ext_norm2 = nullptr; const uint32_t* ext_dir = nullptr; int ext_nw = 0;   // caller-provided rerank prep
 
     // scratch of kneighbors
-    DevBuf<uint16_t> counts; DevBuf<int32_t> cand_idx, cand_cnt, cand_nv, sel_flags;
+    DevBuf<uint16_t> counts; DevBuf<int32_t> cand_idx, cand_cnt, cand_nv, sel_flags, part_idx; DevBuf<float> part_dist;
     DevBuf<uint32_t> sig_masked;   // database signatures with oversized buckets blanked (K2)
     DevBuf<uint32_t> k3h_table, k3h_sizes; DevBuf<uint16_t> sig16;   // packed K3: renaming tables, bucket sizes, renamed signatures
     DevBuf<int32_t> out_idx, out_nv; DevBuf<float> out_dist;
@@ -119,6 +123,9 @@ struct schic_mh_handle {
 };
 
 namespace {
+
+constexpr int RERANK_CHUNK = 1024;   // candidates per K4 launch when a list exceeds one CTA's shared memory
+
 
 int use_device(const schic_mh_handle* h) {
     CU_TRY(cudaSetDevice(h->device));
@@ -281,6 +288,15 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
     return 0;
 }
 
+// Undo schic_mh_set_active_hashes: the fitted [n, H_fit] matrix becomes the live one again.
+void restore_fitted_signatures(schic_mh_handle* h) {
+    if (!h->sliced) return;
+    std::swap(h->sig.p, h->sig_fit.p);
+    std::swap(h->sig.cap, h->sig_fit.cap);
+    h->p.number_of_hash_functions = h->H_fit;
+    h->sliced = false;
+}
+
 int prune_buckets(schic_mh_handle* h, const uint32_t* db_sig, int64_t ndb) {
     const int H = h->p.number_of_hash_functions;
     ST_TRY(h->sig_masked.reserve(ndb * (int64_t)H, 0, h->stream));
@@ -348,6 +364,47 @@ int prepare_packed_counts(schic_mh_handle* h, const uint32_t* db_sig, int64_t nd
     if (nl < 0) return fail(SCHIC_ERR_CUDA, "signature renaming launch failed");
     add_launches(h, nl);
     return 1;
+}
+
+// K4 over candidate lists [nq, kcand] (cand_idx == nullptr: brute force, every database row is a candidate of every
+// query). Lists that fit one CTA's shared memory take one launch; longer ones (and brute force) are reranked in chunks
+// of RERANK_CHUNK candidates - each chunk leaves its best min(k, chunk) sorted in a scratch - and merged per row.
+int rerank_lists(schic_mh_handle* h, const int64_t* db_indptr, const uint32_t* db_feat, const float* db_val, int64_t ndb,
+                 bool ext_prep, int64_t row0, int64_t nq, const int32_t* cand_idx, const int32_t* cand_nv, int kcand, int k,
+                 bool exclude_self, int32_t* d_idx, float* d_dist, int32_t* d_nv) {
+    cudaStream_t s = h->stream;
+    StageTimer t(h, ST_RERANK, s);
+    const double* r_norm2 = ext_prep ? h->ext_norm2 : h->norm2.p;
+    const uint32_t* r_dir = ext_prep ? h->ext_dir : (h->n_windows > 0 ? h->win_dir.p : nullptr);
+    const int r_nw = ext_prep ? h->ext_nw : h->n_windows, r_mode = ext_prep ? 32 : h->window_mode;
+    int nl = -1;
+    if (cand_idx)
+        nl = schic::launch_rerank(db_indptr, db_feat, db_val, 0, r_norm2, r_dir, r_nw, r_mode, row0, nq, cand_idx, cand_nv,
+                                  kcand, 0, kcand, k, d_idx, d_dist, k, 0, 1, d_nv, 0, s);
+    if (nl < 0) {
+        const int kc = (int)std::min<int64_t>((int64_t)k + (exclude_self ? 1 : 0), RERANK_CHUNK);
+        const int nchunks = (kcand + RERANK_CHUNK - 1) / RERANK_CHUNK;
+        const int64_t stride = (int64_t)nchunks * kc;
+        if (stride > 16384) return fail(SCHIC_ERR_UNSUPPORTED, "rerank: candidate lists too long for the per-row merge (chunks * min(k, 1024) > 16384)");
+        ST_TRY(h->part_idx.reserve(nq * stride, 0, s));
+        ST_TRY(h->part_dist.reserve(nq * stride, 0, s));
+        nl = 0;
+        for (int ci = 0; ci < nchunks; ++ci) {
+            const int c0 = ci * RERANK_CHUNK, cn = std::min(RERANK_CHUNK, kcand - c0);
+            const int r = schic::launch_rerank(db_indptr, db_feat, db_val, 0, r_norm2, r_dir, r_nw, r_mode, row0, nq,
+                                               cand_idx, cand_nv, kcand, c0, cn, kc, h->part_idx.p, h->part_dist.p,
+                                               (int)stride, ci * kc, 0, d_nv, (int)ndb, s);
+            if (r < 0) return fail(SCHIC_ERR_UNSUPPORTED, "rerank: chunk does not fit in shared memory");
+            nl += r;
+        }
+        const int r = schic::launch_rerank_merge(h->part_idx.p, h->part_dist.p, (int)stride, cand_idx ? cand_nv : nullptr,
+                                                 kcand, (int)ndb, exclude_self ? row0 : -1, nq, k, d_idx, d_dist, d_nv, s);
+        if (r < 0) return fail(SCHIC_ERR_UNSUPPORTED, "rerank: merge does not fit in shared memory");
+        nl += r;
+    }
+    add_launches(h, nl);
+    CU_TRY(cudaGetLastError());
+    return 0;
 }
 
 // The whole query side on device. Results land in h->out_idx / out_dist / out_nv ([n, k]) unless
@@ -450,17 +507,91 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
             StageTimer t(h, ST_PREP, s);     // row norms + window directory of the database (once per fit)
             ST_TRY(ensure_norms(h, db_indptr, db_feat, db_val, ndb));
         }
-        StageTimer t(h, ST_RERANK, s);
-        const int nl = schic::launch_rerank(db_indptr, db_feat, db_val, 0, ext_prep ? h->ext_norm2 : h->norm2.p,
-                                            ext_prep ? h->ext_dir : (h->n_windows > 0 ? h->win_dir.p : nullptr),
-                                            ext_prep ? h->ext_nw : h->n_windows, ext_prep ? 32 : h->window_mode, row0, nq,
-                                            h->cand_idx.p,
-                                            h->cand_nv.p, kcand, k, d_idx, d_dist, d_nv, s);
-        if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k * excess_factor too large for the in-shared-memory rerank");
-        add_launches(h, nl);
+        ST_TRY(rerank_lists(h, db_indptr, db_feat, db_val, ndb, ext_prep, row0, nq, h->cand_idx.p, h->cand_nv.p, kcand, k,
+                            false, d_idx, d_dist, d_nv));
     }
     CU_TRY(cudaGetLastError());
     return 0;
+}
+
+// brute-force exact euclidean kNN (the scHicCluster -drm knn step) = K4 with every database row as a
+// candidate of every query. Results in h->out_* unless device outputs are given.
+int exact_knn_on_device(schic_mh_handle* h, int k, bool include_self, int32_t* d_idx, float* d_dist, int32_t* d_nv) {
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    if (k < 1) return fail(SCHIC_ERR_INVALID_ARG, "k must be >= 1");
+    const int64_t nq = h->n;
+    const int64_t ndb = h->ext ? h->db_n : h->n;
+    const int64_t row0 = h->ext ? h->db_row0 : 0;
+    const int64_t* db_indptr = h->ext ? h->db_indptr : h->d_indptr();
+    const uint32_t* db_feat = h->ext ? h->db_feat : h->d_feat();
+    const float* db_val = h->ext ? h->db_val : h->d_val();
+    if (!db_val || !db_feat) return fail(SCHIC_ERR_INVALID_ARG, "exact kNN needs the CSR values (fit with data)");
+    if (h->have_hi) return fail(SCHIC_ERR_UNSUPPORTED, "exact kNN supports 32-bit feature ids only");
+    if (ndb > INT32_MAX) return fail(SCHIC_ERR_UNSUPPORTED, "too many rows");
+    reset_stage(h, {ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_PREP});
+    cudaStream_t s = h->stream;
+    if (!d_idx) {
+        ST_TRY(h->out_idx.reserve(nq * k, 0, s));
+        ST_TRY(h->out_dist.reserve(nq * k, 0, s));
+        ST_TRY(h->out_nv.reserve(nq, 0, s));
+        d_idx = h->out_idx.p; d_dist = h->out_dist.p; d_nv = h->out_nv.p;
+    }
+    if (h->ext && h->db_ready) CU_TRY(cudaStreamWaitEvent(s, h->db_ready, 0));
+    const bool ext_prep = h->ext && h->ext_norm2 && h->ext_dir && h->ext_nw > 0;
+    if (!ext_prep) {
+        StageTimer t(h, ST_PREP, s);
+        ST_TRY(ensure_norms(h, db_indptr, db_feat, db_val, ndb));
+    }
+    return rerank_lists(h, db_indptr, db_feat, db_val, ndb, ext_prep, row0, nq, nullptr, nullptr, (int)ndb, k, !include_self,
+                        d_idx, d_dist, d_nv);
+}
+
+// D2H of h->out_* ([n, ke]) into caller arrays of row stride k (columns [ke, k) padded).
+int results_to_host(schic_mh_handle* h, int ke, int k, int32_t* idx, float* dist, int32_t* n_valid) {
+    const int64_t n = h->n;
+    {
+        StageTimer t(h, ST_D2H, h->stream);
+        if (ke == k) {
+            CU_TRY(cudaMemcpyAsync(idx, h->out_idx.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaMemcpyAsync(dist, h->out_dist.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, h->stream));
+        } else {   // k > n_fitted: pad columns [ke, k)
+            for (int64_t e = 0; e < n * (int64_t)k; ++e) { idx[e] = -1; dist[e] = __builtin_inff(); }
+            CU_TRY(cudaMemcpy2DAsync(idx, (size_t)k * 4, h->out_idx.p, (size_t)ke * 4, (size_t)ke * 4, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaMemcpy2DAsync(dist, (size_t)k * 4, h->out_dist.p, (size_t)ke * 4, (size_t)ke * 4, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        }
+        if (n_valid) CU_TRY(cudaMemcpyAsync(n_valid, h->out_nv.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return check_range_flag(h);
+}
+
+// Graph emit from h->out_* ([n, ke]) and D2H of the CSR.
+int graph_to_host(schic_mh_handle* h, int ke, int64_t* indptr, int32_t* indices, float* data) {
+    const int64_t n = h->n;
+    cudaStream_t s = h->stream;
+    ST_TRY(h->g_indptr.reserve(n + 1, 0, s));
+    ST_TRY(h->g_indices.reserve(n * ke, 0, s));
+    ST_TRY(h->g_data.reserve(n * ke, 0, s));
+    {
+        StageTimer t(h, ST_GRAPH, s);
+        const int nl = schic::launch_graph_emit(h->out_idx.p, h->out_dist.p, h->out_nv.p, n, ke, h->g_indptr.p,
+                                                h->g_indices.p, h->g_data.p, s);
+        if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k too large for the in-shared-memory graph emit");
+        add_launches(h, nl);
+    }
+    CU_TRY(cudaGetLastError());
+    {
+        StageTimer t(h, ST_D2H, s);
+        CU_TRY(cudaMemcpyAsync(indptr, h->g_indptr.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        const int64_t nnz = indptr[n];
+        if (nnz > 0) {
+            CU_TRY(cudaMemcpyAsync(indices, h->g_indices.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaMemcpyAsync(data, h->g_data.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(s));
+    return check_range_flag(h);
 }
 
 int effective_k(const schic_mh_handle* h, int k) {
@@ -584,6 +715,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
         if (indptr[r + 1] < indptr[r]) return fail(SCHIC_ERR_INVALID_ARG, "indptr not monotone");
     ST_TRY(use_device(h));
     if (h->borrowed && append) return fail(SCHIC_ERR_UNSUPPORTED, "cannot append to a borrowed device CSR");
+    if (h->sliced) { CU_TRY(cudaStreamSynchronize(h->stream)); restore_fitted_signatures(h); }
     CU_TRY(cudaStreamSynchronize(h->copy_stream));   // an earlier async upload may still use the buffers / host vectors
     if (!append || h->borrowed) {
         CU_TRY(cudaStreamSynchronize(h->stream));
@@ -749,6 +881,7 @@ int schic_mh_fit_csr_device(schic_mh_handle* h, int64_t n_rows, int64_t nnz, con
     if (n_rows < 0 || nnz < 0 || !d_indptr || (nnz > 0 && !d_indices)) return fail(SCHIC_ERR_INVALID_ARG, "bad CSR arguments");
     if (!h->p.fast && !d_data) return fail(SCHIC_ERR_INVALID_ARG, "data is required when fast=0");
     ST_TRY(use_device(h));
+    if (h->sliced) { CU_TRY(cudaStreamSynchronize(h->stream)); restore_fitted_signatures(h); }
     reset_stage(h, {ST_H2D, ST_SIG});
     const int H = h->p.number_of_hash_functions;
     h->k1t_prebuilt = false;
@@ -812,6 +945,7 @@ int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t ro
     h->ext_norm2 = nullptr; h->ext_dir = nullptr; h->ext_nw = 0;
     if (!d_sig_all) { h->ext = false; h->norm_of = nullptr; return SCHIC_OK; }
     if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "fit the local shard first");
+    if (h->sliced) return fail(SCHIC_ERR_UNSUPPORTED, "external database while an active-hash prefix is set");
     if (row0 < 0 || row0 + h->n > n_total) return fail(SCHIC_ERR_INVALID_ARG, "local rows do not fit in the database");
     h->ext = true; h->db_n = n_total; h->db_row0 = row0; h->db_sig = d_sig_all;
     h->db_indptr = d_indptr_all; h->db_feat = d_indices_all; h->db_val = d_data_all;
@@ -907,21 +1041,7 @@ int schic_mh_kneighbors(schic_mh_handle* h, int32_t k, int32_t fast, int32_t* id
     if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
     const int ke = effective_k(h, k);
     ST_TRY(kneighbors_on_device(h, ke, fast, nullptr, nullptr, nullptr));
-    const int64_t n = h->n;
-    {
-        StageTimer t(h, ST_D2H, h->stream);
-        if (ke == k) {
-            CU_TRY(cudaMemcpyAsync(idx, h->out_idx.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, h->stream));
-            CU_TRY(cudaMemcpyAsync(dist, h->out_dist.p, (size_t)n * k * 4, cudaMemcpyDeviceToHost, h->stream));
-        } else {   // k > n_fitted: pad columns [ke, k)
-            for (int64_t e = 0; e < n * (int64_t)k; ++e) { idx[e] = -1; dist[e] = __builtin_inff(); }
-            CU_TRY(cudaMemcpy2DAsync(idx, (size_t)k * 4, h->out_idx.p, (size_t)ke * 4, (size_t)ke * 4, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
-            CU_TRY(cudaMemcpy2DAsync(dist, (size_t)k * 4, h->out_dist.p, (size_t)ke * 4, (size_t)ke * 4, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
-        }
-        if (n_valid) CU_TRY(cudaMemcpyAsync(n_valid, h->out_nv.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-    }
-    CU_TRY(cudaStreamSynchronize(h->stream));
-    return check_range_flag(h);
+    return results_to_host(h, ke, k, idx, dist, n_valid);
 }
 
 int schic_mh_kneighbors_graph(schic_mh_handle* h, int32_t k, int32_t fast, int64_t* indptr, int32_t* indices, float* data) {
@@ -931,31 +1051,57 @@ int schic_mh_kneighbors_graph(schic_mh_handle* h, int32_t k, int32_t fast, int64
     if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
     const int ke = effective_k(h, k);
     ST_TRY(kneighbors_on_device(h, ke, fast, nullptr, nullptr, nullptr));
-    const int64_t n = h->n;
+    return graph_to_host(h, ke, indptr, indices, data);
+}
+
+int schic_mh_kneighbors_exact(schic_mh_handle* h, int32_t k, int32_t include_self, int32_t* idx, float* dist, int32_t* n_valid) {
+    ST_TRY(check(h));
+    if (k < 1 || !idx || !dist) return fail(SCHIC_ERR_INVALID_ARG, "bad kneighbors arguments");
+    ST_TRY(use_device(h));
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    const int ke = std::max(1, std::min(k, effective_k(h, INT32_MAX) - (include_self ? 0 : 1)));
+    ST_TRY(exact_knn_on_device(h, ke, include_self != 0, nullptr, nullptr, nullptr));
+    return results_to_host(h, ke, k, idx, dist, n_valid);
+}
+
+int schic_mh_kneighbors_exact_graph(schic_mh_handle* h, int32_t k, int32_t include_self, int64_t* indptr, int32_t* indices, float* data) {
+    ST_TRY(check(h));
+    if (k < 1 || !indptr || !indices || !data) return fail(SCHIC_ERR_INVALID_ARG, "bad kneighbors_graph arguments");
+    ST_TRY(use_device(h));
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    const int ke = std::max(1, std::min(k, effective_k(h, INT32_MAX) - (include_self ? 0 : 1)));
+    ST_TRY(exact_knn_on_device(h, ke, include_self != 0, nullptr, nullptr, nullptr));
+    return graph_to_host(h, ke, indptr, indices, data);
+}
+
+int schic_mh_kneighbors_exact_device(schic_mh_handle* h, int32_t k, int32_t include_self, int32_t* d_idx, float* d_dist, int32_t* d_nvalid) {
+    ST_TRY(check(h));
+    if (!d_idx || !d_dist || !d_nvalid) return fail(SCHIC_ERR_INVALID_ARG, "null output");
+    ST_TRY(use_device(h));
+    if (h->n > 0 && k > effective_k(h, k)) return fail(SCHIC_ERR_INVALID_ARG, "k exceeds the number of fitted rows");
+    return exact_knn_on_device(h, k, include_self != 0, d_idx, d_dist, d_nvalid);
+}
+
+int schic_mh_set_active_hashes(schic_mh_handle* h, int32_t n_hashes) {
+    ST_TRY(check(h));
+    ST_TRY(use_device(h));
+    const int H_fit = h->sliced ? h->H_fit : h->p.number_of_hash_functions;
+    if (n_hashes < 1 || n_hashes > H_fit) return fail(SCHIC_ERR_INVALID_ARG, "n_hashes must be in [1, number_of_hash_functions as created]");
+    if (h->ext) return fail(SCHIC_ERR_UNSUPPORTED, "active-hash prefix with an external database");
     cudaStream_t s = h->stream;
-    ST_TRY(h->g_indptr.reserve(n + 1, 0, s));
-    ST_TRY(h->g_indices.reserve(n * ke, 0, s));
-    ST_TRY(h->g_data.reserve(n * ke, 0, s));
-    {
-        StageTimer t(h, ST_GRAPH, s);
-        const int nl = schic::launch_graph_emit(h->out_idx.p, h->out_dist.p, h->out_nv.p, n, ke, h->g_indptr.p,
-                                                h->g_indices.p, h->g_data.p, s);
-        if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k too large for the in-shared-memory graph emit");
-        add_launches(h, nl);
-    }
-    CU_TRY(cudaGetLastError());
-    {
-        StageTimer t(h, ST_D2H, s);
-        CU_TRY(cudaMemcpyAsync(indptr, h->g_indptr.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaStreamSynchronize(s));
-        const int64_t nnz = indptr[n];
-        if (nnz > 0) {
-            CU_TRY(cudaMemcpyAsync(indices, h->g_indices.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost, s));
-            CU_TRY(cudaMemcpyAsync(data, h->g_data.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost, s));
-        }
-    }
     CU_TRY(cudaStreamSynchronize(s));
-    return check_range_flag(h);
+    restore_fitted_signatures(h);
+    if (n_hashes == H_fit) return SCHIC_OK;
+    h->H_fit = H_fit;
+    std::swap(h->sig.p, h->sig_fit.p);     // sig_fit: fitted matrix; sig: the compacted prefix (buffer reused between calls)
+    std::swap(h->sig.cap, h->sig_fit.cap);
+    h->sliced = true;
+    h->p.number_of_hash_functions = n_hashes;
+    ST_TRY(h->sig.reserve(std::max<int64_t>(1, h->n * (int64_t)n_hashes), 0, s));
+    if (h->n > 0)
+        CU_TRY(cudaMemcpy2DAsync(h->sig.p, (size_t)n_hashes * 4, h->sig_fit.p, (size_t)H_fit * 4, (size_t)n_hashes * 4,
+                                 (size_t)h->n, cudaMemcpyDeviceToDevice, s));
+    return SCHIC_OK;
 }
 
 int schic_mh_stage_ms(schic_mh_handle* h, float* out, int32_t n_out) {

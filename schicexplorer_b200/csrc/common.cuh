@@ -89,10 +89,20 @@ int launch_row_window_dir(const int64_t* d_indptr, const uint32_t* d_feat, int64
 // For query q (database row q_row0+q) and each of its candidates: euclidean distance over the
 // union of supports; then order by (dist asc, idx asc), keep k. CSR arrays are the database's.
 // d_dir != nullptr selects the windowed kernel (needs the directory above), else the hash-table kernel.
+// A launch handles candidate columns [cand_off, cand_off+kcand) of lists with row stride cand_stride and writes the k
+// best (sorted) to output columns [out_off, out_off+k) of arrays with row stride out_stride; final != 0 also writes
+// d_nvalid_out. Returns -1 when kcand does not fit one CTA's shared memory (the caller then chunks + merges).
 int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* d_val, int64_t indptr0,
                   const double* d_norm2, const uint32_t* d_dir, int n_windows, int window_mode /* 32 | 64: entry width */,
-                  int64_t q_row0, int64_t nq, const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int kcand, int k,
-                  int32_t* d_idx_out, float* d_dist_out, int32_t* d_nvalid_out, cudaStream_t stream);
+                  int64_t q_row0, int64_t nq, const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int cand_stride,
+                  int cand_off, int kcand, int k, int32_t* d_idx_out, float* d_dist_out, int out_stride, int out_off,
+                  int final, int32_t* d_nvalid_out, int n_all /* d_cand_idx == nullptr: candidates = rows [0, n_all) */,
+                  cudaStream_t stream);
+// Per row: sort the [part_stride] chunk-sorted (distance, index) pairs by (dist asc, idx asc), keep k, write n_valid
+// (= min(k, list length); list length = min(cand_nvalid, kcand), or n_all [- 1 if exclude_row0 >= 0] for brute force).
+int launch_rerank_merge(const int32_t* d_part_idx, const float* d_part_dist, int part_stride,
+                        const int32_t* d_cand_nvalid, int kcand, int n_all, int64_t exclude_row0, int64_t nq, int k,
+                        int32_t* d_idx_out, float* d_dist_out, int32_t* d_nvalid_out, cudaStream_t stream);
 
 // ---- K5: graph emit (k5_graph.cu) ---------------------------------------------------------
 // CSR of the kNN graph: indptr = exclusive scan of n_valid, rows sorted by column.

@@ -22,6 +22,17 @@
 
 namespace schic {
 
+// Which slice of every query's candidate list a launch works on and where its (sorted) results go: lists longer than
+// the shared-memory limit are reranked in chunks and merged by k4_merge_rows_kernel.
+struct K4Chunk {
+    int cand_stride;   // row stride of cand_idx
+    int cand_off;      // first candidate column of this launch
+    int out_stride;    // row stride of idx_out / dist_out
+    int out_off;       // first output column
+    int write_nvalid;  // 1: this launch produces the final lists (also writes nvalid_out)
+    int n_all;         // cand_idx == nullptr (brute force): candidate c of every query is database row cand_off + c, n_all rows in all
+};
+
 constexpr int K4_THREADS = 256;
 constexpr int K4_SLOTS = 8192;            // hash table slots (32 KB keys + 32 KB values)
 constexpr int K4_BUCKETS = K4_SLOTS / 4;  // a bucket = 4 consecutive keys = one LDS.128
@@ -117,7 +128,7 @@ __device__ __forceinline__ K4Probe k4_probe(const uint32_t* __restrict__ tkey, u
 __global__ void __launch_bounds__(K4_THREADS)
 k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat, const float* __restrict__ val,
                  const double* __restrict__ norm2, int64_t q_row0, const int32_t* __restrict__ cand_idx,
-                 const int32_t* __restrict__ cand_nvalid, int kcand, int P, int k, int32_t* __restrict__ idx_out,
+                 const int32_t* __restrict__ cand_nvalid, int kcand, int P, int k, K4Chunk ck, int32_t* __restrict__ idx_out,
                  float* __restrict__ dist_out, int32_t* __restrict__ nvalid_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* tkey = reinterpret_cast<uint32_t*>(smem_raw);              // [K4_SLOTS]
@@ -131,11 +142,11 @@ k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict_
 
     const int64_t q = blockIdx.x;
     const int64_t qrow = q_row0 + q;
-    const int ncand = min(cand_nvalid[q], kcand);
+    const int ncand = max(0, min((cand_idx ? cand_nvalid[q] : ck.n_all) - ck.cand_off, kcand));
     const int lane = threadIdx.x & 31;
 
     for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
-        const int32_t d = cand_idx[q * kcand + c];
+        const int32_t d = cand_idx ? cand_idx[q * ck.cand_stride + ck.cand_off + c] : ck.cand_off + c;
         cand[c] = d;
         dot[c] = 0.0;
         cursor[c] = indptr[d];
@@ -263,10 +274,10 @@ k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict_
             oi = (int32_t)(uint32_t)(key & 0xFFFFFFFFull);
             od = __uint_as_float((uint32_t)(key >> 32));
         }
-        idx_out[q * k + t] = oi;
-        dist_out[q * k + t] = od;
+        idx_out[q * ck.out_stride + ck.out_off + t] = oi;
+        dist_out[q * ck.out_stride + ck.out_off + t] = od;
     }
-    if (threadIdx.x == 0) nvalid_out[q] = nv;
+    if (threadIdx.x == 0 && ck.write_nvalid) nvalid_out[q] = nv;
 }
 
 
@@ -362,7 +373,7 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
                         const float* __restrict__ val, const double* __restrict__ norm2,
                         const uint32_t* __restrict__ dir, int n_windows, int64_t q_row0,
                         const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_nvalid, int kcand, int P,
-                        int k, int32_t* __restrict__ idx_out, float* __restrict__ dist_out,
+                        int k, K4Chunk ck, int32_t* __restrict__ idx_out, float* __restrict__ dist_out,
                         int32_t* __restrict__ nvalid_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem_raw);                      // [K4W_WORDS]
@@ -378,12 +389,12 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
 
     const int64_t q = blockIdx.x;
     const int64_t qrow = q_row0 + q;
-    const int ncand = min(cand_nvalid[q], kcand);
+    const int ncand = max(0, min((cand_idx ? cand_nvalid[q] : ck.n_all) - ck.cand_off, kcand));
     const int lane = threadIdx.x & 31;
     const int64_t nw1 = (int64_t)n_windows + 1;
 
     for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
-        const int32_t d = cand_idx[q * kcand + c];
+        const int32_t d = cand_idx ? cand_idx[q * ck.cand_stride + ck.cand_off + c] : ck.cand_off + c;
         cand[c] = d;
         cbeg[c] = indptr[d];
         dot[c] = 0.0;
@@ -565,10 +576,10 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
             oi = (int32_t)(uint32_t)(key & 0xFFFFFFFFull);
             od = __uint_as_float((uint32_t)(key >> 32));
         }
-        idx_out[q * k + t] = oi;
-        dist_out[q * k + t] = od;
+        idx_out[q * ck.out_stride + ck.out_off + t] = oi;
+        dist_out[q * ck.out_stride + ck.out_off + t] = od;
     }
-    if (threadIdx.x == 0) nvalid_out[q] = nv;
+    if (threadIdx.x == 0 && ck.write_nvalid) nvalid_out[q] = nv;
 }
 
 int launch_row_max_feature(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, uint32_t* d_out_max,
@@ -597,12 +608,77 @@ int launch_row_norms(const int64_t* d_indptr, const float* d_val, int64_t n_rows
     return 1;
 }
 
+// Merge of chunked rerank results: one CTA per query sorts the row's [part_stride] (distance, index) pairs (the best
+// of every chunk, each chunk sorted and padded with (inf, -1)) by (distance, index) in shared memory and keeps the
+// first k. cand_nvalid == nullptr: brute force over n_all rows. exclude_row0 >= 0: the query's own row
+// (exclude_row0 + q) is dropped (sklearn's kneighbors_graph() convention).
+__global__ void __launch_bounds__(1024)
+k4_merge_rows_kernel(const int32_t* __restrict__ part_idx, const float* __restrict__ part_dist, int part_stride,
+                     const int32_t* __restrict__ cand_nvalid, int kcand, int n_all, int64_t exclude_row0, int P, int k,
+                     int32_t* __restrict__ idx_out, float* __restrict__ dist_out, int32_t* __restrict__ nvalid_out) {
+    extern __shared__ unsigned long long mkeys[];
+    const int64_t q = blockIdx.x;
+    const int64_t self = exclude_row0 >= 0 ? exclude_row0 + q : -1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (i < part_stride) {
+            const int32_t d = part_idx[q * part_stride + i];
+            // distances are >= 0, so their float bit patterns order like unsigned integers
+            if (d >= 0 && d != self)
+                key = ((unsigned long long)__float_as_uint(part_dist[q * part_stride + i]) << 32) | (uint32_t)d;
+        }
+        mkeys[i] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool up = (i & size) == 0;
+                    const unsigned long long a = mkeys[i], b = mkeys[j];
+                    if ((a > b) == up) { mkeys[i] = b; mkeys[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int total = cand_nvalid ? min(cand_nvalid[q], kcand) : n_all - (self >= 0 && self < n_all ? 1 : 0);
+    const int nv = min(total, k);
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const unsigned long long key = mkeys[t < P ? t : P - 1];
+        const bool ok = t < nv && t < P && key != ~0ull;
+        idx_out[q * k + t] = ok ? (int32_t)(uint32_t)key : -1;
+        dist_out[q * k + t] = ok ? __uint_as_float((uint32_t)(key >> 32)) : INFINITY;
+    }
+    if (threadIdx.x == 0) nvalid_out[q] = nv;
+}
+
+int launch_rerank_merge(const int32_t* d_part_idx, const float* d_part_dist, int part_stride,
+                        const int32_t* d_cand_nvalid, int kcand, int n_all, int64_t exclude_row0, int64_t nq, int k,
+                        int32_t* d_idx_out, float* d_dist_out, int32_t* d_nvalid_out, cudaStream_t stream) {
+    if (nq <= 0) return 0;
+    const int P = next_pow2(part_stride);
+    const size_t smem = (size_t)P * 8;
+    if (smem > 220 * 1024) return -1;
+    cudaFuncSetAttribute(k4_merge_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k4_merge_rows_kernel<<<(unsigned)nq, 1024, smem, stream>>>(d_part_idx, d_part_dist, part_stride, d_cand_nvalid, kcand,
+                                                              n_all, exclude_row0, P, k, d_idx_out, d_dist_out,
+                                                              d_nvalid_out);
+    return 1;
+}
+
+// One launch over candidate columns [cand_off, cand_off + kcand) of lists with row stride cand_stride; results to
+// output columns [out_off, out_off + k) of arrays with row stride out_stride. final != 0: nvalid_out is written.
+// d_cand_idx == nullptr: brute force, the candidates of every query are the database rows [0, n_all).
 int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* d_val, int64_t indptr0,
                   const double* d_norm2, const uint32_t* d_dir, int n_windows, int window_mode, int64_t q_row0,
-                  int64_t nq, const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int kcand, int k,
-                  int32_t* d_idx_out, float* d_dist_out, int32_t* d_nvalid_out, cudaStream_t stream) {
+                  int64_t nq, const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int cand_stride, int cand_off,
+                  int kcand, int k, int32_t* d_idx_out, float* d_dist_out, int out_stride, int out_off, int final,
+                  int32_t* d_nvalid_out, int n_all, cudaStream_t stream) {
     (void)indptr0;
     if (nq <= 0) return 0;
+    const K4Chunk ck{cand_stride, cand_off, out_stride, out_off, final, n_all};
     const int P = next_pow2(kcand);
     if (d_dir && n_windows > 0) {
         const size_t smem = (size_t)K4W_WORDS * 4 + (size_t)(K4W_KCAP + 32) * 4 + (size_t)P * 8 +
@@ -611,16 +687,16 @@ int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* 
             auto kern = window_mode == 64 ? k4_rerank_window_kernel<true> : k4_rerank_window_kernel<false>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             kern<<<(unsigned)nq, K4W_THREADS, smem, stream>>>(d_indptr, d_feat, d_val, d_norm2, d_dir, n_windows, q_row0,
-                                                              d_cand_idx, d_cand_nvalid, kcand, P, k, d_idx_out, d_dist_out,
-                                                              d_nvalid_out);
+                                                              d_cand_idx, d_cand_nvalid, kcand, P, k, ck, d_idx_out,
+                                                              d_dist_out, d_nvalid_out);
             return 1;
         }
     }
     const size_t smem = (size_t)K4_SLOTS * 8 + (size_t)P * 8 + (size_t)kcand * (8 + 8 + 8 + 4) + 16;
-    if (smem > 220 * 1024) return -1;   // caller reports SCHIC_ERR_UNSUPPORTED
+    if (smem > 220 * 1024) return -1;   // caller chunks the candidate lists
     cudaFuncSetAttribute(k4_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k4_rerank_kernel<<<(unsigned)nq, K4_THREADS, smem, stream>>>(d_indptr, d_feat, d_val, d_norm2, q_row0, d_cand_idx,
-                                                                 d_cand_nvalid, kcand, P, k, d_idx_out, d_dist_out,
+                                                                 d_cand_nvalid, kcand, P, k, ck, d_idx_out, d_dist_out,
                                                                  d_nvalid_out);
     return 1;
 }

@@ -66,6 +66,7 @@ class MinHash:
     def _ensure(self):
         if self._h is None:
             self._api = self._api_factory()
+            self._n_hashes_created = self.number_of_hash_functions
             self._h = self._api.create(
                 n_neighbors=self.n_neighbors, number_of_hash_functions=self.number_of_hash_functions,
                 hash_width=self.hash_width, fast=self.fast, absolute_numbers=self.absolute_numbers,
@@ -122,6 +123,7 @@ class MinHash:
             indices = indices.astype(np.uint32)
         api.set_feature_range(h, X.shape[1])      # ids are column indices of X: all < X.shape[1]
         api.fit_csr(h, X.indptr, indices, data, append)
+        self.number_of_hash_functions = self._created_hashes()    # a fit ends any active-hash prefix
         self._n_features = X.shape[1]
         return self
 
@@ -138,6 +140,26 @@ class MinHash:
     @property
     def n_fitted_(self) -> int:
         return 0 if self._h is None else self._api.n_fitted(self._h)
+
+    # ---- hyperopt fast path ------------------------------------------------------
+    def set_number_of_hash_functions(self, n_hashes: int):
+        """Switch the query side to the first ``n_hashes`` hash functions WITHOUT re-fitting: h_j depends only on j,
+        so that prefix of the fitted signatures is exactly what a fit with ``number_of_hash_functions=n_hashes``
+        computes. ``scHicClusterMinHashHyperopt.py:119-148`` re-runs the whole tool per trial with ``-nh`` drawn from a
+        range; with this a sweep fits once (at the largest ``-nh``) and keeps the CSR resident on the device.
+        ``n_hashes`` must not exceed the value the object was constructed with. The next fit switches back."""
+        api, h = self._ensure()
+        n_hashes = int(n_hashes)
+        if not 1 <= n_hashes <= self._created_hashes():
+            raise ValueError(f"n_hashes must be in [1, {self._created_hashes()}]")
+        api.set_active_hashes(h, n_hashes)
+        self.number_of_hash_functions = n_hashes
+        return self
+
+    def _created_hashes(self) -> int:
+        if getattr(self, "_n_hashes_created", None) is None:
+            self._n_hashes_created = self.number_of_hash_functions
+        return self._n_hashes_created
 
     # ---- parity hooks --------------------------------------------------------------------------
     def signatures(self) -> np.ndarray:

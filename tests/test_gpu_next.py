@@ -1,0 +1,162 @@
+"""GPU suite (-m gpu): the SURVEY 8(f) "next" rows built on the hot path's kernels.
+
+Row 3 - exact kNN (scHicCluster -drm knn, scHicCluster.py:179-180): K4 run as a brute-force sparse euclidean kNN,
+checked against the oracle AND against vectors produced by the reference's own scikit-learn call
+(tests/golden/knn_golden.npz) - this row is pinned.
+Row 4 - hyperopt fast path (scHicClusterMinHashHyperopt.py:119-148): one resident fit, the number of hash functions
+switched per trial; every switch must equal a fresh fit with that hash count."""
+import os
+
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix, vstack
+
+from conftest import GOLDEN, REF_KWARGS, Fitted
+from schicexplorer_b200 import MinHash, NearestNeighbors, synth
+from test_exact_knn import assert_graph_equal_up_to_ties, exact_graph, synthetic150
+from test_gpu_parity import RTOL, assert_neighbours_equal_up_to_ties, synth_csr
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- row 3: exact kNN ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,k", [("f20", 5), ("f20", 19), ("s150", 10)])
+def test_exact_knn_matches_reference_golden_and_oracle(cuda, oracle, fixture20, tag, k):
+    g = np.load(os.path.join(GOLDEN, "knn_golden.npz"))
+    X = fixture20[0] if tag == "f20" else synthetic150()
+    got = exact_graph(cuda, X, k)
+    assert_graph_equal_up_to_ties(got, (g[f"{tag}_k{k}_indptr"], g[f"{tag}_k{k}_indices"], g[f"{tag}_k{k}_data"]))
+    assert_graph_equal_up_to_ties(got, exact_graph(oracle, X, k))
+
+
+@pytest.mark.parametrize("mode", ["window", "hash"])
+def test_exact_knn_lists_vs_oracle(cuda, oracle, monkeypatch, mode):
+    """Neighbour lists (not only the graph), with and without the query row, on clustered cells plus empty, tiny and
+    duplicated rows; k from 1 to n - 1; both K4 kernels."""
+    monkeypatch.setenv("SCHIC_K4_MODE", mode)
+    Xs = synth_csr(180, seed=23)
+    ncols = Xs.shape[1]
+    one = csr_matrix(([2.0], ([0], [17])), shape=(1, ncols))
+    X = vstack([csr_matrix((1, ncols)), Xs[:90], one, Xs[40:43], Xs[90:], csr_matrix((1, ncols))]).tocsr()
+    n = X.shape[0]
+    for include_self in (False, True):
+        for k in (1, 25, n - 1):
+            hg = cuda.create(n_neighbors=k, number_of_hash_functions=1, fast=False)
+            ho = oracle.create(n_neighbors=k, number_of_hash_functions=1, fast=False)
+            for api, h in ((cuda, hg), (oracle, ho)):
+                api.fit_csr(h, X.indptr, X.indices, X.data.astype(np.float32), False)
+            a = cuda.kneighbors_exact(hg, k, include_self)
+            b = oracle.kneighbors_exact(ho, k, include_self)
+            assert_neighbours_equal_up_to_ties(*a, *b, RTOL)
+            assert (a[2] == k).all()
+            if not include_self:
+                assert (a[0] != np.arange(n)[:, None]).all()
+            cuda.destroy(hg); oracle.destroy(ho)
+
+
+def test_exact_knn_many_chunks(cuda, oracle):
+    """2 500 rows: three K4 chunks per query and a merge over 3 * min(k + 1, 1024) partial results."""
+    rng = np.random.default_rng(3)
+    ncols = 1 << 20
+    rows, cols = [], []
+    pools = [rng.choice(ncols, size=1500, replace=False) for _ in range(4)]
+    for r in range(2500):
+        c = np.unique(rng.choice(pools[r % 4], size=60, replace=False))
+        rows.append(np.full(len(c), r)); cols.append(c)
+    cc = np.concatenate(cols)
+    X = csr_matrix((rng.integers(1, 20, size=len(cc)).astype(np.float64), (np.concatenate(rows), cc)), shape=(2500, ncols))
+    for k in (30, 1100):
+        assert_graph_equal_up_to_ties(exact_graph(cuda, X, k), exact_graph(oracle, X, k))
+
+
+def test_nearest_neighbors_class_on_the_gpu(cuda):
+    from sklearn.neighbors import NearestNeighbors as SkNN
+    X = synthetic150()
+    nn = NearestNeighbors(n_neighbors=12, algorithm="ball_tree").fit(X)
+    assert nn._api.backend == "cuda"
+    dist, idx = nn.kneighbors()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sd, si = SkNN(n_neighbors=12, algorithm="ball_tree").fit(X).kneighbors()
+    np.testing.assert_allclose(dist, sd, rtol=RTOL)
+    same = idx == si
+    assert same.mean() > 0.99 and np.allclose(dist[~same], sd[~same], rtol=RTOL)     # only ties may swap
+    g = nn.kneighbors_graph(mode="distance")
+    assert g.shape == (150, 150) and (np.diff(g.indptr) == 12).all()
+    nn.close()
+
+
+def test_exact_knn_s10_shape_sampled(cuda):
+    """1 500 full-length S10-shaped cells (14 k non-zeros each): 2.2e6 pairs through the windowed kernel; sampled lists
+    recomputed directly from the sparse rows in float64."""
+    cfg = synth.SynthConfig(**{**synth.CONFIGS["s10"].__dict__, "n_cells": 1500})
+    ip, ix, dt, _ = synth.generate_csr(cfg, 0, 1500, workers=min(16, os.cpu_count() or 1))
+    X = synth.to_scipy(cfg, ip, ix, dt)
+    h = cuda.create(n_neighbors=20, number_of_hash_functions=1, fast=False)
+    cuda.set_feature_range(h, X.shape[1])
+    cuda.fit_csr(h, ip, ix, dt, False)
+    idx, dist, nv = cuda.kneighbors_exact(h, 20, include_self=False)
+    cuda.destroy(h)
+    assert (nv == 20).all() and (np.diff(dist, axis=1) >= 0).all()
+    rng = np.random.default_rng(1)
+    Xd = X.astype(np.float64)
+    sq = np.asarray(Xd.multiply(Xd).sum(axis=1)).ravel()
+    for q in rng.choice(1500, size=12, replace=False):
+        d2 = sq[q] + sq - 2.0 * np.asarray((Xd @ Xd[q].T).todense()).ravel()
+        d = np.sqrt(np.maximum(d2, 0.0)); d[q] = np.inf
+        order = np.lexsort((np.arange(1500), d))[:20]
+        np.testing.assert_allclose(dist[q], d[order], rtol=RTOL)
+        assert set(idx[q].tolist()) == set(order.tolist())
+
+
+# ---- row 4: hyperopt fast path ------------------------------------------------------------------------------------
+def test_active_hash_prefix_equals_fresh_fit(cuda, oracle):
+    """One resident fit at the sweep's largest hash count; every switched-to hash count gives the signatures, counts
+    and neighbour lists of a fresh fit with that count (the oracle's)."""
+    X = synth_csr(260, seed=29)
+    kw = dict(REF_KWARGS, number_of_hash_functions=1200)
+    hg = cuda.create(n_neighbors=30, fast=False, **kw)
+    cuda.fit_csr(hg, X.indptr, X.indices, X.data.astype(np.float32), False)
+    for H in (400, 1200, 37, 800, 800, 1):
+        cuda.set_active_hashes(hg, H)
+        okw = dict(REF_KWARGS, number_of_hash_functions=H, minimal_blocks_in_common=min(100, H))
+        with Fitted(oracle, X, fast=False, n_neighbors=30, **okw) as o:
+            assert np.array_equal(cuda.signatures(hg, H), o.sig())
+            if H >= 100:     # handle keeps minimal_blocks_in_common = 100 (as the reference's CLI does across -nh)
+                assert np.array_equal(cuda.collision_counts(hg), oracle.collision_counts(o.h))
+                assert_neighbours_equal_up_to_ties(*cuda.kneighbors(hg, 30), *oracle.kneighbors(o.h, 30), RTOL)
+                a, b = cuda.kneighbors(hg, 30, fast=1), oracle.kneighbors(o.h, 30, fast=1)
+                assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    with pytest.raises(Exception):
+        cuda.set_active_hashes(hg, 1201)
+    # a partial_fit switches back to the created hash count and appends to the full signatures
+    cuda.set_active_hashes(hg, 300)
+    Y = synth_csr(40, seed=30)
+    cuda.fit_csr(hg, Y.indptr, Y.indices, Y.data.astype(np.float32), True)
+    XY = vstack([X, Y]).tocsr()
+    with Fitted(oracle, XY, fast=False, n_neighbors=30, **kw) as o:
+        assert np.array_equal(cuda.signatures(hg, 1200), o.sig())
+        cuda.set_active_hashes(hg, 600)
+    with Fitted(oracle, XY, fast=True, n_neighbors=30, **dict(kw, number_of_hash_functions=600)) as o:
+        a, b = cuda.kneighbors(hg, 30, fast=1), oracle.kneighbors(o.h, 30, fast=1)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    cuda.destroy(hg)
+
+
+def test_minhash_class_hash_sweep(cuda, oracle):
+    """MinHash.set_number_of_hash_functions: the sweep of scHicClusterMinHashHyperopt without re-fitting."""
+    X = synth_csr(150, seed=33)
+    mh = MinHash(n_neighbors=150, fast=True, **dict(REF_KWARGS, number_of_hash_functions=1000))
+    mh.fit(X)
+    for H in (200, 600, 1000):
+        g = mh.set_number_of_hash_functions(H).kneighbors_graph(mode="distance")
+        with Fitted(oracle, X, fast=True, n_neighbors=150, **dict(REF_KWARGS, number_of_hash_functions=H)) as o:
+            ip, ix, dt = oracle.kneighbors_graph(o.h, 150)
+        assert np.array_equal(g.indptr, ip) and np.array_equal(g.indices, ix)
+        np.testing.assert_array_equal(g.data.astype(np.float32), dt)
+    with pytest.raises(ValueError):
+        mh.set_number_of_hash_functions(1001)
+    mh.fit(X)
+    assert mh.number_of_hash_functions == 1000 and mh.signatures().shape == (150, 1000)
+    mh.close()

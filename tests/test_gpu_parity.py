@@ -563,3 +563,32 @@ def test_table_prebuilt_during_upload(cuda, oracle):
     oracle.fit_csr(ho, sub_ip, sub_ix, None, False)
     assert np.array_equal(oracle.signatures(ho, 800), sig_pre[rows])
     oracle.destroy(ho)
+
+
+@pytest.mark.parametrize("k,ef", [(3200, 1), (800, 3)])
+def test_rerank_long_candidate_lists_are_chunked(cuda, oracle, k, ef):
+    """Exact rerank with k * excess_factor beyond what one CTA holds in shared memory (the CLI default k = n on a
+    few thousand cells with -em): K4 runs over chunks of 1024 candidates and a per-row merge picks the final k.
+    Three clusters of different sizes, so the lists end inside the first, the second and the third chunk."""
+    rng = np.random.default_rng(31)
+    ncols = 1 << 21
+    rows, cols = [], []
+    r = 0
+    for size in (2400, 700, 100):
+        pool = rng.choice(ncols, size=3000, replace=False)
+        for _ in range(size):
+            c = np.unique(rng.choice(pool, size=240, replace=False))
+            rows.append(np.full(len(c), r)); cols.append(c); r += 1
+    cc = np.concatenate(cols)
+    X = csr_matrix((rng.integers(1, 30, size=len(cc)).astype(np.float64), (np.concatenate(rows), cc)), shape=(r, ncols))
+    kw = dict(fast=False, n_neighbors=k, excess_factor=ef, number_of_hash_functions=128, minimal_blocks_in_common=2)
+    with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
+        a, b = cuda.kneighbors(g.h, k), oracle.kneighbors(o.h, k)
+        if ef == 1:
+            assert b[2].max() > 2048 and b[2].min() < 1024    # the lists really end in different chunks
+        assert_neighbours_equal_up_to_ties(*a, *b, RTOL)
+        if ef == 1:
+            gi, gc, gd = cuda.kneighbors_graph(g.h, k)
+            oi, oc, od = oracle.kneighbors_graph(o.h, k)
+            assert np.array_equal(gi, oi)
+            np.testing.assert_allclose(np.sort(gd), np.sort(od), rtol=RTOL)
