@@ -113,6 +113,15 @@ int schic_mh_kneighbors_exact(schic_mh_handle* h, int32_t k, int32_t include_sel
 int schic_mh_kneighbors_exact_graph(schic_mh_handle* h, int32_t k, int32_t include_self,
                                     int64_t* indptr, int32_t* indices, float* data);
 
+/* SURVEY 8(f)-4, the hyperopt fast path (scHicClusterMinHashHyperopt.py:119-148 re-runs the whole tool once per trial,
+ * with -nh drawn from a range): keep ONE fitted handle (created with the largest hash count of the sweep) and switch
+ * the number of hash functions the query side uses. h_j depends only on j, so the first n_hashes columns of the fitted
+ * signatures are exactly the signatures a fit with number_of_hash_functions = n_hashes would produce; the CSR stays
+ * resident and nothing is re-hashed. Afterwards signatures / collision_counts / kneighbors* behave as if the handle
+ * had been created with n_hashes (minimal_blocks_in_common etc. unchanged). The next fit (append or not) switches back
+ * to the created hash count. n_hashes in [1, number_of_hash_functions as created]. */
+int schic_mh_set_active_hashes(schic_mh_handle* h, int32_t n_hashes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,7 @@ struct schic_mh_handle {
     std::vector<uint64_t> idx;
     std::vector<float> val;
     std::vector<uint32_t> sig;  // [n, H]
+    int H_created = 0;          // hash count the handle was created with (schic_mh_set_active_hashes changes p's)
     // inverse index (rule 5), rebuilt lazily after every fit
     bool index_ok = false;
     std::vector<int32_t> order;        // [H, n] cells of table j sorted by (value, cell)
@@ -262,6 +263,7 @@ int schic_mh_create(const schic_mh_params* p, schic_mh_handle** out) {
     if (p->n_neighbors < 1) return fail(SCHIC_ERR_INVALID_ARG, "n_neighbors must be >= 1");
     auto* h = new schic_mh_handle();
     h->p = *p;
+    h->H_created = p->number_of_hash_functions;
     if (h->p.excess_factor < 1) h->p.excess_factor = 1;
     if (h->p.max_bin_size < 1) h->p.max_bin_size = std::numeric_limits<int64_t>::max();
     *out = h;
@@ -280,6 +282,11 @@ int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, 
     if (!h->p.fast && nnz > 0 && !data) return fail(SCHIC_ERR_INVALID_ARG, "data is required when fast=0");
     if (!append) {
         h->n = 0; h->indptr.assign(1, 0); h->idx.clear(); h->val.clear(); h->sig.clear();
+    }
+    if (h->p.number_of_hash_functions != h->H_created) {   // a fit ends schic_mh_set_active_hashes
+        h->p.number_of_hash_functions = h->H_created;
+        h->sig.clear();
+        compute_signatures(h, 0, h->n);
     }
     const int64_t r0 = h->n;
     const int64_t base = h->indptr.back();
@@ -416,6 +423,21 @@ int schic_mh_kneighbors_exact(schic_mh_handle* h, int32_t k, int32_t include_sel
             if (n_valid) n_valid[c] = (int32_t)cand.size();
         }
     }
+    return SCHIC_OK;
+}
+
+// SURVEY §8(f)-4 (hyperopt sweeps over -nh, scHicClusterMinHashHyperopt.py:119-148): from now on the handle behaves as
+// if created with n_hashes hash functions. The checker does NOT use the prefix property of the hash family: it simply
+// re-hashes every fitted row with n_hashes functions.
+int schic_mh_set_active_hashes(schic_mh_handle* h, int32_t n_hashes) {
+    if (int e = check_handle(h)) return e;
+    if (n_hashes < 1 || n_hashes > h->H_created)
+        return fail(SCHIC_ERR_INVALID_ARG, "n_hashes must be in [1, number_of_hash_functions as created]");
+    if (n_hashes == h->p.number_of_hash_functions) return SCHIC_OK;
+    h->p.number_of_hash_functions = n_hashes;
+    h->sig.clear();
+    compute_signatures(h, 0, h->n);
+    h->index_ok = false;
     return SCHIC_OK;
 }
 

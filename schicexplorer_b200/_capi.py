@@ -51,6 +51,7 @@ BASE_SYMBOLS = (
     "schic_mh_create", "schic_mh_destroy", "schic_mh_last_error", "schic_mh_backend",
     "schic_mh_fit_csr", "schic_mh_n_fitted", "schic_mh_signatures", "schic_mh_collision_counts",
     "schic_mh_kneighbors", "schic_mh_kneighbors_graph", "schic_mh_kneighbors_exact", "schic_mh_kneighbors_exact_graph",
+    "schic_mh_set_active_hashes",
 )
 # symbols only the CUDA library exports (include/schic_mh_cuda.h)
 CUDA_SYMBOLS = (
@@ -59,7 +60,6 @@ CUDA_SYMBOLS = (
     "schic_mh_rerank_prep_rows", "schic_mh_set_database_prep_device", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free", "schic_mh_kneighbors_exact_device",
-    "schic_mh_set_active_hashes",
 )
 
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
@@ -96,13 +96,13 @@ class CApi:
         L.schic_mh_kneighbors_graph.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
         L.schic_mh_kneighbors_exact.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
         L.schic_mh_kneighbors_exact_graph.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
+        L.schic_mh_set_active_hashes.argtypes = [_vp, _i32]
         self.backend = L.schic_mh_backend().decode()
         self.is_cuda = self.backend == "cuda"
         if self.is_cuda:
             L.schic_mh_fit_csr_async.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32]
             L.schic_mh_set_feature_range.argtypes = [_vp, C.c_uint64]
             L.schic_mh_kneighbors_exact_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
-            L.schic_mh_set_active_hashes.argtypes = [_vp, _i32]
             L.schic_mh_set_database_ready_event.argtypes = [_vp, _vp]
             L.schic_mh_rerank_windows.argtypes = [_vp, C.POINTER(_i32)]
             L.schic_mh_rerank_prep_rows.argtypes = [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp]
@@ -242,14 +242,14 @@ class CApi:
         nnz = int(indptr[-1])
         return indptr, indices[:nnz], data[:nnz]
 
+    def set_active_hashes(self, h, n_hashes: int):
+        """Query side uses the first n_hashes hash functions of the fitted signatures (hyperopt sweeps over -nh)."""
+        self.check(self.lib.schic_mh_set_active_hashes(_vp(h), int(n_hashes)))
+
     # -- include/schic_mh_cuda.h (device-pointer entry points) -------------------------------
     def kneighbors_exact_device(self, h, k, include_self, d_idx, d_dist, d_nvalid):
         self.check(self.lib.schic_mh_kneighbors_exact_device(_vp(h), k, int(include_self), _ptr(d_idx), _ptr(d_dist),
                                                              _ptr(d_nvalid)))
-
-    def set_active_hashes(self, h, n_hashes: int):
-        """Query side uses the first n_hashes hash functions of the fitted signatures (hyperopt sweeps over -nh)."""
-        self.check(self.lib.schic_mh_set_active_hashes(_vp(h), int(n_hashes)))
 
     def fit_csr_device(self, h, n_rows, nnz, d_indptr, d_indices, d_data, append: bool):
         self.check(self.lib.schic_mh_fit_csr_device(_vp(h), n_rows, nnz, _ptr(d_indptr), _ptr(d_indices),

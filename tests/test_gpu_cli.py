@@ -44,3 +44,29 @@ def test_cli_graph_equals_oracle(cuda, oracle, fixture20):
     with Fitted(oracle, X, fast=True, n_neighbors=20) as f:
         oi, oc, od = oracle.kneighbors_graph(f.h, 20)
     assert np.array_equal(gg.indptr, oi) and np.array_equal(gg.indices, oc) and np.array_equal(gg.data, od)
+
+
+@pytest.mark.parametrize("method,extra", [("spectral", "-drm knn"), ("kmeans", "-drm knn"), ("kmeans", "-drm knn -ic"),
+                                          ("kmeans", "-drm knn -pca -dim_pca 10"), ("spectral", "-drm knn -k 7")])
+def test_schiccluster_knn_cli_on_gpu(cuda, tmp_path, method, extra):
+    """scHicCluster -drm knn (reference cases test_scHicCluster.py:100-135, 219-235) with the kNN step on the GPU."""
+    from schicexplorer_b200 import scHicCluster
+    out = str(tmp_path / "clusters.txt")
+    args = f"--matrix {MATRIX} --numberOfClusters 3 --clusterMethod {method} --outFileName {out} -t 2 {extra}".split()
+    scHicCluster.main(args)
+    rows = [l.split(" ") for l in open(out).read().strip().split("\n")]
+    assert [r[0] for r in rows] == scool.list_scool_cells(MATRIX)
+    assert len({r[1] for r in rows}) == 3
+
+
+def test_schiccluster_knn_graph_equals_sklearn(cuda):
+    import warnings
+    from sklearn.neighbors import NearestNeighbors as SkNN
+    from schicexplorer_b200 import loader, scHicCluster
+    cells, chroms = scool.read_scool(MATRIX)
+    X, _ = loader.cells_to_csr(cells, chroms)
+    g = scHicCluster.knn_graph(X, 19)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        s = SkNN(n_neighbors=19, algorithm="ball_tree").fit(X).kneighbors_graph(mode="distance")
+    np.testing.assert_allclose(np.asarray(g.todense()), np.asarray(s.todense()), rtol=1e-5)

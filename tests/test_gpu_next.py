@@ -160,3 +160,24 @@ def test_minhash_class_hash_sweep(cuda, oracle):
     mh.fit(X)
     assert mh.number_of_hash_functions == 1000 and mh.signatures().shape == (150, 1000)
     mh.close()
+
+
+def test_hyperopt_tool_on_gpu(cuda, oracle, fixture20, tmp_path):
+    """scHicClusterMinHashHyperopt on the CUDA back end: each CSR hashed once, every trial's graph == a fresh fit's."""
+    from schicexplorer_b200 import loader, scHicClusterMinHashHyperopt as hyper
+    matrix = os.path.join(GOLDEN, "test_matrix.scool")
+    res = hyper.ResidentCells(matrix, 1000, 1000)
+    for intra, H in [(False, 400), (True, 1000), (False, 1000), (True, 250), (False, 400)]:
+        g = res.graph(intra, H)
+        X, _ = loader.cells_to_csr(res.cells, res.chroms, intra_only=intra)
+        with Fitted(oracle, X, fast=True, n_neighbors=20, **dict(REF_KWARGS, number_of_hash_functions=H)) as fresh:
+            ip, ix, dt = oracle.kneighbors_graph(fresh.h, 20)
+        assert np.array_equal(g.indptr, ip) and np.array_equal(g.indices, ix)
+        np.testing.assert_array_equal(g.data.astype(np.float32), dt)
+    assert res.fits == 2 and res.minhash(False)._api.backend == "cuda"
+    res.close()
+    colors = tmp_path / "cell_types.txt"
+    colors.write_text("".join(f"{n}\t{'ABC'[i % 3]}\n" for i, n in enumerate(res.names)))
+    out = tmp_path / "best.txt"
+    best = hyper.main(f"-m {matrix} -c {colors} -o {out} --runs 4 -noh 200 900 200 -noc 2 5 -nop 5 16 5 -me random".split())
+    assert out.read_text().startswith("# Created by scHiCExplorer") and best["numberOfHashFunctions"] in (200, 400, 600, 800)
