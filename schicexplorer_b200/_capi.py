@@ -103,6 +103,9 @@ class CApi:
             L.schic_mh_fit_csr_async.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32]
             L.schic_mh_set_feature_range.argtypes = [_vp, C.c_uint64]
             L.schic_mh_kneighbors_exact_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
+            L.schic_pca_fit_transform.argtypes = [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]
+            L.schic_pca_fit_transform_csr.argtypes = [_i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]
+            L.schic_pca_stage_ms.argtypes = [_vp, _i32]
             L.schic_mh_set_database_ready_event.argtypes = [_vp, _vp]
             L.schic_mh_rerank_windows.argtypes = [_vp, C.POINTER(_i32)]
             L.schic_mh_rerank_prep_rows.argtypes = [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp]
@@ -267,6 +270,35 @@ class CApi:
         a, b, c, n = _vp(), _vp(), _vp(), _i64()
         self.check(self.lib.schic_mh_csr_device(_vp(h), C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
         return a.value, b.value, c.value, n.value
+
+    # -- include/schic_pca.h ---------------------------------------------------------------------
+    def pca_fit_transform(self, X, n_components: int, device: int = -1, want_components: bool = False):
+        """PCA(...).fit_transform(X)[:, :n_components] on the device. X: dense float64 [n, c] or a scipy CSR whose
+        arrays are int64 / int32 / float32 (the graph entry points' layout). Returns (embedding, singular values,
+        components or None)."""
+        from scipy.sparse import issparse
+        n_rows, n_cols = X.shape
+        m = int(n_components)
+        out = np.empty((n_rows, m), dtype=np.float64)
+        sv = np.empty(m, dtype=np.float64)
+        comp = np.empty((m, n_cols), dtype=np.float64) if want_components else None
+        if issparse(X):
+            X = X.tocsr()
+            indptr = np.ascontiguousarray(X.indptr, dtype=np.int64)
+            indices = np.ascontiguousarray(X.indices, dtype=np.int32)
+            data = np.ascontiguousarray(X.data, dtype=np.float32)
+            self.check(self.lib.schic_pca_fit_transform_csr(n_rows, n_cols, _ptr(indptr), _ptr(indices), _ptr(data), m,
+                                                            device, _ptr(out), _ptr(sv), _ptr(comp)))
+        else:
+            Xd = np.ascontiguousarray(X, dtype=np.float64)
+            self.check(self.lib.schic_pca_fit_transform(_ptr(Xd), n_rows, n_cols, m, device, _ptr(out), _ptr(sv), _ptr(comp)))
+        return out, sv, comp
+
+    def pca_stage_ms(self) -> dict:
+        out = np.zeros(7, dtype=np.float32)
+        self.check(self.lib.schic_pca_stage_ms(_ptr(out), 7))
+        names = ("upload_centre", "covariance", "tridiagonalise", "eigenvalues", "eigenvectors", "project", "total")
+        return dict(zip(names, out.tolist()))
 
     def set_database_device(self, h, n_total, row0, d_sig, d_indptr=None, d_indices=None, d_data=None):
         self.check(self.lib.schic_mh_set_database_device(_vp(h), n_total, row0, _ptr(d_sig), _ptr(d_indptr),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libschic_mh.so")
 SOURCES = ["capi.cu", "k1_signatures.cu", "k1_table.cu", "k2_buckets.cu", "k3_collisions.cu", "k3_select.cu", "k4_rerank.cu", "k5_graph.cu",
-           "int_peak.cu"]
+           "int_peak.cu", "pca_dense.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 # SCHIC_K1_ALL_VARIANTS=1 also compiles the 20 instruction-selection variants of K1 that
@@ -30,7 +30,7 @@ def _stale(target: str, deps) -> bool:
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "nvcc")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    headers += [os.path.join(HERE, "..", "include", f) for f in ("schic_mh.h", "schic_mh_cuda.h")]
+    headers += [os.path.join(HERE, "..", "include", f) for f in ("schic_mh.h", "schic_mh_cuda.h", "schic_pca.h")]
     headers.append(os.path.abspath(__file__))
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)

@@ -4,8 +4,9 @@ Mirrors the call sites ``/root/reference/schicexplorer/scHicClusterMinHash.py:39
 409-415``: ``fit(X, pSaveMemory=, pPca=, pPcaDimensions=, pUmap=, pUmapDict=)`` builds the kNN
 graph with :class:`MinHash` (the GPU hot path), then runs the same host post-processing that the
 ``--saveMemory`` branch spells out in-tree (:355-390): nan/inf scrub, PCA with ``n-1`` components
-cut to ``pPcaDimensions``, optional UMAP, ``clusteringObject.fit``. PCA / UMAP / clustering stay on
-the host (scikit-learn), exactly as in the reference.
+cut to ``pPcaDimensions``, optional UMAP, ``clusteringObject.fit``. The PCA runs on the GPU
+(:class:`schicexplorer_b200.pca.PCA`, SURVEY 8(f)-2: same numbers as scikit-learn's, only the columns that are
+kept are extracted); UMAP / clustering stay on the host (umap-learn, scikit-learn), exactly as in the reference.
 """
 from __future__ import annotations
 
@@ -38,13 +39,11 @@ class MinHashClustering:
     @staticmethod
     def _post_process(graph, pPca, pPcaDimensions, pUmap, pUmapDict):
         if pPca:
-            from sklearn.decomposition import PCA
-            dense = np.nan_to_num(np.asarray(graph.todense()) if issparse(graph) else np.asarray(graph))
-            dense[np.isinf(dense)] = 0
-            pca = PCA(n_components=min(dense.shape) - 1)     # :358-362
-            graph = pca.fit_transform(dense)
-            if pPcaDimensions:
-                graph = graph[:, :min(pPcaDimensions, graph.shape[0])]   # :364-366
+            from .pca import PCA
+            n_components = max(1, min(graph.shape) - 1)      # :358-362
+            keep = min(pPcaDimensions, graph.shape[0]) if pPcaDimensions else None   # :364-366
+            # (non-finite entries are zeroed on the device while the graph is densified)
+            graph = PCA(n_components=n_components, keep=keep).fit_transform(graph)
         if pUmap:
             try:
                 import umap

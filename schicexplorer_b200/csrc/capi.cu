@@ -63,6 +63,10 @@ enum Stage { ST_H2D = 0, ST_SIG, ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H
 
 }  // namespace
 
+namespace schic {
+int set_error(int code, const std::string& msg) { return fail(code, msg); }
+}  // namespace schic
+
 struct schic_mh_handle {
     schic_mh_params p{};
     int device = 0;

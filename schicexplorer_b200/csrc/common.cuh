@@ -4,9 +4,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 #include "../../include/schic_mh.h"
 
 namespace schic {
+
+// Sets the thread-local message schic_mh_last_error() returns (capi.cu); returns code.
+int set_error(int code, const std::string& msg);
 
 constexpr uint32_t kModulus = SCHIC_MH_MODULUS;  // 2^31 - 1; also the empty-row sentinel
 

@@ -5,7 +5,8 @@ choices); ``main`` follows ``:127-210``: load the cells into one (cells x bins^2
 ``pca``), cluster (``spectral`` | ``kmeans``), write ``<cell name> <cluster id>`` lines. The one compute-heavy step, the
 exact euclidean kNN graph of ``:179-180`` (sklearn ``NearestNeighbors(...).kneighbors_graph(mode='distance')``, brute
 force on 7.5 M-dimensional sparse rows), runs on the B200 through :class:`schicexplorer_b200.knn.NearestNeighbors`;
-PCA / k-means / spectral clustering stay on the host with scikit-learn exactly as in the reference.
+the PCA on top of it (``-pca``, ``:183-188``) through :class:`schicexplorer_b200.pca.PCA`; ``-drm pca``, k-means and
+spectral clustering stay on the host (numpy / scikit-learn) exactly as in the reference.
 The cell-type colouring / LaTeX-table extras of the reference (``-cct``, ``-ccb``, ``-lt``) are accepted and skipped
 with a warning (plot cosmetics, out of scope per SURVEY 8).
 """
@@ -90,12 +91,11 @@ def main(args=None):
             args.numberOfNearestNeighbors = reduce_to_dimension
         neighborhood_matrix = knn_graph(neighborhood_matrix, args.numberOfNearestNeighbors)
         if args.additionalPCA:
-            from sklearn.decomposition import PCA
-            pca = PCA(n_components=min(neighborhood_matrix.shape) - 1)
-            neighborhood_matrix = pca.fit_transform(np.asarray(neighborhood_matrix.todense()))
+            from .pca import PCA                     # :183-188 on the GPU; only the kept columns are extracted
             if args.dimensionsPCA:
                 args.dimensionsPCA = min(args.dimensionsPCA, neighborhood_matrix.shape[0])
-                neighborhood_matrix = neighborhood_matrix[:, :args.dimensionsPCA]
+            pca = PCA(n_components=min(neighborhood_matrix.shape) - 1, keep=args.dimensionsPCA or None)
+            neighborhood_matrix = pca.fit_transform(neighborhood_matrix)
     elif args.dimensionReductionMethod == 'pca':
         from scipy import linalg
         corrmatrix = np.cov(np.asarray(neighborhood_matrix.todense()))

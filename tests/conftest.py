@@ -74,3 +74,23 @@ class Fitted:
 
     def __exit__(self, *a):
         self.close()
+
+
+class OraclePcaApi:
+    """Stands in for the CUDA library behind schicexplorer_b200.pca.PCA in the CPU suite: same method, numpy oracle."""
+    backend = "oracle"
+
+    def pca_fit_transform(self, X, n_components, device=-1, want_components=False):
+        from scipy.sparse import issparse
+        from oracle import pca_np
+        dense = np.asarray(X.todense(), dtype=np.float64) if issparse(X) else np.asarray(X, dtype=np.float64)
+        emb, sv, comp = pca_np.pca_fit_transform(dense, n_components)
+        return emb, sv, (comp if want_components else None)
+
+
+@pytest.fixture(autouse=True)
+def _oracle_pca_in_the_cpu_suite(request, monkeypatch):
+    """CPU tests exercise the host logic with the oracles injected behind the C-ABI shells; -m gpu tests run the product."""
+    if request.node.get_closest_marker("gpu") is None:
+        from schicexplorer_b200.pca import PCA
+        monkeypatch.setattr(PCA, "_api_factory", staticmethod(lambda: OraclePcaApi()))

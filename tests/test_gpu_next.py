@@ -181,3 +181,100 @@ def test_hyperopt_tool_on_gpu(cuda, oracle, fixture20, tmp_path):
     out = tmp_path / "best.txt"
     best = hyper.main(f"-m {matrix} -c {colors} -o {out} --runs 4 -noh 200 900 200 -noc 2 5 -nop 5 16 5 -me random".split())
     assert out.read_text().startswith("# Created by scHiCExplorer") and best["numberOfHashFunctions"] in (200, 400, 600, 800)
+
+
+# ---- row 2: dense-graph PCA -------------------------------------------------------------------------------------------
+def _pca_reference(X, dim):
+    from sklearn.decomposition import PCA as SkPCA
+    full = SkPCA(n_components=min(X.shape) - 1).fit(X)
+    return full.transform(X)[:, :dim], full.singular_values_[:dim], full.components_[:dim]
+
+
+def _close(got, want, rtol=1e-9):
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= rtol * np.abs(want).max()
+
+
+def test_pca_fixture_graph_vs_sklearn_and_oracle(cuda, oracle, fixture20):
+    """The graph scHicClusterMinHash builds on the reference's 20 cells -> PCA(n-1 components)[:, :dim]: device ==
+    scikit-learn (the reference's call) == numpy oracle; CSR input (densified on the device) == dense input."""
+    from oracle import pca_np
+    with Fitted(cuda, fixture20[0], fast=True, n_neighbors=20) as f:
+        ip, ix, dt = cuda.kneighbors_graph(f.h, 20)
+    G = csr_matrix((dt, ix, ip), shape=(20, 20))
+    X = np.asarray(G.todense(), dtype=np.float64)
+    for dim in (2, 19):
+        emb, sv, comp = _pca_reference(X, dim)
+        got, gsv, gcomp = cuda.pca_fit_transform(X, dim, want_components=True)
+        _close(got, emb); _close(gcomp, comp)
+        np.testing.assert_allclose(gsv, sv, rtol=1e-10, atol=1e-12 * sv[0])
+        got2, gsv2, _ = cuda.pca_fit_transform(G, dim)
+        _close(got2, emb)
+        o_emb, o_sv, _ = pca_np.pca_fit_transform(X, dim)
+        _close(got, o_emb)
+    st = cuda.pca_stage_ms()
+    assert st["total"] > 0 and abs(sum(v for k, v in st.items() if k != "total") - st["total"]) < 1e-3 * st["total"] + 1e-3
+
+
+@pytest.mark.parametrize("n,dim,seed", [(1, 1, 0), (2, 1, 0), (3, 2, 0), (65, 64, 0), (150, 100, 1), (700, 100, 2), (1500, 60, 3)])
+def test_pca_graph_like_matrices(cuda, n, dim, seed):
+    from test_pca import graph_like
+    if n < 4:
+        X = np.random.default_rng(seed).standard_normal((n + 3, n))      # tiny feature counts
+        want = None
+    else:
+        X = graph_like(n, seed)
+    got, gsv, comp = cuda.pca_fit_transform(X, dim, want_components=True)
+    if n < 4:
+        from sklearn.decomposition import PCA as SkPCA
+        full = SkPCA(n_components=dim).fit(X)
+        _close(got, full.transform(X)); _close(comp, full.components_)
+        return
+    emb, sv, rcomp = _pca_reference(X, dim)
+    _close(got, emb); _close(comp, rcomp)
+    np.testing.assert_allclose(gsv, sv, rtol=1e-10, atol=1e-12 * sv[0])
+
+
+def test_pca_rectangular_scrub_and_errors(cuda):
+    from test_pca import graph_like
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((120, 70))
+    emb, _, _ = _pca_reference(X, 30)
+    _close(cuda.pca_fit_transform(X, 30)[0], emb)
+    X = rng.standard_normal((70, 120))
+    emb, _, _ = _pca_reference(X, 30)
+    _close(cuda.pca_fit_transform(X, 30)[0], emb)
+    Y = graph_like(90, 4)
+    Y[[5, 17, 60]] = 0.0; Y[:, [5, 17, 60]] = 0.0
+    Z = Y.copy(); Z[3, 8] = np.inf; Z[4, 9] = np.nan
+    Y[3, 8] = 0.0; Y[4, 9] = 0.0
+    emb, _, _ = _pca_reference(Y, 25)
+    _close(cuda.pca_fit_transform(Z, 25)[0], emb)
+    Zs = csr_matrix(Z.astype(np.float32))
+    emb32, _, _ = _pca_reference(np.nan_to_num(np.asarray(Zs.todense(), dtype=np.float64), nan=0.0, posinf=0.0, neginf=0.0), 25)
+    _close(cuda.pca_fit_transform(Zs, 25)[0], emb32)
+    with pytest.raises(Exception):
+        cuda.pca_fit_transform(Y, 91)
+    with pytest.raises(Exception):
+        cuda.pca_fit_transform(Y, 0)
+
+
+def test_pca_class_and_clustering_post_step(cuda, fixture20):
+    """schicexplorer_b200.PCA mirrors the sklearn surface the tools use; MinHashClustering's post-step runs on it."""
+    from sklearn.decomposition import PCA as SkPCA
+    from schicexplorer_b200 import MinHashClustering
+    from schicexplorer_b200.pca import PCA
+    from test_pca import graph_like
+    X = graph_like(200, 7)
+    ref = SkPCA(n_components=199).fit(X)
+    p = PCA(n_components=199, keep=40)
+    emb = p.fit_transform(X)
+    _close(emb, ref.transform(X)[:, :40])
+    _close(p.components_, ref.components_[:40])
+    np.testing.assert_allclose(p.singular_values_, ref.singular_values_[:40], rtol=1e-10)
+    np.testing.assert_allclose(p.explained_variance_, ref.explained_variance_[:40], rtol=1e-9)
+    _close(p.transform(X[:10]), ref.transform(X[:10])[:, :40])
+    G = csr_matrix(X.astype(np.float32))         # graphs cross the C ABI as float32 (as kneighbors_graph returns them)
+    ref32 = SkPCA(n_components=199).fit_transform(np.asarray(G.todense(), dtype=np.float64))
+    out = MinHashClustering._post_process(G, True, 30, False, None)
+    _close(out, ref32[:, :30])
