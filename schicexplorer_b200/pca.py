@@ -18,7 +18,13 @@ from . import _capi
 class PCA:
     _api_factory = staticmethod(_capi.cuda_api)
 
-    def __init__(self, n_components=None, keep=None, device=-1):
+    def __init__(self, n_components=None, keep=None, device=-1, **kwargs):
+        # svd_solver / whiten / random_state ... of sklearn's constructor: this class is the full-SVD, non-whitening
+        # PCA the reference asks for; other settings are refused rather than silently ignored
+        unsupported = {k: v for k, v in kwargs.items() if not (k == "svd_solver" and v in ("auto", "full")) and
+                       not (k == "whiten" and not v) and k not in ("random_state", "copy")}
+        if unsupported:
+            raise ValueError(f"unsupported PCA arguments: {sorted(unsupported)}")
         self.n_components = n_components
         self.keep = keep
         self.device = int(device)
