@@ -14,6 +14,7 @@
 // The numpy restatement of exactly these steps is oracle/pca_np.py (pinned to scikit-learn).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -137,7 +138,7 @@ pca_gemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restr
         for (int kk = 0; kk < GK; ++kk) {
             double a[4], b[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { a[u] = As[kk][ty * 4 + u]; b[u] = Bs[kk][tx * 4 + u]; }
+            for (int u = 0; u < 4; ++u) { a[u] = As[kk][ty + 16 * u]; b[u] = Bs[kk][tx + 16 * u]; }   // conflict-free: consecutive lanes, consecutive doubles
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -149,7 +150,7 @@ pca_gemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restr
     for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            const int64_t i = i0 + ty * 4 + u, j = j0 + tx * 4 + v;
+            const int64_t i = i0 + ty + 16 * u, j = j0 + tx + 16 * v;
             if (i < M && j < N) {
                 out[i * ldo + j] = acc[u][v];
                 if (SYM && blockIdx.x != blockIdx.y) out[j * ldo + i] = acc[u][v];
@@ -162,8 +163,11 @@ pca_gemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restr
 //   w_j = tau_j S v_j - (tau_j^2 (v_j^T S v_j) / 2) v_j          (praw = S v_j comes from the previous pass; j = -1: 0)
 //   x   = row r = j+1 of S with the pending rank-2 update (v_j, w_j) applied;  d[r] = x[r]
 //   reflector r from x[r+1:]: beta, tau_r, v_r (v_r[r+1] = 1); e[r] = beta; v_r is also kept in S[r][r+2:].
+// LOWER: the passes keep only the lower triangle up to date (pca_tridiag_lower_pass_kernel), so row r is read as
+// column r below the diagonal, and praw -- accumulated there with atomics -- is zeroed here once consumed.
+template <bool LOWER>
 __global__ void __launch_bounds__(1024)
-pca_tridiag_step_kernel(double* __restrict__ S, int64_t n, int64_t j, const double* __restrict__ praw,
+pca_tridiag_step_kernel(double* __restrict__ S, int64_t n, int64_t j, double* __restrict__ praw,
                         const double* __restrict__ vcur, double* __restrict__ w, double* __restrict__ vnext,
                         double* __restrict__ d, double* __restrict__ e, double* __restrict__ tau) {
     __shared__ double red[33];
@@ -174,7 +178,10 @@ pca_tridiag_step_kernel(double* __restrict__ S, int64_t n, int64_t j, const doub
         for (int64_t i = r + threadIdx.x; i < n; i += blockDim.x) part += praw[i] * vcur[i];
         const double alpha = block_sum(part, red);
         const double coef = 0.5 * tj * tj * alpha;
-        for (int64_t i = r + threadIdx.x; i < n; i += blockDim.x) w[i] = tj * praw[i] - coef * vcur[i];
+        for (int64_t i = r + threadIdx.x; i < n; i += blockDim.x) {
+            w[i] = tj * praw[i] - coef * vcur[i];
+            if (LOWER) praw[i] = 0.0;
+        }
     } else {
         for (int64_t i = threadIdx.x; i < n; i += blockDim.x) w[i] = 0.0;
     }
@@ -183,7 +190,7 @@ pca_tridiag_step_kernel(double* __restrict__ S, int64_t n, int64_t j, const doub
     double* __restrict__ row = S + r * n;
     double part = 0.0;
     for (int64_t k = r + threadIdx.x; k < n; k += blockDim.x) {
-        const double x = row[k] - vr * w[k] - wr * (j >= 0 ? vcur[k] : 0.0);
+        const double x = (LOWER ? S[k * n + r] : row[k]) - vr * w[k] - wr * (j >= 0 ? vcur[k] : 0.0);
         vnext[k] = x;
         if (k >= r + 2) part += x * x;
     }
@@ -225,6 +232,83 @@ pca_tridiag_pass_kernel(double* __restrict__ S, int64_t n, int64_t t0, const dou
     }
     acc = warp_sum(acc);
     if (lane == 0) praw[i] = acc;
+}
+
+// The same pass on the lower triangle only (half the traffic): rows i >= t0, columns t0 <= k <= i.
+//   S[i][k] -= v_j[i] w_j[k] + w_j[i] v_j[k];   praw[i] += S_new[i][k] v_{j+1}[k];   praw[k] += S_new[i][k] v_{j+1}[i] (k < i)
+// Grid (band of 32 rows, chunk of 8 column tiles); a warp owns one 32 x 32 tile, a lane one of its columns: the column
+// sum stays in a register over the 32 rows, the 32 row sums are transposed across the warp at the end (31 shuffles), so
+// a tile costs 2 x 32 atomics. Short CTAs keep the per-step critical path at a few load round trips.
+__device__ __forceinline__ double tile_row_sums(double (&racc)[32], int lane) {
+    // after round h (16, 8, 4, 2, 1) a lane keeps the accumulators whose index agrees with its lane bits so far;
+    // at the end lane l holds the warp-wide sum of row l
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+        const bool upper = (lane & h) != 0;
+#pragma unroll
+        for (int u = 0; u < h; ++u) {
+            const double send = upper ? racc[u] : racc[u + h];
+            const double keep = upper ? racc[u + h] : racc[u];
+            racc[u] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return racc[0];
+}
+
+__global__ void __launch_bounds__(256, 2)
+pca_tridiag_lower_pass_kernel(double* __restrict__ S, int64_t n, int64_t t0, const double* __restrict__ vcur,
+                              const double* __restrict__ w, const double* __restrict__ vnext, double* __restrict__ praw) {
+    __shared__ double vs[32], ws[32], vns[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i0 = t0 + 32 * (int64_t)blockIdx.x;
+    const int rows = (int)min((int64_t)32, n - i0);
+    const int64_t kfirst = t0 & ~(int64_t)31;                 // tiles aligned to 256 B
+    const int64_t k0 = kfirst + 32 * ((int64_t)blockIdx.y * 8 + warp);
+    if (kfirst + 32 * (int64_t)blockIdx.y * 8 > i0 + rows - 1) return;      // whole CTA right of the diagonal block
+    if (threadIdx.x < 32) {
+        const int64_t i = i0 + threadIdx.x;
+        vs[threadIdx.x] = i < n ? vcur[i] : 0.0;
+        ws[threadIdx.x] = i < n ? w[i] : 0.0;
+        vns[threadIdx.x] = i < n ? vnext[i] : 0.0;
+    }
+    __syncthreads();
+    if (k0 > i0 + rows - 1) return;
+    const int64_t k = k0 + lane;
+    const bool kin = k >= t0 && k < n;
+    const double wk = kin ? w[k] : 0.0, vk = kin ? vcur[k] : 0.0, vnk = kin ? vnext[k] : 0.0;
+    const bool inner = k0 + 31 < i0 && k0 >= t0;              // tile entirely left of the band's diagonal block
+    double racc[32];
+    double cacc = 0.0;
+    double* __restrict__ gp = S + i0 * n + k;                // walks down the band's rows
+    // rows in groups of 8: all loads of a group are issued before its first store (the compiler keeps loads behind
+    // earlier stores through the same base pointer, which would leave one load in flight per warp)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        double x[8];
+        bool ok[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = 8 * g + u;
+            ok[u] = r < rows && (inner || (kin && k <= i0 + r));
+            x[u] = ok[u] ? gp[u * n] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = 8 * g + u;
+            double ra = 0.0;
+            if (ok[u]) {
+                const double sv = x[u] - vs[r] * wk - ws[r] * vk;
+                gp[u * n] = sv;
+                ra = sv * vnk;
+                if (inner || k < i0 + r) cacc = fma(sv, vns[r], cacc);
+            }
+            racc[r] = ra;
+        }
+        gp += 8 * n;
+    }
+    if (kin && cacc != 0.0) atomicAdd(&praw[k], cacc);
+    const double rsum = tile_row_sums(racc, lane);
+    if (lane < rows && rsum != 0.0) atomicAdd(&praw[i0 + lane], rsum);
 }
 
 // ---- P4: Sturm bisection ----------------------------------------------------------------------------------------
@@ -481,12 +565,21 @@ int pca_device(double* X, int64_t n_rows, int64_t n_cols, int m, cudaStream_t s,
     PCA_CU(cudaMemsetAsync(e.p, 0, n * sizeof(double), s));
     {
         double* vcur = va.p; double* vnext = vb.p;
+        const char* mode = getenv("SCHIC_PCA_TRIDIAG");          // "full": the full-square pass (tests compare the two)
+        const bool lower = !(mode && strcmp(mode, "full") == 0);
         for (int64_t j = -1; j <= n - 2; ++j) {
-            pca_tridiag_step_kernel<<<1, 1024, 0, s>>>(C.p, n, j, praw.p, vcur, w.p, vnext, d.p, e.p, tau.p);
+            if (lower) pca_tridiag_step_kernel<true><<<1, 1024, 0, s>>>(C.p, n, j, praw.p, vcur, w.p, vnext, d.p, e.p, tau.p);
+            else pca_tridiag_step_kernel<false><<<1, 1024, 0, s>>>(C.p, n, j, praw.p, vcur, w.p, vnext, d.p, e.p, tau.p);
             const int64_t t0 = j + 2;
             if (t0 < n) {
                 const int64_t rows = n - t0;
-                pca_tridiag_pass_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(C.p, n, t0, vcur, w.p, vnext, praw.p);
+                if (lower) {
+                    const int64_t nb = (rows + 31) / 32;       // bands; band b has at most b + 2 column tiles
+                    dim3 grid((unsigned)nb, (unsigned)((nb + 1 + 7) / 8));
+                    pca_tridiag_lower_pass_kernel<<<grid, 256, 0, s>>>(C.p, n, t0, vcur, w.p, vnext, praw.p);
+                }
+                else
+                    pca_tridiag_pass_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(C.p, n, t0, vcur, w.p, vnext, praw.p);
             }
             std::swap(vcur, vnext);
         }

@@ -235,6 +235,19 @@ def test_pca_graph_like_matrices(cuda, n, dim, seed):
     np.testing.assert_allclose(gsv, sv, rtol=1e-10, atol=1e-12 * sv[0])
 
 
+def test_pca_full_square_tridiagonal_pass_agrees(cuda, monkeypatch):
+    """SCHIC_PCA_TRIDIAG=full selects the first (full-square) trailing pass; the default walks the lower triangle only."""
+    from test_pca import graph_like
+    X = graph_like(333, 11)
+    a = cuda.pca_fit_transform(X, 80, want_components=True)
+    monkeypatch.setenv("SCHIC_PCA_TRIDIAG", "full")
+    b = cuda.pca_fit_transform(X, 80, want_components=True)
+    _close(a[0], b[0]); _close(a[2], b[2])
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-12)
+    emb, _, _ = _pca_reference(X, 80)
+    _close(b[0], emb)
+
+
 def test_pca_rectangular_scrub_and_errors(cuda):
     from test_pca import graph_like
     rng = np.random.default_rng(3)

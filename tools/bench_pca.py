@@ -37,7 +37,8 @@ for n in sizes:
     n3 = float(n) ** 3
     st = run["device_stage_ms"]
     run["covariance_tflops_fp64"] = round(n3 / (st["covariance"] * 1e-3) / 1e12, 2)      # n^3 FMA-flops of the upper half x 2
-    run["tridiag_GBps"] = round(16.0 / 3.0 * n3 / (st["tridiagonalise"] * 1e-3) / 1e9, 1)
+    # lower-triangle passes: 16 B (read + write) per element of the trailing lower triangle and step = 8/3 n^3 bytes
+    run["tridiag_GBps"] = round(8.0 / 3.0 * n3 / (st["tridiagonalise"] * 1e-3) / 1e9, 1)
     if n <= 4000:
         from sklearn.decomposition import PCA as SkPCA
         dense = np.asarray(G.todense(), dtype=np.float64)
