@@ -62,6 +62,9 @@ CUDA_SYMBOLS = (
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free", "schic_mh_kneighbors_exact_device",
 )
 
+# the dense-graph PCA post-step, CUDA library only (include/schic_pca.h)
+PCA_SYMBOLS = ("schic_pca_fit_transform", "schic_pca_fit_transform_csr", "schic_pca_stage_ms")
+
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
 
 

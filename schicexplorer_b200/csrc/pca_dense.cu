@@ -654,8 +654,12 @@ int pca_entry(const double* X_host, int64_t n_rows, int64_t n_cols, const int64_
         return schic::set_error(SCHIC_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
     }
     if (device >= 0) PCA_CU(cudaSetDevice(device));
-    cudaStream_t s = nullptr;
-    PCA_CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    struct Stream {
+        cudaStream_t s = nullptr;
+        ~Stream() { if (s) cudaStreamDestroy(s); }
+    } stream;
+    PCA_CU(cudaStreamCreateWithFlags(&stream.s, cudaStreamNonBlocking));
+    cudaStream_t s = stream.s;
     Events ev;
     for (auto& e : ev.ev) PCA_CU(cudaEventCreate(&e));
     int rc = SCHIC_OK;
@@ -698,7 +702,6 @@ int pca_entry(const double* X_host, int64_t n_rows, int64_t n_cols, const int64_
         }
         g_stage_ms[6] = total;
     }
-    cudaStreamDestroy(s);
     return rc;
 }
 

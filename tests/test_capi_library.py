@@ -18,12 +18,13 @@ def declared_functions(header):
 def test_headers_and_binding_tables_agree():
     assert sorted(_capi.BASE_SYMBOLS) == declared_functions("schic_mh.h")
     assert sorted(_capi.CUDA_SYMBOLS) == declared_functions("schic_mh_cuda.h")
+    assert sorted(_capi.PCA_SYMBOLS) == declared_functions("schic_pca.h")
 
 
 def test_cuda_library_exports_every_declared_symbol():
     api = _capi.CApi(_capi.CUDA_LIB_PATH)     # loads without a GPU (cudart is linked statically)
     assert api.backend == "cuda"
-    assert api.has_symbols(_capi.BASE_SYMBOLS + _capi.CUDA_SYMBOLS) == []
+    assert api.has_symbols(_capi.BASE_SYMBOLS + _capi.CUDA_SYMBOLS + _capi.PCA_SYMBOLS) == []
 
 
 def test_oracle_library_exports_the_base_abi(oracle):
