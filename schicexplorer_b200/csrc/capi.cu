@@ -223,7 +223,7 @@ bool k1_table_candidate(const schic_mh_handle* h, int64_t n_rows, int64_t nnz) {
     if (m == K1_TABLE) return n_rows > 0 && nnz > 0;
     if (m != K1_AUTO) return false;
     const int H = h->p.number_of_hash_functions;
-    return n_rows > 0 && nnz >= ((int64_t)1 << 21) && 2.0 * ((double)nnz / (double)n_rows) / (double)H >= 4.0;
+    return n_rows > 0 && nnz >= ((int64_t)1 << 21) && schic::k1t_tau(n_rows, nnz, H) >= 4.0;
 }
 
 // K1 on rows [r0, r1) of the handle's CSR (positions are absolute in the device arrays).
@@ -261,7 +261,7 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
                 CU_TRY(cudaStreamSynchronize(s));
             }
             if (mode == K1_TABLE ? (max_id < 134217728u && H <= 65535) : schic::k1t_applicable(n_rows, nnz, max_id, H)) {
-                const size_t ecap = schic::k1t_entries_capacity(nnz, max_id);
+                const size_t ecap = schic::k1t_entries_capacity(n_rows, nnz, max_id, H);
                 ST_TRY(h->k1t_present.reserve((int64_t)max_id + 1, 0, s));
                 ST_TRY(h->k1t_slot.reserve((int64_t)max_id + 1, 0, s));
                 ST_TRY(h->k1t_entries.reserve((int64_t)ecap, 0, s));
@@ -802,10 +802,13 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
     // of the range): it is computed on the compute stream while the ids are still crossing PCIe, and the batch only
     // needs the lookup + fallback once it has landed.
     h->k1t_prebuilt = false;
+    // (only when building for the WHOLE range costs less than the upload it hides behind: ~2.4e12 table evaluations/s
+    // against ~55 GB/s of ids, i.e. range * H < 175 * nnz; otherwise the table is built from the ids present, later)
     if (whole_batch && k1_mode_from_env() == K1_AUTO && h->feature_range > 0 && h->feature_range <= 134217728ull &&
+        (double)h->feature_range * (double)H < 175.0 * (double)nnz &&
         schic::k1t_applicable(n_rows, nnz, (uint32_t)(h->feature_range - 1), H)) {
         const uint32_t max_id = (uint32_t)(h->feature_range - 1);
-        const size_t ecap = schic::k1t_entries_capacity(nnz, max_id);
+        const size_t ecap = schic::k1t_entries_capacity(n_rows, nnz, max_id, H);
         ST_TRY(ensure_counters(h));
         ST_TRY(h->k1t_present.reserve((int64_t)max_id + 1, 0, s));
         ST_TRY(h->k1t_slot.reserve((int64_t)max_id + 1, 0, s));
@@ -1163,7 +1166,7 @@ int schic_k1_variant_ms(int32_t variant, int64_t n_rows, int64_t nnz, const int6
         schic::launch_max_id(d_indices + pos0, nnz, counters + 2, nullptr);
         CU_TRY(cudaMemcpy(&max_id, counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         if (max_id >= 134217728u) return fail(SCHIC_ERR_UNSUPPORTED, "id range too large for the table path");
-        ecap = schic::k1t_entries_capacity(nnz, max_id);
+        ecap = schic::k1t_entries_capacity(n_rows, nnz, max_id, n_hash);
         CU_TRY(cudaMalloc(&present, (size_t)max_id + 1));
         CU_TRY(cudaMalloc(&slot, ((size_t)max_id + 1) * sizeof(uint2)));
         CU_TRY(cudaMalloc(&entries, ecap * sizeof(uint16_t)));

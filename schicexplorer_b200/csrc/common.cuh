@@ -30,7 +30,8 @@ int launch_signatures32_filter(const int64_t* d_indptr, const uint32_t* d_feat, 
                                cudaStream_t stream);
 // Shared-table variant (k1_table.cu): every (feature id, hash function) is evaluated once for the whole batch.
 bool k1t_applicable(int64_t n_rows, int64_t nnz, uint32_t max_id, int H);
-size_t k1t_entries_capacity(int64_t nnz, uint32_t max_id);
+double k1t_tau(int64_t n_rows, int64_t nnz, int H);
+size_t k1t_entries_capacity(int64_t n_rows, int64_t nnz, uint32_t max_id, int H);
 size_t k1t_items_bytes(int64_t n_rows, int64_t nnz);
 int launch_max_id(const uint32_t* d_feat, int64_t nnz, uint32_t* d_out_max, cudaStream_t stream);
 int launch_signatures_table(int width /* 32 | 64: HashSpec */, const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int64_t nnz,

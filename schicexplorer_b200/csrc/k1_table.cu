@@ -310,20 +310,32 @@ __global__ void k1t_fill_kernel(uint32_t* __restrict__ p, int64_t n, uint32_t v)
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
+// Threshold of the table: hash values below T = tau * 2^31 / mean_row are stored, so a (row, hash function) pair finds
+// about tau stored candidates (none with probability e^-tau: those go to the fallback kernel) and an id stores
+// H * tau / mean_row values. tau = 12 where rows are long; for short rows / many hash functions it is what
+// K1T_MAX_PER_ID stored values per id allow.
+constexpr double K1T_MAX_PER_ID = 8.0;
+double k1t_tau(int64_t n_rows, int64_t nnz, int H) {
+    const double tau = K1T_MAX_PER_ID * ((double)nnz / (double)n_rows) / (double)H;
+    return tau > 12.0 ? 12.0 : tau;
+}
+
 // Table mode pays off when ids are shared: id range <= nnz / 2 (every id then occurs twice on average at
-// least), rows long enough that tau = min(12, 2 * mean_row / H) >= 4, and the per-id arrays stay small.
+// least), rows long enough that tau >= 4 (under 2 % of the pairs fall back), and the per-id arrays stay small.
 bool k1t_applicable(int64_t n_rows, int64_t nnz, uint32_t max_id, int H) {
     if (n_rows <= 0 || nnz <= 0 || H > 65535) return false;
     const double ids = (double)max_id + 1.0;
     if (ids > 134217728.0 || ids * 2.0 > (double)nnz) return false;
-    const double tau = 2.0 * ((double)nnz / (double)n_rows) / (double)H;
-    return tau >= 4.0;
+    return k1t_tau(n_rows, nnz, H) >= 4.0;
 }
 
-size_t k1t_entries_capacity(int64_t nnz, uint32_t max_id) {
+// expected stored values (every id of the range present: the prebuilt case) + 25 % + slack
+size_t k1t_entries_capacity(int64_t n_rows, int64_t nnz, uint32_t max_id, int H) {
     const double ids = (double)max_id + 1.0;
     const double d = ids < (double)nnz ? ids : (double)nnz;
-    return (size_t)(2.5 * d) + 65536;
+    double per_id = k1t_tau(n_rows, nnz, H) * (double)H / ((double)nnz / (double)n_rows);
+    if (per_id < 2.0) per_id = 2.0;
+    return (size_t)(1.25 * per_id * d) + 65536;
 }
 
 int64_t k1t_item_capacity(int64_t n_rows, int64_t nnz) { return n_rows + nnz / K1T_PART + 1; }
@@ -361,8 +373,7 @@ int launch_signatures_table(int width, const int64_t* d_indptr, const uint32_t* 
     }
     const uint32_t n_ids = max_id + 1u;
     const double mean_row = (double)nnz / (double)n_rows;
-    double tau = 2.0 * mean_row / (double)H;
-    tau = tau > 12.0 ? 12.0 : tau;
+    const double tau = k1t_tau(n_rows, nnz, H);
     double Td = tau * 2147483647.0 / mean_row;
     if (Td > 2147483646.0) Td = 2147483646.0;
     const uint32_t T = (uint32_t)Td;
