@@ -384,7 +384,9 @@ int rerank_lists(schic_mh_handle* h, const int64_t* db_indptr, const uint32_t* d
     int nl = -1;
     if (cand_idx)
         nl = schic::launch_rerank(db_indptr, db_feat, db_val, 0, r_norm2, r_dir, r_nw, r_mode, row0, nq, cand_idx, cand_nv,
-                                  kcand, 0, kcand, k, d_idx, d_dist, k, 0, 1, d_nv, 0, s);
+                                  kcand, 0, kcand, k, d_idx, d_dist, k, 0, 1, d_nv, 0,
+                                  /* a long list: the windowed kernel on chunks beats the hash-table kernel on the whole */
+                                  (r_dir && r_nw > 0 && kcand > RERANK_CHUNK) ? 0 : 1, s);
     if (nl < 0) {
         const int kc = (int)std::min<int64_t>((int64_t)k + (exclude_self ? 1 : 0), RERANK_CHUNK);
         const int nchunks = (kcand + RERANK_CHUNK - 1) / RERANK_CHUNK;
@@ -397,7 +399,7 @@ int rerank_lists(schic_mh_handle* h, const int64_t* db_indptr, const uint32_t* d
             const int c0 = ci * RERANK_CHUNK, cn = std::min(RERANK_CHUNK, kcand - c0);
             const int r = schic::launch_rerank(db_indptr, db_feat, db_val, 0, r_norm2, r_dir, r_nw, r_mode, row0, nq,
                                                cand_idx, cand_nv, kcand, c0, cn, kc, h->part_idx.p, h->part_dist.p,
-                                               (int)stride, ci * kc, 0, d_nv, (int)ndb, s);
+                                               (int)stride, ci * kc, 0, d_nv, (int)ndb, 1, s);
             if (r < 0) return fail(SCHIC_ERR_UNSUPPORTED, "rerank: chunk does not fit in shared memory");
             nl += r;
         }

@@ -103,7 +103,7 @@ int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* 
                   int64_t q_row0, int64_t nq, const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int cand_stride,
                   int cand_off, int kcand, int k, int32_t* d_idx_out, float* d_dist_out, int out_stride, int out_off,
                   int final, int32_t* d_nvalid_out, int n_all /* d_cand_idx == nullptr: candidates = rows [0, n_all) */,
-                  cudaStream_t stream);
+                  int allow_hash /* 0: windowed kernel or -1 */, cudaStream_t stream);
 // Per row: sort the [part_stride] chunk-sorted (distance, index) pairs by (dist asc, idx asc), keep k, write n_valid
 // (= min(k, list length); list length = min(cand_nvalid, kcand), or n_all [- 1 if exclude_row0 >= 0] for brute force).
 int launch_rerank_merge(const int32_t* d_part_idx, const float* d_part_dist, int part_stride,

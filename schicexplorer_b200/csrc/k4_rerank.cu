@@ -671,11 +671,12 @@ int launch_rerank_merge(const int32_t* d_part_idx, const float* d_part_dist, int
 // One launch over candidate columns [cand_off, cand_off + kcand) of lists with row stride cand_stride; results to
 // output columns [out_off, out_off + k) of arrays with row stride out_stride. final != 0: nvalid_out is written.
 // d_cand_idx == nullptr: brute force, the candidates of every query are the database rows [0, n_all).
+// allow_hash == 0: only the windowed kernel may be used (returns -1 if it does not fit or there is no directory).
 int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* d_val, int64_t indptr0,
                   const double* d_norm2, const uint32_t* d_dir, int n_windows, int window_mode, int64_t q_row0,
                   int64_t nq, const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int cand_stride, int cand_off,
                   int kcand, int k, int32_t* d_idx_out, float* d_dist_out, int out_stride, int out_off, int final,
-                  int32_t* d_nvalid_out, int n_all, cudaStream_t stream) {
+                  int32_t* d_nvalid_out, int n_all, int allow_hash, cudaStream_t stream) {
     (void)indptr0;
     if (nq <= 0) return 0;
     const K4Chunk ck{cand_stride, cand_off, out_stride, out_off, final, n_all};
@@ -692,6 +693,7 @@ int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* 
             return 1;
         }
     }
+    if (!allow_hash) return -1;         // the caller prefers the windowed kernel on chunks over this one on the whole list
     const size_t smem = (size_t)K4_SLOTS * 8 + (size_t)P * 8 + (size_t)kcand * (8 + 8 + 8 + 4) + 16;
     if (smem > 220 * 1024) return -1;   // caller chunks the candidate lists
     cudaFuncSetAttribute(k4_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
