@@ -31,16 +31,17 @@ extern "C" {
  *   device           CUDA ordinal, -1 = current
  *   out              [n_rows, n_components] float64, row major: the embedding (U * S)
  *   singular_values  [n_components] float64 or NULL (PCA.singular_values_)
- *   components       [n_components, n_cols] float64 or NULL (PCA.components_) */
+ *   components       [n_components, n_cols] float64 or NULL (PCA.components_)
+ *   mean             [n_cols] float64 or NULL (PCA.mean_: the column means that were subtracted) */
 int schic_pca_fit_transform(const double* X, int64_t n_rows, int64_t n_cols, int32_t n_components, int32_t device,
-                            double* out, double* singular_values, double* components);
+                            double* out, double* singular_values, double* components, double* mean);
 
 /* The same for X given as the CSR the graph entry points return (schic_mh_kneighbors_graph: indptr int64 [n_rows+1],
  * indices int32, data float32), densified on the device (missing entries 0, non-finite values 0 as the reference's
  * nan_to_num / isinf scrub, scHicClusterMinHash.py:356-357). */
 int schic_pca_fit_transform_csr(int64_t n_rows, int64_t n_cols, const int64_t* indptr, const int32_t* indices,
                                 const float* data, int32_t n_components, int32_t device, double* out,
-                                double* singular_values, double* components);
+                                double* singular_values, double* components, double* mean);
 
 /* Device time of the stages of the last call on this thread, milliseconds:
  * {upload+densify+centre, covariance, tridiagonalisation, eigenvalues, eigenvectors, back-transform+projection, total}. */

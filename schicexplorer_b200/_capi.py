@@ -106,8 +106,8 @@ class CApi:
             L.schic_mh_fit_csr_async.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32]
             L.schic_mh_set_feature_range.argtypes = [_vp, C.c_uint64]
             L.schic_mh_kneighbors_exact_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
-            L.schic_pca_fit_transform.argtypes = [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]
-            L.schic_pca_fit_transform_csr.argtypes = [_i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]
+            L.schic_pca_fit_transform.argtypes = [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp]
+            L.schic_pca_fit_transform_csr.argtypes = [_i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]
             L.schic_pca_stage_ms.argtypes = [_vp, _i32]
             L.schic_mh_set_database_ready_event.argtypes = [_vp, _vp]
             L.schic_mh_rerank_windows.argtypes = [_vp, C.POINTER(_i32)]
@@ -278,23 +278,26 @@ class CApi:
     def pca_fit_transform(self, X, n_components: int, device: int = -1, want_components: bool = False):
         """PCA(...).fit_transform(X)[:, :n_components] on the device. X: dense float64 [n, c] or a scipy CSR whose
         arrays are int64 / int32 / float32 (the graph entry points' layout). Returns (embedding, singular values,
-        components or None)."""
+        components or None); with want_components the column means are kept in ``self.last_pca_mean``."""
         from scipy.sparse import issparse
         n_rows, n_cols = X.shape
         m = int(n_components)
         out = np.empty((n_rows, m), dtype=np.float64)
         sv = np.empty(m, dtype=np.float64)
         comp = np.empty((m, n_cols), dtype=np.float64) if want_components else None
+        mean = np.empty(n_cols, dtype=np.float64) if want_components else None
+        self.last_pca_mean = mean
         if issparse(X):
             X = X.tocsr()
             indptr = np.ascontiguousarray(X.indptr, dtype=np.int64)
             indices = np.ascontiguousarray(X.indices, dtype=np.int32)
             data = np.ascontiguousarray(X.data, dtype=np.float32)
             self.check(self.lib.schic_pca_fit_transform_csr(n_rows, n_cols, _ptr(indptr), _ptr(indices), _ptr(data), m,
-                                                            device, _ptr(out), _ptr(sv), _ptr(comp)))
+                                                            device, _ptr(out), _ptr(sv), _ptr(comp), _ptr(mean)))
         else:
             Xd = np.ascontiguousarray(X, dtype=np.float64)
-            self.check(self.lib.schic_pca_fit_transform(_ptr(Xd), n_rows, n_cols, m, device, _ptr(out), _ptr(sv), _ptr(comp)))
+            self.check(self.lib.schic_pca_fit_transform(_ptr(Xd), n_rows, n_cols, m, device, _ptr(out), _ptr(sv), _ptr(comp),
+                                                        _ptr(mean)))
         return out, sv, comp
 
     def pca_stage_ms(self) -> dict:

@@ -534,7 +534,7 @@ struct Events {
 
 // The whole pipeline on a device-resident, row-major X [n_rows, n_cols] (centred in place).
 int pca_device(double* X, int64_t n_rows, int64_t n_cols, int m, cudaStream_t s, Events& ev, double* out_host,
-               double* sv_host, double* comp_host) {
+               double* sv_host, double* comp_host, double* mean_host) {
     const int64_t n = n_cols;
     Buf<double> mu, C, praw, va, vb, w, d, e, tau, theta, Xv, ws, gsc, Z, outd, svd;
     PCA_CU(mu.alloc(n)); PCA_CU(C.alloc((size_t)n * n)); PCA_CU(praw.alloc(n)); PCA_CU(va.alloc(n)); PCA_CU(vb.alloc(n));
@@ -637,13 +637,17 @@ int pca_device(double* X, int64_t n_rows, int64_t n_cols, int m, cudaStream_t s,
     PCA_CU(cudaMemcpyAsync(out_host, outd.p, (size_t)n_rows * m * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (sv_host) PCA_CU(cudaMemcpyAsync(sv_host, svd.p, m * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (comp_host) PCA_CU(cudaMemcpyAsync(comp_host, Z.p, (size_t)n * m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (mean_host) PCA_CU(cudaMemcpyAsync(mean_host, mu.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));   // column sums
     PCA_CU(cudaEventRecord(ev.ev[6], s));
     PCA_CU(cudaStreamSynchronize(s));
+    if (mean_host)
+        for (int64_t c = 0; c < n; ++c) mean_host[c] /= (double)n_rows;
     return SCHIC_OK;
 }
 
 int pca_entry(const double* X_host, int64_t n_rows, int64_t n_cols, const int64_t* indptr, const int32_t* indices,
-              const float* data, int32_t n_components, int32_t device, double* out, double* sv, double* comp) {
+              const float* data, int32_t n_components, int32_t device, double* out, double* sv, double* comp,
+              double* mean) {
     if (n_rows < 1 || n_cols < 1 || !out) return schic::set_error(SCHIC_ERR_INVALID_ARG, "bad PCA arguments");
     if (!X_host && !indptr) return schic::set_error(SCHIC_ERR_INVALID_ARG, "no input matrix");
     if (n_components < 1 || n_components > std::min(n_rows, n_cols))
@@ -688,7 +692,7 @@ int pca_entry(const double* X_host, int64_t n_rows, int64_t n_cols, const int64_
                                                                                    n_cols, X.p);
             }
             PCA_CU(cudaGetLastError());
-            return pca_device(X.p, n_rows, n_cols, n_components, s, ev, out, sv, comp);
+            return pca_device(X.p, n_rows, n_cols, n_components, s, ev, out, sv, comp, mean);
         };
         rc = body();
     }
@@ -710,16 +714,16 @@ int pca_entry(const double* X_host, int64_t n_rows, int64_t n_cols, const int64_
 extern "C" {
 
 int schic_pca_fit_transform(const double* X, int64_t n_rows, int64_t n_cols, int32_t n_components, int32_t device,
-                            double* out, double* singular_values, double* components) {
+                            double* out, double* singular_values, double* components, double* mean) {
     if (!X) return schic::set_error(SCHIC_ERR_INVALID_ARG, "null matrix");
-    return pca_entry(X, n_rows, n_cols, nullptr, nullptr, nullptr, n_components, device, out, singular_values, components);
+    return pca_entry(X, n_rows, n_cols, nullptr, nullptr, nullptr, n_components, device, out, singular_values, components, mean);
 }
 
 int schic_pca_fit_transform_csr(int64_t n_rows, int64_t n_cols, const int64_t* indptr, const int32_t* indices,
                                 const float* data, int32_t n_components, int32_t device, double* out,
-                                double* singular_values, double* components) {
+                                double* singular_values, double* components, double* mean) {
     if (!indptr) return schic::set_error(SCHIC_ERR_INVALID_ARG, "null indptr");
-    return pca_entry(nullptr, n_rows, n_cols, indptr, indices, data, n_components, device, out, singular_values, components);
+    return pca_entry(nullptr, n_rows, n_cols, indptr, indices, data, n_components, device, out, singular_values, components, mean);
 }
 
 int schic_pca_stage_ms(float* out, int32_t n_out) {

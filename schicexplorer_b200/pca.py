@@ -3,8 +3,7 @@
 Boundary mirrored: ``sklearn.decomposition.PCA`` as the reference uses it --
 ``PCA(n_components=min(shape) - 1).fit_transform(graph.todense())`` followed by ``[:, :dimensionsPCA]``
 (``/root/reference/schicexplorer/scHicClusterMinHash.py:358-366``, ``scHicCluster.py:183-188``). Same constructor
-argument, ``fit_transform`` / ``fit`` / ``transform``, ``components_``, ``singular_values_``, ``mean_``,
-``explained_variance_``. ``keep`` (the only addition) tells the device how many leading columns the caller will
+argument, ``fit_transform`` / ``fit``, ``components_``, ``singular_values_``, ``mean_``, ``explained_variance_``. ``keep`` (the only addition) tells the device how many leading columns the caller will
 actually use, so that only those eigenpairs are extracted; the numbers are those of the full decomposition.
 Every number comes from ``csrc/pca_dense.cu`` through ``include/schic_pca.h``; no CPU fallback."""
 from __future__ import annotations
@@ -48,14 +47,10 @@ class PCA:
         self.components_ = comp
         self.singular_values_ = sv
         self.explained_variance_ = sv ** 2 / max(n - 1, 1)
-        self.mean_ = np.asarray(X.mean(axis=0)).ravel()
+        self.mean_ = getattr(api, "last_pca_mean", None)
         self.n_components_ = m
         return out
 
     def fit(self, X, y=None):
         self.fit_transform(X)
         return self
-
-    def transform(self, X):
-        X = np.asarray(X.todense()) if issparse(X) else np.asarray(X, dtype=np.float64)
-        return (X - self.mean_) @ self.components_.T

@@ -85,6 +85,7 @@ class OraclePcaApi:
         from oracle import pca_np
         dense = np.asarray(X.todense(), dtype=np.float64) if issparse(X) else np.asarray(X, dtype=np.float64)
         emb, sv, comp = pca_np.pca_fit_transform(dense, n_components)
+        self.last_pca_mean = np.where(np.isfinite(dense), dense, 0.0).mean(axis=0) if want_components else None
         return emb, sv, (comp if want_components else None)
 
 

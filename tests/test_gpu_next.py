@@ -286,7 +286,7 @@ def test_pca_class_and_clustering_post_step(cuda, fixture20):
     _close(p.components_, ref.components_[:40])
     np.testing.assert_allclose(p.singular_values_, ref.singular_values_[:40], rtol=1e-10)
     np.testing.assert_allclose(p.explained_variance_, ref.explained_variance_[:40], rtol=1e-9)
-    _close(p.transform(X[:10]), ref.transform(X[:10])[:, :40])
+    np.testing.assert_allclose(p.mean_, ref.mean_, rtol=1e-12)
     G = csr_matrix(X.astype(np.float32))         # graphs cross the C ABI as float32 (as kneighbors_graph returns them)
     ref32 = SkPCA(n_components=199).fit_transform(np.asarray(G.todense(), dtype=np.float64))
     out = MinHashClustering._post_process(G, True, 30, False, None)
