@@ -305,6 +305,21 @@ class ShardedMinHash:
         return out
 
 
+    def kneighbors_exact_local(self, k: int, include_self: bool = False, out=None):
+        """Exact euclidean kNN (scHicCluster -drm knn) of this rank's rows against the whole gathered
+        data set: brute-force K4, no candidate generation. Rows shard with no exchange beyond the CSR all-gather
+        ``gather()`` already did (needs ``fast=False`` so that the CSR is there)."""
+        if self.fast:
+            raise ValueError("kneighbors_exact_local needs the CSR values: create the shard with fast=False")
+        if out is None:
+            out = (torch.empty((self.n_local, k), dtype=torch.int32, device=self.device),
+                   torch.empty((self.n_local, k), dtype=torch.float32, device=self.device),
+                   torch.empty(self.n_local, dtype=torch.int32, device=self.device))
+        idx, dst, nv = out
+        self.api.kneighbors_exact_device(self.h, k, include_self, idx.data_ptr(), dst.data_ptr(), nv.data_ptr())
+        return out
+
+
 def _wrap_device(ptr: int, shape, typestr: str, dtype, device) -> torch.Tensor:
     """Zero-copy torch view of a device buffer owned by the C library (uint32 is viewed as int32)."""
     n = int(np.prod(shape))

@@ -80,6 +80,19 @@ class HostEmulatedDeviceApi:
         _np_at(p_nv, st["n"], np.int32)[:] = nv[a:b]
 
 
+    def kneighbors_exact_device(self, h, k, include_self, p_idx, p_dist, p_nv):
+        st = self.state[h]
+        db, kw = st["db"], st["kw"]
+        g = self.o.create(**kw)
+        self.o.fit_csr(g, db["ip"], db["ix"], db["dt"], False)
+        idx, dst, nv = self.o.kneighbors_exact(g, k, include_self)
+        self.o.destroy(g)
+        a, b = db["row0"], db["row0"] + st["n"]
+        _np_at(p_idx, st["n"] * k, np.int32)[:] = idx[a:b].ravel()
+        _np_at(p_dist, st["n"] * k, np.float32)[:] = dst[a:b].ravel()
+        _np_at(p_nv, st["n"], np.int32)[:] = nv[a:b]
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -106,7 +119,9 @@ def _worker(rank, world, port, n, k, by_nnz, out_dir):
         sh.fit_local(t_ip, t_ix, t_dt)
         sh.gather()
         idx, dst, nv = sh.kneighbors_local(k)
+        eidx, edst, env = sh.kneighbors_exact_local(k)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), idx=idx.numpy(), dist=dst.numpy(), nv=nv.numpy(),
+                 eidx=eidx.numpy(), edist=edst.numpy(), env=env.numpy(),
                  lo=lo, hi=hi, sig_all=sh._keep["sig_all"].numpy().view(np.uint32))
         sh.close()
     finally:
@@ -124,6 +139,7 @@ def test_shard_and_gather_equals_single_process(oracle, tmp_path, world, by_nnz)
     oracle.fit_csr(h, ip, ix, dt, False)
     ref_sig = oracle.signatures(h, 128)
     ridx, rdist, rnv = oracle.kneighbors(h, k)
+    eidx, edist, env = oracle.kneighbors_exact(h, k, False)
     oracle.destroy(h)
     covered = 0
     for r in range(world):
@@ -132,6 +148,9 @@ def test_shard_and_gather_equals_single_process(oracle, tmp_path, world, by_nnz)
         assert np.array_equal(z["sig_all"], ref_sig)               # every rank holds the whole database
         assert np.array_equal(z["idx"], ridx[lo:hi]) and np.array_equal(z["nv"], rnv[lo:hi])
         assert np.array_equal(z["dist"], rdist[lo:hi])
+        # the exact-kNN sibling shards the same way (brute force over the gathered CSR)
+        assert np.array_equal(z["eidx"], eidx[lo:hi]) and np.array_equal(z["edist"], edist[lo:hi])
+        assert np.array_equal(z["env"], env[lo:hi]) and (z["eidx"] != np.arange(lo, hi)[:, None]).all()
         covered += hi - lo
     assert covered == n
 

@@ -69,6 +69,38 @@ def test_exact_knn_many_chunks(cuda, oracle):
         assert_graph_equal_up_to_ties(exact_graph(cuda, X, k), exact_graph(oracle, X, k))
 
 
+def test_exact_knn_against_an_external_database(cuda, oracle):
+    """The sharded form on one GPU: two handles hold half of the rows each, both are pointed at the whole CSR
+    (schic_mh_set_database_device) and answer for their own rows - the query row is excluded by its GLOBAL index."""
+    import torch
+    X = synth_csr(170, seed=37)
+    dev = torch.device("cuda:0")
+    k = 9
+    ip = torch.from_numpy(X.indptr.astype(np.int64)).to(dev)
+    ix = torch.from_numpy(X.indices.astype(np.int32)).to(dev)
+    dt = torch.from_numpy(X.data.astype(np.float32)).to(dev)
+    ho = oracle.create(n_neighbors=k, number_of_hash_functions=8, fast=False)
+    oracle.fit_csr(ho, X.indptr, X.indices, X.data.astype(np.float32), False)
+    ref = {inc: oracle.kneighbors_exact(ho, k, inc) for inc in (False, True)}
+    oracle.destroy(ho)
+    sig_all = torch.zeros((170, 8), dtype=torch.int32, device=dev)       # not used by the exact search
+    for a, b in ((0, 60), (60, 170)):
+        h = cuda.create(n_neighbors=k, number_of_hash_functions=8, fast=False, device=0)
+        S = X[a:b]
+        cuda.fit_csr(h, S.indptr, S.indices, S.data.astype(np.float32), False)
+        cuda.set_database_device(h, 170, a, sig_all.data_ptr(), ip.data_ptr(), ix.data_ptr(), dt.data_ptr())
+        out = (torch.empty((b - a, k), dtype=torch.int32, device=dev), torch.empty((b - a, k), dtype=torch.float32, device=dev),
+               torch.empty(b - a, dtype=torch.int32, device=dev))
+        for inc in (False, True):
+            cuda.kneighbors_exact_device(h, k, inc, *(t.data_ptr() for t in out))
+            cuda.synchronize(h)
+            got = [t.cpu().numpy() for t in out]
+            assert_neighbours_equal_up_to_ties(*got, ref[inc][0][a:b], ref[inc][1][a:b], ref[inc][2][a:b], RTOL)
+            if not inc:
+                assert (got[0] != np.arange(a, b)[:, None]).all()
+        cuda.destroy(h)
+
+
 def test_nearest_neighbors_class_on_the_gpu(cuda):
     from sklearn.neighbors import NearestNeighbors as SkNN
     X = synthetic150()
