@@ -55,10 +55,16 @@ def main():
         api.fit_csr(h, ip, ix, None if fast else dt, False)
         ridx, rdst, rnv = api.kneighbors(h, k)
         rsig = api.signatures(h, 800)
-        api.destroy(h)
         same = (np.array_equal(idx.cpu().numpy(), ridx[lo:hi]) and np.array_equal(nv.cpu().numpy(), rnv[lo:hi])
                 and np.array_equal(dst.cpu().numpy(), rdst[lo:hi])
                 and np.array_equal(sh._keep["sig_all"].cpu().numpy().view(np.uint32), rsig))
+        if not fast and exchange == "nccl":      # the exact-kNN sibling shards the same way (brute-force K4)
+            eidx, edst, env = sh.kneighbors_exact_local(k)
+            torch.cuda.synchronize()
+            xidx, xdst, xnv = api.kneighbors_exact(h, k, False)
+            same = (same and np.array_equal(eidx.cpu().numpy(), xidx[lo:hi]) and np.array_equal(edst.cpu().numpy(), xdst[lo:hi])
+                    and np.array_equal(env.cpu().numpy(), xnv[lo:hi]))
+        api.destroy(h)
         flag = torch.tensor([int(same)], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         ok = ok and bool(flag.item())
