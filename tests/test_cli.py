@@ -4,7 +4,6 @@ schicexplorer/test/test_scHicClusterMinHash.py:35-216 -- cell order of the outpu
 3 distinct labels -- on the same 20 cells."""
 import os
 
-import numpy as np
 import pytest
 
 from conftest import GOLDEN

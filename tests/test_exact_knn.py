@@ -9,7 +9,7 @@ import warnings
 
 import numpy as np
 import pytest
-from scipy.sparse import csr_matrix, random as sprandom
+from scipy.sparse import random as sprandom
 
 from conftest import GOLDEN
 from schicexplorer_b200 import synth

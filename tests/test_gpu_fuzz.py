@@ -4,7 +4,6 @@ Rows are drawn to hit the awkward spots: ids right at the borders of the rerank'
 table entries, ids 0 and 2^32-1, empty / single-element rows, duplicated rows (ties everywhere), H not a multiple of
 32 or 2, k larger than the number of rows, thresholds that exclude everything. Bit-exact signatures, counts and
 neighbour indices; 1e-5 relative distances."""
-import os
 
 import numpy as np
 import pytest
