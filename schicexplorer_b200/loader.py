@@ -106,19 +106,31 @@ def cells_to_csr(cells, chroms: ChromTable, chromosomes=None, intra_only=False, 
     Returns ``(csr, names)``."""
     nbins = chroms.nbins
     dbins = None if distance is None else distance // chroms.binsize
-    indptr = [0]
+    counts = np.zeros(len(cells) + 1, dtype=np.int64)
     feats, vals = [], []
-    for cell in cells:
+    for i, cell in enumerate(cells):
         b1, b2, cnt = select_pixels(cell, chroms, chromosomes, intra_only, dbins)
-        feats.append(b1 * np.int64(nbins) + b2)
-        vals.append(cnt)
-        indptr.append(indptr[-1] + len(b1))
-    rows = np.repeat(np.arange(len(cells)), np.diff(indptr))
+        f = b1 * np.int64(nbins) + b2
+        # what the COO -> CSR constructor of utilities.py:131 does per row (duplicates summed, columns sorted), done
+        # row by row: pixel tables come sorted and duplicate free from a cooler, so this is normally just a check
+        if len(f) > 1 and not np.all(f[1:] > f[:-1]):
+            order = np.argsort(f, kind="stable")
+            f, cnt = f[order], np.asarray(cnt, dtype=np.float64)[order]
+            first = np.concatenate([[True], f[1:] != f[:-1]])
+            cnt = np.add.reduceat(cnt, np.nonzero(first)[0])
+            f = f[first]
+        feats.append(f)
+        vals.append(np.asarray(cnt, dtype=np.float64))
+        counts[i + 1] = len(f)
+    indptr = np.cumsum(counts)
     f = np.concatenate(feats) if feats else np.zeros(0, dtype=np.int64)
     v = np.concatenate(vals) if vals else np.zeros(0)
-    # same constructor call as utilities.py:131 (COO triplets -> CSR: duplicates summed, columns sorted)
-    m = csr_matrix((v, (rows, f)), shape=(len(cells), nbins * nbins), dtype=np.float64)
-    m.sort_indices()
+    shape = (len(cells), nbins * nbins)
+    # index dtype as scipy picks it for this shape (int32 while nbins^2 < 2^31: SURVEY 8(c))
+    idx_dtype = np.int32 if max(shape) < 2 ** 31 and indptr[-1] < 2 ** 31 else np.int64
+    m = csr_matrix((v, f.astype(idx_dtype, copy=False), indptr.astype(idx_dtype)), shape=shape, dtype=np.float64)
+    m.has_sorted_indices = True
+    m.has_canonical_format = True
     return m, [c.name for c in cells]
 
 
