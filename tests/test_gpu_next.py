@@ -244,6 +244,10 @@ def test_pca_fixture_graph_vs_sklearn_and_oracle(cuda, oracle, fixture20):
         _close(got2, emb)
         o_emb, o_sv, _ = pca_np.pca_fit_transform(X, dim)
         _close(got, o_emb)
+    g = np.load(os.path.join(GOLDEN, "pca_golden.npz"))          # committed sklearn output (make_pca_golden.py)
+    got, gsv, gcomp = cuda.pca_fit_transform(G, 19, want_components=True)
+    _close(got, g["embedding"]); _close(gcomp, g["components"])
+    np.testing.assert_allclose(cuda.last_pca_mean, g["mean"], rtol=1e-12, atol=1e-15)
     st = cuda.pca_stage_ms()
     assert st["total"] > 0 and abs(sum(v for k, v in st.items() if k != "total") - st["total"]) < 1e-3 * st["total"] + 1e-3
 

@@ -50,6 +50,20 @@ def test_oracle_on_the_reference_fixture_graph(fixture_graph):
         assert_embedding_close(gcomp, comp)
 
 
+def test_oracle_against_committed_golden_vectors(fixture_graph):
+    """tests/golden/pca_golden.npz (make_pca_golden.py): sklearn's output on the fixture graph, committed."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "pca_golden.npz"))
+    assert np.array_equal(fixture_graph.indptr, g["graph_indptr"]) and np.array_equal(fixture_graph.indices, g["graph_indices"])
+    assert np.array_equal(fixture_graph.data, g["graph_data"])
+    X = np.asarray(fixture_graph.todense(), dtype=np.float64)
+    got, sv, comp = pca_np.pca_fit_transform(X, 19)
+    assert_embedding_close(got, g["embedding"])
+    assert_embedding_close(comp, g["components"])
+    np.testing.assert_allclose(sv, g["singular_values"], rtol=1e-10, atol=1e-12 * sv[0])
+
+
 @pytest.mark.parametrize("n,dim,seed", [(64, 63, 0), (150, 100, 1), (300, 40, 2)])
 def test_oracle_on_graph_like_matrices(n, dim, seed):
     X = graph_like(n, seed)
