@@ -81,6 +81,8 @@ def select_pixels(cell: CellPixels, chroms: ChromTable, chromosomes=None, intra_
     * ``distance_bins`` (-d, already divided by the bin size, utilities.py:167-168): keep
       ``|bin1-bin2| < d`` and only if ``d > 5`` -- a scalar test, so d <= 5 drops everything
       (utilities.py:106-113)."""
+    if chromosomes is None and not intra_only and distance_bins is None:
+        return cell.bin1, cell.bin2, cell.count          # nothing to filter: no per-pixel chromosome lookup
     c1 = chroms.chrom_of_bin(cell.bin1)
     if chromosomes is None:
         parts = [np.arange(len(cell.bin1))]
