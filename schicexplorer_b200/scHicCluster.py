@@ -80,7 +80,7 @@ def main(args=None):
     for flag in ('cell_coloring_type', 'cell_coloring_batch', 'latexTable'):
         if getattr(args, flag):
             log.warning('--%s is accepted for compatibility but not used', flag)
-    cells, chroms = load_cells(args.matrix)
+    cells, chroms = load_cells(args.matrix, args.threads)
     names = [c.name for c in cells]
     neighborhood_matrix, _ = loader.cells_to_csr(cells, chroms, chromosomes=args.chromosomes,
                                                  intra_only=args.intraChromosomalContactsOnly)

@@ -106,15 +106,15 @@ def parse_arguments(args=None):
 
 
 # ---- input ---------------------------------------------------------------------------------------
-def load_cells(path: str):
-    """Per-cell pixel tables + chromosome table from any supported container."""
+def load_cells(path: str, threads: int = 1):
+    """Per-cell pixel tables + chromosome table from any supported container (``threads``: concurrent scool reads)."""
     from . import loader
     if os.path.isdir(path):
         return loader.read_sparse_matrix_files(path)
     if path.endswith('.npz'):
         return loader.load_cells_npz(path)
     from . import scool
-    return scool.read_scool(path)
+    return scool.read_scool(path, threads=threads)
 
 
 def make_cluster_object(method: str, n_clusters: int, threads: int):
@@ -141,7 +141,7 @@ def _umap_available() -> bool:
 def main(args=None):
     args = parse_arguments().parse_args(args)
     from . import loader
-    cells, chroms = load_cells(args.matrix)
+    cells, chroms = load_cells(args.matrix, args.threads)
     if args.numberOfNearestNeighbors is None:
         args.numberOfNearestNeighbors = len(cells)           # the kNN graph is dense by default
 

@@ -101,7 +101,7 @@ class ResidentCells:
     def __init__(self, matrix: str, max_hashes: int, n_neighbors: int, threads: int = 8):
         from . import loader
         self._loader = loader
-        self.cells, self.chroms = load_cells(matrix)
+        self.cells, self.chroms = load_cells(matrix, threads)
         self.names = [c.name for c in self.cells]
         self.max_hashes = int(max_hashes)
         self.n_neighbors = min(int(n_neighbors), len(self.cells))
