@@ -148,3 +148,35 @@ def test_wire_values_pick_the_narrowest_exact_format():
     assert w(np.array([1.0, np.nan])).dtype == np.float32
     assert w(np.array([], dtype=np.float64)).dtype == np.float32
     assert np.array_equal(w(np.array([3.0, 4.0])), [3, 4])
+
+
+def test_loader_matches_the_coo_constructor_on_unsorted_and_duplicated_pixels(fixture20):
+    """cells_to_csr builds the CSR row by row; the result must be what utilities.py:131's COO -> CSR constructor gives
+    (duplicates summed, columns sorted, scipy's index dtype), also for pixel tables that are not sorted / not unique
+    and for --chromosomes given in another order than the file's."""
+    from scipy.sparse import csr_matrix
+    from schicexplorer_b200 import loader
+    from schicexplorer_b200.loader import CellPixels
+    _, _, cells, chroms = fixture20
+    rng = np.random.default_rng(4)
+    messy = []
+    for i, c in enumerate(cells[:8]):
+        p = rng.permutation(len(c.bin1))
+        dup = rng.integers(0, len(c.bin1), size=7)
+        b1 = np.concatenate([c.bin1[p], c.bin1[dup]]); b2 = np.concatenate([c.bin2[p], c.bin2[dup]])
+        cnt = np.concatenate([c.count[p], c.count[dup] + i])
+        messy.append(CellPixels(c.name, b1, b2, cnt))
+    messy.append(CellPixels("/cells/empty", np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0)))
+    for kw in (dict(), dict(intra_only=True), dict(chromosomes=["chr2", "chr1"]), dict(distance=30_000_000)):
+        X, names = loader.cells_to_csr(messy, chroms, **kw)
+        rows, feats, vals = [], [], []
+        dbins = None if "distance" not in kw else kw["distance"] // chroms.binsize
+        for r, c in enumerate(messy):
+            b1, b2, cnt = loader.select_pixels(c, chroms, kw.get("chromosomes"), kw.get("intra_only", False), dbins)
+            rows.append(np.full(len(b1), r)); feats.append(b1 * np.int64(chroms.nbins) + b2); vals.append(cnt)
+        want = csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(feats))),
+                          shape=(len(messy), chroms.nbins ** 2), dtype=np.float64)
+        want.sort_indices()
+        assert X.shape == want.shape and X.indices.dtype == want.indices.dtype and X.has_sorted_indices
+        assert np.array_equal(X.indptr, want.indptr) and np.array_equal(X.indices, want.indices)
+        assert np.array_equal(X.data, want.data) and names[-1] == "/cells/empty"
