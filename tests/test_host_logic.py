@@ -180,3 +180,16 @@ def test_loader_matches_the_coo_constructor_on_unsorted_and_duplicated_pixels(fi
         assert X.shape == want.shape and X.indices.dtype == want.indices.dtype and X.has_sorted_indices
         assert np.array_equal(X.indptr, want.indptr) and np.array_equal(X.indices, want.indices)
         assert np.array_equal(X.data, want.data) and names[-1] == "/cells/empty"
+
+
+def test_tools_and_entry_points_parse():
+    """Every script under tools/ and bin/, bench.py and __graft_entry__.py at least parses (they only run on the GPU box)."""
+    import ast
+    import glob
+    import os
+    from conftest import ROOT
+    files = glob.glob(os.path.join(ROOT, "tools", "*.py")) + glob.glob(os.path.join(ROOT, "bin", "*"))
+    files += [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    assert len(files) > 10
+    for f in files:
+        ast.parse(open(f).read(), filename=f)
