@@ -118,7 +118,7 @@ def tridiag_vectors(d, e, theta, sweeps=3, seed=0):
     """Eigenvectors for the eigenvalues theta: inverse iteration + classical Gram-Schmidt (twice), in order."""
     n, m = len(d), len(theta)
     tn = np.max(np.abs(d) + np.abs(np.r_[e, 0.0]) + np.abs(np.r_[0.0, e])) if n else 0.0
-    pivmin = max(tn, 1e-300) * np.finfo(np.float64).eps
+    pivmin = (tn if tn > 0 else 1.0) * np.finfo(np.float64).eps      # tn == 0: the all-zero matrix (any basis is right)
     X = np.random.default_rng(seed).random((n, m)) - 0.5
     for _ in range(sweeps):
         for i in range(m):

@@ -600,7 +600,7 @@ int pca_device(double* X, int64_t n_rows, int64_t n_cols, int m, cudaStream_t s,
         double tn = 0.0;
         for (int64_t i = 0; i < n; ++i)
             tn = std::max(tn, std::fabs(hd[i]) + (i > 0 ? std::fabs(he[i - 1]) : 0.0) + (i + 1 < n ? std::fabs(he[i]) : 0.0));
-        const double pivmin = std::max(tn, 1e-300) * 2.220446049250313e-16;
+        const double pivmin = (tn > 0.0 ? tn : 1.0) * 2.220446049250313e-16;   // tn == 0: the all-zero matrix (any basis is right)
         pca_init_vectors_kernel<<<148 * 4, 256, 0, s>>>(Xv.p, n, m);
         const int gs_blocks = (int)std::min<int64_t>(148 * 2, std::max<int64_t>(1, n / 32));
         for (int sweep = 0; sweep < 3; ++sweep) {

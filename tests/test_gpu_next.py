@@ -327,3 +327,11 @@ def test_pca_class_and_clustering_post_step(cuda, fixture20):
     ref32 = SkPCA(n_components=199).fit_transform(np.asarray(G.todense(), dtype=np.float64))
     out = MinHashClustering._post_process(G, True, 30, False, None)
     _close(out, ref32[:, :30])
+
+
+def test_pca_degenerate_inputs_stay_finite(cuda):
+    """All-zero graph (no cell has a neighbour) and identical rows: an all-zero, finite embedding, as scikit-learn gives."""
+    for X in (np.zeros((12, 12)), np.tile(np.arange(9.0), (9, 1))):
+        got, sv, comp = cuda.pca_fit_transform(X, 4, want_components=True)
+        assert np.isfinite(got).all() and np.isfinite(comp).all() and np.isfinite(sv).all()
+        assert np.abs(got).max() < 1e-9 and sv.max() < 1e-9

@@ -106,3 +106,12 @@ def test_oracle_stages():
     np.testing.assert_allclose(T @ X, X * ev[:30], atol=1e-8 * ev[0])
     Z = pca_np.back_transform(V, tau, X)
     np.testing.assert_allclose(C @ Z, Z * ev[:30], atol=1e-8 * ev[0])
+
+
+def test_oracle_degenerate_inputs_stay_finite():
+    """No neighbours anywhere (all-zero graph) or identical rows: sklearn returns an all-zero embedding; so must we."""
+    for X in (np.zeros((12, 12)), np.tile(np.arange(9.0), (9, 1))):
+        want = SkPCA(n_components=min(X.shape) - 1).fit_transform(X)[:, :4]
+        got, sv, comp = pca_np.pca_fit_transform(X, 4)
+        assert np.isfinite(got).all() and np.isfinite(comp).all() and np.isfinite(sv).all()
+        assert np.abs(got).max() < 1e-9 and np.abs(want).max() < 1e-9 and sv.max() < 1e-9
