@@ -335,3 +335,21 @@ def test_pca_degenerate_inputs_stay_finite(cuda):
         got, sv, comp = cuda.pca_fit_transform(X, 4, want_components=True)
         assert np.isfinite(got).all() and np.isfinite(comp).all() and np.isfinite(sv).all()
         assert np.abs(got).max() < 1e-9 and sv.max() < 1e-9
+
+
+def test_exact_knn_tiny_inputs(cuda, oracle):
+    """One, two and three rows (a single row has no neighbour once it is excluded itself), an empty row among them."""
+    rows = [csr_matrix(([1.0, 2.0, 5.0], ([0, 0, 0], [3, 10, 77])), shape=(1, 100)),
+            csr_matrix((1, 100)),
+            csr_matrix(([4.0, 2.0], ([0, 0], [10, 50])), shape=(1, 100))]
+    for n in (1, 2, 3):
+        X = vstack(rows[:n]).tocsr()
+        for include_self in (False, True):
+            for k in (1, 3):
+                res = []
+                for api in (cuda, oracle):
+                    h = api.create(n_neighbors=k, number_of_hash_functions=4, fast=False)
+                    api.fit_csr(h, X.indptr, X.indices, X.data.astype(np.float32), False)
+                    res.append(api.kneighbors_exact(h, k, include_self))
+                    api.destroy(h)
+                assert_neighbours_equal_up_to_ties(*res[0], *res[1], RTOL)
