@@ -49,6 +49,50 @@ def tridiagonalize(C):
     return d, e, V, tau
 
 
+def tridiagonalize_blocked(C, nb=32):
+    """The same reduction in panels of nb reflectors (LAPACK dlatrd / dsytrd scheme): inside a panel the trailing matrix
+    is only READ (S v, corrected by the panel's V W^T + W V^T so far); it is updated once per panel by a rank-2nb
+    product. Same d, e, V, tau as :func:`tridiagonalize` up to rounding. This is the formulation the device kernel should
+    move to next (halves the HBM traffic of the tridiagonalisation again); kept here, tested against the
+    unblocked version, so that the CUDA port has a stage-by-stage checker."""
+    S = np.array(C, dtype=np.float64)
+    n = S.shape[0]
+    d, e, tau = np.zeros(n), np.zeros(max(n - 1, 0)), np.zeros(max(n - 1, 0))
+    V = np.zeros((n, n))
+    j0 = 0
+    while j0 < n - 1:
+        jb = min(nb, n - 1 - j0)
+        Vp, Wp = np.zeros((n, jb)), np.zeros((n, jb))
+        for t in range(jb):
+            j = j0 + t
+            col = S[j:, j] - Vp[j:, :t] @ Wp[j, :t] - Wp[j:, :t] @ Vp[j, :t]      # column j with the panel applied
+            d[j] = col[0]
+            x = col[1:].copy()
+            alpha, xnorm = x[0], np.linalg.norm(x[1:])
+            if xnorm == 0.0:
+                tj, beta = 0.0, alpha
+                v = np.zeros_like(x)
+            else:
+                beta = -np.copysign(np.hypot(alpha, xnorm), alpha)
+                tj = (beta - alpha) / beta
+                v = x / (alpha - beta)
+            v[0] = 1.0
+            e[j], tau[j] = beta, tj
+            V[j + 1:, j] = v
+            Vp[j + 1:, t] = v
+            if tj != 0.0:
+                p = S[j + 1:, j + 1:] @ v
+                p -= Vp[j + 1:, :t] @ (Wp[j + 1:, :t].T @ v) + Wp[j + 1:, :t] @ (Vp[j + 1:, :t].T @ v)
+                p *= tj
+                Wp[j + 1:, t] = p - (0.5 * tj * (p @ v)) * v
+        r = j0 + jb
+        S[r:, r:] -= Vp[r:, :] @ Wp[r:, :].T + Wp[r:, :] @ Vp[r:, :].T
+        j0 = r
+    if n:
+        d[n - 1] = S[n - 1, n - 1]
+    return d, e, V, tau
+
+
 def sturm_count(d, e2, x):
     """Number of eigenvalues of the tridiagonal matrix below x (vectorised over x)."""
     x = np.atleast_1d(np.asarray(x, dtype=np.float64))

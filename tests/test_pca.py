@@ -115,3 +115,17 @@ def test_oracle_degenerate_inputs_stay_finite():
         got, sv, comp = pca_np.pca_fit_transform(X, 4)
         assert np.isfinite(got).all() and np.isfinite(comp).all() and np.isfinite(sv).all()
         assert np.abs(got).max() < 1e-9 and np.abs(want).max() < 1e-9 and sv.max() < 1e-9
+
+
+@pytest.mark.parametrize("n,nb", [(1, 4), (2, 4), (7, 3), (40, 8), (97, 32), (130, 64)])
+def test_blocked_tridiagonalisation_equals_unblocked(n, nb):
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n + 5, n))
+    C = A.T @ A
+    d0, e0, V0, t0 = pca_np.tridiagonalize(C)
+    d1, e1, V1, t1 = pca_np.tridiagonalize_blocked(C, nb)
+    scale = np.abs(d0).max()
+    np.testing.assert_allclose(d1, d0, atol=1e-11 * scale)
+    np.testing.assert_allclose(e1, e0, atol=1e-11 * scale)
+    np.testing.assert_allclose(t1, t0, atol=1e-10)
+    np.testing.assert_allclose(V1, V0, atol=1e-9)
