@@ -4,18 +4,25 @@
 Workload (config.workload = "s10"): 10 000 synthetic cells at 1 Mb (nbins 2744, ~14 k non-zero
 bin pairs per cell), 800 hash functions, k = 100, exact euclidean rerank (fast=False) -- BASELINE
 configs[2], the configuration the metric is quoted on. One "step" = one whole kNN-graph build:
-K1 signatures -> (signature / CSR all-gather when N > 1) -> K3 collision counts -> top-k select ->
-K4 rerank, neighbour lists left in HBM.
+K1 signatures -> (signature / CSR exchange when N > 1) -> K3 collision counts -> top-k select ->
+K4 rerank -> K5 graph emit (CSR of kneighbors_graph(mode='distance')).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (N>1: launch with torchrun)
-  python bench.py --impl reference [...]                        CPU arm: the oracle port on host cores
+  python bench.py --impl reference [...]                        CPU arm: the oracle port on ALL host cores,
+                                                                the SAME workload (all cells), K timed steps
 
-`value`  : inputs resident in HBM, device-timed with CUDA events, max over ranks.
-`e2e`    : same build through the C-ABI host entry points (pinned host CSR in, neighbour lists out),
-           H2D and D2H inside the timed region.
-`roofline`: the dominant kernel of the step -- K4, the exact rerank -- against the measured HBM copy peak
-           (MEASURED_PEAKS.json), algorithmic bytes of SURVEY 8(d); K1 (signatures) is reported beside it with
-           the INT32 issue rates measured live by schic_int32_peak.
+Legs of our arm (all in the one JSON line):
+`value`     : inputs resident in HBM, graph left in HBM; device-timed with CUDA events, max over ranks.
+`e2e`       : the same build through the C-ABI host entry points: pinned host CSR in, graph CSR out in host
+              memory; H2D and D2H inside the timed region (N GPUs).
+`e2e_class` : (N = 1) the call a scHiCExplorer user makes -- MinHash(...).fit(X); kneighbors_graph(mode='distance')
+              with X the float64 scipy CSR the loader produces (scHicClusterMinHash.py:402-406).
+`hash_width_64`: the device-resident leg with the width-64 HashSpec (SURVEY 8(c) rule 2, decision point D1).
+`parity`    : every rank folds its neighbour lists into a checksum (comparable across N); at N = 1 the whole result
+              of the headline configuration is compared with the CPU oracle run that also provides `cpu_baseline`.
+`roofline`  : dominant kernel (K4, exact rerank): measured DRAM traffic (ncu capture named in `traffic_source`,
+              committed under profiles/) / live CUDA-event time vs the measured HBM copy peak, next to the literal
+              SURVEY 8(d) algorithmic figure.
 The total work is fixed as N grows ("scaling": "strong"): the 10 k cells are sharded over the ranks.
 """
 from __future__ import annotations
@@ -37,6 +44,7 @@ if ROOT not in sys.path:
 METRIC = "cells/s kNN-graph build, 10k cells@1Mb, 800 hashes"
 UNIT = "cells/s"
 INT_OPS_PER_EVAL = 15      # algorithmic int32 ops per hash evaluation (reference formulation)
+CHECK_P = 2147483629       # prime < 2^31 of the parity checksum
 
 
 def parse():
@@ -54,6 +62,9 @@ def parse():
     ap.add_argument("--fast", type=int, default=None, help="1: collision distances, 0: exact rerank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: device-resident leg alone")
+    ap.add_argument("--ref-budget-s", type=float, default=900.0,
+                    help="reference arm: wall-clock budget; warm-up steps beyond the first are dropped (and reported) "
+                         "when W + K full steps would exceed it -- cells are never sampled")
     return ap.parse_args()
 
 
@@ -67,6 +78,24 @@ def workload(args):
               minimal_blocks_in_common=100, excess_factor=1, max_bin_size=100000, shingle_size=5,
               hash_width=args.hash_width)
     return cfg, kw
+
+
+def make_config(args, cfg, kw, world):
+    """The `config` object -- identical for our arm and the reference arm at the same N."""
+    return {"workload": args.workload, "n_cells": cfg.n_cells, "n_hash": args.hashes, "k": args.k,
+            "fast": int(kw["fast"]), "hash_width": args.hash_width, "sharding": f"cells/{world}",
+            "l2": "inputs (CSR ~1.15 GB at s10) larger than L2; no flush needed"}
+
+
+def fold_checksum(rows, idx, dist_bits):
+    """Row-decomposable checksum of neighbour lists (numpy int64 in, python int out): summing the per-shard values
+    mod CHECK_P over any row partition gives the same number, so SCALE N = 2/4/8 can be compared with N = 1."""
+    k = idx.shape[1]
+    w = (np.arange(k, dtype=np.int64) + 1)
+    r = (rows.astype(np.int64) + 1) % CHECK_P
+    a = (((idx.astype(np.int64) + 2) * w) % CHECK_P).sum(axis=1) % CHECK_P
+    b = (((dist_bits.astype(np.int64) % CHECK_P) * w) % CHECK_P).sum(axis=1) % CHECK_P
+    return int((r * a % CHECK_P).sum() % CHECK_P), int((r * b % CHECK_P).sum() % CHECK_P)
 
 
 class ClockSampler:
@@ -111,67 +140,81 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores (also the cpu_baseline of our arm)
 # ---------------------------------------------------------------------------------------------
-def oracle_step(ora, kw, k, ip, ix, dt, m):
-    """One bounded-sample build on the CPU: the first m cells, fit + kneighbors."""
-    h = ora.create(**kw)
-    a = int(ip[m])
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def oracle_step(ora, kw, k, ip, ix, dt, cores, want_result=False):
+    """One whole build on the CPU: all cells, fit + kneighbors. The thread count is passed explicitly
+    (number_of_cores), so torchrun's OMP_NUM_THREADS=1 does not apply."""
+    h = ora.create(**dict(kw, number_of_cores=cores))
+    n = len(ip) - 1
     t0 = time.perf_counter()
-    ora.fit_csr(h, ip[:m + 1], ix[:a], None if kw["fast"] else dt[:a], False)
-    ora.kneighbors(h, min(k, m), -1)
+    ora.fit_csr(h, ip, ix, None if kw["fast"] else dt, False)
+    res = ora.kneighbors(h, min(k, n), -1)
     t = time.perf_counter() - t0
     ora.destroy(h)
-    return t
-
-
-def pick_sample(ora, kw, k, ip, ix, dt, budget_s):
-    """Largest sample (whole workload if it fits) whose estimated CPU time stays within budget_s."""
-    n = len(ip) - 1
-    m0 = min(n, 256)
-    t0 = oracle_step(ora, kw, k, ip, ix, dt, m0)
-    for m in (n, n // 2, n // 4, n // 8, n // 16):
-        if m <= m0:
-            break
-        est = t0 * (m / m0) ** 1.5      # between linear (hashing) and quadratic (collision counting)
-        if est <= budget_s:
-            return m
-    return m0
+    return (t, res) if want_result else t
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of this path is the third-party package
     sparse-neighbors-search, absent from /root/reference and not installable, so this
-    arm times the oracle port (oracle/oracle.cpp, OpenMP, all host threads) -- kind "port"."""
+    arm times the oracle port (oracle/oracle.cpp, OpenMP, all host threads) -- kind "port" -- on the SAME
+    workload as our arm: every cell, every step."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     from oracle import oracle_api
     from schicexplorer_b200 import synth
     cfg, kw = workload(args)
     ora = oracle_api()
-    cores = os.cpu_count() or 1
-    ip, ix, dt, _ = synth.generate_csr(cfg)
-    # the whole arm (warm-up + K steps) stays within a few minutes: ~150 s of CPU work in total
-    m = pick_sample(ora, kw, args.k, ip, ix, dt, budget_s=min(25.0, 150.0 / (args.steps + min(args.warmup, 1))))
-    for _ in range(max(0, min(args.warmup, 1))):
-        oracle_step(ora, kw, args.k, ip, ix, dt, m)
-    times = [oracle_step(ora, kw, args.k, ip, ix, dt, m) for _ in range(args.steps)]
+    cores = host_cores()
+    ip, ix, dt, _ = synth.generate_csr(cfg, workers=min(32, cores))
+    n = cfg.n_cells
+    t_first, res = oracle_step(ora, kw, args.k, ip, ix, dt, cores, want_result=True)    # counts as warm-up step 1
+    warm_done = 1
+    while warm_done < args.warmup and (warm_done + 1 + args.steps) * t_first <= args.ref_budget_s:
+        oracle_step(ora, kw, args.k, ip, ix, dt, cores)
+        warm_done += 1
+    times = [oracle_step(ora, kw, args.k, ip, ix, dt, cores) for _ in range(args.steps)]
     t = float(np.mean(times))
-    v = m / t
-    sample = f"first {m} of {cfg.n_cells} cells per step (fit + kneighbors k={min(args.k, m)}, fast={int(kw['fast'])})"
+    v = n / t
+    idx, dist, _ = res
+    cs = fold_checksum(np.arange(n), idx, dist.view(np.int32))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": args.workload, "n_cells": cfg.n_cells, "n_hash": args.hashes, "k": args.k,
-                   "fast": int(kw["fast"]), "sample_cells": m},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "warmup": args.warmup, "warmup_executed": warm_done, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": make_config(args, cfg, kw, world),
+        "nnz_total": int(ip[-1]),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"all {n} cells every step (fit + kneighbors k={min(args.k, n)}, fast={int(kw['fast'])}); "
+                                   f"{cores} OpenMP threads (number_of_cores passed explicitly)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "parity_checksum": {"idx": cs[0], "dist_bits": cs[1]},
     }))
 
 
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def load_k4_profile(workload_name, kernel):
+    """DRAM traffic / pipe utilisation of the K4 kernel from the committed ncu capture (profiles/k4_ncu.json)."""
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "k4_ncu.json")))
+    except Exception:
+        return None
+    for p in prof.get("captures", []):
+        if p.get("workload") == workload_name and p.get("kernel") == kernel:
+            return p
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -191,7 +234,8 @@ def run_ours(args):
     n_total, H, k = cfg.n_cells, args.hashes, args.k
     bounds = partition_rows(n_total, world)
     lo, hi = bounds[rank], bounds[rank + 1]
-    workers = max(1, min(32, (os.cpu_count() or 8) // world))
+    n_local = hi - lo
+    workers = max(1, min(32, host_cores() // world))
     ip, ix, dt, _ = synth.generate_csr(cfg, lo, hi, workers=workers)
     nnz_local = int(ip[-1])
     fast = kw["fast"]
@@ -214,61 +258,89 @@ def run_ours(args):
         shard_nnz = [int(x) for x in t_nnz.tolist()]
     else:
         shard_nnz = [nnz_local]
-    sh = ShardedMinHash(api, n_total, bounds, dev, n_features=n_features, shard_nnz=shard_nnz, **kw)
-    out = (torch.empty((hi - lo, k), dtype=torch.int32, device=dev),
-           torch.empty((hi - lo, k), dtype=torch.float32, device=dev),
-           torch.empty(hi - lo, dtype=torch.int32, device=dev))
-
-    def step():
-        sh.fit_local(d_ip, d_ix, d_dt)
-        sh.gather()
-        sh.kneighbors_local(k, out)
+    kk = min(k, n_total)
+    g_out = (torch.empty(n_local + 1, dtype=torch.int64, device=dev),
+             torch.empty(n_local * kk, dtype=torch.int32, device=dev),
+             torch.empty(n_local * kk, dtype=torch.float32, device=dev))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    launches0 = api.launch_count(sh.h)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_acc = {}
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = api.launch_count(sh.h) - launches0
-    stage = api.stage_ms(sh.h)          # stages of the last timed step (CUDA events on the launch stream)
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    n_launch = torch.tensor([launches], dtype=torch.int64, device=dev)
+    def device_leg(kw_leg, steps, warmup, sample_clocks):
+        sh = ShardedMinHash(api, n_total, bounds, dev, n_features=n_features, shard_nnz=shard_nnz, **kw_leg)
+
+        def step():
+            sh.fit_local(d_ip, d_ix, d_dt, indptr0=0)
+            sh.gather()
+            sh.kneighbors_graph_local(kk, g_out)
+
+        for _ in range(max(warmup, 3)):
+            step()
+        barrier()
+        launches0 = api.launch_count(sh.h)
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+        launches = api.launch_count(sh.h) - launches0
+        stage = api.stage_ms(sh.h)          # stages of the last timed step (CUDA events on the launch stream)
+        t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        n_launch = torch.tensor([launches], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(n_launch, op=dist.ReduceOp.SUM)
+        return sh, float(t_ms.item()) / steps, int(n_launch.item()), stage, clocks
+
+    sh, ms_per_step, n_launch, stage, clocks = device_leg(kw, args.steps, args.warmup, True)
+    value = n_total / (ms_per_step * 1e-3)
     nnz_all = torch.tensor([nnz_local], dtype=torch.int64, device=dev)
     k1_ms = torch.tensor([stage["signatures"]], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(n_launch, op=dist.ReduceOp.SUM)
         dist.all_reduce(nnz_all, op=dist.ReduceOp.SUM)
-    ms_per_step = float(t_ms.item()) / args.steps
-    value = n_total / (ms_per_step * 1e-3)
+    rerank_kernel = api.rerank_kernel_name(sh.h) if hasattr(api, "rerank_kernel_name") else "k4_rerank_window_kernel"
 
-    # ---- end to end through the C-ABI host entry points ("e2e") -----------------------------
+    # ---- parity: neighbour lists of this rank's rows, folded into a checksum (not timed) ---------------------
+    idx_t, dst_t, nv_t = sh.kneighbors_local(kk)
+    torch.cuda.synchronize()
+    idx_h, dst_h = idx_t.cpu().numpy(), dst_t.cpu().numpy()
+    cs = fold_checksum(np.arange(lo, hi), idx_h, dst_h.view(np.int32))
+    cs_t = torch.tensor(cs, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(cs_t, op=dist.ReduceOp.SUM)
+    parity = {"checksum": {"idx": int(cs_t[0].item()) % CHECK_P, "dist_bits": int(cs_t[1].item()) % CHECK_P},
+              "note": "row-decomposable checksum of (neighbour index, distance bits) over all cells; equal across N "
+                      "and equal to the reference arm's parity_checksum when the graphs are identical"}
+
+    # ---- the width-64 HashSpec beside the default (device-resident leg, shorter) ------------------------------
+    other_width = None
+    if not args.skip_e2e:
+        w2 = 64 if args.hash_width == 32 else 32
+        sh_w, ms_w, _, stage_w, _ = device_leg(dict(kw, hash_width=w2), max(3, min(5, args.steps)), 3, False)
+        other_width = {"hash_width": w2, "value": n_total / (ms_w * 1e-3), "unit": UNIT, "ms_per_step": ms_w,
+                       "k1_ms": stage_w["signatures"]}
+        sh_w.close()
+
     if args.skip_e2e:
         if rank == 0:
             print(json.dumps({"profiling_only": True, "value": value, "ms_per_step": ms_per_step, "stage_ms": stage,
-                              "gpu_launches": int(n_launch.item())}))
+                              "gpu_launches": n_launch, "rerank_kernel": rerank_kernel, "parity": parity}))
         sh.close()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
+
+    # ---- end to end through the C-ABI host entry points ("e2e") -----------------------------
     p_ip = api.pinned_empty(ip.shape, np.int64); p_ip[:] = ip
     p_ix = api.pinned_empty(ix.shape, np.uint32); p_ix[:] = ix
     p_dt = None
@@ -277,22 +349,17 @@ def run_ours(args):
         # (MinHash._wire_values: uint8 / uint16 when the data allows, else float32)
         wire = MinHash._wire_values(dt)
         p_dt = api.pinned_empty(wire.shape, wire.dtype); p_dt[:] = wire
-    h_idx = torch.empty((hi - lo, k), dtype=torch.int32).pin_memory()
-    h_dst = torch.empty((hi - lo, k), dtype=torch.float32).pin_memory()
-    h_nv = torch.empty(hi - lo, dtype=torch.int32).pin_memory()
+    g_host = (api.pinned_empty((n_local + 1,), np.int64), api.pinned_empty((n_local * kk,), np.int32),
+              api.pinned_empty((n_local * kk,), np.float32))
     sh2 = ShardedMinHash(api, n_total, bounds, dev, n_features=n_features, shard_nnz=shard_nnz, **kw)
-
-    host_ms = {"fit_csr": 0.0, "gather": 0.0, "kneighbors": 0.0, "d2h_sync": 0.0}
+    host_ms = {"fit_csr": 0.0, "gather": 0.0, "kneighbors_graph": 0.0}
 
     def step_e2e():
         t = [time.perf_counter()]
         sh2.fit_local_host(p_ip, p_ix, p_dt, async_upload=True); t.append(time.perf_counter())
         sh2.gather(); t.append(time.perf_counter())
-        sh2.kneighbors_local(k, out); t.append(time.perf_counter())
-        h_idx.copy_(out[0], non_blocking=True)
-        h_dst.copy_(out[1], non_blocking=True)
-        h_nv.copy_(out[2], non_blocking=True)
-        torch.cuda.synchronize(); t.append(time.perf_counter())
+        # K3 -> select -> K4 -> K5 and the D2H of the graph CSR; returns when the graph is in host memory
+        api.kneighbors_graph(sh2.h, kk, -1, n_rows=n_local, out=g_host); t.append(time.perf_counter())
         for name, a, b in zip(host_ms, t[:-1], t[1:]):
             host_ms[name] += (b - a) * 1e3
 
@@ -311,34 +378,69 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n_total / float(e2e_s.item())
     h2d = ip.nbytes + ix.nbytes + (0 if fast else p_dt.nbytes)
-    d2h = h_idx.numel() * 4 + h_dst.numel() * 4 + h_nv.numel() * 4
+    g_nnz = int(g_host[0][-1])
+    d2h = g_host[0].nbytes + g_nnz * 8
     stage_e2e = api.stage_ms(sh2.h)
+    sh2.close()
+
+    # ---- the class call a scHiCExplorer user makes (N = 1) ---------------------------------------------------
+    e2e_class = None
+    if world == 1:
+        X = synth.to_scipy(cfg, ip, ix, dt)      # float64 data, int32 indices, int64->scipy-chosen indptr: the loader's output
+        mh = MinHash(device=local_rank, **kw)
+
+        def step_class():
+            mh.fit(X)
+            return mh.kneighbors_graph(mode="distance")
+
+        for _ in range(2):
+            g = step_class()
+        torch.cuda.synchronize()
+        n_cls = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_cls):
+            g = step_class()
+        t_cls = (time.perf_counter() - t0) / n_cls
+        e2e_class = {"value": n_total / t_cls, "unit": UNIT, "ms_per_step": t_cls * 1e3, "steps": n_cls,
+                     "call": "MinHash(**kw).fit(X); kneighbors_graph(mode='distance') -- X scipy CSR float64 / int32 "
+                             "indices in pageable memory, result a scipy CSR",
+                     "graph_nnz": int(g.nnz), "ratio_to_c_abi_e2e": t_cls / float(e2e_s.item())}
+        mh.close()
 
     if rank == 0:
         peak = api.int32_peak(local_rank, 2048)
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-            hbm_src = "measured (MEASURED_PEAKS.json)"
+            hbm_src = "measured (MEASURED_PEAKS.json, burst copy figure: K4 is timed alone by its own CUDA events)"
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-        # ---- roofline of the dominant kernel: K4 (exact rerank), HBM bound ---------------------------
-        # algorithmic bytes: 8 B (id + value) per non-zero of every candidate row; the units of one
-        # launch are this rank's n_local * k candidate pairs of the mean row length
+        # ---- roofline of the dominant kernel: K4 (exact rerank) ---------------------------------------
         mean_row = nnz_all.item() / max(1, n_total)
+        pairs = n_local * kk
         k4_s = stage["rerank"] * 1e-3
-        k4_bytes = 8.0 * mean_row * (hi - lo) * min(k, n_total)
         roofline = None
         if not fast and k4_s > 0:
-            gbs = k4_bytes / k4_s / 1e9
+            # literal SURVEY 8(d): 8 B (id + value) per non-zero of BOTH rows of every candidate pair
+            alg_bytes = 8.0 * 2.0 * mean_row * pairs
+            prof = load_k4_profile(args.workload, rerank_kernel)
+            traffic = None
+            if prof:
+                traffic = prof["dram_bytes"] * pairs / prof["pairs"]      # per launch of this rank
+            ach = (traffic if traffic else alg_bytes) / k4_s / 1e9
             roofline = {
-                "kernel": "k4_rerank_window_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": gbs / hbm_peak, "traffic": 58.78e9 * (hi - lo) / 10000.0 if args.workload == "s10" else None,
+                "kernel": rerank_kernel, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": traffic,
+                "traffic_source": (prof or {}).get("source"),
+                "achieved_is": "measured DRAM bytes per launch (ncu capture named in traffic_source, scaled by candidate "
+                               "pairs) / live CUDA-event kernel time" if traffic else
+                               "algorithmic bytes / live kernel time (no ncu capture of this kernel/workload committed)",
                 "peak_source": hbm_src, "kernel_ms": stage["rerank"], "share_of_step": stage["rerank"] / ms_per_step,
-                "algorithmic_bytes": k4_bytes,
-                "note": "achieved = 8 B x mean row length x (n_local*k candidate pairs) / K4 CUDA-event time of the last timed "
-                        "step. frac can exceed 1: 31 % of the sectors hit in L2 and windows the query row does not touch are "
-                        "never read, so DRAM traffic (ncu dram__bytes of one S10 launch, profiles/, scaled by rows) is about "
-                        "half the algorithmic bytes. ncu: L1/shared data pipe 67 % and issue 68 % busy, DRAM 46 %.",
+                "algorithmic": {"bytes": alg_bytes, "rule": "SURVEY 8(d): 8*(nnz_c + nnz_d) per candidate pair",
+                                "gbs": alg_bytes / k4_s / 1e9, "frac": alg_bytes / k4_s / 1e9 / hbm_peak,
+                                "note": "the query row is read once per query (not per pair) and lives in shared memory; "
+                                        "a value above the HBM peak means the 8(d) byte model over-counts what the kernel "
+                                        "has to move, not that HBM was exceeded"},
+                "binding_unit": (prof or {}).get("binding_unit"),
             }
         # ---- K1 (signatures): reference-formulation rate vs. what is executed ------------------------
         evals = nnz_local * H
@@ -350,44 +452,58 @@ def run_ours(args):
             "reference_formulation_tintops": evals * INT_OPS_PER_EVAL / k1_s / 1e12 if k1_s > 0 else 0.0,
             "int32_issue_peak_tintops": peak["mix_lop3_imad"],
             "note": "SURVEY 8(d) counts nnz*H evaluations x 15 int32 ops. The shared-table path evaluates each (distinct id, "
-                    "hash function) once per batch (S10: 3.77e6 ids x 800 = 3.0e9 evaluations, 1.26 ms, ALU pipe 79 % busy) "
-                    "and looks the rest up, so the reference-formulation rate exceeds the issue peak many times over without "
-                    "any evaluation being approximated (bit-exact vs the oracle). Per-cell filtered kernel for comparison: "
-                    "35.6 ms, 9.3 issued ops/evaluation, ALU pipe 91 % busy.",
+                    "hash function) once per batch and looks the rest up, so the reference-formulation rate exceeds the "
+                    "issue peak without any evaluation being approximated (bit-exact vs the oracle).",
             "int32_peaks_tops": peak,
         }
         if roofline is None:      # fast path (no rerank): K3 is the dominant kernel, INT32 issue bound
             k3_s = stage["collisions"] * 1e-3
-            compares = (hi - lo) * n_total * H * (0.5 if world == 1 else 1.0)
+            compares = n_local * n_total * H * (0.5 if world == 1 else 1.0)
             ach = compares / k3_s / 1e12 if k3_s > 0 else 0.0
-            roofline = {"kernel": "k3_collision_kernel", "bound": "int32-issue", "achieved": ach, "peak": peak["lop3"],
-                        "unit": "Tcompare/s", "frac": ach / peak["lop3"], "traffic": None,
-                        "note": "one ISETP (ALU pipe) per signature compare; peak = measured single-pipe issue rate"}
+            roofline = {"kernel": "k3h_collision_kernel", "bound": "int32-issue", "achieved": ach,
+                        "peak": peak["mix_hset2_hadd2"], "unit": "Tcompare/s", "frac": ach / peak["mix_hset2_hadd2"],
+                        "traffic": None,
+                        "note": "one HSET2 + one HADD2 per two signature compares; peak = measured 1:1 issue rate of the pair"}
         roofline["k1_signatures"] = k1
+        config = make_config(args, cfg, kw, world)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": args.workload, "n_cells": n_total, "n_hash": H, "k": k, "fast": int(fast),
-                       "hash_width": args.hash_width,
-                       "nnz_total": int(nnz_all.item()), "sharding": f"cells/{world}",
-                       "l2": "inputs (CSR %.2f GB/rank) larger than L2" % (h2d / 1e9)},
-            "stage_ms": stage, "gpu_launches": int(n_launch.item()), "clocks": clocks,
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
+            "nnz_total": int(nnz_all.item()),
+            "stage_ms": stage, "gpu_launches": n_launch, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": float(e2e_s.item()) * 1e3, "stage_ms": stage_e2e, "host_call_ms": host_ms},
-            "roofline": roofline,
+                    "ms_per_step": float(e2e_s.item()) * 1e3, "stage_ms": stage_e2e, "host_call_ms": host_ms,
+                    "call": "schic_mh_fit_csr_counts(async) -> [exchange] -> schic_mh_kneighbors_graph: pinned host CSR in, "
+                            "graph CSR (K5) out in host memory"},
+            "e2e_class": e2e_class, "hash_width_other": other_width, "parity": parity, "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle_api
             ora = oracle_api()
-            m = pick_sample(ora, kw, k, ip, ix, dt, budget_s=20.0)
-            t = oracle_step(ora, kw, k, ip, ix, dt, m)
-            line["cpu_baseline"] = {"value": m / t, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"first {m} of {n_total} cells, fit + kneighbors k={min(k, m)}, "
-                                              f"fast={int(fast)}, {t:.1f} s on the host cores (oracle/oracle.cpp, OpenMP)"}
+            cores = host_cores()
+            t, (oidx, odist, onv) = oracle_step(ora, kw, k, ip, ix, dt, cores, want_result=True)
+            line["cpu_baseline"] = {"value": n_total / t, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"all {n_total} cells, one step: fit + kneighbors k={kk}, fast={int(fast)}, "
+                                              f"{t:.1f} s on {cores} host threads (oracle/oracle.cpp, OpenMP)"}
+            # the whole headline result against the oracle (indices identical up to distance ties, distances 1e-5)
+            same = idx_h == oidx
+            rel = np.abs(dst_h - odist) / np.maximum(np.abs(odist), 1e-30)
+            rel[~np.isfinite(odist)] = 0.0
+            tie_ok = True
+            bad_rows = np.nonzero(~same.all(axis=1))[0]
+            for r in bad_rows[:2000]:        # differing positions must be permutations inside runs of equal distance
+                if not np.array_equal(np.sort(idx_h[r]), np.sort(oidx[r])) or not np.allclose(dst_h[r], odist[r], rtol=1e-5):
+                    tie_ok = False
+                    break
+            ocs = fold_checksum(np.arange(n_total), oidx, odist.view(np.int32))
+            line["parity"]["vs_oracle"] = {
+                "cells": n_total, "index_equal_fraction": float(same.mean()), "rows_differing": int(len(bad_rows)),
+                "differences_are_ties": bool(tie_ok), "dist_max_rel_err": float(rel.max()) if rel.size else 0.0,
+                "n_valid_equal": bool(np.array_equal(nv_t.cpu().numpy(), onv)),
+                "oracle_checksum": {"idx": ocs[0], "dist_bits": ocs[1]}}
         print(json.dumps(line))
     sh.close()
-    sh2.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

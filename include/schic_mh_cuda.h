@@ -33,10 +33,22 @@ int schic_mh_fit_csr_async(schic_mh_handle* h, int64_t n_rows, const int64_t* in
 int schic_mh_fit_csr_device(schic_mh_handle* h, int64_t n_rows, int64_t nnz, const int64_t* d_indptr,
                             const uint32_t* d_indices, const float* d_data, int32_t append);
 
+/* The same with the value of d_indptr[0] given by the caller (0 for a stand-alone shard): nothing is read back, so
+ * the call enqueues without draining the stream -- with schic_mh_set_feature_range a whole build then runs
+ * without a single host synchronisation. */
+int schic_mh_fit_csr_device_at(schic_mh_handle* h, int64_t n_rows, int64_t nnz, int64_t indptr0, const int64_t* d_indptr,
+                               const uint32_t* d_indices, const float* d_data, int32_t append);
+
 /* MinHash.kneighbors with results left in HBM: d_idx [n_local,k] int32, d_dist [n_local,k] float32,
  * d_nvalid [n_local] int32. Asynchronous on the handle's stream. */
 int schic_mh_kneighbors_device(schic_mh_handle* h, int32_t k, int32_t fast, int32_t* d_idx, float* d_dist,
                                int32_t* d_nvalid);
+
+/* MinHash.kneighbors_graph(mode='distance') (scHicClusterMinHash.py:355) with the CSR left in HBM: d_indptr
+ * [n_local+1] int64, d_indices / d_data with room for n_local*k entries (the first d_indptr[n_local] are written).
+ * Asynchronous on the handle's stream. */
+int schic_mh_kneighbors_graph_device(schic_mh_handle* h, int32_t k, int32_t fast, int64_t* d_indptr, int32_t* d_indices,
+                                     float* d_data);
 
 /* scHicCluster -drm knn on device outputs: as schic_mh_kneighbors_exact (include/schic_mh.h), results left in HBM. */
 int schic_mh_kneighbors_exact_device(schic_mh_handle* h, int32_t k, int32_t include_self, int32_t* d_idx, float* d_dist,

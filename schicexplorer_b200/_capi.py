@@ -60,6 +60,7 @@ CUDA_SYMBOLS = (
     "schic_mh_rerank_prep_rows", "schic_mh_set_database_prep_device", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free", "schic_mh_kneighbors_exact_device",
+    "schic_mh_fit_csr_device_at", "schic_mh_kneighbors_graph_device",
 )
 
 # the dense-graph PCA post-step, CUDA library only (include/schic_pca.h)
@@ -116,6 +117,8 @@ class CApi:
             L.schic_mh_fit_csr_counts.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32]
             L.schic_mh_fit_csr_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _i32]
             L.schic_mh_kneighbors_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
+            L.schic_mh_fit_csr_device_at.argtypes = [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32]
+            L.schic_mh_kneighbors_graph_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
             L.schic_mh_signatures_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_i64)]
             L.schic_mh_csr_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]
             L.schic_mh_set_database_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _vp]
@@ -220,11 +223,18 @@ class CApi:
         self.check(self.lib.schic_mh_kneighbors(_vp(h), k, fast, _ptr(idx), _ptr(dist), _ptr(nv)))
         return idx, dist, nv
 
-    def kneighbors_graph(self, h, k: int, fast: int = -1, n_rows=None):
+    def kneighbors_graph(self, h, k: int, fast: int = -1, n_rows=None, out=None):
+        """``out``: optional (indptr int64 [n+1], indices int32 [n*k], data float32 [n*k]) host arrays to fill (e.g.
+        page-locked ones that are reused between calls)."""
         n = self.n_fitted(h) if n_rows is None else n_rows
-        indptr = np.empty(n + 1, dtype=np.int64)
-        indices = np.empty(n * k, dtype=np.int32)
-        data = np.empty(n * k, dtype=np.float32)
+        if out is not None:
+            indptr, indices, data = out
+            assert indptr.dtype == np.int64 and indices.dtype == np.int32 and data.dtype == np.float32
+            assert len(indptr) >= n + 1 and len(indices) >= n * k and len(data) >= n * k
+        else:
+            indptr = np.empty(n + 1, dtype=np.int64)
+            indices = np.empty(n * k, dtype=np.int32)
+            data = np.empty(n * k, dtype=np.float32)
         self.check(self.lib.schic_mh_kneighbors_graph(_vp(h), k, fast, _ptr(indptr), _ptr(indices), _ptr(data)))
         nnz = int(indptr[-1])
         return indptr, indices[:nnz], data[:nnz]
@@ -257,9 +267,19 @@ class CApi:
         self.check(self.lib.schic_mh_kneighbors_exact_device(_vp(h), k, int(include_self), _ptr(d_idx), _ptr(d_dist),
                                                              _ptr(d_nvalid)))
 
-    def fit_csr_device(self, h, n_rows, nnz, d_indptr, d_indices, d_data, append: bool):
+    def fit_csr_device(self, h, n_rows, nnz, d_indptr, d_indices, d_data, append: bool, indptr0=None):
+        """``indptr0``: the value of d_indptr[0] when the caller knows it (0 for a stand-alone shard) -- the call then
+        enqueues without reading anything back."""
+        if indptr0 is not None and self.is_cuda:
+            self.check(self.lib.schic_mh_fit_csr_device_at(_vp(h), n_rows, nnz, int(indptr0), _ptr(d_indptr),
+                                                           _ptr(d_indices), _ptr(d_data), int(append)))
+            return
         self.check(self.lib.schic_mh_fit_csr_device(_vp(h), n_rows, nnz, _ptr(d_indptr), _ptr(d_indices),
                                                     _ptr(d_data), int(append)))
+
+    def kneighbors_graph_device(self, h, k, fast, d_indptr, d_indices, d_data):
+        self.check(self.lib.schic_mh_kneighbors_graph_device(_vp(h), k, fast, _ptr(d_indptr), _ptr(d_indices),
+                                                             _ptr(d_data)))
 
     def kneighbors_device(self, h, k, fast, d_idx, d_dist, d_nvalid):
         self.check(self.lib.schic_mh_kneighbors_device(_vp(h), k, fast, _ptr(d_idx), _ptr(d_dist), _ptr(d_nvalid)))
@@ -275,11 +295,19 @@ class CApi:
         return a.value, b.value, c.value, n.value
 
     # -- include/schic_pca.h ---------------------------------------------------------------------
-    def pca_fit_transform(self, X, n_components: int, device: int = -1, want_components: bool = False):
-        """PCA(...).fit_transform(X)[:, :n_components] on the device. X: dense float64 [n, c] or a scipy CSR whose
-        arrays are int64 / int32 / float32 (the graph entry points' layout). Returns (embedding, singular values,
-        components or None); with want_components the column means are kept in ``self.last_pca_mean``."""
+    def pca_fit_transform(self, X, n_components: int, device: int = -1, want_components: bool = False,
+                          return_mean: bool = False):
+        """PCA(...).fit_transform(X)[:, :n_components] on the device. X: dense float64 [n, c] or a scipy CSR. A CSR goes
+        down in the graph entry points' layout (int64 / int32 / float32) when its values are exactly representable in
+        float32 (every graph this package produces is); otherwise it is densified on the host and takes the float64
+        dense entry point, so nothing is rounded silently. Returns (embedding, singular values, components or None),
+        plus the column means with ``return_mean`` (``last_pca_mean`` on the shared object is kept for older callers
+        only -- it is not safe with two PCA objects or threads)."""
         from scipy.sparse import issparse
+        if issparse(X):
+            X = X.tocsr()
+            if X.data.dtype != np.float32 and not np.array_equal(X.data.astype(np.float32).astype(X.data.dtype), X.data):
+                X = np.asarray(X.todense(), dtype=np.float64)
         n_rows, n_cols = X.shape
         m = int(n_components)
         out = np.empty((n_rows, m), dtype=np.float64)
@@ -298,7 +326,7 @@ class CApi:
             Xd = np.ascontiguousarray(X, dtype=np.float64)
             self.check(self.lib.schic_pca_fit_transform(_ptr(Xd), n_rows, n_cols, m, device, _ptr(out), _ptr(sv), _ptr(comp),
                                                         _ptr(mean)))
-        return out, sv, comp
+        return (out, sv, comp, mean) if return_mean else (out, sv, comp)
 
     def pca_stage_ms(self) -> dict:
         out = np.zeros(7, dtype=np.float32)

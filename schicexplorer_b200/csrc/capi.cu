@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/schic_mh_cuda.h"
 #include "common.cuh"
 
@@ -60,6 +62,9 @@ struct DevBuf {
 };
 
 enum Stage { ST_H2D = 0, ST_SIG, ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_PREP, ST_COUNT };
+// NVTX range names of the stages (host-side enqueue ranges; a timeline tool attributes the kernels launched inside)
+const char* const kStageName[ST_COUNT] = {"schic:h2d", "schic:K1 signatures", "schic:K3 collisions", "schic:select",
+                                          "schic:K4 rerank", "schic:K5 graph", "schic:d2h", "schic:rerank prep"};
 
 }  // namespace
 
@@ -157,12 +162,14 @@ cudaEvent_t get_misc_event(schic_mh_handle* h) {
 struct StageTimer {
     schic_mh_handle* h; Stage st; cudaStream_t s; cudaEvent_t a;
     StageTimer(schic_mh_handle* hh, Stage stage, cudaStream_t stream) : h(hh), st(stage), s(stream) {
+        nvtxRangePushA(kStageName[st]);
         a = get_event(h);
         if (a) cudaEventRecord(a, s);
     }
     ~StageTimer() {
         cudaEvent_t b = get_event(h);
         if (a && b) { cudaEventRecord(b, s); h->ev[st].push_back({a, b}); }
+        nvtxRangePop();
     }
 };
 
@@ -883,8 +890,8 @@ int schic_mh_fit_csr_counts(schic_mh_handle* h, int64_t n_rows, const int64_t* i
     return fit_csr_impl(h, n_rows, indptr, indices, index_bits, counts, count_bits == 16 ? 1 : 2, append, async_upload != 0);
 }
 
-int schic_mh_fit_csr_device(schic_mh_handle* h, int64_t n_rows, int64_t nnz, const int64_t* d_indptr,
-                            const uint32_t* d_indices, const float* d_data, int32_t append) {
+static int fit_csr_device_impl(schic_mh_handle* h, int64_t n_rows, int64_t nnz, int64_t pos0, const int64_t* d_indptr,
+                               const uint32_t* d_indices, const float* d_data, int32_t append) {
     ST_TRY(check(h));
     if (append) return fail(SCHIC_ERR_UNSUPPORTED, "device-resident fit does not append");
     if (n_rows < 0 || nnz < 0 || !d_indptr || (nnz > 0 && !d_indices)) return fail(SCHIC_ERR_INVALID_ARG, "bad CSR arguments");
@@ -898,15 +905,27 @@ int schic_mh_fit_csr_device(schic_mh_handle* h, int64_t n_rows, int64_t nnz, con
     h->have_val = d_data != nullptr; h->have_hi = false;
     h->n = n_rows; h->nnz = nnz; h->norm_of = nullptr; h->ext = false; h->db_ready = nullptr;
     ST_TRY(h->sig.reserve(n_rows * (int64_t)H, 0, h->stream));
-    // indptr[0] of a borrowed CSR: read back one value (8 bytes) -- positions are absolute
-    int64_t pos0 = 0;
-    CU_TRY(cudaMemcpyAsync(&pos0, d_indptr, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (pos0 < 0) {
+        // indptr[0] of a borrowed CSR not given: read back one value (8 bytes, drains the stream) -- positions are absolute
+        CU_TRY(cudaMemcpyAsync(&pos0, d_indptr, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+    }
     {
         StageTimer t(h, ST_SIG, h->stream);
         ST_TRY(hash_rows(h, 0, n_rows, pos0, pos0 + nnz, h->stream));
     }
     return SCHIC_OK;
+}
+
+int schic_mh_fit_csr_device(schic_mh_handle* h, int64_t n_rows, int64_t nnz, const int64_t* d_indptr,
+                            const uint32_t* d_indices, const float* d_data, int32_t append) {
+    return fit_csr_device_impl(h, n_rows, nnz, -1, d_indptr, d_indices, d_data, append);
+}
+
+int schic_mh_fit_csr_device_at(schic_mh_handle* h, int64_t n_rows, int64_t nnz, int64_t indptr0, const int64_t* d_indptr,
+                               const uint32_t* d_indices, const float* d_data, int32_t append) {
+    if (indptr0 < 0) return fail(SCHIC_ERR_INVALID_ARG, "indptr0 must be the (non-negative) value of d_indptr[0]");
+    return fit_csr_device_impl(h, n_rows, nnz, indptr0, d_indptr, d_indices, d_data, append);
 }
 
 int schic_mh_n_fitted(const schic_mh_handle* h, int64_t* n_out) {
@@ -1061,6 +1080,23 @@ int schic_mh_kneighbors_graph(schic_mh_handle* h, int32_t k, int32_t fast, int64
     const int ke = effective_k(h, k);
     ST_TRY(kneighbors_on_device(h, ke, fast, nullptr, nullptr, nullptr));
     return graph_to_host(h, ke, indptr, indices, data);
+}
+
+int schic_mh_kneighbors_graph_device(schic_mh_handle* h, int32_t k, int32_t fast, int64_t* d_indptr, int32_t* d_indices,
+                                     float* d_data) {
+    ST_TRY(check(h));
+    if (k < 1 || !d_indptr || !d_indices || !d_data) return fail(SCHIC_ERR_INVALID_ARG, "bad kneighbors_graph arguments");
+    ST_TRY(use_device(h));
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    const int ke = effective_k(h, k);
+    ST_TRY(kneighbors_on_device(h, ke, fast, nullptr, nullptr, nullptr));
+    StageTimer t(h, ST_GRAPH, h->stream);
+    const int nl = schic::launch_graph_emit(h->out_idx.p, h->out_dist.p, h->out_nv.p, h->n, ke, d_indptr, d_indices, d_data,
+                                            h->stream);
+    if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k too large for the in-shared-memory graph emit");
+    add_launches(h, nl);
+    CU_TRY(cudaGetLastError());
+    return SCHIC_OK;
 }
 
 int schic_mh_kneighbors_exact(schic_mh_handle* h, int32_t k, int32_t include_self, int32_t* idx, float* dist, int32_t* n_valid) {

@@ -176,7 +176,9 @@ class ShardedMinHash:
             self.h = None
 
     # -- step 1: hash the local shard (device-resident CSR) ---------------------------------
-    def fit_local(self, d_indptr: torch.Tensor, d_indices: torch.Tensor, d_data):
+    def fit_local(self, d_indptr: torch.Tensor, d_indices: torch.Tensor, d_data, indptr0=None):
+        """``indptr0``: the value of ``d_indptr[0]`` if the caller knows it (0 for a stand-alone shard); the fit then
+        enqueues without reading it back from the device (no host synchronisation in the build)."""
         self._keep["csr"] = (d_indptr, d_indices, d_data)
         self._keep.pop("prep_local", None)
         if self._nw > 0:
@@ -187,8 +189,9 @@ class ShardedMinHash:
             self._keep["prep_local"] = (norms, wdir)
         self._start_csr_gather()
         nnz = int(d_indices.numel())
+        extra = {} if indptr0 is None else {"indptr0": int(indptr0)}
         self.api.fit_csr_device(self.h, self.n_local, nnz, d_indptr.data_ptr(), d_indices.data_ptr(),
-                                None if d_data is None else d_data.data_ptr(), False)
+                                None if d_data is None else d_data.data_ptr(), False, **extra)
 
     def fit_local_host(self, indptr: np.ndarray, indices: np.ndarray, data, async_upload: bool = False):
         """Same, from HOST buffers (pinned for full PCIe speed): the H2D copy is part of the call and
@@ -304,6 +307,17 @@ class ShardedMinHash:
         self.api.kneighbors_device(self.h, k, -1, idx.data_ptr(), dst.data_ptr(), nv.data_ptr())
         return out
 
+
+    def kneighbors_graph_local(self, k: int, out=None):
+        """``kneighbors_graph(mode='distance')`` rows of this rank's cells (columns are global cell ids), CSR left on
+        the device: (indptr int64 [n_local+1], indices int32, data float32; the first indptr[-1] entries are valid)."""
+        if out is None:
+            out = (torch.empty(self.n_local + 1, dtype=torch.int64, device=self.device),
+                   torch.empty(self.n_local * k, dtype=torch.int32, device=self.device),
+                   torch.empty(self.n_local * k, dtype=torch.float32, device=self.device))
+        ip, ix, dt = out
+        self.api.kneighbors_graph_device(self.h, k, -1, ip.data_ptr(), ix.data_ptr(), dt.data_ptr())
+        return out
 
     def kneighbors_exact_local(self, k: int, include_self: bool = False, out=None):
         """Exact euclidean kNN (scHicCluster -drm knn) of this rank's rows against the whole gathered

@@ -42,12 +42,12 @@ class PCA:
             raise ValueError("X must be two-dimensional")
         m = self._columns(X.shape)
         api = self._api_factory()
-        out, sv, comp = api.pca_fit_transform(X, m, self.device, want_components=True)
+        out, sv, comp, mean = api.pca_fit_transform(X, m, self.device, want_components=True, return_mean=True)
         n = X.shape[0]
         self.components_ = comp
         self.singular_values_ = sv
         self.explained_variance_ = sv ** 2 / max(n - 1, 1)
-        self.mean_ = getattr(api, "last_pca_mean", None)
+        self.mean_ = mean
         self.n_components_ = m
         return out
 

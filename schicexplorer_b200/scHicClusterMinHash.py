@@ -60,8 +60,11 @@ def parse_arguments(args=None):
                      help='Share of the matrix handed to the hashing back end per chunk.')
     opt.add_argument('--saveMemory', '-sm', action='store_true',
                      help='Load and hash the cells chunk by chunk.')
-    opt.add_argument('--cell_coloring_type', '-cct', required=False, help='Two-column file: cell name, cell type.')
-    opt.add_argument('--cell_coloring_batch', '-ccb', required=False, help='Two-column file: cell name, batch.')
+    opt.add_argument('--cell_coloring_type', '-cct', required=False,
+                     help='Two-column file: cell name, cell type. Writes the cluster/type overlap (matches.txt, or the '
+                          'table of -lt) and the score file correct_associated; colours a second scatter plot.')
+    opt.add_argument('--cell_coloring_batch', '-ccb', required=False,
+                     help='Two-column file: cell name, batch. Only colours a scatter plot (needs matplotlib).')
     opt.add_argument('--noPCA', action='store_true', help='Skip the PCA of the kNN graph.')
     opt.add_argument('--noUMAP', action='store_true', help='Skip the UMAP embedding.')
     opt.add_argument('--dimensionsPCA', '-dim_pca', default=100, type=int, help='PCA dimensions kept.')
@@ -73,7 +76,8 @@ def parse_arguments(args=None):
                      help='Figure size.')
     opt.add_argument('--chromosomes', nargs='+', help='Restrict to these chromosomes.')
     opt.add_argument('--absoluteValues', '-av', help='Accepted for compatibility (parsed but unused, as in the reference).')
-    opt.add_argument('--latexTable', '-lt', help='Write the cluster/type overlap as a LaTeX table.')
+    opt.add_argument('--latexTable', '-lt', help='With -cct: write the cluster/type overlap as a LaTeX table to this file '
+                                                 '(instead of matches.txt).')
     opt.add_argument('--runInHyperoptMode', action='store_true', help='Accepted for compatibility (unused).')
     opt.add_argument('--threads', '-t', required=False, default=8, type=int, help='Host threads.')
     opt.add_argument('--help', '-h', action='help', help='show this help message and exit')
@@ -195,6 +199,18 @@ def main(args=None):
             _scatter_plot(args, mhc._precomputed_graph, labels)
         except ImportError:
             log.warning('matplotlib is not installed: skipping %s', args.createScatterPlot)
+        if args.cell_coloring_batch:
+            log.warning('-ccb/--cell_coloring_batch only colours an extra scatter plot in the reference; that plot is '
+                        'not produced here (no other output depends on it)')
+        if args.cell_coloring_type:
+            # the non-plot outputs of -cct (reference :470-580): overlap table / matches.txt and the hyperopt score file
+            from . import overlap
+            score = overlap.report(names, labels, args.cell_coloring_type, latex_table=args.latexTable)
+            log.info('correct_associated: %s', score)
+    elif args.cell_coloring_type or args.cell_coloring_batch or args.latexTable:
+        log.warning('-cct / -ccb / -lt have no effect without --createScatterPlot (as in the reference)')
+    if args.latexTable and not args.cell_coloring_type:
+        log.warning('-lt/--latexTable needs -cct/--cell_coloring_type: no table written')
 
     matrices_cluster = np.array(list(zip(names, labels)))
     np.savetxt(args.outFileName, matrices_cluster, fmt="%s")

@@ -24,7 +24,8 @@ import numpy as np
 from . import __version__
 from .clustering import MinHashClustering
 from .minhash import MinHash
-from .scHicClusterMinHash import _umap_available, load_cells
+from .overlap import correct_associated, read_cell_types  # noqa: F401  (re-exported: tests and callers import them from here)
+from .scHicClusterMinHash import _umap_available, load_cells, parse_arguments as _tool_arguments
 
 log = logging.getLogger(__name__)
 
@@ -61,37 +62,7 @@ def parse_arguments(args=None):
     return parser
 
 
-# ---- the score of scHicClusterMinHash.py:470-580 (non-LaTeX branch) --------------------------------------------------
-def read_cell_types(path: str) -> dict:
-    """cell name -> cell type from a two-column file (tab or four blanks), as scHicClusterMinHash.py:258-272."""
-    out = {}
-    with open(path) as fh:
-        for line in fh:
-            line = line.strip()
-            if not line:
-                continue
-            try:
-                name, kind = line.split('\t')
-            except ValueError:
-                name, kind = line.split('    ')
-            out[name] = kind
-    return out
-
-
-def correct_associated(labels, cell_types, percentage_threshold: float = 0.8) -> float:
-    """Share of each cell type that sits in clusters dominated (>= 80 %) by that type, averaged over the types
-    (scHicClusterMinHash.py:538-572); 1 - this is the hyperopt error score."""
-    labels = np.asarray(labels)
-    cell_types = np.asarray(cell_types)
-    kinds = list(dict.fromkeys(cell_types.tolist()))        # first-appearance order, as the reference numbers them
-    detected = dict.fromkeys(kinds, 0.0)
-    for cluster in set(labels.tolist()):
-        in_cluster = labels == cluster
-        for kind in kinds:
-            matches = int(np.sum(in_cluster & (cell_types == kind)))
-            if matches / np.sum(in_cluster) >= percentage_threshold:
-                detected[kind] += matches
-    return float(np.mean([detected[kind] / np.sum(cell_types == kind) for kind in kinds]))
+# the score of scHicClusterMinHash.py:470-580 lives in overlap.py (shared with the tool's -cct output)
 
 
 # ---- resident state --------------------------------------------------------------------------------------------------
@@ -135,6 +106,17 @@ class ResidentCells:
         self._fitted = {}
 
 
+def trial_umap_dict(params: dict) -> dict:
+    """The umap arguments of one trial. The reference objective runs the tool itself, i.e. with ALL of the tool's
+    ``--umap_*`` defaults (notably ``--umap_metric canberra``, scHicClusterMinHash.py:165-168, consumed at :374-382) and
+    only the three searched values overridden (scHicClusterMinHashHyperopt.py:132-140); ``umap_random`` is 42 (:316)."""
+    defaults = vars(_tool_arguments().parse_args(['-m', 'unused', '-o', 'unused']))
+    umap_dict = {k: v for k, v in defaults.items() if 'umap_' in k}
+    umap_dict.update({'umap_n_neighbors': params['umap_n_neighbors'], 'umap_n_components': params['umap_n_components'],
+                      'umap_min_dist': params['umap_min_dist'], 'umap_random': 42})
+    return umap_dict
+
+
 def objective(params: dict, resident: ResidentCells, cell_types) -> float:
     """One trial (reference objective, :119-148): error score = 1 - correct_associated."""
     if params['dimensionsPCA'] <= params['umap_n_components']:
@@ -142,10 +124,7 @@ def objective(params: dict, resident: ResidentCells, cell_types) -> float:
     from sklearn.cluster import SpectralClustering
     graph = resident.graph(params['intraChromosomalContactsOnly'], params['numberOfHashFunctions'])
     use_umap = _umap_available()
-    umap_dict = {}
-    if use_umap:
-        umap_dict = {'umap_n_neighbors': params['umap_n_neighbors'], 'umap_n_components': params['umap_n_components'],
-                     'umap_min_dist': params['umap_min_dist'], 'umap_random': 42}
+    umap_dict = trial_umap_dict(params) if use_umap else {}
     embedding = MinHashClustering._post_process(graph, not params['noPCA'], params['dimensionsPCA'], use_umap, umap_dict)
     cluster = SpectralClustering(n_clusters=params['numberOfClusters'], affinity='nearest_neighbors',
                                  n_jobs=params['threads'], random_state=0)

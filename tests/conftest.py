@@ -80,13 +80,14 @@ class OraclePcaApi:
     """Stands in for the CUDA library behind schicexplorer_b200.pca.PCA in the CPU suite: same method, numpy oracle."""
     backend = "oracle"
 
-    def pca_fit_transform(self, X, n_components, device=-1, want_components=False):
+    def pca_fit_transform(self, X, n_components, device=-1, want_components=False, return_mean=False):
         from scipy.sparse import issparse
         from oracle import pca_np
         dense = np.asarray(X.todense(), dtype=np.float64) if issparse(X) else np.asarray(X, dtype=np.float64)
         emb, sv, comp = pca_np.pca_fit_transform(dense, n_components)
         self.last_pca_mean = np.where(np.isfinite(dense), dense, 0.0).mean(axis=0) if want_components else None
-        return emb, sv, (comp if want_components else None)
+        out = (emb, sv, (comp if want_components else None))
+        return out + (self.last_pca_mean,) if return_mean else out
 
 
 @pytest.fixture(autouse=True)

@@ -84,3 +84,50 @@ def test_cli_on_real_scool(tmp_path, fname, prefix):
     rows = [l.split(" ") for l in open(out).read().strip().split("\n")]
     assert len(rows) == 20 and all(r[0].startswith(prefix) for r in rows)
     assert len({r[1] for r in rows}) == 3
+
+
+def _type_file(tmp_path, names):
+    path = tmp_path / "types.txt"
+    kinds = ["G1", "S", "G2"]
+    path.write_text("".join(f"{n}\t{kinds[i % 3]}\n" for i, n in enumerate(names)))
+    return str(path)
+
+
+def test_cell_coloring_type_writes_matches_and_score(tmp_path, fixture20, monkeypatch):
+    """-cct: the non-plot outputs of the reference (scHicClusterMinHash.py:519-580) -- matches.txt in the working
+    directory and the score file `correct_associated` that scHicClusterMinHashHyperopt reads back."""
+    from schicexplorer_b200 import overlap
+    monkeypatch.chdir(tmp_path)
+    names = fixture20[1]
+    out = run(tmp_path, f"-dim_pca 100 -cct {_type_file(tmp_path, names)}")
+    labels = [int(l.split(" ")[1]) for l in open(out).read().strip().split("\n")]
+    types = overlap.read_cell_types(_type_file(tmp_path, names))
+    score = float(open(tmp_path / "correct_associated").read())
+    assert score == overlap.correct_associated(labels, [types[n] for n in names])
+    lines = [l for l in open(tmp_path / "matches.txt").read().split("\n") if l]
+    assert len(lines) == 3 * 3 and all(l.startswith("Computed cluster ") for l in lines)
+    # the counts of one line, recomputed
+    import re
+    m = re.match(r"Computed cluster (\d+) \(size: (\d+)\) matching with cell type (\S+) \(size: (\d+)\) (\d+) times\.", lines[0])
+    cluster, kind = int(m.group(1)), m.group(3)
+    assert int(m.group(2)) == labels.count(cluster)
+    assert int(m.group(5)) == sum(1 for n, lab in zip(names, labels) if lab == cluster and types[n] == kind)
+
+
+def test_latex_table_replaces_matches(tmp_path, fixture20, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    table = tmp_path / "table.tex"
+    run(tmp_path, f"-dim_pca 100 -cct {_type_file(tmp_path, fixture20[1])} -lt {table}")
+    text = table.read_text()
+    assert text.startswith("\\begin{table}[!htb]") and text.rstrip().endswith("\\end{table}")
+    assert text.count("\\hline Cluster ") == 1 + 3 and "Correct identified $>80\\%$" in text
+    assert not (tmp_path / "matches.txt").exists() and (tmp_path / "correct_associated").exists()
+
+
+def test_coloring_flags_without_effect_warn(tmp_path, fixture20, caplog):
+    import logging
+    with caplog.at_level(logging.WARNING):
+        run(tmp_path, f"-dim_pca 100 -ccb {_type_file(tmp_path, fixture20[1])} -lt {tmp_path / 't.tex'}")
+    text = caplog.text
+    assert "-ccb" in text and "-lt/--latexTable needs -cct" in text
+    assert not (tmp_path / "t.tex").exists()

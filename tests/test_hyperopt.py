@@ -100,3 +100,31 @@ def test_flag_contract():
     assert tuple(a.umap_n_components) == (2, 10, 1) and tuple(a.umap_min_dist) == (0.0, 0.5) and a.threads == 16
     with pytest.raises(SystemExit):
         p.parse_args("-m x -c y -me grid".split())
+
+
+def test_trial_umap_arguments_start_from_the_tool_defaults():
+    """The reference objective runs scHicClusterMinHash.main, i.e. with every --umap_* default of the tool (notably
+    --umap_metric canberra, scHicClusterMinHash.py:165-168) and only the searched values overridden."""
+    d = hyper.trial_umap_dict({'umap_n_neighbors': 41, 'umap_n_components': 3, 'umap_min_dist': 0.11})
+    assert d['umap_metric'] == 'canberra' and d['umap_init'] == 'spectral' and d['umap_random'] == 42
+    assert d['umap_n_neighbors'] == 41 and d['umap_n_components'] == 3 and d['umap_min_dist'] == 0.11
+    assert d['umap_negative_sample_rate'] == 5 and d['umap_target_metric'] == 'categorical'
+
+
+def test_objective_hands_the_tool_defaults_to_the_embedding(oracle_backed, monkeypatch):
+    seen = {}
+
+    def fake_post(graph, pca, dims, use_umap, umap_dict):
+        seen.update(umap_dict=umap_dict, use_umap=use_umap)
+        return np.asarray(graph.todense())
+
+    from schicexplorer_b200.clustering import MinHashClustering
+    monkeypatch.setattr(MinHashClustering, "_post_process", staticmethod(fake_post))
+    monkeypatch.setattr(hyper, "_umap_available", lambda: True)
+    resident = hyper.ResidentCells(MATRIX, 800, 20, threads=2)
+    types = ["a" if i % 2 else "b" for i in range(20)]
+    params = {'dimensionsPCA': 10, 'umap_n_components': 2, 'umap_n_neighbors': 5, 'umap_min_dist': 0.2, 'noPCA': False,
+              'intraChromosomalContactsOnly': False, 'numberOfHashFunctions': 800, 'numberOfClusters': 2, 'threads': 1}
+    hyper.objective(params, resident, types)
+    resident.close()
+    assert seen['use_umap'] and seen['umap_dict']['umap_metric'] == 'canberra'
