@@ -124,3 +124,43 @@ def test_config3_full_size(cuda, oracle, monkeypatch):
             dot = sum(xq.get(f, 0.0) * v for f, v in zip(yi.tolist(), yv.tolist()))
             want = np.sqrt(max(0.0, nq2 + float((yv * yv).sum()) - 2.0 * dot))
             assert abs(got - want) <= RTOL * want + 1e-12
+
+
+def test_config3_full_size_against_the_oracle(cuda, oracle):
+    """The headline configuration as a WHOLE against the CPU oracle, nothing sampled: 10 000 cells, H = 800, k = 100,
+    exact rerank. Signature matrix byte for byte, a 1024-row block of collision counts against all 10 000 columns, all
+    10^6 neighbour indices identical up to distance ties, n_valid identical, distances within 1e-5 relative. The same
+    comparison through the reference-facing classes (MinHash.fit -> kneighbors_graph) for the graph structure."""
+    cfg, ip, ix, dt, X = cells("s10", 10_000)
+    n, H, k = 10_000, 800, 100
+    kw = dict(n_neighbors=k, fast=False, **REF_KWARGS)
+    ho = oracle.create(number_of_cores=os.cpu_count() or 1, **kw)
+    oracle.fit_csr(ho, ip, ix, dt, False)
+    o_sig = oracle.signatures(ho, H)
+    o_idx, o_dist, o_nv = oracle.kneighbors(ho, k)
+    o_cnt = oracle.collision_counts(ho, 4096, 5120)
+    o_gip, o_gix, o_gdt = oracle.kneighbors_graph(ho, k)
+    oracle.destroy(ho)
+
+    h = cuda.create(**kw)
+    cuda.set_feature_range(h, cfg.chroms.nbins ** 2)
+    cuda.fit_csr(h, ip, ix, dt, False)
+    g_sig = cuda.signatures(h, H)
+    assert g_sig.tobytes() == o_sig.tobytes()                      # memcmp of the 32 MB signature matrix
+    assert np.array_equal(cuda.collision_counts(h, 4096, 5120), o_cnt)
+    g_idx, g_dist, g_nv = cuda.kneighbors(h, k)
+    cuda.destroy(h)
+    assert np.array_equal(g_nv, o_nv)
+    assert_neighbours_equal_up_to_ties(g_idx, g_dist, g_nv, o_idx, o_dist, o_nv, RTOL)
+    # integer counts: both sides compute sqrt of the exact integer squared distance -> identical fp32 bits
+    assert np.array_equal(g_dist, o_dist)
+
+    from schicexplorer_b200 import MinHash
+    mh = MinHash(device=0, **kw)
+    g = mh.fit(X).kneighbors_graph(mode="distance")
+    mh.close()
+    assert g.shape == (n, n) and np.array_equal(g.indptr, o_gip)
+    same_cols = np.array_equal(g.indices, o_gix)
+    if not same_cols:            # ties at the k-th distance may swap equidistant columns
+        assert (g.indices != o_gix).mean() < 1e-4
+    np.testing.assert_allclose(np.sort(g.data), np.sort(o_gdt.astype(np.float64)), rtol=RTOL)

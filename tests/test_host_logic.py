@@ -193,3 +193,36 @@ def test_tools_and_entry_points_parse():
     assert len(files) > 10
     for f in files:
         ast.parse(open(f).read(), filename=f)
+
+
+def test_reconcile_upstream_tool(tmp_path, oracle, monkeypatch, capsys):
+    """tools/reconcile_upstream.py: (1) today -- no real sparse_neighbors_search anywhere -- it says so and exits 3, and
+    it does not mistake this repository's import shim for upstream; (2) the day an install appears under a path it is
+    given, it runs the reference's call sequence on the 20-cell fixture and pins the HashSpec: exercised here with a
+    stand-in package whose MinHash is the oracle-backed class (so width 32 must reproduce the golden vectors, width 64
+    must not)."""
+    import importlib.util
+    import json
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("reconcile_upstream", os.path.join(ROOT, "tools", "reconcile_upstream.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    assert tool.main(["--json"]) == 3
+    assert json.loads(capsys.readouterr().out)["pinned"] is False
+    mod, why = tool.find_upstream(os.path.join(ROOT))       # the shim's parent directory: must be refused
+    assert mod is None
+
+    pkg = tmp_path / "sparse_neighbors_search"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text(
+        "from schicexplorer_b200 import MinHash as _M\n"
+        "from oracle import oracle_api\n"
+        "__version__ = 'stand-in'\n"
+        "class MinHash(_M):\n"
+        "    _api_factory = staticmethod(oracle_api)\n")
+    assert tool.main(["--json", "--path", str(tmp_path)]) == 0
+    rep = json.loads(capsys.readouterr().out)
+    assert rep["pinned"] and rep["hash_width_matching_upstream"] == [32]
+    assert rep["checks"]["fast_counts_width32"]["equal"] and not rep["checks"]["fast_counts_width64"]["equal"]
+    assert rep["checks"]["signatures_width32"]["equal"] and rep["checks"]["exact_distances"]["identical_up_to_ties"]
