@@ -269,7 +269,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def device_leg(kw_leg, steps, warmup, sample_clocks):
-        sh = ShardedMinHash(api, n_total, bounds, dev, n_features=n_features, shard_nnz=shard_nnz, **kw_leg)
+        # (the values are Hi-C contact counts: stated to the sharded layer, which then exchanges the packed stream)
+        sh = ShardedMinHash(api, n_total, bounds, dev, n_features=n_features, shard_nnz=shard_nnz, integer_counts=True,
+                            **kw_leg)
 
         def step():
             sh.fit_local(d_ip, d_ix, d_dt, indptr0=0)
@@ -307,7 +309,7 @@ def run_ours(args):
     k1_ms = torch.tensor([stage["signatures"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(nnz_all, op=dist.ReduceOp.SUM)
-    rerank_kernel = api.rerank_kernel_name(sh.h) if hasattr(api, "rerank_kernel_name") else "k4_rerank_window_kernel"
+    rerank_kernel = "none" if fast else api.rerank_kernel_name(sh.h)
 
     # ---- parity: neighbour lists of this rank's rows, folded into a checksum (not timed) ---------------------
     idx_t, dst_t, nv_t = sh.kneighbors_local(kk)
@@ -351,7 +353,7 @@ def run_ours(args):
         p_dt = api.pinned_empty(wire.shape, wire.dtype); p_dt[:] = wire
     g_host = (api.pinned_empty((n_local + 1,), np.int64), api.pinned_empty((n_local * kk,), np.int32),
               api.pinned_empty((n_local * kk,), np.float32))
-    sh2 = ShardedMinHash(api, n_total, bounds, dev, n_features=n_features, shard_nnz=shard_nnz, **kw)
+    sh2 = ShardedMinHash(api, n_total, bounds, dev, n_features=n_features, shard_nnz=shard_nnz, integer_counts=True, **kw)
     host_ms = {"fit_csr": 0.0, "gather": 0.0, "kneighbors_graph": 0.0}
 
     def step_e2e():

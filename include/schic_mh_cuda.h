@@ -78,20 +78,34 @@ int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t ro
  * schic_mh_set_database_device / fit. */
 int schic_mh_set_database_ready_event(schic_mh_handle* h, void* cuda_event);
 
-/* Per-row preparation of the exact rerank (fp64 row norms, window directory), normally computed by the library for
- * the whole database on first use. In a sharded run every rank can instead prepare its OWN rows and exchange the two
- * small arrays:
+/* Per-row preparation of the exact rerank, normally computed by the library for the whole database on first use, in one
+ * pass over ids + values: fp64 row norms, the window directory (offsets of 2^17-id windows in every row), the PACKED
+ * STREAM of the counts kernel -- one uint32 per non-zero, (id mod 2^17) << 15 | count, same indexing as d_indices -- and
+ * four flags {a value is not an integer in [0, 32767]; number of values >= 255; an id beyond the declared range; -}.
+ * In a sharded run every rank prepares its OWN rows and the arrays are exchanged instead of being recomputed by everyone:
  *   schic_mh_rerank_windows      number of id windows for the range declared with schic_mh_set_feature_range
  *                                (0: no hint, or the range needs the hash-table kernel -- then do not use the two below)
- *   schic_mh_rerank_prep_rows    norms2[n_rows] (float64) and dir[n_rows, n_windows+1] (uint32) of the given CSR rows,
- *                                queued on the handle's stream
- *   schic_mh_set_database_prep_device   norms / directory of ALL database rows for the next kneighbors call on an
- *                                external database (call after schic_mh_set_database_device, which clears them) */
+ *   schic_mh_rerank_prep_rows    norms2[n_rows] (float64), dir[n_rows, n_windows+1] (uint32), packed[nnz] (uint32, may be
+ *                                NULL), flags[4] (uint32, zeroed here) of the given CSR rows, queued on the handle's stream
+ *   schic_mh_set_database_prep_device   norms / directory (and optionally packed stream + flags, OR-ed / summed over the
+ *                                ranks, + total non-zeros) of ALL database rows for the next kneighbors call on an external
+ *                                database (call after schic_mh_set_database_device, which clears them). The packed
+ *                                stream must be 16-byte aligned and followed by >= 16 readable bytes. With a packed
+ *                                stream the exact rerank does not need d_indices_all / d_data_all of
+ *                                schic_mh_set_database_device (pass NULL: half the exchange volume) -- valid when the
+ *                                values are small integer counts, which the flags verify: if they are not, the next
+ *                                synchronising call reports SCHIC_ERR_INVALID_ARG instead of returning wrong distances.
+ *   schic_mh_rerank_kernel_name  which kernel did the work of the last exact rerank ("k4c_rerank_kernel" = counts
+ *                                kernel, "k4_rerank_window_kernel" / "k4_rerank_kernel" = generic float kernels);
+ *                                out must hold 32 bytes. Synchronises the stream. */
 int schic_mh_rerank_windows(schic_mh_handle* h, int32_t* n_windows_out);
 int schic_mh_rerank_prep_rows(schic_mh_handle* h, int64_t n_rows, const int64_t* d_indptr, const uint32_t* d_indices,
-                              const float* d_data, int32_t n_windows, double* d_norm2_out, uint32_t* d_dir_out);
+                              const float* d_data, int32_t n_windows, double* d_norm2_out, uint32_t* d_dir_out,
+                              uint32_t* d_packed_out, uint32_t* d_flags_out);
 int schic_mh_set_database_prep_device(schic_mh_handle* h, const double* d_norm2_all, const uint32_t* d_dir_all,
-                                      int32_t n_windows);
+                                      int32_t n_windows, const uint32_t* d_packed_all, const uint32_t* d_flags_all,
+                                      int64_t nnz_total);
+int schic_mh_rerank_kernel_name(schic_mh_handle* h, char* out, int32_t n_out);
 
 /* Run on the caller's stream (a cudaStream_t, e.g. torch's current stream) instead of the
  * handle's own. NULL selects the legacy default stream. */

@@ -60,7 +60,7 @@ CUDA_SYMBOLS = (
     "schic_mh_rerank_prep_rows", "schic_mh_set_database_prep_device", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free", "schic_mh_kneighbors_exact_device",
-    "schic_mh_fit_csr_device_at", "schic_mh_kneighbors_graph_device",
+    "schic_mh_fit_csr_device_at", "schic_mh_kneighbors_graph_device", "schic_mh_rerank_kernel_name",
 )
 
 # the dense-graph PCA post-step, CUDA library only (include/schic_pca.h)
@@ -112,8 +112,9 @@ class CApi:
             L.schic_pca_stage_ms.argtypes = [_vp, _i32]
             L.schic_mh_set_database_ready_event.argtypes = [_vp, _vp]
             L.schic_mh_rerank_windows.argtypes = [_vp, C.POINTER(_i32)]
-            L.schic_mh_rerank_prep_rows.argtypes = [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp]
-            L.schic_mh_set_database_prep_device.argtypes = [_vp, _vp, _vp, _i32]
+            L.schic_mh_rerank_prep_rows.argtypes = [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]
+            L.schic_mh_set_database_prep_device.argtypes = [_vp, _vp, _vp, _i32, _vp, _vp, _i64]
+            L.schic_mh_rerank_kernel_name.argtypes = [_vp, C.c_char_p, _i32]
             L.schic_mh_fit_csr_counts.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32]
             L.schic_mh_fit_csr_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _i32]
             L.schic_mh_kneighbors_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
@@ -348,12 +349,23 @@ class CApi:
         self.check(self.lib.schic_mh_rerank_windows(_vp(h), C.byref(n)))
         return n.value
 
-    def rerank_prep_rows(self, h, n_rows, d_indptr, d_indices, d_data, n_windows, d_norm2_out, d_dir_out):
+    def rerank_prep_rows(self, h, n_rows, d_indptr, d_indices, d_data, n_windows, d_norm2_out, d_dir_out, d_flags_out,
+                         d_packed_out=None):
+        """Row norms, window directory, flags[4] and (optionally) the packed stream of the given CSR rows."""
         self.check(self.lib.schic_mh_rerank_prep_rows(_vp(h), n_rows, _ptr(d_indptr), _ptr(d_indices), _ptr(d_data),
-                                                      n_windows, _ptr(d_norm2_out), _ptr(d_dir_out)))
+                                                      n_windows, _ptr(d_norm2_out), _ptr(d_dir_out), _ptr(d_packed_out),
+                                                      _ptr(d_flags_out)))
 
-    def set_database_prep_device(self, h, d_norm2_all, d_dir_all, n_windows):
-        self.check(self.lib.schic_mh_set_database_prep_device(_vp(h), _ptr(d_norm2_all), _ptr(d_dir_all), n_windows))
+    def set_database_prep_device(self, h, d_norm2_all, d_dir_all, n_windows, d_packed_all=None, d_flags_all=None,
+                                 nnz_total=0):
+        self.check(self.lib.schic_mh_set_database_prep_device(_vp(h), _ptr(d_norm2_all), _ptr(d_dir_all), n_windows,
+                                                              _ptr(d_packed_all), _ptr(d_flags_all), int(nnz_total)))
+
+    def rerank_kernel_name(self, h) -> str:
+        """Which kernel did the work of the last exact rerank (counts kernel or a generic float kernel)."""
+        buf = C.create_string_buffer(64)
+        self.check(self.lib.schic_mh_rerank_kernel_name(_vp(h), buf, 64))
+        return buf.value.decode()
 
     def set_feature_range(self, h, n_features: int):
         """Hint (CUDA back end): every feature id is < n_features (the CSR's column count); lets fit / kneighbors

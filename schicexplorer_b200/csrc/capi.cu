@@ -101,8 +101,15 @@ struct schic_mh_handle {
     int64_t count_budget = 0;                 // elements of the uint16 count matrix we allow ourselves (cached)
     uint64_t feature_range = 0;               // caller's hint: all ids < feature_range (0: unknown, read the maximum back)
     DevBuf<double> norm2; int64_t norm_rows = 0; const void* norm_of = nullptr;
-    DevBuf<uint32_t> win_dir, max_feat; int n_windows = 0;   // window directory of the windowed rerank (0: hash kernel)
+    DevBuf<uint32_t> win_dir, max_feat; int n_windows = 0;   // window directory (2^17-id windows) of the rerank (0: hash kernel)
     int window_mode = 32;
+    // counts rerank (k4c_rerank.cu): packed stream (id mod 2^17) << 15 | count of the prepared database, the prep flags
+    // {not packable, #values >= 255, id beyond the range, -} and the uint64 dot-product accumulator
+    DevBuf<uint32_t> packed, k4_flags; DevBuf<unsigned long long> dotacc;
+    bool packed_ok = false; int64_t prep_nnz = 0;
+    int64_t b_end = 0;                        // end position of a borrowed CSR (indptr[n])
+    int fit_data_kind = 0;                    // how the values of the last fit arrived: 0 float32, 1 uint16, 2 uint8
+    int rerank_path = 0;                      // what the last rerank launched: 1 counts only, 2 counts + generic behind it, 3 generic only
 
     // external database (distributed query)
     bool ext = false;
@@ -111,6 +118,7 @@ struct schic_mh_handle {
     const uint32_t* db_feat = nullptr; const float* db_val = nullptr;
     cudaEvent_t db_ready = nullptr;      // caller's event: the external CSR is complete once it has fired
     const double* ext_norm2 = nullptr; const uint32_t* ext_dir = nullptr; int ext_nw = 0;   // caller-provided rerank prep
+    const uint32_t* ext_packed = nullptr; const uint32_t* ext_flags = nullptr; int64_t ext_nnz = 0;
 
     // scratch of kneighbors
     DevBuf<uint16_t> counts; DevBuf<int32_t> cand_idx, cand_cnt, cand_nv, sel_flags, part_idx; DevBuf<float> part_dist;
@@ -210,14 +218,31 @@ int ensure_counters(schic_mh_handle* h) {
     return 0;
 }
 
-// After a host synchronisation: did a kernel see an id beyond the caller's feature-range hint?
+uint32_t esc_limit_for(int64_t nnz) { return (uint32_t)std::min<int64_t>(nnz / 64, 0x7FFFFFFF); }
+
+// After a host synchronisation: did a kernel see an id beyond the caller's feature-range hint (K1 table path: counters[3];
+// rerank preparation: flags[2])? Was a database that came as packed counts only (no ids / values for the generic
+// kernels) not packable after all?
 int check_range_flag(schic_mh_handle* h) {
-    if (h->feature_range == 0 || h->k1t_counters.cap < 4) return 0;
-    uint32_t flag = 0;
-    CU_TRY(cudaMemcpyAsync(&flag, h->k1t_counters.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (h->ext && h->ext_packed && h->ext_flags && !h->db_val && h->rerank_path == 1) {
+        uint32_t f[4] = {0, 0, 0, 0};
+        CU_TRY(cudaMemcpyAsync(f, h->ext_flags, sizeof(f), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        if (f[0] != 0 || f[1] > esc_limit_for(h->ext_nnz))
+            return fail(SCHIC_ERR_INVALID_ARG, "the database was handed over as packed integer counts only, but its values are not "
+                                               "small non-negative integers: exchange the CSR ids and values as well");
+        if (f[2]) return fail(SCHIC_ERR_INVALID_ARG, "a feature id is >= the range declared with schic_mh_set_feature_range");
+    }
+    if (h->feature_range == 0) return 0;
+    uint32_t flag = 0, pflag = 0;
+    if (h->k1t_counters.cap >= 4)
+        CU_TRY(cudaMemcpyAsync(&flag, h->k1t_counters.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (h->k4_flags.cap >= 4 && h->norm_of)
+        CU_TRY(cudaMemcpyAsync(&pflag, h->k4_flags.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
-    if (flag) {
-        CU_TRY(cudaMemsetAsync(h->k1t_counters.p + 3, 0, sizeof(uint32_t), h->stream));
+    if (flag || pflag) {
+        if (flag) CU_TRY(cudaMemsetAsync(h->k1t_counters.p + 3, 0, sizeof(uint32_t), h->stream));
+        if (pflag) { CU_TRY(cudaMemsetAsync(h->k4_flags.p + 2, 0, sizeof(uint32_t), h->stream)); h->norm_of = nullptr; }
         return fail(SCHIC_ERR_INVALID_ARG, "a feature id is >= the range declared with schic_mh_set_feature_range");
     }
     return 0;
@@ -316,20 +341,25 @@ int prune_buckets(schic_mh_handle* h, const uint32_t* db_sig, int64_t ndb) {
     return 0;
 }
 
-// Per-database preparation of the exact rerank, cached until the next fit: fp64 row norms and, when the
-// feature space spans at most kMaxWindows windows, the window directory of the windowed kernel.
-// SCHIC_K4_MODE=hash forces the hash-table kernel (tests compare the two).
-int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const uint32_t* feat, const float* val, int64_t rows) {
+// Per-database preparation of the exact rerank, cached until the next fit -- ONE pass over ids + values
+// (k4c_prep_kernel): fp64 row norms and, when the id range spans at most kMaxWindows windows of 2^17 ids, the window
+// directory, the packed stream of the counts kernel and the flags that say whether the data is packable.
+// SCHIC_K4_MODE: "hash" = norms only (hash-table kernel), "window" / "window64" = directory, generic windowed kernel
+// only, default = counts kernel with the generic kernels behind it (tests compare them all).
+int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const uint32_t* feat, const float* val, int64_t rows, int64_t nnz_end) {
     if (h->norm_of == (const void*)indptr && h->norm_rows == rows) return 0;
-    constexpr int kMaxWindows = 1024;
+    constexpr int kMaxWindows = 4096;
     cudaStream_t s = h->stream;
     if (h->val_done) CU_TRY(cudaStreamWaitEvent(s, h->val_done, 0));   // async fit: the values may still be in flight
     ST_TRY(h->norm2.reserve(rows, 0, s));
-    add_launches(h, schic::launch_row_norms(indptr, val, rows, 0, h->norm2.p, s));
-    CU_TRY(cudaGetLastError());
+    ST_TRY(h->k4_flags.reserve(4, 0, s));
+    CU_TRY(cudaMemsetAsync(h->k4_flags.p, 0, 4 * sizeof(uint32_t), s));
     h->n_windows = 0;
+    h->packed_ok = false;
+    h->prep_nnz = 0;
     const char* mode = getenv("SCHIC_K4_MODE");
     h->window_mode = (mode && strcmp(mode, "window64") == 0) ? 64 : 32;
+    int nw = 0;
     if (!(mode && strcmp(mode, "hash") == 0)) {
         uint32_t mx = 0;
         if (h->feature_range > 0 && h->feature_range <= 0xFFFFFFFFull) {
@@ -342,14 +372,22 @@ int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const uint32_t* feat
             CU_TRY(cudaMemcpyAsync(&mx, h->max_feat.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             CU_TRY(cudaStreamSynchronize(s));
         }
-        const int nw = schic::rerank_window_count(mx);
-        if (nw <= kMaxWindows) {
-            ST_TRY(h->win_dir.reserve(rows * (int64_t)(nw + 1), 0, s));
-            add_launches(h, schic::launch_row_window_dir(indptr, feat, rows, nw, h->win_dir.p, s));
-            CU_TRY(cudaGetLastError());
-            h->n_windows = nw;
-        }
+        nw = schic::k4c_window_count(mx);
+        if (nw > kMaxWindows) nw = 0;
     }
+    const bool want_packed = nw > 0 && !(mode && (strcmp(mode, "window") == 0 || strcmp(mode, "window64") == 0));
+    if (want_packed && nnz_end < 0) {      // external database without its own preparation: one read-back of indptr[rows]
+        CU_TRY(cudaMemcpyAsync(&nnz_end, indptr + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+    }
+    if (nw > 0) ST_TRY(h->win_dir.reserve(rows * (int64_t)(nw + 1), 0, s));
+    if (want_packed) ST_TRY(h->packed.reserve(nnz_end + 4, 0, s));      // slices are read as aligned 16-byte words
+    add_launches(h, schic::launch_rerank_prep(indptr, feat, val, rows, nw, h->norm2.p, nw > 0 ? h->win_dir.p : nullptr,
+                                              want_packed ? h->packed.p : nullptr, h->k4_flags.p, s));
+    CU_TRY(cudaGetLastError());
+    h->n_windows = nw;
+    h->packed_ok = want_packed;
+    h->prep_nnz = want_packed ? nnz_end : 0;
     h->norm_of = indptr;
     h->norm_rows = rows;
     return 0;
@@ -380,6 +418,8 @@ int prepare_packed_counts(schic_mh_handle* h, const uint32_t* db_sig, int64_t nd
 // K4 over candidate lists [nq, kcand] (cand_idx == nullptr: brute force, every database row is a candidate of every
 // query). Lists that fit one CTA's shared memory take one launch; longer ones (and brute force) are reranked in chunks
 // of RERANK_CHUNK candidates - each chunk leaves its best min(k, chunk) sorted in a scratch - and merged per row.
+// Every launch is the counts kernel (when the database has a packed stream) with the generic float kernels behind it:
+// the prep flags on the device decide which of the two does the work, the other exits at once.
 int rerank_lists(schic_mh_handle* h, const int64_t* db_indptr, const uint32_t* db_feat, const float* db_val, int64_t ndb,
                  bool ext_prep, int64_t row0, int64_t nq, const int32_t* cand_idx, const int32_t* cand_nv, int kcand, int k,
                  bool exclude_self, int32_t* d_idx, float* d_dist, int32_t* d_nv) {
@@ -388,12 +428,50 @@ int rerank_lists(schic_mh_handle* h, const int64_t* db_indptr, const uint32_t* d
     const double* r_norm2 = ext_prep ? h->ext_norm2 : h->norm2.p;
     const uint32_t* r_dir = ext_prep ? h->ext_dir : (h->n_windows > 0 ? h->win_dir.p : nullptr);
     const int r_nw = ext_prep ? h->ext_nw : h->n_windows, r_mode = ext_prep ? 32 : h->window_mode;
+    const uint32_t* r_packed = ext_prep ? h->ext_packed : (h->packed_ok ? h->packed.p : nullptr);
+    const uint32_t* r_flags = ext_prep ? h->ext_flags : (h->packed_ok ? h->k4_flags.p : nullptr);
+    const int64_t r_nnz = ext_prep ? h->ext_nnz : h->prep_nnz;
+    const char* mode = getenv("SCHIC_K4_MODE");
+    const bool forced_generic = mode && (strcmp(mode, "hash") == 0 || strcmp(mode, "window") == 0 || strcmp(mode, "window64") == 0);
+    const bool counts = r_packed && r_flags && r_dir && r_nw > 0 && !forced_generic;
+    const bool have_generic = db_feat && db_val;
+    // uint8 counts straight from the host are packable by construction: nothing to fall back to
+    const bool generic = have_generic && !(counts && !h->ext && !h->borrowed && h->fit_data_kind == 2);
+    if (!counts && !have_generic) return fail(SCHIC_ERR_INVALID_ARG, "exact rerank needs the CSR ids and values (or a packed database)");
+    const uint32_t esc_limit = esc_limit_for(r_nnz);
+    int64_t group_bytes = (int64_t)40 << 20;         // share of the packed stream one window group spans (L2-resident)
+    if (const char* g = getenv("SCHIC_K4_GROUP_MB")) group_bytes = (int64_t)atoll(g) << 20;              // 0: one group
+    if (const char* g = getenv("SCHIC_K4_GROUP_WINDOWS")) group_bytes = -std::max<int64_t>(1, atoll(g));  // windows per group
+    h->rerank_path = counts ? (generic ? 2 : 1) : 3;
+    if (counts) ST_TRY(h->dotacc.reserve((int64_t)schic::k4c_dotacc_elems(nq, std::min(kcand, RERANK_CHUNK)), 0, s));
+
+    // one launch (counts and / or generic) over candidate columns [c0, c0 + cn); -1: does not fit, chunk the lists
+    auto launch_one = [&](int c0, int cn, int kout, int32_t* o_idx, float* o_dist, int o_stride, int o_off, int final,
+                          int n_all, int allow_hash) -> int {
+        int nl = 0;
+        bool did_counts = false;
+        if (counts) {
+            const int r = schic::launch_rerank_counts(db_indptr, r_packed, r_norm2, r_dir, r_nw, r_nnz, group_bytes, row0, nq,
+                                                      cand_idx, cand_nv, kcand, c0, cn, kout, o_idx, o_dist, o_stride, o_off,
+                                                      final, d_nv, n_all, r_flags, esc_limit, h->dotacc.p, s);
+            if (r < 0 && !generic) return -1;
+            if (r >= 0) { nl += r; did_counts = true; }
+        }
+        if (generic) {
+            const int r = schic::launch_rerank(db_indptr, db_feat, db_val, 0, r_norm2, r_dir, r_nw, r_mode, row0, nq, cand_idx,
+                                               cand_nv, kcand, c0, cn, kout, o_idx, o_dist, o_stride, o_off, final, d_nv, n_all,
+                                               allow_hash, did_counts ? r_flags : nullptr, esc_limit, s);
+            if (r < 0) return -1;
+            nl += r;
+        }
+        return nl;
+    };
+
     int nl = -1;
-    if (cand_idx)
-        nl = schic::launch_rerank(db_indptr, db_feat, db_val, 0, r_norm2, r_dir, r_nw, r_mode, row0, nq, cand_idx, cand_nv,
-                                  kcand, 0, kcand, k, d_idx, d_dist, k, 0, 1, d_nv, 0,
-                                  /* a long list: the windowed kernel on chunks beats the hash-table kernel on the whole */
-                                  (r_dir && r_nw > 0 && kcand > RERANK_CHUNK) ? 0 : 1, s);
+    if (cand_idx && (!counts || kcand <= RERANK_CHUNK))
+        nl = launch_one(0, kcand, k, d_idx, d_dist, k, 0, 1, 0,
+                        /* a long list: the windowed kernel on chunks beats the hash-table kernel on the whole */
+                        (r_dir && r_nw > 0 && kcand > RERANK_CHUNK) ? 0 : 1);
     if (nl < 0) {
         const int kc = (int)std::min<int64_t>((int64_t)k + (exclude_self ? 1 : 0), RERANK_CHUNK);
         const int nchunks = (kcand + RERANK_CHUNK - 1) / RERANK_CHUNK;
@@ -404,9 +482,7 @@ int rerank_lists(schic_mh_handle* h, const int64_t* db_indptr, const uint32_t* d
         nl = 0;
         for (int ci = 0; ci < nchunks; ++ci) {
             const int c0 = ci * RERANK_CHUNK, cn = std::min(RERANK_CHUNK, kcand - c0);
-            const int r = schic::launch_rerank(db_indptr, db_feat, db_val, 0, r_norm2, r_dir, r_nw, r_mode, row0, nq,
-                                               cand_idx, cand_nv, kcand, c0, cn, kc, h->part_idx.p, h->part_dist.p,
-                                               (int)stride, ci * kc, 0, d_nv, (int)ndb, 1, s);
+            const int r = launch_one(c0, cn, kc, h->part_idx.p, h->part_dist.p, (int)stride, ci * kc, 0, (int)ndb, 1);
             if (r < 0) return fail(SCHIC_ERR_UNSUPPORTED, "rerank: chunk does not fit in shared memory");
             nl += r;
         }
@@ -437,8 +513,9 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
     if (k > ndb) k = (int)ndb;   // cannot have more neighbours than fitted rows; outputs keep stride k
     const int64_t kc64 = fast ? (int64_t)k : std::min<int64_t>((int64_t)k * std::max(1, h->p.excess_factor), ndb);
     const int kcand = (int)kc64;
+    const bool packed_db = h->ext && h->ext_packed && h->ext_flags && h->ext_norm2 && h->ext_dir && h->ext_nw > 0;
     if (!fast) {
-        if (!db_val || !db_feat) return fail(SCHIC_ERR_INVALID_ARG, "exact rerank needs the CSR values (fit with data)");
+        if ((!db_val || !db_feat) && !packed_db) return fail(SCHIC_ERR_INVALID_ARG, "exact rerank needs the CSR values (fit with data)");
         if (h->have_hi) return fail(SCHIC_ERR_UNSUPPORTED, "exact rerank supports 32-bit feature ids only");
     }
     reset_stage(h, {ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_PREP});
@@ -518,7 +595,7 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
         const bool ext_prep = h->ext && h->ext_norm2 && h->ext_dir && h->ext_nw > 0;
         if (!ext_prep) {
             StageTimer t(h, ST_PREP, s);     // row norms + window directory of the database (once per fit)
-            ST_TRY(ensure_norms(h, db_indptr, db_feat, db_val, ndb));
+            ST_TRY(ensure_norms(h, db_indptr, db_feat, db_val, ndb, h->ext ? -1 : (h->borrowed ? h->b_end : h->nnz)));
         }
         ST_TRY(rerank_lists(h, db_indptr, db_feat, db_val, ndb, ext_prep, row0, nq, h->cand_idx.p, h->cand_nv.p, kcand, k,
                             false, d_idx, d_dist, d_nv));
@@ -538,7 +615,8 @@ int exact_knn_on_device(schic_mh_handle* h, int k, bool include_self, int32_t* d
     const int64_t* db_indptr = h->ext ? h->db_indptr : h->d_indptr();
     const uint32_t* db_feat = h->ext ? h->db_feat : h->d_feat();
     const float* db_val = h->ext ? h->db_val : h->d_val();
-    if (!db_val || !db_feat) return fail(SCHIC_ERR_INVALID_ARG, "exact kNN needs the CSR values (fit with data)");
+    const bool packed_db = h->ext && h->ext_packed && h->ext_flags && h->ext_norm2 && h->ext_dir && h->ext_nw > 0;
+    if ((!db_val || !db_feat) && !packed_db) return fail(SCHIC_ERR_INVALID_ARG, "exact kNN needs the CSR values (fit with data)");
     if (h->have_hi) return fail(SCHIC_ERR_UNSUPPORTED, "exact kNN supports 32-bit feature ids only");
     if (ndb > INT32_MAX) return fail(SCHIC_ERR_UNSUPPORTED, "too many rows");
     reset_stage(h, {ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_PREP});
@@ -553,7 +631,7 @@ int exact_knn_on_device(schic_mh_handle* h, int k, bool include_self, int32_t* d
     const bool ext_prep = h->ext && h->ext_norm2 && h->ext_dir && h->ext_nw > 0;
     if (!ext_prep) {
         StageTimer t(h, ST_PREP, s);
-        ST_TRY(ensure_norms(h, db_indptr, db_feat, db_val, ndb));
+        ST_TRY(ensure_norms(h, db_indptr, db_feat, db_val, ndb, h->ext ? -1 : (h->borrowed ? h->b_end : h->nnz)));
     }
     return rerank_lists(h, db_indptr, db_feat, db_val, ndb, ext_prep, row0, nq, nullptr, nullptr, (int)ndb, k, !include_self,
                         d_idx, d_dist, d_nv);
@@ -796,6 +874,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
     h->nnz = pos0 + nnz;
     h->have_val = want_val;
     h->have_hi = want_hi;
+    h->fit_data_kind = (r0 > 0 && h->fit_data_kind != data_kind) ? 0 : data_kind;   // appended batches: the weakest guarantee
 
     // Upload the feature ids in row-aligned chunks on the copy stream; K1 for chunk i runs on the
     // compute stream while chunk i+1 is still in flight.
@@ -910,6 +989,8 @@ static int fit_csr_device_impl(schic_mh_handle* h, int64_t n_rows, int64_t nnz, 
         CU_TRY(cudaMemcpyAsync(&pos0, d_indptr, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
     }
+    h->b_end = pos0 + nnz;
+    h->fit_data_kind = 0;
     {
         StageTimer t(h, ST_SIG, h->stream);
         ST_TRY(hash_rows(h, 0, n_rows, pos0, pos0 + nnz, h->stream));
@@ -971,6 +1052,7 @@ int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t ro
     ST_TRY(check(h));
     h->db_ready = nullptr;
     h->ext_norm2 = nullptr; h->ext_dir = nullptr; h->ext_nw = 0;
+    h->ext_packed = nullptr; h->ext_flags = nullptr; h->ext_nnz = 0;
     if (!d_sig_all) { h->ext = false; h->norm_of = nullptr; return SCHIC_OK; }
     if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "fit the local shard first");
     if (h->sliced) return fail(SCHIC_ERR_UNSUPPORTED, "external database while an active-hash prefix is set");
@@ -994,28 +1076,58 @@ int schic_mh_rerank_windows(schic_mh_handle* h, int32_t* n_windows_out) {
     const char* mode = getenv("SCHIC_K4_MODE");
     if (mode && (strcmp(mode, "hash") == 0 || strcmp(mode, "window64") == 0)) return SCHIC_OK;
     if (h->feature_range == 0 || h->feature_range > 0xFFFFFFFFull) return SCHIC_OK;
-    const int nw = schic::rerank_window_count((uint32_t)(h->feature_range - 1));
-    if (nw <= 1024) *n_windows_out = nw;
+    const int nw = schic::k4c_window_count((uint32_t)(h->feature_range - 1));
+    if (nw <= 4096) *n_windows_out = nw;
     return SCHIC_OK;
 }
 
 int schic_mh_rerank_prep_rows(schic_mh_handle* h, int64_t n_rows, const int64_t* d_indptr, const uint32_t* d_indices,
-                              const float* d_data, int32_t n_windows, double* d_norm2_out, uint32_t* d_dir_out) {
+                              const float* d_data, int32_t n_windows, double* d_norm2_out, uint32_t* d_dir_out,
+                              uint32_t* d_packed_out, uint32_t* d_flags_out) {
     ST_TRY(check(h));
-    if (n_rows < 0 || !d_indptr || !d_norm2_out || !d_dir_out || n_windows < 1) return fail(SCHIC_ERR_INVALID_ARG, "bad arguments");
+    if (n_rows < 0 || !d_indptr || !d_norm2_out || !d_dir_out || !d_flags_out || n_windows < 1)
+        return fail(SCHIC_ERR_INVALID_ARG, "bad arguments");
     if (n_rows > 0 && (!d_indices || !d_data)) return fail(SCHIC_ERR_INVALID_ARG, "the rerank preparation needs ids and values");
     ST_TRY(use_device(h));
-    add_launches(h, schic::launch_row_norms(d_indptr, d_data, n_rows, 0, d_norm2_out, h->stream));
-    add_launches(h, schic::launch_row_window_dir(d_indptr, d_indices, n_rows, n_windows, d_dir_out, h->stream));
+    CU_TRY(cudaMemsetAsync(d_flags_out, 0, 4 * sizeof(uint32_t), h->stream));
+    add_launches(h, schic::launch_rerank_prep(d_indptr, d_indices, d_data, n_rows, n_windows, d_norm2_out, d_dir_out,
+                                              d_packed_out, d_flags_out, h->stream));
     CU_TRY(cudaGetLastError());
     return SCHIC_OK;
 }
 
 int schic_mh_set_database_prep_device(schic_mh_handle* h, const double* d_norm2_all, const uint32_t* d_dir_all,
-                                      int32_t n_windows) {
+                                      int32_t n_windows, const uint32_t* d_packed_all, const uint32_t* d_flags_all,
+                                      int64_t nnz_total) {
     ST_TRY(check(h));
     if (!h->ext) return fail(SCHIC_ERR_INVALID_ARG, "set the external database first");
+    if (d_packed_all && ((uintptr_t)d_packed_all & 15u)) return fail(SCHIC_ERR_INVALID_ARG, "the packed stream must be 16-byte aligned");
+    if (d_packed_all && (!d_flags_all || nnz_total < 0)) return fail(SCHIC_ERR_INVALID_ARG, "a packed stream needs its flags and length");
     h->ext_norm2 = d_norm2_all; h->ext_dir = d_dir_all; h->ext_nw = (d_norm2_all && d_dir_all) ? n_windows : 0;
+    h->ext_packed = h->ext_nw > 0 ? d_packed_all : nullptr;
+    h->ext_flags = h->ext_packed ? d_flags_all : nullptr;
+    h->ext_nnz = h->ext_packed ? nnz_total : 0;
+    return SCHIC_OK;
+}
+
+int schic_mh_rerank_kernel_name(schic_mh_handle* h, char* out, int32_t n_out) {
+    ST_TRY(check(h));
+    if (!out || n_out < 32) return fail(SCHIC_ERR_INVALID_ARG, "out must hold 32 bytes");
+    ST_TRY(use_device(h));
+    const char* name = "none";
+    if (h->rerank_path == 3) {
+        name = h->n_windows > 0 || (h->ext && h->ext_nw > 0) ? "k4_rerank_window_kernel" : "k4_rerank_kernel";
+    } else if (h->rerank_path == 1) {
+        name = "k4c_rerank_kernel";
+    } else if (h->rerank_path == 2) {      // both were launched: the flags on the device say which one did the work
+        const uint32_t* fl = (h->ext && h->ext_flags) ? h->ext_flags : h->k4_flags.p;
+        const int64_t nnz = (h->ext && h->ext_flags) ? h->ext_nnz : h->prep_nnz;
+        uint32_t f[4] = {0, 0, 0, 0};
+        CU_TRY(cudaMemcpyAsync(f, fl, sizeof(f), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        name = (f[0] == 0 && f[1] <= esc_limit_for(nnz)) ? "k4c_rerank_kernel" : "k4_rerank_window_kernel";
+    }
+    snprintf(out, (size_t)n_out, "%s", name);
     return SCHIC_OK;
 }
 

@@ -79,22 +79,41 @@ int launch_fast_distance(const int32_t* d_idx_in, const int32_t* d_cnt_in, const
                          int64_t nq, int kcand, int k, int H, int absolute, int32_t* d_idx_out,
                          float* d_dist_out, int32_t* d_nvalid_out, cudaStream_t stream);
 
-// ---- K4: exact euclidean rerank (k4_rerank.cu) ----------------------------------------------
-// norms2[r] = sum of squares of row r (fp64).
-int launch_row_norms(const int64_t* d_indptr, const float* d_val, int64_t n_rows, int64_t indptr0,
-                     double* d_norm2, cudaStream_t stream);
+// ---- K4: exact euclidean rerank (k4_rerank.cu, k4c_rerank.cu) ---------------------------------
+// id windows of the rerank: the per-row window directory is built for windows of 2^SCHIC_K4C_WIN_BITS ids (the byte
+// table of the counts kernel); the generic windowed kernel works on 2^19-id windows = 4 of them.
+#ifndef SCHIC_K4C_WIN_BITS
+#define SCHIC_K4C_WIN_BITS 17
+#endif
+// Per-fit preparation in one pass over ids + values: fp64 row norms, window directory dir[row][0..n_windows] (uint32
+// offsets from the row start), the packed stream ((id mod 2^17) << 15 | count, indexed like d_feat; nullable) and
+// d_flags[4] (accumulated, zero them first): [0] a value is not an integer in [0, 32767], [1] number of values >= 255,
+// [2] an id lies beyond the last window.
+int k4c_window_count(uint32_t max_feature);
+int launch_rerank_prep(const int64_t* d_indptr, const uint32_t* d_feat, const float* d_val, int64_t n_rows, int n_windows,
+                       double* d_norm2, uint32_t* d_dir, uint32_t* d_packed, uint32_t* d_flags, cudaStream_t stream);
+// Counts kernel (packed stream + byte table + window-group-major grid) and its finalize; output contract of
+// launch_rerank. Both exit at once unless d_flags says the data is packable (flags[0] == 0 && flags[1] <= esc_limit).
+// d_dotacc: k4c_dotacc_elems(nq, kcand) uint64 of scratch. group_bytes: share of the packed stream one window group
+// may span (sized for L2; <= 0: one group). Returns the number of launches, -1 when kcand does not fit.
+size_t k4c_dotacc_elems(int64_t nq, int kcand);
+int launch_rerank_counts(const int64_t* d_indptr, const uint32_t* d_packed, const double* d_norm2, const uint32_t* d_dir,
+                         int n_windows, int64_t db_nnz, int64_t group_bytes, int64_t q_row0, int64_t nq,
+                         const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int cand_stride, int cand_off, int kcand,
+                         int k, int32_t* d_idx_out, float* d_dist_out, int out_stride, int out_off, int final,
+                         int32_t* d_nvalid_out, int n_all, const uint32_t* d_flags, uint32_t esc_limit,
+                         unsigned long long* d_dotacc, cudaStream_t stream);
 // uint16 / uint8 counts -> float32 values (host uploads of integer counts cross PCIe narrow)
 int launch_widen_counts(const void* d_src, int bits, int64_t n, float* d_dst, cudaStream_t stream);
 // Window directory of the windowed rerank kernel: largest feature id of the database (device
 // scalar), number of windows for it, and dir[row][0..n_windows] (uint32 offsets from the row start).
 int launch_row_max_feature(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, uint32_t* d_out_max,
                            cudaStream_t stream);
-int rerank_window_count(uint32_t max_feature);
-int launch_row_window_dir(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int n_windows,
-                          uint32_t* d_dir, cudaStream_t stream);
 // For query q (database row q_row0+q) and each of its candidates: euclidean distance over the
 // union of supports; then order by (dist asc, idx asc), keep k. CSR arrays are the database's.
-// d_dir != nullptr selects the windowed kernel (needs the directory above), else the hash-table kernel.
+// d_dir != nullptr selects the windowed kernel (needs the directory of launch_rerank_prep: n_windows counts its
+// 2^SCHIC_K4C_WIN_BITS-id windows), else the hash-table kernel. d_skip_flags != nullptr: the kernels exit at once when
+// the flags say the counts kernel (launched before them) has done the work.
 // A launch handles candidate columns [cand_off, cand_off+kcand) of lists with row stride cand_stride and writes the k
 // best (sorted) to output columns [out_off, out_off+k) of arrays with row stride out_stride; final != 0 also writes
 // d_nvalid_out. Returns -1 when kcand does not fit one CTA's shared memory (the caller then chunks + merges).
@@ -103,7 +122,8 @@ int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* 
                   int64_t q_row0, int64_t nq, const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int cand_stride,
                   int cand_off, int kcand, int k, int32_t* d_idx_out, float* d_dist_out, int out_stride, int out_off,
                   int final, int32_t* d_nvalid_out, int n_all /* d_cand_idx == nullptr: candidates = rows [0, n_all) */,
-                  int allow_hash /* 0: windowed kernel or -1 */, cudaStream_t stream);
+                  int allow_hash /* 0: windowed kernel or -1 */, const uint32_t* d_skip_flags, uint32_t esc_limit,
+                  cudaStream_t stream);
 // Per row: sort the [part_stride] chunk-sorted (distance, index) pairs by (dist asc, idx asc), keep k, write n_valid
 // (= min(k, list length); list length = min(cand_nvalid, kcand), or n_all [- 1 if exclude_row0 >= 0] for brute force).
 int launch_rerank_merge(const int32_t* d_part_idx, const float* d_part_dist, int part_stride,

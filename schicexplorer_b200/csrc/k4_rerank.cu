@@ -40,21 +40,6 @@ constexpr int K4_BUCKET_BITS = 11;
 constexpr int K4_PART = 2560;             // query non-zeros per table fill: load factor 0.31
 constexpr uint32_t K4_EMPTY = 0xFFFFFFFFu;
 
-__global__ void row_norms_kernel(const int64_t* __restrict__ indptr, const float* __restrict__ val, int64_t n_rows,
-                                 double* __restrict__ norm2) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= n_rows) return;
-    double acc = 0.0;
-    for (int64_t i = indptr[row] + lane; i < indptr[row + 1]; i += 32) {
-        const double v = (double)__ldg(val + i);
-        acc += v * v;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) norm2[row] = acc;
-}
-
 // uint16 / uint8 counts (as uploaded) -> float32 values
 template <typename T>
 __global__ void widen_counts_kernel(const T* __restrict__ src, int64_t n, float* __restrict__ dst) {
@@ -102,6 +87,12 @@ __device__ __forceinline__ double k4_sqdist(const int64_t* __restrict__ indptr, 
     return d2 < 0.0 ? 0.0 : d2;
 }
 
+// the counts kernel (k4c_rerank.cu), launched before these kernels, has done the work when the prep flags say the data
+// is packable; same predicate as k4c_usable
+__device__ __forceinline__ bool k4_skipped(const uint32_t* __restrict__ skip_flags, uint32_t esc_limit) {
+    return skip_flags != nullptr && skip_flags[0] == 0u && skip_flags[1] <= esc_limit;
+}
+
 __device__ __forceinline__ uint32_t k4_bucket(uint32_t f) { return (f * 2654435761u) >> (32 - K4_BUCKET_BITS); }
 
 // first position in [b, e) whose feature is >= key (plain binary search, one thread)
@@ -129,7 +120,9 @@ __global__ void __launch_bounds__(K4_THREADS)
 k4_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat, const float* __restrict__ val,
                  const double* __restrict__ norm2, int64_t q_row0, const int32_t* __restrict__ cand_idx,
                  const int32_t* __restrict__ cand_nvalid, int kcand, int P, int k, K4Chunk ck, int32_t* __restrict__ idx_out,
-                 float* __restrict__ dist_out, int32_t* __restrict__ nvalid_out) {
+                 float* __restrict__ dist_out, int32_t* __restrict__ nvalid_out, const uint32_t* __restrict__ skip_flags,
+                 uint32_t esc_limit) {
+    if (k4_skipped(skip_flags, esc_limit)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* tkey = reinterpret_cast<uint32_t*>(smem_raw);              // [K4_SLOTS]
     float* tval = reinterpret_cast<float*>(tkey + K4_SLOTS);             // [K4_SLOTS]
@@ -325,26 +318,6 @@ __global__ void row_max_feature_kernel(const int64_t* __restrict__ indptr, const
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out_max, m);
 }
 
-// dir[row][w] = offset (relative to the row start) of the first non-zero with (id >> WIN_BITS) >= w,
-// w = 0..n_windows (dir[row][n_windows] = row length). One 128-thread CTA per row; every entry is written once.
-__global__ void __launch_bounds__(128)
-row_window_dir_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat,
-                      int64_t n_rows, int n_windows, uint32_t* __restrict__ dir) {
-    const int64_t row = blockIdx.x;
-    if (row >= n_rows) return;
-    const int64_t b = indptr[row], e = indptr[row + 1];
-    uint32_t* __restrict__ d = dir + row * (int64_t)(n_windows + 1);
-    // (ids beyond the last window -- only possible with a wrong feature-range hint, reported elsewhere -- are
-    // clamped to window n_windows, which no slice covers: memory safe)
-    for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
-        const int w = min((int)(__ldg(feat + i) >> K4W_WIN_BITS), n_windows);
-        const int wp = i == b ? -1 : min((int)(__ldg(feat + i - 1) >> K4W_WIN_BITS), n_windows);
-        for (int x = wp + 1; x <= w; ++x) d[x] = (uint32_t)(i - b);
-    }
-    const int wl = e > b ? min((int)(__ldg(feat + e - 1) >> K4W_WIN_BITS), n_windows) : -1;
-    for (int x = wl + 1 + threadIdx.x; x <= n_windows; x += blockDim.x) d[x] = (uint32_t)(e - b);
-}
-
 // Table entry layouts (E64 = false / true), both 4 feature ids per byte of shared memory:
 //   32-bit entry per 16 ids: presence mask in the low half, rank of the entry's first key in the high half;
 //   64-bit entry per 32 ids: {presence mask, BYTE offset of the first key's value} -- one LDS.64, and the
@@ -371,10 +344,15 @@ template <bool E64>
 __global__ void __launch_bounds__(K4W_THREADS, K4W_CTAS_DEF)
 k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat,
                         const float* __restrict__ val, const double* __restrict__ norm2,
-                        const uint32_t* __restrict__ dir, int n_windows, int64_t q_row0,
+                        const uint32_t* __restrict__ dir, int n_windows, int dir_windows, int64_t q_row0,
                         const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_nvalid, int kcand, int P,
                         int k, K4Chunk ck, int32_t* __restrict__ idx_out, float* __restrict__ dist_out,
-                        int32_t* __restrict__ nvalid_out) {
+                        int32_t* __restrict__ nvalid_out, const uint32_t* __restrict__ skip_flags, uint32_t esc_limit) {
+    if (k4_skipped(skip_flags, esc_limit)) return;
+    // the directory is kept for the finer windows of the counts kernel: window w of this kernel starts at directory
+    // entry min(w << DSH, dir_windows)
+    constexpr int DSH = K4W_WIN_BITS - SCHIC_K4C_WIN_BITS;
+    auto dent = [&](int w) { return min(w << DSH, dir_windows); };
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem_raw);                      // [K4W_WORDS]
     float* tval = reinterpret_cast<float*>(tab + K4W_WORDS);                    // [K4W_KCAP + 32]
@@ -391,7 +369,7 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
     const int64_t qrow = q_row0 + q;
     const int ncand = max(0, min((cand_idx ? cand_nvalid[q] : ck.n_all) - ck.cand_off, kcand));
     const int lane = threadIdx.x & 31;
-    const int64_t nw1 = (int64_t)n_windows + 1;
+    const int64_t nw1 = (int64_t)dir_windows + 1;
 
     for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
         const int32_t d = cand_idx ? cand_idx[q * ck.cand_stride + ck.cand_off + c] : ck.cand_off + c;
@@ -399,7 +377,7 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
         cbeg[c] = indptr[d];
         dot[c] = 0.0;
     }
-    for (int w = threadIdx.x; w <= n_windows; w += blockDim.x) qdir[w] = dir[qrow * nw1 + w];
+    for (int w = threadIdx.x; w <= n_windows; w += blockDim.x) qdir[w] = dir[qrow * nw1 + dent(w)];
     for (int i = threadIdx.x; i < K4W_KCAP + 32; i += blockDim.x) tval[i] = 0.f;
     for (int i = threadIdx.x; i < K4W_WORDS / 4; i += blockDim.x)
         reinterpret_cast<uint4*>(tab)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -423,7 +401,7 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
                 const int64_t d = cand[c];
                 const int64_t cb = cbeg[c];
                 const uint32_t* __restrict__ dc = dir + d * nw1;
-                const int64_t wb = cb + __ldg(dc + w), we = cb + __ldg(dc + w + 1);
+                const int64_t wb = cb + __ldg(dc + dent(w)), we = cb + __ldg(dc + dent(w + 1));
                 const int64_t ys = first ? wb : lower_bound_feat(feat, wb, we, f_lo);
                 const int64_t ye = last ? we : lower_bound_feat(feat, wb, we, f_hi);
                 sl_pos[c] = ys;
@@ -465,7 +443,7 @@ k4_rerank_window_kernel(const int64_t* __restrict__ indptr, const uint32_t* __re
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(val + at));
                     }
                     for (int c = threadIdx.x; c < ncand; c += blockDim.x)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(dir + (int64_t)cand[c] * nw1 + nwin));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(dir + (int64_t)cand[c] * nw1 + dent(nwin)));
                 }
             }
             // Streaming: every warp walks a flattened sequence of (candidate, 256-non-zero block) pairs --
@@ -590,24 +568,6 @@ int launch_row_max_feature(const int64_t* d_indptr, const uint32_t* d_feat, int6
     return 1;
 }
 
-int rerank_window_count(uint32_t max_feature) { return (int)(max_feature >> K4W_WIN_BITS) + 1; }
-
-int launch_row_window_dir(const int64_t* d_indptr, const uint32_t* d_feat, int64_t n_rows, int n_windows,
-                          uint32_t* d_dir, cudaStream_t stream) {
-    if (n_rows <= 0) return 0;
-    row_window_dir_kernel<<<(unsigned)n_rows, 128, 0, stream>>>(d_indptr, d_feat, n_rows, n_windows, d_dir);
-    return 1;
-}
-
-int launch_row_norms(const int64_t* d_indptr, const float* d_val, int64_t n_rows, int64_t indptr0,
-                     double* d_norm2, cudaStream_t stream) {
-    (void)indptr0;
-    if (n_rows <= 0) return 0;
-    const int64_t threads = n_rows * 32;
-    row_norms_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_indptr, d_val, n_rows, d_norm2);
-    return 1;
-}
-
 // Merge of chunked rerank results: one CTA per query sorts the row's [part_stride] (distance, index) pairs (the best
 // of every chunk, each chunk sorted and padded with (inf, -1)) by (distance, index) in shared memory and keeps the
 // first k. cand_nvalid == nullptr: brute force over n_all rows. exclude_row0 >= 0: the query's own row
@@ -676,20 +636,25 @@ int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* 
                   const double* d_norm2, const uint32_t* d_dir, int n_windows, int window_mode, int64_t q_row0,
                   int64_t nq, const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int cand_stride, int cand_off,
                   int kcand, int k, int32_t* d_idx_out, float* d_dist_out, int out_stride, int out_off, int final,
-                  int32_t* d_nvalid_out, int n_all, int allow_hash, cudaStream_t stream) {
+                  int32_t* d_nvalid_out, int n_all, int allow_hash, const uint32_t* d_skip_flags, uint32_t esc_limit,
+                  cudaStream_t stream) {
     (void)indptr0;
     if (nq <= 0) return 0;
     const K4Chunk ck{cand_stride, cand_off, out_stride, out_off, final, n_all};
     const int P = next_pow2(kcand);
+    static_assert(K4W_WIN_BITS >= SCHIC_K4C_WIN_BITS, "the directory's windows must not be coarser than this kernel's");
+    const int dir_windows = n_windows;                                            // windows of the directory (2^17 ids)
+    constexpr int DSH = K4W_WIN_BITS - SCHIC_K4C_WIN_BITS;
+    n_windows = (dir_windows + (1 << DSH) - 1) >> DSH;                            // windows of this kernel (2^19 ids)
     if (d_dir && n_windows > 0) {
         const size_t smem = (size_t)K4W_WORDS * 4 + (size_t)(K4W_KCAP + 32) * 4 + (size_t)P * 8 +
                             (size_t)kcand * (8 + 8 + 8 + 4 + 4) + (size_t)(n_windows + 1) * 4 + 16;
         if (smem <= 220 * 1024) {
             auto kern = window_mode == 64 ? k4_rerank_window_kernel<true> : k4_rerank_window_kernel<false>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kern<<<(unsigned)nq, K4W_THREADS, smem, stream>>>(d_indptr, d_feat, d_val, d_norm2, d_dir, n_windows, q_row0,
-                                                              d_cand_idx, d_cand_nvalid, kcand, P, k, ck, d_idx_out,
-                                                              d_dist_out, d_nvalid_out);
+            kern<<<(unsigned)nq, K4W_THREADS, smem, stream>>>(d_indptr, d_feat, d_val, d_norm2, d_dir, n_windows, dir_windows,
+                                                              q_row0, d_cand_idx, d_cand_nvalid, kcand, P, k, ck, d_idx_out,
+                                                              d_dist_out, d_nvalid_out, d_skip_flags, esc_limit);
             return 1;
         }
     }
@@ -699,7 +664,7 @@ int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* 
     cudaFuncSetAttribute(k4_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k4_rerank_kernel<<<(unsigned)nq, K4_THREADS, smem, stream>>>(d_indptr, d_feat, d_val, d_norm2, q_row0, d_cand_idx,
                                                                  d_cand_nvalid, kcand, P, k, ck, d_idx_out, d_dist_out,
-                                                                 d_nvalid_out);
+                                                                 d_nvalid_out, d_skip_flags, esc_limit);
     return 1;
 }
 

@@ -1,0 +1,440 @@
+// k4c_rerank.cu -- K4 for integer contact counts: packed candidate stream + byte table, sm_100a.
+//
+// Same contract as k4_rerank.cu (the fast=False branch of MinHash.kneighbors, selected by `-em`,
+// /root/reference/schicexplorer/scHicClusterMinHash.py:66-68 -> :348/:403; SURVEY 8(c) rule 9): for every query
+// cell and each of its candidates the euclidean distance of the two raw sparse rows, (distance asc, index asc), keep k.
+//
+// Hi-C values are contact counts -- small non-negative integers. For such data the rerank is organised differently
+// from the generic float kernel (k4_rerank_window_kernel, 2 x 4-byte loads and ~23 issued instructions per candidate
+// non-zero, 58.7 GB of DRAM traffic per S10 build):
+//   * per fit ONE pass over the CSR (k4c_prep_kernel) produces, besides the fp64 row norms and the window directory,
+//     a PACKED STREAM: one 32-bit word per non-zero = (id mod 2^17) << 15 | count. Half the bytes and half the loads
+//     of (id, float value); also what a multi-GPU run exchanges instead of the two CSR arrays.
+//   * the id axis is cut into windows of 2^17 ids. For one window the query row is a DIRECT BYTE TABLE in shared
+//     memory (128 KB): tab[id mod 2^17] = count (0 = absent). A probe is one LDS.U8 and one IMAD -- a miss
+//     multiplies by zero, so there is no bit test, no rank/popcount, no second load and no predicate.
+//     Counts >= 255 in a query row are stored as 255 and resolved exactly by a (rare) binary search in the query row;
+//     the build phase knows whether a window has any, so windows without them run a loop that never checks.
+//   * x.y is accumulated in integers (8 products < 2^26 in a 32-bit register, then 64 bit), ||x-y||^2 =
+//     ||x||^2 + ||y||^2 - 2 x.y is exact, so there is no cancellation case and no second exact pass.
+//   * the grid is WINDOW-GROUP MAJOR: CTA = (group of consecutive windows, query), groups slow-varying, so the 148
+//     resident CTAs stream the same ~1/G slice of the database at the same time and it is served by the 126 MB L2
+//     instead of HBM. Partial dot products go to a global uint64 accumulator (one atomic per candidate and CTA);
+//     k4c_finalize_kernel turns them into distances and sorts.
+// Data that is not small integer counts (non-integer, negative, > 32767, or so many >= 255 that the escape path
+// would dominate) is detected by the prep pass in a device flag; these kernels then exit at once and the generic
+// float kernels of k4_rerank.cu, launched behind them with the same flag, do the work. No host round trip decides.
+#include <algorithm>
+
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace schic {
+
+// must match k4_rerank.cu
+struct K4Chunk {
+    int cand_stride, cand_off, out_stride, out_off, write_nvalid, n_all;
+};
+
+constexpr int K4C_WIN_BITS = SCHIC_K4C_WIN_BITS;
+constexpr int K4C_TAB = 1 << K4C_WIN_BITS;                    // table bytes = ids per window
+constexpr int K4C_CNT_BITS = 32 - K4C_WIN_BITS;               // 15
+constexpr uint32_t K4C_CNT_MASK = (1u << K4C_CNT_BITS) - 1u;  // largest packable count (32767)
+constexpr int K4C_THREADS = 1024;
+constexpr int K4C_U = 2;                                      // 16-byte loads per lane and block
+constexpr int K4C_BLK = 32 * 4 * K4C_U;                       // candidate non-zeros per warp and block (256)
+
+__device__ __forceinline__ bool k4c_usable(const uint32_t* __restrict__ flags, uint32_t esc_limit) {
+    return flags[0] == 0u && flags[1] <= esc_limit;
+}
+
+int k4c_window_count(uint32_t max_feature) { return (int)(max_feature >> K4C_WIN_BITS) + 1; }
+
+// ---- per-fit preparation: norms, window directory, packed stream, flags -- one pass over ids + values -------------
+// dir[row][w] = offset (from the row start) of the first non-zero with (id >> 17) >= w, w = 0..n_windows.
+// flags[0] |= 1: a value is not an integer in [0, 32767]; flags[1] += number of values >= 255; flags[2] = 1: an id
+// lies beyond the last window (wrong feature-range hint; such ids are clamped into a window no slice covers).
+// packed may be nullptr (directory + norms only); dir may be nullptr (norms + flags only).
+__global__ void __launch_bounds__(256)
+k4c_prep_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ feat, const float* __restrict__ val,
+                int64_t n_rows, int n_windows, double* __restrict__ norm2, uint32_t* __restrict__ dir,
+                uint32_t* __restrict__ packed, uint32_t* __restrict__ flags) {
+    __shared__ double s_acc[8];
+    const int64_t row = blockIdx.x;
+    if (row >= n_rows) return;
+    const int64_t b = indptr[row], e = indptr[row + 1];
+    uint32_t* __restrict__ d = dir ? dir + row * (int64_t)(n_windows + 1) : nullptr;
+    double acc = 0.0;
+    uint32_t bad = 0u, big = 0u, oor = 0u;
+#pragma unroll 4
+    for (int64_t i = b + threadIdx.x; i < e; i += 256) {
+        const uint32_t f = __ldg(feat + i);
+        const float v = __ldg(val + i);
+        acc += (double)v * (double)v;
+        const bool ok = v >= 0.f && v <= (float)K4C_CNT_MASK && v == truncf(v);      // NaN fails every comparison
+        bad |= ok ? 0u : 1u;
+        const uint32_t c = ok ? (uint32_t)v : 0u;
+        big += c >= 255u ? 1u : 0u;
+        if (packed) packed[i] = ((f & (uint32_t)(K4C_TAB - 1)) << K4C_CNT_BITS) | c;
+        if (d) {
+            int w = (int)(f >> K4C_WIN_BITS);
+            if (w >= n_windows) { oor = 1u; w = n_windows; }
+            const int wp = i == b ? -1 : min((int)(__ldg(feat + i - 1) >> K4C_WIN_BITS), n_windows);
+            for (int x = wp + 1; x <= w; ++x) d[x] = (uint32_t)(i - b);
+        }
+    }
+    if (d) {
+        const int wl = e > b ? min((int)(__ldg(feat + e - 1) >> K4C_WIN_BITS), n_windows) : -1;
+        for (int x = wl + 1 + threadIdx.x; x <= n_windows; x += 256) d[x] = (uint32_t)(e - b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        big += __shfl_xor_sync(0xffffffffu, big, o);
+    }
+    bad = __any_sync(0xffffffffu, bad) ? 1u : 0u;
+    oor = __any_sync(0xffffffffu, oor) ? 1u : 0u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_acc[warp] = acc;
+        if (bad) atomicOr(&flags[0], 1u);
+        if (big) atomicAdd(&flags[1], big);
+        if (oor) flags[2] = 1u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_acc[w];      // fixed order: the norm is reproducible
+        norm2[row] = t;
+    }
+}
+
+int launch_rerank_prep(const int64_t* d_indptr, const uint32_t* d_feat, const float* d_val, int64_t n_rows, int n_windows,
+                       double* d_norm2, uint32_t* d_dir, uint32_t* d_packed, uint32_t* d_flags, cudaStream_t stream) {
+    if (n_rows <= 0) return 0;
+    k4c_prep_kernel<<<(unsigned)n_rows, 256, 0, stream>>>(d_indptr, d_feat, d_val, n_rows, n_windows, d_norm2, d_dir,
+                                                          d_packed, d_flags);
+    return 1;
+}
+
+// exact count of query key t (window-relative id) whose table byte saturated at 255: binary search in the query's
+// window slice of the packed stream (keys ascend with the ids)
+__device__ __noinline__ uint32_t k4c_escape_value(const uint32_t* __restrict__ qp, int qn, uint32_t t) {
+    int lo = 0, hi = qn;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((__ldg(qp + mid) >> K4C_CNT_BITS) < t) lo = mid + 1; else hi = mid;
+    }
+    return lo < qn ? (__ldg(qp + lo) & K4C_CNT_MASK) : 0u;
+}
+
+// One CTA = (window group g, query q); blockIdx.x = g * nq + q. dotacc [nq, kcand] uint64, zeroed by the caller.
+// Per window three barriers (un-build | build | stream). What would otherwise sit exposed between them is taken out of
+// the phases: the query's keys of the NEXT window are fetched into registers during the stream phase (and the same
+// registers un-build the table afterwards), and every warp issues the loads of its first slice of the next window
+// (statically assigned: candidate = warp index) before it waits at the barrier that ends the current one.
+__global__ void __launch_bounds__(K4C_THREADS, 1)
+k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ packed,
+                  const uint32_t* __restrict__ dir, int n_windows, int wg, int64_t q_row0, int64_t nq,
+                  const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_nvalid, int kcand, K4Chunk ck,
+                  const uint32_t* __restrict__ flags, uint32_t esc_limit, unsigned long long* __restrict__ dotacc) {
+    if (!k4c_usable(flags, esc_limit)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint8_t* tab = smem_raw;                                                            // [K4C_TAB]
+    unsigned long long* dotc = reinterpret_cast<unsigned long long*>(smem_raw + K4C_TAB);   // [kcand]
+    int64_t* cbeg = reinterpret_cast<int64_t*>(dotc + kcand);                           // [kcand] row start of the candidate
+    uint32_t* sl = reinterpret_cast<uint32_t*>(cbeg + kcand);                           // [kcand][wg + 1] window offsets
+    int32_t* cand = reinterpret_cast<int32_t*>(sl + (size_t)kcand * (wg + 1));          // [kcand]
+    uint32_t* qdir = reinterpret_cast<uint32_t*>(cand + kcand);                         // [wg + 1]
+    __shared__ int s_next, s_esc;
+
+    const int64_t g = blockIdx.x / nq;
+    const int64_t q = blockIdx.x - g * nq;
+    const int64_t qrow = q_row0 + q;
+    const int w0 = (int)g * wg;
+    const int nwin = min(wg, n_windows - w0);
+    const int64_t nw1 = (int64_t)n_windows + 1;
+    const int wg1 = wg + 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NWARPS = K4C_THREADS / 32;
+    const int ncand = max(0, min((cand_idx ? cand_nvalid[q] : ck.n_all) - ck.cand_off, kcand));
+
+    for (int w = threadIdx.x; w <= nwin; w += K4C_THREADS) qdir[w] = __ldg(dir + qrow * nw1 + w0 + w);
+    if (threadIdx.x == 0) s_esc = 0;
+    __syncthreads();
+    if (qdir[0] == qdir[nwin] || ncand == 0) return;       // the query row is empty in this whole group (uniform)
+
+    const int64_t xb = indptr[qrow];
+    // first non-empty window of the query, and its keys (two per thread in registers; longer windows loop)
+    auto next_window = [&](int j) { while (j < nwin && qdir[j + 1] == qdir[j]) ++j; return j; };
+    uint32_t qn0 = 0u, qn1 = 0u;
+    auto prefetch_keys = [&](int j) {
+        if (j >= nwin) return;
+        const uint32_t i0 = qdir[j] + threadIdx.x, e = qdir[j + 1];
+        if (i0 < e) qn0 = __ldg(packed + xb + i0);
+        if (i0 + K4C_THREADS < e) qn1 = __ldg(packed + xb + i0 + K4C_THREADS);
+    };
+    int j = next_window(0);
+    prefetch_keys(j);
+
+    for (int c = threadIdx.x; c < ncand; c += K4C_THREADS) {
+        const int32_t d = cand_idx ? cand_idx[q * ck.cand_stride + ck.cand_off + c] : ck.cand_off + c;
+        cand[c] = d;
+        cbeg[c] = indptr[d];
+        dotc[c] = 0ull;
+    }
+    {
+        const int per = nwin + 1, total = ncand * per;
+        for (int x = threadIdx.x; x < total; x += K4C_THREADS) {
+            const int c = x / per, jj = x - c * per;
+            const int32_t d = cand_idx ? cand_idx[q * ck.cand_stride + ck.cand_off + c] : ck.cand_off + c;
+            sl[c * wg1 + jj] = __ldg(dir + (int64_t)d * nw1 + w0 + jj);
+        }
+    }
+    for (int i = threadIdx.x; i < K4C_TAB / 16; i += K4C_THREADS)
+        reinterpret_cast<uint4*>(tab)[i] = make_uint4(0u, 0u, 0u, 0u);
+
+    // streaming state of the warp; a slice is read as aligned 16-byte words, `lead` elements before its start masked
+    const uint4* __restrict__ base = nullptr;
+    int n = 0, lead = 0, off = 0;
+    uint4 nx[K4C_U];
+    bool pref = false;                                     // nx holds the first block of slice (wid, window j)
+    auto setup = [&](int c, int jw) {
+        const int64_t ys = cbeg[c] + sl[c * wg1 + jw];
+        lead = (int)(ys & 3);
+        n = (int)(sl[c * wg1 + jw + 1] - sl[c * wg1 + jw]) + lead;
+        base = reinterpret_cast<const uint4*>(packed + (ys - lead));
+        off = 0;
+    };
+    auto load = [&]() {
+        if (off + K4C_BLK <= n) {                          // warp-uniform: full block, no guards
+#pragma unroll
+            for (int u = 0; u < K4C_U; ++u) nx[u] = __ldg(base + (off >> 2) + lane + 32 * u);
+        } else {
+#pragma unroll
+            for (int u = 0; u < K4C_U; ++u)
+                nx[u] = off + 4 * (lane + 32 * u) < n ? __ldg(base + (off >> 2) + lane + 32 * u) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+
+    while (j < nwin) {
+        const uint32_t k0 = qdir[j], k1 = qdir[j + 1];
+        const uint32_t qc0 = qn0, qc1 = qn1;               // this window's keys (prefetched)
+        __syncthreads();                                   // table clear / previous un-build done, slices visible
+        // ---- build: tab[id mod 2^17] = min(count, 255) ------------------------------------------------------
+        bool any_big = false;
+        {
+            const uint32_t i0 = k0 + threadIdx.x;
+            if (i0 < k1) { const uint32_t v = qc0 & K4C_CNT_MASK; tab[qc0 >> K4C_CNT_BITS] = (uint8_t)min(v, 255u); any_big |= v >= 255u; }
+            if (i0 + K4C_THREADS < k1) { const uint32_t v = qc1 & K4C_CNT_MASK; tab[qc1 >> K4C_CNT_BITS] = (uint8_t)min(v, 255u); any_big |= v >= 255u; }
+            for (uint32_t i = i0 + 2 * K4C_THREADS; i < k1; i += K4C_THREADS) {
+                const uint32_t p = __ldg(packed + xb + i);
+                const uint32_t v = p & K4C_CNT_MASK;
+                tab[p >> K4C_CNT_BITS] = (uint8_t)min(v, 255u);
+                any_big |= v >= 255u;
+            }
+        }
+        if (any_big) s_esc = j + 1;                        // (j + 1 never repeats within a CTA: no reset needed)
+        if (threadIdx.x == 0) s_next = NWARPS;             // candidates 0..31 are the warps' static first slices
+        const int jn = next_window(j + 1);
+        prefetch_keys(jn);                                 // consumed at the top of the next iteration
+        __syncthreads();
+        // ---- stream: every warp walks a flattened sequence of (candidate, 256-non-zero block) pairs; after its
+        // static first candidate they are handed out dynamically; the next block's loads are in flight while the
+        // current one is probed ---------------------------------------------------------------------------------
+        {
+            const bool esc = s_esc == j + 1;
+            const uint32_t* __restrict__ qp = packed + xb + k0;
+            const int qn = (int)(k1 - k0);
+            auto fetch = [&]() {                           // next candidate with a non-empty slice, or ncand
+                int c;
+                do {
+                    c = 0;
+                    if (lane == 0) c = atomicAdd(&s_next, 1);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                } while (c < ncand && sl[c * wg1 + j + 1] <= sl[c * wg1 + j]);
+                return c;
+            };
+            int c;
+            if (pref) {
+                c = wid;
+            } else if (wid < ncand && sl[wid * wg1 + j + 1] > sl[wid * wg1 + j]) {
+                c = wid; setup(c, j); load();
+            } else {
+                c = fetch();
+                if (c < ncand) { setup(c, j); load(); }
+            }
+            pref = false;
+            unsigned long long acc = 0ull;
+            while (c < ncand) {
+                uint4 cur[K4C_U];
+#pragma unroll
+                for (int u = 0; u < K4C_U; ++u) cur[u] = nx[u];
+                const int cur_c = c, cur_off = off, cur_n = n, cur_lead = lead;
+                off += K4C_BLK;
+                const bool done = off >= n;                // last block of the current candidate
+                if (done) {
+                    c = fetch();
+                    if (c < ncand) setup(c, j);
+                }
+                if (c < ncand) load();
+                // mask what lies outside the slice (p = 0: table byte x count 0 contributes nothing)
+                if (!((cur_off > 0 || cur_lead == 0) && cur_off + K4C_BLK <= cur_n)) {
+#pragma unroll
+                    for (int u = 0; u < K4C_U; ++u) {
+                        const int e0 = cur_off + 4 * (lane + 32 * u);
+                        if (e0 < cur_lead || e0 >= cur_n) cur[u].x = 0u;
+                        if (e0 + 1 < cur_lead || e0 + 1 >= cur_n) cur[u].y = 0u;
+                        if (e0 + 2 < cur_lead || e0 + 2 >= cur_n) cur[u].z = 0u;
+                        if (e0 + 3 < cur_lead || e0 + 3 >= cur_n) cur[u].w = 0u;
+                    }
+                }
+                uint32_t a32 = 0u;                         // 8 products of (<= 255) x (<= 32767): < 2^26
+                if (!esc) {
+#pragma unroll
+                    for (int u = 0; u < K4C_U; ++u) {
+                        a32 += (uint32_t)tab[cur[u].x >> K4C_CNT_BITS] * (cur[u].x & K4C_CNT_MASK);
+                        a32 += (uint32_t)tab[cur[u].y >> K4C_CNT_BITS] * (cur[u].y & K4C_CNT_MASK);
+                        a32 += (uint32_t)tab[cur[u].z >> K4C_CNT_BITS] * (cur[u].z & K4C_CNT_MASK);
+                        a32 += (uint32_t)tab[cur[u].w >> K4C_CNT_BITS] * (cur[u].w & K4C_CNT_MASK);
+                    }
+                } else {
+                    // this window of the query holds counts >= 255: table bytes of 255 are looked up exactly
+#pragma unroll
+                    for (int u = 0; u < K4C_U; ++u) {
+                        const uint32_t pw[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) {
+                            const uint32_t t = pw[s] >> K4C_CNT_BITS, cnt = pw[s] & K4C_CNT_MASK;
+                            const uint32_t tv = tab[t];
+                            a32 += tv * cnt;
+                            if (tv == 255u && cnt != 0u)
+                                acc += (unsigned long long)(k4c_escape_value(qp, qn, t) - 255u) * (unsigned long long)cnt;
+                        }
+                    }
+                }
+                acc += a32;
+                if (done) {
+                    unsigned long long tot;
+                    if (!__any_sync(0xffffffffu, (acc >> 27) != 0ull)) {
+                        tot = __reduce_add_sync(0xffffffffu, (uint32_t)acc);      // 32 values < 2^27
+                    } else {
+                        tot = acc;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                    }
+                    if (lane == 0) dotc[cur_c] += tot;     // only this warp touches cur_c in this window
+                    acc = 0ull;
+                }
+            }
+            // the warp's first slice of the NEXT window: loads issued now, consumed after the barriers
+            if (jn < nwin && wid < ncand && sl[wid * wg1 + jn + 1] > sl[wid * wg1 + jn]) {
+                setup(wid, jn);
+                load();
+                pref = true;
+            }
+        }
+        // ---- un-build: zero exactly the bytes this window set ----------------------------------------------------
+        __syncthreads();
+        {
+            const uint32_t i0 = k0 + threadIdx.x;
+            if (i0 < k1) tab[qc0 >> K4C_CNT_BITS] = 0;
+            if (i0 + K4C_THREADS < k1) tab[qc1 >> K4C_CNT_BITS] = 0;
+            for (uint32_t i = i0 + 2 * K4C_THREADS; i < k1; i += K4C_THREADS) tab[__ldg(packed + xb + i) >> K4C_CNT_BITS] = 0;
+        }
+        j = jn;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < ncand; c += K4C_THREADS)
+        if (dotc[c] != 0ull) atomicAdd(&dotacc[q * (int64_t)kcand + c], dotc[c]);
+}
+
+// distances from the exact integer dot products, (distance asc, index asc) order, keep k
+__global__ void __launch_bounds__(256)
+k4c_finalize_kernel(const uint32_t* __restrict__ flags, uint32_t esc_limit, const unsigned long long* __restrict__ dotacc,
+                    const double* __restrict__ norm2, int64_t q_row0, const int32_t* __restrict__ cand_idx,
+                    const int32_t* __restrict__ cand_nvalid, int kcand, int P, int k, K4Chunk ck,
+                    int32_t* __restrict__ idx_out, float* __restrict__ dist_out, int32_t* __restrict__ nvalid_out) {
+    if (!k4c_usable(flags, esc_limit)) return;
+    extern __shared__ unsigned long long fkeys[];
+    const int64_t q = blockIdx.x;
+    const int64_t qrow = q_row0 + q;
+    const int ncand = max(0, min((cand_idx ? cand_nvalid[q] : ck.n_all) - ck.cand_off, kcand));
+    const double nq2 = norm2[qrow];
+    for (int c = threadIdx.x; c < P; c += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (c < ncand) {
+            const int32_t d = cand_idx ? cand_idx[q * ck.cand_stride + ck.cand_off + c] : ck.cand_off + c;
+            // integers below 2^53: every term and the result are exact in fp64
+            double d2 = d == qrow ? 0.0 : nq2 + norm2[d] - 2.0 * (double)dotacc[q * (int64_t)kcand + c];
+            if (d2 < 0.0) d2 = 0.0;
+            const float dist = (float)sqrt(d2);
+            key = ((unsigned long long)__float_as_uint(dist) << 32) | (unsigned long long)(uint32_t)d;
+        }
+        fkeys[c] = key;
+    }
+    bitonic_sort_shared(fkeys, P);
+    const int nv = min(ncand, k);
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        int32_t oi = -1;
+        float od = __int_as_float(0x7f800000);
+        if (t < nv) {
+            const unsigned long long key = fkeys[t];
+            oi = (int32_t)(uint32_t)(key & 0xFFFFFFFFull);
+            od = __uint_as_float((uint32_t)(key >> 32));
+        }
+        idx_out[q * ck.out_stride + ck.out_off + t] = oi;
+        dist_out[q * ck.out_stride + ck.out_off + t] = od;
+    }
+    if (threadIdx.x == 0 && ck.write_nvalid) nvalid_out[q] = nv;
+}
+
+// windows per group: the group's share of the packed stream (4 B x nnz x wg / n_windows) should fit the part of L2 we
+// want it to live in (group_bytes), and the per-candidate window offsets must fit in shared memory
+int k4c_windows_per_group(int n_windows, int64_t db_nnz, int kcand, int64_t group_bytes) {
+    const int64_t smem_left = 220 * 1024 - K4C_TAB - (int64_t)kcand * (8 + 8 + 4) - 64;
+    if (smem_left < (int64_t)kcand * 8) return -1;
+    int64_t wg_smem = smem_left / ((int64_t)kcand * 4) - 1;                  // (wg + 1) * 4 * kcand + (wg + 1) * 4 <= left
+    while (wg_smem > 1 && (wg_smem + 1) * 4 * ((int64_t)kcand + 1) > smem_left) --wg_smem;
+    if (wg_smem < 1) return -1;
+    int64_t wg = n_windows;
+    const int64_t stream_bytes = 4 * std::max<int64_t>(db_nnz, 1);
+    if (group_bytes < 0) wg = -group_bytes;                                  // forced (tests, experiments)
+    else if (group_bytes > 0 && stream_bytes > group_bytes) wg = std::max<int64_t>(1, group_bytes * n_windows / stream_bytes);
+    wg = std::min<int64_t>(std::min<int64_t>(wg, wg_smem), n_windows);
+    return (int)wg;
+}
+
+size_t k4c_dotacc_elems(int64_t nq, int kcand) { return (size_t)nq * (size_t)kcand; }
+
+// One launch (pair) over candidate columns [cand_off, cand_off + kcand); same output contract as launch_rerank.
+// d_dotacc: >= nq * kcand uint64 scratch (zeroed here). Returns launches, or -1 when kcand does not fit.
+int launch_rerank_counts(const int64_t* d_indptr, const uint32_t* d_packed, const double* d_norm2, const uint32_t* d_dir,
+                         int n_windows, int64_t db_nnz, int64_t group_bytes, int64_t q_row0, int64_t nq,
+                         const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int cand_stride, int cand_off, int kcand,
+                         int k, int32_t* d_idx_out, float* d_dist_out, int out_stride, int out_off, int final,
+                         int32_t* d_nvalid_out, int n_all, const uint32_t* d_flags, uint32_t esc_limit,
+                         unsigned long long* d_dotacc, cudaStream_t stream) {
+    if (nq <= 0) return 0;
+    if (kcand > 1024) return -1;
+    const int wg = k4c_windows_per_group(n_windows, db_nnz, kcand, group_bytes);
+    if (wg < 1) return -1;
+    const int64_t groups = (n_windows + wg - 1) / wg;
+    if (groups * nq > 0x7FFFFFFFll) return -1;
+    const K4Chunk ck{cand_stride, cand_off, out_stride, out_off, final, n_all};
+    const size_t smem = (size_t)K4C_TAB + (size_t)kcand * (8 + 8 + 4) + (size_t)kcand * (wg + 1) * 4 + (size_t)(wg + 1) * 4 + 16;
+    if (smem > 220 * 1024) return -1;
+    if (cudaMemsetAsync(d_dotacc, 0, (size_t)nq * kcand * sizeof(unsigned long long), stream) != cudaSuccess) return -1;
+    cudaFuncSetAttribute(k4c_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k4c_rerank_kernel<<<(unsigned)(groups * nq), K4C_THREADS, smem, stream>>>(
+        d_indptr, d_packed, d_dir, n_windows, wg, q_row0, nq, d_cand_idx, d_cand_nvalid, kcand, ck, d_flags, esc_limit,
+        d_dotacc);
+    const int P = next_pow2(kcand);
+    k4c_finalize_kernel<<<(unsigned)nq, 256, (size_t)P * 8, stream>>>(d_flags, esc_limit, d_dotacc, d_norm2, q_row0,
+                                                                      d_cand_idx, d_cand_nvalid, kcand, P, k, ck, d_idx_out,
+                                                                      d_dist_out, d_nvalid_out);
+    return 2;
+}
+
+}  // namespace schic

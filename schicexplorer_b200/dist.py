@@ -37,22 +37,26 @@ def partition_rows_by_nnz(indptr: np.ndarray, world: int) -> list:
     return bounds
 
 
-def _gather_padded(local: torch.Tensor, counts: list, group) -> torch.Tensor:
-    """All-gather of unequal first-dimension shards: pad to the largest, gather, compact."""
+def _gather_padded(local: torch.Tensor, counts: list, group, tail_pad: int = 0) -> torch.Tensor:
+    """All-gather of unequal first-dimension shards: pad to the largest, gather, compact. ``tail_pad``: extra
+    (uninitialised) elements allocated behind the result; the returned tensor is the view without them."""
     world = len(counts)
     mx = max(counts)
     tail = local.shape[1:]
+    total = sum(counts)
     if local.shape[0] < mx:
         pad = torch.empty((mx,) + tuple(tail), dtype=local.dtype, device=local.device)
         pad[:local.shape[0]] = local
         local = pad
     if len(set(counts)) == 1:
-        out = torch.empty((world * mx,) + tuple(tail), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-        return out
+        out = torch.empty((world * mx + tail_pad,) + tuple(tail), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out[:world * mx], local.contiguous(), group=group)
+        return out[:world * mx]
     buf = torch.empty((world, mx) + tuple(tail), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(buf.view((world * mx,) + tuple(tail)), local.contiguous(), group=group)
-    return torch.cat([buf[r, :counts[r]] for r in range(world)], dim=0)
+    out = torch.empty((total + tail_pad,) + tuple(tail), dtype=local.dtype, device=local.device)
+    torch.cat([buf[r, :counts[r]] for r in range(world)], dim=0, out=out[:total])
+    return out[:total]
 
 
 class PeerExchange:
@@ -122,7 +126,7 @@ class ShardedMinHash:
     """
 
     def __init__(self, api, n_total: int, row_bounds: list, device, group=None, n_features=None, shard_nnz=None,
-                 **minhash_kwargs):
+                 integer_counts: bool = False, **minhash_kwargs):
         self.api, self.group, self.device = api, group, device
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -141,6 +145,12 @@ class ShardedMinHash:
         if n_features is not None and hasattr(api, "set_feature_range"):
             api.set_feature_range(self.h, int(n_features))
         self.shard_nnz = None if shard_nnz is None else [int(x) for x in shard_nnz]
+        # integer_counts: the caller states that the values are small non-negative integers (Hi-C contact counts). The
+        # exact rerank then exchanges ONE packed 32-bit word per non-zero ((id mod 2^17) << 15 | count, produced by the
+        # owning rank's preparation pass) instead of the id and value arrays -- half the NVLink volume. The statement is
+        # verified on the device (flags of the preparation pass): if it does not hold, the next synchronising call
+        # raises instead of returning wrong distances.
+        self.integer_counts = bool(integer_counts)
         # The CSR exchange gets its own communicator: collectives of one NCCL communicator run in issue order on one
         # internal stream, so on the default group the (small, urgent) signature all-gather would queue behind the
         # 1 GB CSR all-gather that was issued before K1 and K3 could not start until it had finished.
@@ -180,18 +190,26 @@ class ShardedMinHash:
         """``indptr0``: the value of ``d_indptr[0]`` if the caller knows it (0 for a stand-alone shard); the fit then
         enqueues without reading it back from the device (no host synchronisation in the build)."""
         self._keep["csr"] = (d_indptr, d_indices, d_data)
-        self._keep.pop("prep_local", None)
-        if self._nw > 0:
-            norms = torch.empty(self.n_local, dtype=torch.float64, device=self.device)
-            wdir = torch.empty((self.n_local, self._nw + 1), dtype=torch.int32, device=self.device)
-            self.api.rerank_prep_rows(self.h, self.n_local, d_indptr.data_ptr(), d_indices.data_ptr(), d_data.data_ptr(),
-                                      self._nw, norms.data_ptr(), wdir.data_ptr())
-            self._keep["prep_local"] = (norms, wdir)
+        self._prep_local(d_indptr, d_indices, d_data)
         self._start_csr_gather()
         nnz = int(d_indices.numel())
         extra = {} if indptr0 is None else {"indptr0": int(indptr0)}
         self.api.fit_csr_device(self.h, self.n_local, nnz, d_indptr.data_ptr(), d_indices.data_ptr(),
                                 None if d_data is None else d_data.data_ptr(), False, **extra)
+
+    def _prep_local(self, d_indptr, d_indices, d_data):
+        """Rerank preparation of this rank's rows (norms, window directory, flags, packed stream), exchanged with the CSR."""
+        self._keep.pop("prep_local", None)
+        if self._nw <= 0 or d_data is None:
+            return
+        norms = torch.empty(self.n_local, dtype=torch.float64, device=self.device)
+        wdir = torch.empty((self.n_local, self._nw + 1), dtype=torch.int32, device=self.device)
+        flags = torch.empty(4, dtype=torch.int32, device=self.device)
+        packed = torch.empty(d_indices.numel(), dtype=torch.int32, device=self.device) if self.integer_counts else None
+        self.api.rerank_prep_rows(self.h, self.n_local, d_indptr.data_ptr(), d_indices.data_ptr(), d_data.data_ptr(),
+                                  self._nw, norms.data_ptr(), wdir.data_ptr(), flags.data_ptr(),
+                                  None if packed is None else packed.data_ptr())
+        self._keep["prep_local"] = (norms, wdir, flags, packed)
 
     def fit_local_host(self, indptr: np.ndarray, indices: np.ndarray, data, async_upload: bool = False):
         """Same, from HOST buffers (pinned for full PCIe speed): the H2D copy is part of the call and
@@ -208,9 +226,9 @@ class ShardedMinHash:
         d_ix = _wrap_device(p_ix, (nnz,), "<i4", torch.int32, self.device)
         d_dt = None if not p_dt else _wrap_device(p_dt, (nnz,), "<f4", torch.float32, self.device)
         self._keep["csr"] = (d_ip, d_ix, d_dt)
-        self._keep.pop("prep_local", None)
         if async_upload and self.world > 1 and not self.fast:
             self.api.synchronize(self.h)       # the CSR exchange reads the value array: it must have landed
+        self._prep_local(d_ip, d_ix, d_dt)
         self._start_csr_gather()
 
     # -- step 2: the exchange ------------------------------------------------------------------
@@ -228,7 +246,10 @@ class ShardedMinHash:
             dist.all_gather_into_tensor(nnz_all, nnz_local, group=group)
             nnzs = [int(x) for x in nnz_all.tolist()]
         ev = None
-        if self._peer is not None:
+        packed_only = "prep_local" in self._keep and self._keep["prep_local"][3] is not None
+        if packed_only:
+            ix_all = dt_all = None            # the packed stream (gathered below) is all the rerank reads
+        elif self._peer is not None:
             ix_all, dt_all, ev = self._peer.exchange(d_indices, d_data)
         else:
             ix_all = _gather_padded(d_indices, nnzs, group)
@@ -242,8 +263,16 @@ class ShardedMinHash:
             torch.cuda.current_stream(self.device).wait_event(ev)
         self._keep.pop("prep_all", None)
         if "prep_local" in self._keep:
-            norms, wdir = self._keep["prep_local"]
-            self._keep["prep_all"] = (_gather_padded(norms, counts, group), _gather_padded(wdir, counts, group))
+            norms, wdir, flags, packed = self._keep["prep_local"]
+            flags_all = torch.empty(self.world * 4, dtype=torch.int32, device=self.device)
+            dist.all_gather_into_tensor(flags_all, flags, group=group)
+            flags_all = flags_all.view(self.world, 4).sum(dim=0).to(torch.int32)     # 0/1 flags and one count: a sum combines them
+            packed_all = None
+            if packed is not None:
+                # (16 readable bytes behind the stream: the counts kernel reads slices as aligned 16-byte words)
+                packed_all = _gather_padded(packed, nnzs, group, tail_pad=4)
+            self._keep["prep_all"] = (_gather_padded(norms, counts, group), _gather_padded(wdir, counts, group), flags_all,
+                                      packed_all, sum(nnzs))
         return ip_all, ix_all, dt_all
 
     def _start_csr_gather(self):
@@ -294,8 +323,12 @@ class ShardedMinHash:
         if pending is not None:
             self.api.set_database_ready_event(self.h, pending.cuda_event)
         if not self.fast and self.world > 1 and "prep_all" in self._keep:
-            norms_all, dir_all = self._keep["prep_all"]
-            self.api.set_database_prep_device(self.h, norms_all.data_ptr(), dir_all.data_ptr(), self._nw)
+            norms_all, dir_all, flags_all, packed_all, nnz_total = self._keep["prep_all"]
+            if packed_all is None:
+                self.api.set_database_prep_device(self.h, norms_all.data_ptr(), dir_all.data_ptr(), self._nw)
+            else:
+                self.api.set_database_prep_device(self.h, norms_all.data_ptr(), dir_all.data_ptr(), self._nw,
+                                                  packed_all.data_ptr(), flags_all.data_ptr(), nnz_total)
 
     # -- step 3: local queries -------------------------------------------------------------------
     def kneighbors_local(self, k: int, out=None):

@@ -149,11 +149,14 @@ def test_ids_beyond_32_bits(cuda, oracle, width):
 
 
 @pytest.mark.parametrize("seed", range(6))
-def test_sharded_query_path_on_one_gpu(cuda, oracle, seed):
+@pytest.mark.parametrize("exchange", ["csr", "csr+packed", "packed"])
+def test_sharded_query_path_on_one_gpu(cuda, oracle, seed, exchange):
     """The multi-GPU query path emulated on one device: random contiguous shards, one handle per shard; the 'gathered'
     database (signatures, CSR) is handed back to every handle together with the rerank preparation computed shard by
     shard by its owner (schic_mh_rerank_prep_rows -> schic_mh_set_database_prep_device) and a ready event
-    (schic_mh_set_database_ready_event). Every shard must answer exactly like the single-handle build."""
+    (schic_mh_set_database_ready_event). Every shard must answer exactly like the single-handle build.
+    exchange: what the ranks hand over for the exact rerank -- the CSR ids + values (generic kernels), those plus the
+    packed stream (counts kernel, generic behind it), or the packed stream ALONE (half the exchange volume)."""
     import torch
     from schicexplorer_b200 import synth
     rng = np.random.default_rng(77 + seed)
@@ -174,6 +177,8 @@ def test_sharded_query_path_on_one_gpu(cuda, oracle, seed):
     sig_all = torch.empty((n, H), dtype=torch.int32, device=dev)
     handles, nw = [], None
     norms_all = torch.empty(n, dtype=torch.float64, device=dev)
+    packed_all = torch.zeros(int(ip[-1]) + 4, dtype=torch.int32, device=dev) if "packed" in exchange else None
+    flags_all = torch.zeros(4, dtype=torch.int32, device=dev)
     for a, b in zip(cuts[:-1], cuts[1:]):
         h = cuda.create(device=0, **kw)
         cuda.set_stream(h, torch.cuda.current_stream().cuda_stream)
@@ -188,17 +193,27 @@ def test_sharded_query_path_on_one_gpu(cuda, oracle, seed):
             nw = cuda.rerank_windows(h)
             assert nw > 0
             dir_all = torch.empty((n, nw + 1), dtype=torch.int32, device=dev)
+        flags = torch.empty(4, dtype=torch.int32, device=dev)
         cuda.rerank_prep_rows(h, b - a, sub_ip.data_ptr(), d_ix[lo:hi].data_ptr(), d_dt[lo:hi].data_ptr(), nw,
-                              norms_all[a:b].data_ptr(), dir_all[a:b].data_ptr())
+                              norms_all[a:b].data_ptr(), dir_all[a:b].data_ptr(), flags.data_ptr(),
+                              None if packed_all is None else packed_all[lo:hi].data_ptr())
+        flags_all += flags          # [0] / [2] are 0/1 flags, [1] a count: a sum combines all of them
         handles.append((a, b, h, sub_ip))
     ev = torch.cuda.Event()
     ev.record()
     for a, b, h, _ in handles:
-        cuda.set_database_device(h, n, a, sig_all.data_ptr(), d_ip.data_ptr(), d_ix.data_ptr(), d_dt.data_ptr())
+        csr = exchange != "packed"
+        cuda.set_database_device(h, n, a, sig_all.data_ptr(), d_ip.data_ptr(), d_ix.data_ptr() if csr else None,
+                                 d_dt.data_ptr() if csr else None)
         cuda.set_database_ready_event(h, ev.cuda_event)
-        cuda.set_database_prep_device(h, norms_all.data_ptr(), dir_all.data_ptr(), nw)
+        if packed_all is None:
+            cuda.set_database_prep_device(h, norms_all.data_ptr(), dir_all.data_ptr(), nw)
+        else:
+            cuda.set_database_prep_device(h, norms_all.data_ptr(), dir_all.data_ptr(), nw, packed_all.data_ptr(),
+                                          flags_all.data_ptr(), int(ip[-1]))
         idx, dist, nv = cuda.kneighbors(h, k, n_rows=b - a)
         assert_neighbours_equal_up_to_ties(idx, dist, nv, ref[0][a:b], ref[1][a:b], ref[2][a:b], RTOL)
+        assert cuda.rerank_kernel_name(h) == ("k4_rerank_window_kernel" if packed_all is None else "k4c_rerank_kernel")
         cuda.destroy(h)
 
 

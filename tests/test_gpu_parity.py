@@ -321,10 +321,11 @@ def test_max_bin_size_bucket_pruning(cuda, oracle):
             assert_neighbours_equal_up_to_ties(*a, *b, 0 if fast else RTOL)
 
 
-@pytest.mark.parametrize("mode", ["hash", "window", "window64"])
+@pytest.mark.parametrize("mode", ["counts", "hash", "window", "window64"])
 def test_rerank_kernel_variants(cuda, oracle, monkeypatch, mode):
-    """K4 has two implementations (hash table / windowed direct table, the latter with 32- or 64-bit
-    entries); SCHIC_K4_MODE selects one. All must agree with the oracle, including on rows that
+    """K4 has three implementations (counts kernel: packed stream + byte table, the default for integer counts; hash
+    table; windowed direct table with 32- or 64-bit entries); SCHIC_K4_MODE selects one ("counts" = default: counts
+    kernel with the generic ones behind it). All must agree with the oracle, including on rows that
     (a) hold more than one table fill (> 4096 non-zeros) inside ONE window, (b) are empty / tiny,
     (c) use ids near 2^32 (too many windows: the library must fall back to the hash kernel)."""
     monkeypatch.setenv("SCHIC_K4_MODE", mode)
@@ -348,6 +349,7 @@ def test_rerank_kernel_variants(cuda, oracle, monkeypatch, mode):
     with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
         a, b = cuda.kneighbors(g.h, 20), oracle.kneighbors(o.h, 20)
         assert_neighbours_equal_up_to_ties(*a, *b, RTOL)
+        assert cuda.rerank_kernel_name(g.h) == {"counts": "k4c_rerank_kernel", "hash": "k4_rerank_kernel"}.get(mode, "k4_rerank_window_kernel")
     # realistic clustered cells, k*excess_factor candidates
     Xs = synth_csr(200, seed=21)
     kw = dict(fast=False, n_neighbors=15, excess_factor=2, minimal_blocks_in_common=30)
@@ -369,6 +371,77 @@ def test_rerank_kernel_variants(cuda, oracle, monkeypatch, mode):
     with Fitted(cuda, Xw, **kw) as g, Fitted(oracle, Xw, **kw) as o:
         a, b = cuda.kneighbors(g.h, 8), oracle.kneighbors(o.h, 8)
         assert_neighbours_equal_up_to_ties(*a, *b, RTOL)
+
+
+def _count_rows(rng, n_rows, ncols, lens, hi=40, pool=None):
+    rows, cols, vals = [], [], []
+    for r in range(n_rows):
+        m = int(lens[r % len(lens)])
+        src = ncols if pool is None else pool
+        c = np.sort(rng.choice(src, size=min(m, src if np.isscalar(src) else len(src)), replace=False))
+        rows.append(np.full(len(c), r)); cols.append(c); vals.append(rng.integers(1, hi, size=len(c)).astype(np.float64))
+    return csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n_rows, ncols))
+
+
+def test_counts_rerank_kernel(cuda, oracle, monkeypatch):
+    """The counts kernel (k4c_rerank.cu) on its own edge cases, always against the oracle:
+    (a) counts >= 255 in query rows (table bytes saturate at 255, resolved by the escape search), up to the largest
+        packable count 32767; (b) windows with more than 2048 query keys (build / un-build loop past the two
+        prefetched keys); (c) window groups: one group, and one window per group (many CTAs per query, global
+        accumulation); (d) data the kernel must hand to the generic float kernels -- non-integer values, a count above
+        32767, more than 1/64 of the values >= 255 -- decided by the device flag, with identical results;
+    (e) brute-force exact kNN (every row a candidate, 1024-row chunks) through the same kernel."""
+    rng = np.random.default_rng(41)
+    ncols = 1 << 22
+    # clustered rows: a shared pool inside ONE 2^17 window (rows with 3000-6000 keys there) plus scattered ids
+    pool = np.sort(rng.choice(1 << 17, size=20000, replace=False)) + (3 << 17)
+    base = _count_rows(rng, 70, ncols, [3000, 4500, 6000, 800, 2049, 2048], pool=pool)
+    scat = _count_rows(rng, 70, ncols, [700, 50, 1200])
+    X = (base + scat).tocsr()
+    X.sum_duplicates()
+    X.sort_indices()
+    kw = dict(fast=False, n_neighbors=25, number_of_hash_functions=128, minimal_blocks_in_common=1, excess_factor=2)
+
+    def check(M, want_kernel, k=25):
+        with Fitted(cuda, M, **kw) as g, Fitted(oracle, M, **kw) as o:
+            cuda.set_feature_range(g.h, M.shape[1])
+            a, b = cuda.kneighbors(g.h, k), oracle.kneighbors(o.h, k)
+            assert_neighbours_equal_up_to_ties(*a, *b, RTOL)
+            assert cuda.rerank_kernel_name(g.h) == want_kernel
+            return a
+
+    for wg in ("1", "3", "100000", None):                                # (c): one window per group ... one group / default
+        if wg is None:
+            monkeypatch.delenv("SCHIC_K4_GROUP_WINDOWS", raising=False)
+        else:
+            monkeypatch.setenv("SCHIC_K4_GROUP_WINDOWS", wg)
+        check(X, "k4c_rerank_kernel")
+    # (a) a few large counts (escapes) in some rows, incl. the largest packable value
+    Xa = X.copy()
+    big = rng.choice(Xa.nnz, size=Xa.nnz // 200, replace=False)
+    Xa.data[big] = rng.integers(255, 32768, size=len(big)).astype(np.float64)
+    Xa.data[big[:3]] = [255.0, 256.0, 32767.0]
+    check(Xa, "k4c_rerank_kernel")
+    # (d) not packable: every variant must come out of the generic kernel, same answers as the oracle
+    Xf = X.copy(); Xf.data = Xf.data * 0.5                               # non-integer values
+    check(Xf, "k4_rerank_window_kernel")
+    Xb = X.copy(); Xb.data[7] = 32768.0                                  # one count beyond 15 bits
+    check(Xb, "k4_rerank_window_kernel")
+    Xm = X.copy(); Xm.data[rng.choice(Xm.nnz, size=Xm.nnz // 20, replace=False)] = 300.0   # too many escapes
+    check(Xm, "k4_rerank_window_kernel")
+    Xn = X.copy(); Xn.data[11] = -1.0                                    # negative
+    check(Xn, "k4_rerank_window_kernel")
+    # (e) exact kNN (brute force) through the counts kernel == oracle == the generic kernels
+    with Fitted(cuda, Xa, **kw) as g, Fitted(oracle, Xa, **kw) as o:
+        gi, gd, gn = cuda.kneighbors_exact(g.h, 10, False)
+        oi, od, on = oracle.kneighbors_exact(o.h, 10, False)
+        assert cuda.rerank_kernel_name(g.h) == "k4c_rerank_kernel"
+        assert_neighbours_equal_up_to_ties(gi, gd, gn, oi, od, on, RTOL)
+        monkeypatch.setenv("SCHIC_K4_MODE", "window")
+    with Fitted(cuda, Xa, **kw) as g:
+        wi, wd, wn = cuda.kneighbors_exact(g.h, 10, False)
+        assert cuda.rerank_kernel_name(g.h) == "k4_rerank_window_kernel"
+        assert_neighbours_equal_up_to_ties(gi, gd, gn, wi, wd, wn, RTOL)
 
 
 def test_k1_filtered_equals_chunked_kernel(cuda, oracle, monkeypatch):

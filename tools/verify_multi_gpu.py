@@ -29,8 +29,10 @@ def main():
     ok = True
     # (fast, exchange): signatures only / exact rerank with the NCCL all-gather of the CSR shards / exact rerank with
     # the peer-memory exchange (two builds in a row: both buffer sets of the double buffering are used)
-    for fast, exchange in ((True, "nccl"), (False, "nccl"), (False, "p2p"), (False, "p2p")):
-        os.environ["SCHIC_CSR_EXCHANGE"] = exchange
+    # "packed": the ranks exchange the packed count stream of the owning rank's preparation pass instead of ids + values
+    oracle_ref = {}
+    for fast, exchange in ((True, "nccl"), (False, "nccl"), (False, "packed"), (False, "p2p"), (False, "p2p")):
+        os.environ["SCHIC_CSR_EXCHANGE"] = "p2p" if exchange == "p2p" else "nccl"
         kw = dict(n_neighbors=k, number_of_hash_functions=800, fast=fast, minimal_blocks_in_common=100,
                   excess_factor=1, max_bin_size=100000)
         bounds = partition_rows_by_nnz(ip, world)
@@ -40,7 +42,8 @@ def main():
         if exchange == "p2p" and "sh_p2p" in globals():
             sh = globals()["sh_p2p"]                     # second build on the same object
         else:
-            sh = ShardedMinHash(api, n, bounds, dev, n_features=cfg.chroms.nbins ** 2, shard_nnz=shard_nnz, **kw)
+            sh = ShardedMinHash(api, n, bounds, dev, n_features=cfg.chroms.nbins ** 2, shard_nnz=shard_nnz,
+                                integer_counts=(exchange == "packed"), **kw)
             if exchange == "p2p":
                 globals()["sh_p2p"] = sh
                 assert sh._peer is not None, "peer-memory exchange was not set up"
@@ -65,6 +68,19 @@ def main():
             same = (same and np.array_equal(eidx.cpu().numpy(), xidx[lo:hi]) and np.array_equal(edst.cpu().numpy(), xdst[lo:hi])
                     and np.array_equal(env.cpu().numpy(), xnv[lo:hi]))
         api.destroy(h)
+        if exchange == "packed":
+            same = same and api.rerank_kernel_name(sh.h) == "k4c_rerank_kernel"
+        # ... and against the CPU oracle (rank 0 computes it once per mode, everybody compares its own rows)
+        if fast not in oracle_ref:
+            from oracle import oracle_api
+            ora = oracle_api()
+            ho = ora.create(number_of_cores=max(1, (os.cpu_count() or 1) // world), **kw)
+            ora.fit_csr(ho, ip, ix, None if fast else dt, False)
+            oracle_ref[fast] = ora.kneighbors(ho, k)
+            ora.destroy(ho)
+        oidx, odst, onv = oracle_ref[fast]
+        same = (same and np.array_equal(idx.cpu().numpy(), oidx[lo:hi]) and np.array_equal(nv.cpu().numpy(), onv[lo:hi])
+                and np.allclose(dst.cpu().numpy(), odst[lo:hi], rtol=1e-5))
         flag = torch.tensor([int(same)], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         ok = ok and bool(flag.item())
