@@ -79,9 +79,9 @@ int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t ro
 int schic_mh_set_database_ready_event(schic_mh_handle* h, void* cuda_event);
 
 /* Per-row preparation of the exact rerank, normally computed by the library for the whole database on first use, in one
- * pass over ids + values: fp64 row norms, the window directory (offsets of 2^17-id windows in every row), the PACKED
- * STREAM of the counts kernel -- one uint32 per non-zero, (id mod 2^17) << 15 | count, same indexing as d_indices -- and
- * four flags {a value is not an integer in [0, 32767]; number of values >= 255; an id beyond the declared range; -}.
+ * pass over ids + values: fp64 row norms, the window directory (offsets of 2^16-id windows in every row), the PACKED
+ * STREAM of the counts kernel -- one uint32 per non-zero, (id mod 2^16) << 16 | count, same indexing as d_indices -- and
+ * four flags {a value is not an integer in [0, 65535]; number of values >= 255; an id beyond the declared range; -}.
  * In a sharded run every rank prepares its OWN rows and the arrays are exchanged instead of being recomputed by everyone:
  *   schic_mh_rerank_windows      number of id windows for the range declared with schic_mh_set_feature_range
  *                                (0: no hint, or the range needs the hash-table kernel -- then do not use the two below)

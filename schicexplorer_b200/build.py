@@ -27,19 +27,22 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_cuda(force: bool = False, verbose: bool = False) -> str:
+def build_cuda(force: bool = False, verbose: bool = False, variant: str = "", extra_flags=()) -> str:
+    """``variant`` / ``extra_flags``: an experiment build of the same library with other compile-time constants
+    (objects and the .so get the variant name as a suffix; loaded through SCHIC_CUDA_LIB, see tools/)."""
     nvcc = os.environ.get("NVCC", "nvcc")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers += [os.path.join(HERE, "..", "include", f) for f in ("schic_mh.h", "schic_mh_cuda.h", "schic_pca.h")]
     headers.append(os.path.abspath(__file__))
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, "build" + ("_" + variant if variant else ""))
     os.makedirs(objdir, exist_ok=True)
+    out = OUT if not variant else os.path.join(objdir, f"libschic_mh_{variant}.so")
 
     def compile_one(src):
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+            cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             r = subprocess.run(cmd, capture_output=True, text=True)
@@ -49,12 +52,12 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    if force or _stale(OUT, objs):
-        cmd = [nvcc, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    if force or _stale(out, objs):
+        cmd = [nvcc, "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

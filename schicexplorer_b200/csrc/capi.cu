@@ -101,9 +101,9 @@ struct schic_mh_handle {
     int64_t count_budget = 0;                 // elements of the uint16 count matrix we allow ourselves (cached)
     uint64_t feature_range = 0;               // caller's hint: all ids < feature_range (0: unknown, read the maximum back)
     DevBuf<double> norm2; int64_t norm_rows = 0; const void* norm_of = nullptr;
-    DevBuf<uint32_t> win_dir, max_feat; int n_windows = 0;   // window directory (2^17-id windows) of the rerank (0: hash kernel)
+    DevBuf<uint32_t> win_dir, max_feat; int n_windows = 0;   // window directory (2^16-id windows) of the rerank (0: hash kernel)
     int window_mode = 32;
-    // counts rerank (k4c_rerank.cu): packed stream (id mod 2^17) << 15 | count of the prepared database, the prep flags
+    // counts rerank (k4c_rerank.cu): packed stream (id mod 2^16) << 16 | count of the prepared database, the prep flags
     // {not packable, #values >= 255, id beyond the range, -} and the uint64 dot-product accumulator
     DevBuf<uint32_t> packed, k4_flags; DevBuf<unsigned long long> dotacc;
     bool packed_ok = false; int64_t prep_nnz = 0;
@@ -342,13 +342,13 @@ int prune_buckets(schic_mh_handle* h, const uint32_t* db_sig, int64_t ndb) {
 }
 
 // Per-database preparation of the exact rerank, cached until the next fit -- ONE pass over ids + values
-// (k4c_prep_kernel): fp64 row norms and, when the id range spans at most kMaxWindows windows of 2^17 ids, the window
+// (k4c_prep_kernel): fp64 row norms and, when the id range spans at most kMaxWindows windows of 2^16 ids, the window
 // directory, the packed stream of the counts kernel and the flags that say whether the data is packable.
 // SCHIC_K4_MODE: "hash" = norms only (hash-table kernel), "window" / "window64" = directory, generic windowed kernel
 // only, default = counts kernel with the generic kernels behind it (tests compare them all).
 int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const uint32_t* feat, const float* val, int64_t rows, int64_t nnz_end) {
     if (h->norm_of == (const void*)indptr && h->norm_rows == rows) return 0;
-    constexpr int kMaxWindows = 4096;
+    constexpr int kMaxWindows = 8192;
     cudaStream_t s = h->stream;
     if (h->val_done) CU_TRY(cudaStreamWaitEvent(s, h->val_done, 0));   // async fit: the values may still be in flight
     ST_TRY(h->norm2.reserve(rows, 0, s));
@@ -439,7 +439,7 @@ int rerank_lists(schic_mh_handle* h, const int64_t* db_indptr, const uint32_t* d
     const bool generic = have_generic && !(counts && !h->ext && !h->borrowed && h->fit_data_kind == 2);
     if (!counts && !have_generic) return fail(SCHIC_ERR_INVALID_ARG, "exact rerank needs the CSR ids and values (or a packed database)");
     const uint32_t esc_limit = esc_limit_for(r_nnz);
-    int64_t group_bytes = (int64_t)40 << 20;         // share of the packed stream one window group spans (L2-resident)
+    int64_t group_bytes = (int64_t)80 << 20;         // share of the packed stream one window group spans (L2-resident; measured: 20/40/80/160 MB -> 17.9/16.8/16.2/16.5 ms)
     if (const char* g = getenv("SCHIC_K4_GROUP_MB")) group_bytes = (int64_t)atoll(g) << 20;              // 0: one group
     if (const char* g = getenv("SCHIC_K4_GROUP_WINDOWS")) group_bytes = -std::max<int64_t>(1, atoll(g));  // windows per group
     h->rerank_path = counts ? (generic ? 2 : 1) : 3;
@@ -1077,7 +1077,7 @@ int schic_mh_rerank_windows(schic_mh_handle* h, int32_t* n_windows_out) {
     if (mode && (strcmp(mode, "hash") == 0 || strcmp(mode, "window64") == 0)) return SCHIC_OK;
     if (h->feature_range == 0 || h->feature_range > 0xFFFFFFFFull) return SCHIC_OK;
     const int nw = schic::k4c_window_count((uint32_t)(h->feature_range - 1));
-    if (nw <= 4096) *n_windows_out = nw;
+    if (nw <= 8192) *n_windows_out = nw;
     return SCHIC_OK;
 }
 

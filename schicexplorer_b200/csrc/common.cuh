@@ -83,11 +83,11 @@ int launch_fast_distance(const int32_t* d_idx_in, const int32_t* d_cnt_in, const
 // id windows of the rerank: the per-row window directory is built for windows of 2^SCHIC_K4C_WIN_BITS ids (the byte
 // table of the counts kernel); the generic windowed kernel works on 2^19-id windows = 4 of them.
 #ifndef SCHIC_K4C_WIN_BITS
-#define SCHIC_K4C_WIN_BITS 17
+#define SCHIC_K4C_WIN_BITS 16
 #endif
 // Per-fit preparation in one pass over ids + values: fp64 row norms, window directory dir[row][0..n_windows] (uint32
-// offsets from the row start), the packed stream ((id mod 2^17) << 15 | count, indexed like d_feat; nullable) and
-// d_flags[4] (accumulated, zero them first): [0] a value is not an integer in [0, 32767], [1] number of values >= 255,
+// offsets from the row start), the packed stream ((id mod 2^16) << 16 | count, indexed like d_feat; nullable) and
+// d_flags[4] (accumulated, zero them first): [0] a value is not an integer in [0, 65535], [1] number of values >= 255,
 // [2] an id lies beyond the last window.
 int k4c_window_count(uint32_t max_feature);
 int launch_rerank_prep(const int64_t* d_indptr, const uint32_t* d_feat, const float* d_val, int64_t n_rows, int n_windows,

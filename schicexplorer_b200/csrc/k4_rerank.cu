@@ -643,7 +643,7 @@ int launch_rerank(const int64_t* d_indptr, const uint32_t* d_feat, const float* 
     const K4Chunk ck{cand_stride, cand_off, out_stride, out_off, final, n_all};
     const int P = next_pow2(kcand);
     static_assert(K4W_WIN_BITS >= SCHIC_K4C_WIN_BITS, "the directory's windows must not be coarser than this kernel's");
-    const int dir_windows = n_windows;                                            // windows of the directory (2^17 ids)
+    const int dir_windows = n_windows;                                            // windows of the directory (2^16 ids)
     constexpr int DSH = K4W_WIN_BITS - SCHIC_K4C_WIN_BITS;
     n_windows = (dir_windows + (1 << DSH) - 1) >> DSH;                            // windows of this kernel (2^19 ids)
     if (d_dir && n_windows > 0) {

@@ -8,10 +8,10 @@
 // from the generic float kernel (k4_rerank_window_kernel, 2 x 4-byte loads and ~23 issued instructions per candidate
 // non-zero, 58.7 GB of DRAM traffic per S10 build):
 //   * per fit ONE pass over the CSR (k4c_prep_kernel) produces, besides the fp64 row norms and the window directory,
-//     a PACKED STREAM: one 32-bit word per non-zero = (id mod 2^17) << 15 | count. Half the bytes and half the loads
+//     a PACKED STREAM: one 32-bit word per non-zero = (id mod 2^16) << 16 | count. Half the bytes and half the loads
 //     of (id, float value); also what a multi-GPU run exchanges instead of the two CSR arrays.
-//   * the id axis is cut into windows of 2^17 ids. For one window the query row is a DIRECT BYTE TABLE in shared
-//     memory (128 KB): tab[id mod 2^17] = count (0 = absent). A probe is one LDS.U8 and one IMAD -- a miss
+//   * the id axis is cut into windows of 2^16 ids. For one window the query row is a DIRECT BYTE TABLE in shared
+//     memory (64 KB): tab[id mod 2^16] = count (0 = absent). A probe is one LDS.U8 and one IDP.2A -- a miss
 //     multiplies by zero, so there is no bit test, no rank/popcount, no second load and no predicate.
 //     Counts >= 255 in a query row are stored as 255 and resolved exactly by a (rare) binary search in the query row;
 //     the build phase knows whether a window has any, so windows without them run a loop that never checks.
@@ -21,10 +21,11 @@
 //     resident CTAs stream the same ~1/G slice of the database at the same time and it is served by the 126 MB L2
 //     instead of HBM. Partial dot products go to a global uint64 accumulator (one atomic per candidate and CTA);
 //     k4c_finalize_kernel turns them into distances and sorts.
-// Data that is not small integer counts (non-integer, negative, > 32767, or so many >= 255 that the escape path
+// Data that is not small integer counts (non-integer, negative, > 65535, or so many >= 255 that the escape path
 // would dominate) is detected by the prep pass in a device flag; these kernels then exit at once and the generic
 // float kernels of k4_rerank.cu, launched behind them with the same flag, do the work. No host round trip decides.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "sort.cuh"
@@ -38,11 +39,20 @@ struct K4Chunk {
 
 constexpr int K4C_WIN_BITS = SCHIC_K4C_WIN_BITS;
 constexpr int K4C_TAB = 1 << K4C_WIN_BITS;                    // table bytes = ids per window
-constexpr int K4C_CNT_BITS = 32 - K4C_WIN_BITS;               // 15
-constexpr uint32_t K4C_CNT_MASK = (1u << K4C_CNT_BITS) - 1u;  // largest packable count (32767)
-constexpr int K4C_THREADS = 1024;
-constexpr int K4C_U = 2;                                      // 16-byte loads per lane and block
-constexpr int K4C_BLK = 32 * 4 * K4C_U;                       // candidate non-zeros per warp and block (256)
+constexpr int K4C_CNT_BITS = 32 - K4C_WIN_BITS;               // 16
+constexpr uint32_t K4C_CNT_MASK = (1u << K4C_CNT_BITS) - 1u;  // largest packable count (65535)
+// count x table byte, accumulated. With the 16/16 split one IDP.2A does it (the id half of the word meets a zero byte).
+__device__ __forceinline__ uint32_t k4c_mac(uint32_t word, uint32_t table_byte, uint32_t acc) {
+    if (K4C_WIN_BITS == 16) return __dp2a_lo(word, table_byte, acc);
+    return acc + table_byte * (word & K4C_CNT_MASK);
+}
+// 64 KB table (2^16-id windows): 512 threads, two CTAs per SM. Experiment build -DSCHIC_K4C_WIN_BITS=17: 128 KB table,
+// 1024 threads, one CTA per SM, counts up to 32767.
+constexpr int K4C_THREADS = K4C_WIN_BITS == 16 ? 512 : 1024;
+#ifndef K4C_CTAS_DEF
+#define K4C_CTAS_DEF (SCHIC_K4C_WIN_BITS == 16 ? 2 : 1)
+#endif
+constexpr int K4C_CTAS = K4C_CTAS_DEF;                        // CTAs per SM the kernel is built for (register budget)
 
 __device__ __forceinline__ bool k4c_usable(const uint32_t* __restrict__ flags, uint32_t esc_limit) {
     return flags[0] == 0u && flags[1] <= esc_limit;
@@ -52,7 +62,7 @@ int k4c_window_count(uint32_t max_feature) { return (int)(max_feature >> K4C_WIN
 
 // ---- per-fit preparation: norms, window directory, packed stream, flags -- one pass over ids + values -------------
 // dir[row][w] = offset (from the row start) of the first non-zero with (id >> 17) >= w, w = 0..n_windows.
-// flags[0] |= 1: a value is not an integer in [0, 32767]; flags[1] += number of values >= 255; flags[2] = 1: an id
+// flags[0] |= 1: a value is not an integer in [0, 65535]; flags[1] += number of values >= 255; flags[2] = 1: an id
 // lies beyond the last window (wrong feature-range hint; such ids are clamped into a window no slice covers).
 // packed may be nullptr (directory + norms only); dir may be nullptr (norms + flags only).
 __global__ void __launch_bounds__(256)
@@ -129,25 +139,55 @@ __device__ __noinline__ uint32_t k4c_escape_value(const uint32_t* __restrict__ q
     return lo < qn ? (__ldg(qp + lo) & K4C_CNT_MASK) : 0u;
 }
 
+// Candidate order of every query for the rerank kernel: columns of the launch's candidate slice sorted by row length
+// (descending, then by column). The rerank kernel gives each slice to 8 lanes and runs four slices per warp in lock
+// step, so neighbours in this order -- rows of similar length, hence window slices of similar length -- share a warp.
+__global__ void __launch_bounds__(128)
+k4c_order_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ cand_idx,
+                 const int32_t* __restrict__ cand_nvalid, int kcand, int P, K4Chunk ck, const uint32_t* __restrict__ flags,
+                 uint32_t esc_limit, int32_t* __restrict__ order) {
+    if (!k4c_usable(flags, esc_limit)) return;
+    extern __shared__ unsigned long long okeys[];
+    const int64_t q = blockIdx.x;
+    const int ncand = max(0, min((cand_idx ? cand_nvalid[q] : ck.n_all) - ck.cand_off, kcand));
+    for (int c = threadIdx.x; c < P; c += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (c < ncand) {
+            const int32_t d = cand_idx ? cand_idx[q * ck.cand_stride + ck.cand_off + c] : ck.cand_off + c;
+            const uint32_t len = (uint32_t)(indptr[d + 1] - indptr[d]);
+            key = ((unsigned long long)(~len) << 32) | (unsigned long long)(uint32_t)c;
+        }
+        okeys[c] = key;
+    }
+    bitonic_sort_shared(okeys, P);
+    for (int c = threadIdx.x; c < kcand; c += blockDim.x) order[q * (int64_t)kcand + c] = c < ncand ? (int32_t)(uint32_t)okeys[c] : -1;
+}
+
 // One CTA = (window group g, query q); blockIdx.x = g * nq + q. dotacc [nq, kcand] uint64, zeroed by the caller.
-// Per window three barriers (un-build | build | stream). What would otherwise sit exposed between them is taken out of
-// the phases: the query's keys of the NEXT window are fetched into registers during the stream phase (and the same
-// registers un-build the table afterwards), and every warp issues the loads of its first slice of the next window
-// (statically assigned: candidate = warp index) before it waits at the barrier that ends the current one.
-__global__ void __launch_bounds__(K4C_THREADS, 1)
+// 512 threads and a 64 KB table, so that K4C_CTAS CTAs share an SM: while one waits at a barrier or for its loads, the
+// others issue. Per window three barriers (un-build | build | stream). A window's slice of one candidate (~120 non-zeros
+// at S10) is far too short to amortise a warp-wide set-up and reduction, so the unit of work is 8 lanes per slice, four
+// slices per warp, 64 per CTA, statically assigned in the length-sorted candidate order: no hand-out atomics, a 3-step
+// reduction. Every lane group walks its own sequence of BATCHES (4 x 16 bytes per lane = 128 non-zeros; a typical slice
+// is one batch) -- slice after slice, window after window -- and always holds the next batch of that sequence in
+// registers while the current one is probed: loads cross the barriers (they do not depend on the table), as do the
+// query's keys of the next window, which later un-build the table from the same registers.
+// A probe is LEA.HI (table address), LDS.U8, IDP.2A (count x table byte accumulated; the id half of the word meets a
+// zero byte): three instructions per candidate non-zero.
+template <int LPS>     // lanes per slice: 8 (default) or 4
+__global__ void __launch_bounds__(K4C_THREADS, K4C_CTAS)
 k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ packed,
                   const uint32_t* __restrict__ dir, int n_windows, int wg, int64_t q_row0, int64_t nq,
-                  const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_nvalid, int kcand, K4Chunk ck,
-                  const uint32_t* __restrict__ flags, uint32_t esc_limit, unsigned long long* __restrict__ dotacc) {
+                  const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_nvalid,
+                  const int32_t* __restrict__ order, int kcand, K4Chunk ck, const uint32_t* __restrict__ flags,
+                  uint32_t esc_limit, unsigned long long* __restrict__ dotacc) {
     if (!k4c_usable(flags, esc_limit)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint8_t* tab = smem_raw;                                                            // [K4C_TAB]
-    unsigned long long* dotc = reinterpret_cast<unsigned long long*>(smem_raw + K4C_TAB);   // [kcand]
-    int64_t* cbeg = reinterpret_cast<int64_t*>(dotc + kcand);                           // [kcand] row start of the candidate
-    uint32_t* sl = reinterpret_cast<uint32_t*>(cbeg + kcand);                           // [kcand][wg + 1] window offsets
-    int32_t* cand = reinterpret_cast<int32_t*>(sl + (size_t)kcand * (wg + 1));          // [kcand]
-    uint32_t* qdir = reinterpret_cast<uint32_t*>(cand + kcand);                         // [wg + 1]
-    __shared__ int s_next, s_esc;
+    unsigned long long* dotc = reinterpret_cast<unsigned long long*>(smem_raw + K4C_TAB);   // [kcand] by sorted position
+    uint32_t* sl = reinterpret_cast<uint32_t*>(dotc + kcand);                           // [kcand][wg + 1] absolute positions
+    uint32_t* qdir = sl + (size_t)kcand * (wg + 1);                                     // [wg + 1]
+    __shared__ int s_esc;
 
     const int64_t g = blockIdx.x / nq;
     const int64_t q = blockIdx.x - g * nq;
@@ -156,8 +196,13 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
     const int nwin = min(wg, n_windows - w0);
     const int64_t nw1 = (int64_t)n_windows + 1;
     const int wg1 = wg + 1;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr int NWARPS = K4C_THREADS / 32;
+    const int lane = threadIdx.x & 31;
+    const int ql = lane & (LPS - 1);                       // lane within its group of LPS
+    const int quad = threadIdx.x / LPS;                    // lane group = sorted candidate position (mod NQ)
+    constexpr int NQ = K4C_THREADS / LPS;
+    constexpr int NB = 4;                                  // 16-byte words per lane and batch
+    constexpr uint32_t BATCH = (uint32_t)LPS * NB * 4u;    // non-zeros per batch (128 / 64)
+    const uint32_t qmask = (LPS == 8 ? 0xFFu : 0xFu) << (lane & ~(LPS - 1));
     const int ncand = max(0, min((cand_idx ? cand_nvalid[q] : ck.n_all) - ck.cand_off, kcand));
 
     for (int w = threadIdx.x; w <= nwin; w += K4C_THREADS) qdir[w] = __ldg(dir + qrow * nw1 + w0 + w);
@@ -178,51 +223,70 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
     int j = next_window(0);
     prefetch_keys(j);
 
-    for (int c = threadIdx.x; c < ncand; c += K4C_THREADS) {
-        const int32_t d = cand_idx ? cand_idx[q * ck.cand_stride + ck.cand_off + c] : ck.cand_off + c;
-        cand[c] = d;
-        cbeg[c] = indptr[d];
-        dotc[c] = 0ull;
-    }
+    for (int c = threadIdx.x; c < ncand; c += K4C_THREADS) dotc[c] = 0ull;
     {
+        // absolute stream positions of every (sorted candidate, window border) of this group (total nnz < 2^32)
         const int per = nwin + 1, total = ncand * per;
         for (int x = threadIdx.x; x < total; x += K4C_THREADS) {
-            const int c = x / per, jj = x - c * per;
+            const int i = x / per, jj = x - i * per;
+            const int c = __ldg(order + q * (int64_t)kcand + i);
             const int32_t d = cand_idx ? cand_idx[q * ck.cand_stride + ck.cand_off + c] : ck.cand_off + c;
-            sl[c * wg1 + jj] = __ldg(dir + (int64_t)d * nw1 + w0 + jj);
+            sl[i * wg1 + jj] = (uint32_t)(indptr[d] + (int64_t)__ldg(dir + (int64_t)d * nw1 + w0 + jj));
         }
     }
     for (int i = threadIdx.x; i < K4C_TAB / 16; i += K4C_THREADS)
         reinterpret_cast<uint4*>(tab)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();                                       // sl complete
 
-    // streaming state of the warp; a slice is read as aligned 16-byte words, `lead` elements before its start masked
-    const uint4* __restrict__ base = nullptr;
-    int n = 0, lead = 0, off = 0;
-    uint4 nx[K4C_U];
-    bool pref = false;                                     // nx holds the first block of slice (wid, window j)
-    auto setup = [&](int c, int jw) {
-        const int64_t ys = cbeg[c] + sl[c * wg1 + jw];
-        lead = (int)(ys & 3);
-        n = (int)(sl[c * wg1 + jw + 1] - sl[c * wg1 + jw]) + lead;
-        base = reinterpret_cast<const uint4*>(packed + (ys - lead));
-        off = 0;
-    };
-    auto load = [&]() {
-        if (off + K4C_BLK <= n) {                          // warp-uniform: full block, no guards
-#pragma unroll
-            for (int u = 0; u < K4C_U; ++u) nx[u] = __ldg(base + (off >> 2) + lane + 32 * u);
-        } else {
-#pragma unroll
-            for (int u = 0; u < K4C_U; ++u)
-                nx[u] = off + 4 * (lane + 32 * u) < n ? __ldg(base + (off >> 2) + lane + 32 * u) : make_uint4(0u, 0u, 0u, 0u);
+    // ---- the lane group's batch sequence -----------------------------------------------------------------------
+    // A slice [ys, ye) is read as its 16-byte aligned interior [A, B) with 128-bit loads (lane ql takes words ql, ql + 8,
+    // ... of every batch; words beyond B are zero and contribute nothing) plus <= 3 head and <= 3 tail elements: one
+    // 32-bit load on lanes 0-2 / 4-6 of the group, probed with the slice's first batch.
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    int it_i = quad - NQ, it_j = j;                        // slice the iterator reads (advanced before use)
+    uint32_t it_p = 0u, it_B = 0u;                         // next batch position / interior end of that slice
+    uint4 h[NB];                                           // look-ahead batch
+    uint32_t h_sx = 0u, h_tx = 0u;                         // its head / tail boundary element (first batch of a slice, else 0)
+    int h_i = 0, h_j = nwin;                               // its slice; h_j == nwin: the sequence is exhausted
+    bool h_last = false;
+    auto advance = [&]() {
+        h_sx = 0u; h_tx = 0u;
+        if (it_p >= it_B) {                                // open the next non-empty slice of this lane group
+            uint32_t ys = 0u, ye = 0u;
+            for (;;) {
+                it_i += NQ;
+                if (it_i >= ncand) { it_i = quad; it_j = next_window(it_j + 1); }
+                if (it_j >= nwin || quad >= ncand) { h_j = nwin; return; }
+                ys = sl[it_i * wg1 + it_j]; ye = sl[it_i * wg1 + it_j + 1];
+                if (ye > ys) break;
+            }
+            it_p = min((ys + 3u) & ~3u, ye);
+            it_B = max(it_p, ye & ~3u);
+            if (ql < (int)(it_p - ys)) h_sx = __ldg(packed + ys + ql);           // <= 3 elements before the interior
+            if (ql < (int)(ye - it_B)) h_tx = __ldg(packed + it_B + ql);         // <= 3 elements behind it
         }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const uint32_t p = it_p + 4u * ql + 4u * LPS * u;
+            h[u] = p < it_B ? __ldg(reinterpret_cast<const uint4*>(packed + p)) : zero4;
+        }
+        h_i = it_i; h_j = it_j;
+        it_p += BATCH;
+        h_last = it_p >= it_B;
     };
+    it_j = j;
+    if (quad < ncand) {
+        // (the first call must start at window j itself: step the window back so that the wrap-around lands on it)
+        it_i = quad - NQ;
+        advance();
+    }
 
+    unsigned long long acc = 0ull;
     while (j < nwin) {
         const uint32_t k0 = qdir[j], k1 = qdir[j + 1];
         const uint32_t qc0 = qn0, qc1 = qn1;               // this window's keys (prefetched)
-        __syncthreads();                                   // table clear / previous un-build done, slices visible
-        // ---- build: tab[id mod 2^17] = min(count, 255) ------------------------------------------------------
+        __syncthreads();                                   // table clear / previous un-build done
+        // ---- build: tab[id mod 2^16] = min(count, 255) ------------------------------------------------------
         bool any_big = false;
         {
             const uint32_t i0 = k0 + threadIdx.x;
@@ -236,103 +300,54 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
             }
         }
         if (any_big) s_esc = j + 1;                        // (j + 1 never repeats within a CTA: no reset needed)
-        if (threadIdx.x == 0) s_next = NWARPS;             // candidates 0..31 are the warps' static first slices
         const int jn = next_window(j + 1);
         prefetch_keys(jn);                                 // consumed at the top of the next iteration
         __syncthreads();
-        // ---- stream: every warp walks a flattened sequence of (candidate, 256-non-zero block) pairs; after its
-        // static first candidate they are handed out dynamically; the next block's loads are in flight while the
-        // current one is probed ---------------------------------------------------------------------------------
+        // ---- stream: this lane group's batches of window j ------------------------------------------------------------
         {
             const bool esc = s_esc == j + 1;
             const uint32_t* __restrict__ qp = packed + xb + k0;
             const int qn = (int)(k1 - k0);
-            auto fetch = [&]() {                           // next candidate with a non-empty slice, or ncand
-                int c;
-                do {
-                    c = 0;
-                    if (lane == 0) c = atomicAdd(&s_next, 1);
-                    c = __shfl_sync(0xffffffffu, c, 0);
-                } while (c < ncand && sl[c * wg1 + j + 1] <= sl[c * wg1 + j]);
-                return c;
-            };
-            int c;
-            if (pref) {
-                c = wid;
-            } else if (wid < ncand && sl[wid * wg1 + j + 1] > sl[wid * wg1 + j]) {
-                c = wid; setup(c, j); load();
-            } else {
-                c = fetch();
-                if (c < ncand) { setup(c, j); load(); }
-            }
-            pref = false;
-            unsigned long long acc = 0ull;
-            while (c < ncand) {
-                uint4 cur[K4C_U];
+            while (h_j == j) {
+                uint4 v[NB];
 #pragma unroll
-                for (int u = 0; u < K4C_U; ++u) cur[u] = nx[u];
-                const int cur_c = c, cur_off = off, cur_n = n, cur_lead = lead;
-                off += K4C_BLK;
-                const bool done = off >= n;                // last block of the current candidate
-                if (done) {
-                    c = fetch();
-                    if (c < ncand) setup(c, j);
-                }
-                if (c < ncand) load();
-                // mask what lies outside the slice (p = 0: table byte x count 0 contributes nothing)
-                if (!((cur_off > 0 || cur_lead == 0) && cur_off + K4C_BLK <= cur_n)) {
-#pragma unroll
-                    for (int u = 0; u < K4C_U; ++u) {
-                        const int e0 = cur_off + 4 * (lane + 32 * u);
-                        if (e0 < cur_lead || e0 >= cur_n) cur[u].x = 0u;
-                        if (e0 + 1 < cur_lead || e0 + 1 >= cur_n) cur[u].y = 0u;
-                        if (e0 + 2 < cur_lead || e0 + 2 >= cur_n) cur[u].z = 0u;
-                        if (e0 + 3 < cur_lead || e0 + 3 >= cur_n) cur[u].w = 0u;
-                    }
-                }
-                uint32_t a32 = 0u;                         // 8 products of (<= 255) x (<= 32767): < 2^26
+                for (int u = 0; u < NB; ++u) v[u] = h[u];
+                const uint32_t sx = h_sx, tx = h_tx;
+                const int cur_i = h_i;
+                const bool last = h_last;
+                advance();                                 // next batch in flight while this one is probed
                 if (!esc) {
+                    uint32_t a32 = k4c_mac(sx, (uint32_t)tab[sx >> K4C_CNT_BITS], 0u);   // <= 18 products < 2^24 each
+                    a32 = k4c_mac(tx, (uint32_t)tab[tx >> K4C_CNT_BITS], a32);
 #pragma unroll
-                    for (int u = 0; u < K4C_U; ++u) {
-                        a32 += (uint32_t)tab[cur[u].x >> K4C_CNT_BITS] * (cur[u].x & K4C_CNT_MASK);
-                        a32 += (uint32_t)tab[cur[u].y >> K4C_CNT_BITS] * (cur[u].y & K4C_CNT_MASK);
-                        a32 += (uint32_t)tab[cur[u].z >> K4C_CNT_BITS] * (cur[u].z & K4C_CNT_MASK);
-                        a32 += (uint32_t)tab[cur[u].w >> K4C_CNT_BITS] * (cur[u].w & K4C_CNT_MASK);
+                    for (int u = 0; u < NB; ++u) {
+                        a32 = k4c_mac(v[u].x, (uint32_t)tab[v[u].x >> K4C_CNT_BITS], a32);
+                        a32 = k4c_mac(v[u].y, (uint32_t)tab[v[u].y >> K4C_CNT_BITS], a32);
+                        a32 = k4c_mac(v[u].z, (uint32_t)tab[v[u].z >> K4C_CNT_BITS], a32);
+                        a32 = k4c_mac(v[u].w, (uint32_t)tab[v[u].w >> K4C_CNT_BITS], a32);
                     }
+                    acc += a32;
                 } else {
                     // this window of the query holds counts >= 255: table bytes of 255 are looked up exactly
+                    auto probe = [&](uint32_t w) {
+                        const uint32_t t = w >> K4C_CNT_BITS, cnt = w & K4C_CNT_MASK;
+                        const uint32_t tv = tab[t];
+                        acc += (unsigned long long)(tv * cnt);
+                        if (tv == 255u && cnt != 0u)
+                            acc += (unsigned long long)(k4c_escape_value(qp, qn, t) - 255u) * (unsigned long long)cnt;
+                    };
+                    probe(sx);
+                    probe(tx);
 #pragma unroll
-                    for (int u = 0; u < K4C_U; ++u) {
-                        const uint32_t pw[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
-#pragma unroll
-                        for (int s = 0; s < 4; ++s) {
-                            const uint32_t t = pw[s] >> K4C_CNT_BITS, cnt = pw[s] & K4C_CNT_MASK;
-                            const uint32_t tv = tab[t];
-                            a32 += tv * cnt;
-                            if (tv == 255u && cnt != 0u)
-                                acc += (unsigned long long)(k4c_escape_value(qp, qn, t) - 255u) * (unsigned long long)cnt;
-                        }
-                    }
+                    for (int u = 0; u < NB; ++u) { probe(v[u].x); probe(v[u].y); probe(v[u].z); probe(v[u].w); }
                 }
-                acc += a32;
-                if (done) {
-                    unsigned long long tot;
-                    if (!__any_sync(0xffffffffu, (acc >> 27) != 0ull)) {
-                        tot = __reduce_add_sync(0xffffffffu, (uint32_t)acc);      // 32 values < 2^27
-                    } else {
-                        tot = acc;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-                    }
-                    if (lane == 0) dotc[cur_c] += tot;     // only this warp touches cur_c in this window
+                if (last) {
+                    acc += __shfl_xor_sync(qmask, acc, 1);
+                    acc += __shfl_xor_sync(qmask, acc, 2);
+                    if (LPS == 8) acc += __shfl_xor_sync(qmask, acc, 4);
+                    if (ql == 0) dotc[cur_i] += acc;       // only this lane group touches position cur_i
                     acc = 0ull;
                 }
-            }
-            // the warp's first slice of the NEXT window: loads issued now, consumed after the barriers
-            if (jn < nwin && wid < ncand && sl[wid * wg1 + jn + 1] > sl[wid * wg1 + jn]) {
-                setup(wid, jn);
-                load();
-                pref = true;
             }
         }
         // ---- un-build: zero exactly the bytes this window set ----------------------------------------------------
@@ -346,8 +361,8 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
         j = jn;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < ncand; c += K4C_THREADS)
-        if (dotc[c] != 0ull) atomicAdd(&dotacc[q * (int64_t)kcand + c], dotc[c]);
+    for (int i = threadIdx.x; i < ncand; i += K4C_THREADS)
+        if (dotc[i] != 0ull) atomicAdd(&dotacc[q * (int64_t)kcand + __ldg(order + q * (int64_t)kcand + i)], dotc[i]);
 }
 
 // distances from the exact integer dot products, (distance asc, index asc) order, keep k
@@ -393,7 +408,7 @@ k4c_finalize_kernel(const uint32_t* __restrict__ flags, uint32_t esc_limit, cons
 // windows per group: the group's share of the packed stream (4 B x nnz x wg / n_windows) should fit the part of L2 we
 // want it to live in (group_bytes), and the per-candidate window offsets must fit in shared memory
 int k4c_windows_per_group(int n_windows, int64_t db_nnz, int kcand, int64_t group_bytes) {
-    const int64_t smem_left = 220 * 1024 - K4C_TAB - (int64_t)kcand * (8 + 8 + 4) - 64;
+    const int64_t smem_left = (int64_t)(225 * 1024 / K4C_CTAS - 1024) - K4C_TAB - (int64_t)kcand * 8 - 64;
     if (smem_left < (int64_t)kcand * 8) return -1;
     int64_t wg_smem = smem_left / ((int64_t)kcand * 4) - 1;                  // (wg + 1) * 4 * kcand + (wg + 1) * 4 <= left
     while (wg_smem > 1 && (wg_smem + 1) * 4 * ((int64_t)kcand + 1) > smem_left) --wg_smem;
@@ -406,7 +421,8 @@ int k4c_windows_per_group(int n_windows, int64_t db_nnz, int kcand, int64_t grou
     return (int)wg;
 }
 
-size_t k4c_dotacc_elems(int64_t nq, int kcand) { return (size_t)nq * (size_t)kcand; }
+// scratch of one launch: nq * kcand uint64 dot products followed by nq * kcand int32 of candidate order
+size_t k4c_dotacc_elems(int64_t nq, int kcand) { return (size_t)nq * (size_t)kcand + ((size_t)nq * (size_t)kcand + 1) / 2; }
 
 // One launch (pair) over candidate columns [cand_off, cand_off + kcand); same output contract as launch_rerank.
 // d_dotacc: >= nq * kcand uint64 scratch (zeroed here). Returns launches, or -1 when kcand does not fit.
@@ -417,24 +433,31 @@ int launch_rerank_counts(const int64_t* d_indptr, const uint32_t* d_packed, cons
                          int32_t* d_nvalid_out, int n_all, const uint32_t* d_flags, uint32_t esc_limit,
                          unsigned long long* d_dotacc, cudaStream_t stream) {
     if (nq <= 0) return 0;
-    if (kcand > 1024) return -1;
+    if (kcand > 1024 || db_nnz >= 0xFFFFFFF0ll) return -1;      // (stream positions are kept as 32-bit in shared memory)
     const int wg = k4c_windows_per_group(n_windows, db_nnz, kcand, group_bytes);
     if (wg < 1) return -1;
     const int64_t groups = (n_windows + wg - 1) / wg;
     if (groups * nq > 0x7FFFFFFFll) return -1;
     const K4Chunk ck{cand_stride, cand_off, out_stride, out_off, final, n_all};
-    const size_t smem = (size_t)K4C_TAB + (size_t)kcand * (8 + 8 + 4) + (size_t)kcand * (wg + 1) * 4 + (size_t)(wg + 1) * 4 + 16;
-    if (smem > 220 * 1024) return -1;
+    const size_t smem = (size_t)K4C_TAB + (size_t)kcand * 8 + (size_t)kcand * (wg + 1) * 4 + (size_t)(wg + 1) * 4 + 16;
+    if (smem > (size_t)(225 * 1024 / K4C_CTAS - 1024)) return -1;
     if (cudaMemsetAsync(d_dotacc, 0, (size_t)nq * kcand * sizeof(unsigned long long), stream) != cudaSuccess) return -1;
-    cudaFuncSetAttribute(k4c_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k4c_rerank_kernel<<<(unsigned)(groups * nq), K4C_THREADS, smem, stream>>>(
-        d_indptr, d_packed, d_dir, n_windows, wg, q_row0, nq, d_cand_idx, d_cand_nvalid, kcand, ck, d_flags, esc_limit,
-        d_dotacc);
+    int32_t* d_order = reinterpret_cast<int32_t*>(d_dotacc + (size_t)nq * kcand);
     const int P = next_pow2(kcand);
+    k4c_order_kernel<<<(unsigned)nq, 128, (size_t)P * 8, stream>>>(d_indptr, d_cand_idx, d_cand_nvalid, kcand, P, ck, d_flags,
+                                                                   esc_limit, d_order);
+    // lanes per slice: 8 unless the lists are long enough to keep every 4-lane group busy (or SCHIC_K4_LPS says so)
+    int lps = kcand > K4C_THREADS / 8 ? 4 : 8;
+    if (const char* e = getenv("SCHIC_K4_LPS")) lps = atoi(e) == 4 ? 4 : 8;
+    auto kern = lps == 4 ? k4c_rerank_kernel<4> : k4c_rerank_kernel<8>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)(groups * nq), K4C_THREADS, smem, stream>>>(
+        d_indptr, d_packed, d_dir, n_windows, wg, q_row0, nq, d_cand_idx, d_cand_nvalid, d_order, kcand, ck, d_flags,
+        esc_limit, d_dotacc);
     k4c_finalize_kernel<<<(unsigned)nq, 256, (size_t)P * 8, stream>>>(d_flags, esc_limit, d_dotacc, d_norm2, q_row0,
                                                                       d_cand_idx, d_cand_nvalid, kcand, P, k, ck, d_idx_out,
                                                                       d_dist_out, d_nvalid_out);
-    return 2;
+    return 3;
 }
 
 }  // namespace schic

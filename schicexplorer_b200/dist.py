@@ -146,7 +146,7 @@ class ShardedMinHash:
             api.set_feature_range(self.h, int(n_features))
         self.shard_nnz = None if shard_nnz is None else [int(x) for x in shard_nnz]
         # integer_counts: the caller states that the values are small non-negative integers (Hi-C contact counts). The
-        # exact rerank then exchanges ONE packed 32-bit word per non-zero ((id mod 2^17) << 15 | count, produced by the
+        # exact rerank then exchanges ONE packed 32-bit word per non-zero ((id mod 2^16) << 16 | count, produced by the
         # owning rank's preparation pass) instead of the id and value arrays -- half the NVLink volume. The statement is
         # verified on the device (flags of the preparation pass): if it does not hold, the next synchronising call
         # raises instead of returning wrong distances.

@@ -386,10 +386,10 @@ def _count_rows(rng, n_rows, ncols, lens, hi=40, pool=None):
 def test_counts_rerank_kernel(cuda, oracle, monkeypatch):
     """The counts kernel (k4c_rerank.cu) on its own edge cases, always against the oracle:
     (a) counts >= 255 in query rows (table bytes saturate at 255, resolved by the escape search), up to the largest
-        packable count 32767; (b) windows with more than 2048 query keys (build / un-build loop past the two
+        packable count 65535; (b) windows with more than 2048 query keys (build / un-build loop past the two
         prefetched keys); (c) window groups: one group, and one window per group (many CTAs per query, global
         accumulation); (d) data the kernel must hand to the generic float kernels -- non-integer values, a count above
-        32767, more than 1/64 of the values >= 255 -- decided by the device flag, with identical results;
+        65535, more than 1/64 of the values >= 255 -- decided by the device flag, with identical results;
     (e) brute-force exact kNN (every row a candidate, 1024-row chunks) through the same kernel."""
     rng = np.random.default_rng(41)
     ncols = 1 << 22
@@ -419,13 +419,13 @@ def test_counts_rerank_kernel(cuda, oracle, monkeypatch):
     # (a) a few large counts (escapes) in some rows, incl. the largest packable value
     Xa = X.copy()
     big = rng.choice(Xa.nnz, size=Xa.nnz // 200, replace=False)
-    Xa.data[big] = rng.integers(255, 32768, size=len(big)).astype(np.float64)
-    Xa.data[big[:3]] = [255.0, 256.0, 32767.0]
+    Xa.data[big] = rng.integers(255, 65536, size=len(big)).astype(np.float64)
+    Xa.data[big[:3]] = [255.0, 256.0, 65535.0]
     check(Xa, "k4c_rerank_kernel")
     # (d) not packable: every variant must come out of the generic kernel, same answers as the oracle
     Xf = X.copy(); Xf.data = Xf.data * 0.5                               # non-integer values
     check(Xf, "k4_rerank_window_kernel")
-    Xb = X.copy(); Xb.data[7] = 32768.0                                  # one count beyond 15 bits
+    Xb = X.copy(); Xb.data[7] = 65536.0                                  # one count beyond 16 bits
     check(Xb, "k4_rerank_window_kernel")
     Xm = X.copy(); Xm.data[rng.choice(Xm.nnz, size=Xm.nnz // 20, replace=False)] = 300.0   # too many escapes
     check(Xm, "k4_rerank_window_kernel")
