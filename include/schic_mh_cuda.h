@@ -131,6 +131,14 @@ int schic_mh_set_feature_range(schic_mh_handle* h, uint64_t n_features);
  * [6] d2h, [7] rerank preparation (row norms, window directory), [8] sum; n_out >= 9. Synchronises the stream. */
 int schic_mh_stage_ms(schic_mh_handle* h, float* out, int32_t n_out);
 
+/* How K1 of the most recent fit got its shared hash table (k1_table.cu): 0 no table (per-cell kernels), 1 built from the
+ * batch's own ids, 2 built for every id of the range declared with schic_mh_set_feature_range, 3 the whole-range table
+ * of an earlier fit on this handle re-used. Such a table depends only on (range, number of hash functions, hash width)
+ * -- not on the data -- so the handle keeps it across fits of the same shape (repeated builds, partial_fit chunks,
+ * every rank of a sharded run): the second fit of a shape builds it, later ones only look up. SCHIC_K1_NO_CACHE=1
+ * (environment) disables the re-use. Results are bit-identical either way. */
+int schic_mh_k1_table_state(schic_mh_handle* h, int32_t* state_out);
+
 /* Number of kernels this handle has launched so far. */
 int schic_mh_launch_count(schic_mh_handle* h, int64_t* n_out);
 

@@ -60,7 +60,7 @@ CUDA_SYMBOLS = (
     "schic_mh_rerank_prep_rows", "schic_mh_set_database_prep_device", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free", "schic_mh_kneighbors_exact_device",
-    "schic_mh_fit_csr_device_at", "schic_mh_kneighbors_graph_device", "schic_mh_rerank_kernel_name",
+    "schic_mh_fit_csr_device_at", "schic_mh_kneighbors_graph_device", "schic_mh_rerank_kernel_name", "schic_mh_k1_table_state",
 )
 
 # the dense-graph PCA post-step, CUDA library only (include/schic_pca.h)
@@ -126,6 +126,7 @@ class CApi:
             L.schic_mh_set_stream.argtypes = [_vp, _vp]
             L.schic_mh_stage_ms.argtypes = [_vp, _vp, _i32]
             L.schic_mh_launch_count.argtypes = [_vp, C.POINTER(_i64)]
+            L.schic_mh_k1_table_state.argtypes = [_vp, C.POINTER(_i32)]
             L.schic_mh_synchronize.argtypes = [_vp]
             L.schic_int32_peak.argtypes = [_i32, _i32, _vp]
             L.schic_k1_variant_ms.argtypes = [_i32, _i64, _i64, _vp, _vp, _i32, _vp, _i32, C.POINTER(C.c_float)]
@@ -382,6 +383,14 @@ class CApi:
         self.check(self.lib.schic_mh_stage_ms(_vp(h), _ptr(out), 9))
         names = ("h2d", "signatures", "collisions", "select", "rerank", "graph", "d2h", "rerank_prep", "total")
         return dict(zip(names, out.tolist()))
+
+    K1_TABLE_STATES = ("none", "built from the batch's ids", "whole-range table built", "whole-range table re-used")
+
+    def k1_table_state(self, h) -> int:
+        """0 no table, 1 built from the batch's ids, 2 whole-range table built, 3 cached whole-range table re-used."""
+        n = _i32()
+        self.check(self.lib.schic_mh_k1_table_state(_vp(h), C.byref(n)))
+        return n.value
 
     def launch_count(self, h) -> int:
         n = _i64()

@@ -96,6 +96,13 @@ struct schic_mh_handle {
     DevBuf<unsigned char> k1t_present; DevBuf<unsigned long long> k1t_slot; DevBuf<uint16_t> k1t_entries;
     DevBuf<uint32_t> k1t_counters;
     bool k1t_prebuilt = false;                // the table for this batch was built ahead of the upload (phase 1)
+    // A table built for EVERY id of the hinted range (phase 1) does not depend on the data, only on (range, H, hash width)
+    // and -- for speed, not for exactness -- on the mean row length behind its threshold: it is kept and re-used by later
+    // fits of the same shape (repeated builds, partial_fit chunks, every rank of a sharded run). `seen_*`: the key of the
+    // last batch that had to build from its own ids; the second batch of that shape builds the whole-range table.
+    struct { bool valid = false; uint32_t max_id = 0; int H = 0, width = 0; double mean_row = 0.0;
+             uint32_t seen_max_id = 0; int seen_H = 0, seen_width = 0; } k1t_cache;
+    int k1_table_state = 0;                   // K1 of the last fit: 0 no table, 1 built from the batch's ids, 2 whole-range table built, 3 cached table re-used
     std::vector<uint32_t> host_lo, host_hi;   // split 64-bit ids of the last fit (must outlive an async upload)
     DevBuf<unsigned char> val_stage;          // narrow (uint16 / uint8) counts as uploaded, before widening
     int64_t count_budget = 0;                 // elements of the uint16 count matrix we allow ourselves (cached)
@@ -248,6 +255,18 @@ int check_range_flag(schic_mh_handle* h) {
     return 0;
 }
 
+bool k1t_cache_hit(const schic_mh_handle* h, uint32_t max_id, int64_t n_rows, int64_t nnz) {
+    const auto& c = h->k1t_cache;
+    if (!c.valid || c.max_id != max_id || c.H != h->p.number_of_hash_functions || c.width != h->p.hash_width || n_rows <= 0) return false;
+    if (getenv("SCHIC_K1_NO_CACHE")) return false;
+    const double r = ((double)nnz / (double)n_rows) / c.mean_row;
+    return r > 0.6 && r < 1.7;      // the cached threshold still fits: a lower one only sends more (cell, j) to the exact fallback
+}
+void k1t_cache_store(schic_mh_handle* h, uint32_t max_id, int64_t n_rows, int64_t nnz) {
+    h->k1t_cache.valid = true; h->k1t_cache.max_id = max_id; h->k1t_cache.H = h->p.number_of_hash_functions;
+    h->k1t_cache.width = h->p.hash_width; h->k1t_cache.mean_row = (double)nnz / (double)std::max<int64_t>(1, n_rows);
+}
+
 // cheap test before anything touches the device: could this batch qualify for the shared-table path at all?
 bool k1_table_candidate(const schic_mh_handle* h, int64_t n_rows, int64_t nnz) {
     if (h->p.hash_width == 64 && h->have_hi) return false;      // ids >= 2^32: far beyond the per-id arrays
@@ -294,13 +313,44 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
             }
             if (mode == K1_TABLE ? (max_id < 134217728u && H <= 65535) : schic::k1t_applicable(n_rows, nnz, max_id, H)) {
                 const size_t ecap = schic::k1t_entries_capacity(n_rows, nnz, max_id, H);
-                ST_TRY(h->k1t_present.reserve((int64_t)max_id + 1, 0, s));
-                ST_TRY(h->k1t_slot.reserve((int64_t)max_id + 1, 0, s));
-                ST_TRY(h->k1t_entries.reserve((int64_t)ecap, 0, s));
+                const bool hinted = h->feature_range > 0 && h->feature_range <= 134217728ull && mode == K1_AUTO;
+                auto& c = h->k1t_cache;
+                int phase = 0;
+                if (hinted && k1t_cache_hit(h, max_id, n_rows, nnz)) {
+                    phase = 2;                            // whole-range table of an earlier fit: lookup + fallback only
+                    h->k1_table_state = 3;
+                } else if (hinted && !getenv("SCHIC_K1_NO_CACHE") &&
+                           ((double)h->feature_range * (double)H < 175.0 * (double)nnz ||
+                            (c.seen_max_id == max_id && c.seen_H == H && c.seen_width == h->p.hash_width))) {
+                    phase = 1;                            // build it for every id of the range, keep it
+                    h->k1_table_state = 2;
+                } else {
+                    c.valid = false;                      // the per-id arrays are about to hold this batch's own table
+                    c.seen_max_id = max_id; c.seen_H = H; c.seen_width = h->p.hash_width;
+                    h->k1_table_state = 1;
+                }
+                if (phase != 2) {
+                    ST_TRY(h->k1t_present.reserve((int64_t)max_id + 1, 0, s));
+                    ST_TRY(h->k1t_slot.reserve((int64_t)max_id + 1, 0, s));
+                    ST_TRY(h->k1t_entries.reserve((int64_t)ecap, 0, s));
+                }
                 ST_TRY(h->k1_scratch.reserve((int64_t)schic::k1t_items_bytes(n_rows, nnz), 0, s));
-                nl = schic::launch_signatures_table(h->p.hash_width, h->d_indptr() + r0, h->d_feat(), n_rows, nnz, pos0, max_id, H, sig,
-                                                      h->k1t_present.p, reinterpret_cast<uint2*>(h->k1t_slot.p),
-                                                      h->k1t_entries.p, ecap, h->k1t_counters.p, h->k1_scratch.p, 0, s);
+                nl = 0;
+                if (phase == 1) {
+                    c.valid = false;
+                    const int b = schic::launch_signatures_table(h->p.hash_width, nullptr, nullptr, n_rows, nnz, 0, max_id, H, nullptr,
+                                                                 h->k1t_present.p, reinterpret_cast<uint2*>(h->k1t_slot.p),
+                                                                 h->k1t_entries.p, ecap, h->k1t_counters.p, nullptr, 1, s);
+                    if (b < 0) return fail(SCHIC_ERR_CUDA, "K1 table build failed");
+                    nl += b;
+                    k1t_cache_store(h, max_id, n_rows, nnz);
+                    phase = 2;
+                }
+                const int r = schic::launch_signatures_table(h->p.hash_width, h->d_indptr() + r0, h->d_feat(), n_rows, nnz, pos0, max_id, H, sig,
+                                                             h->k1t_present.p, reinterpret_cast<uint2*>(h->k1t_slot.p),
+                                                             h->k1t_entries.p, phase == 2 ? (size_t)h->k1t_entries.cap : ecap,
+                                                             h->k1t_counters.p, h->k1_scratch.p, phase, s);
+                nl = r < 0 ? -1 : nl + r;
             }
         }
         if (nl < 0 && h->p.hash_width == 64) {
@@ -814,6 +864,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
         h->norm_of = nullptr; h->ext = false; h->db_ready = nullptr;
     }
     reset_stage(h, {ST_H2D, ST_SIG});
+    h->k1_table_state = 0;
     for (cudaEvent_t e : h->misc_ev) h->free_ev.push_back(e);
     h->misc_ev.clear();
     h->val_done = nullptr;
@@ -898,15 +949,22 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
         const uint32_t max_id = (uint32_t)(h->feature_range - 1);
         const size_t ecap = schic::k1t_entries_capacity(n_rows, nnz, max_id, H);
         ST_TRY(ensure_counters(h));
-        ST_TRY(h->k1t_present.reserve((int64_t)max_id + 1, 0, s));
-        ST_TRY(h->k1t_slot.reserve((int64_t)max_id + 1, 0, s));
-        ST_TRY(h->k1t_entries.reserve((int64_t)ecap, 0, s));
-        const int nl = schic::launch_signatures_table(h->p.hash_width, nullptr, nullptr, n_rows, nnz, 0, max_id, H, nullptr,
-                                                      h->k1t_present.p, reinterpret_cast<uint2*>(h->k1t_slot.p),
-                                                      h->k1t_entries.p, ecap, h->k1t_counters.p, nullptr, 1, s);
-        if (nl < 0) return fail(SCHIC_ERR_CUDA, "K1 table build failed");
-        add_launches(h, nl);
-        CU_TRY(cudaGetLastError());
+        if (k1t_cache_hit(h, max_id, n_rows, nnz)) {
+            h->k1_table_state = 3;                    // the whole-range table of an earlier fit is still there
+        } else {
+            h->k1t_cache.valid = false;
+            ST_TRY(h->k1t_present.reserve((int64_t)max_id + 1, 0, s));
+            ST_TRY(h->k1t_slot.reserve((int64_t)max_id + 1, 0, s));
+            ST_TRY(h->k1t_entries.reserve((int64_t)ecap, 0, s));
+            const int nl = schic::launch_signatures_table(h->p.hash_width, nullptr, nullptr, n_rows, nnz, 0, max_id, H, nullptr,
+                                                          h->k1t_present.p, reinterpret_cast<uint2*>(h->k1t_slot.p),
+                                                          h->k1t_entries.p, ecap, h->k1t_counters.p, nullptr, 1, s);
+            if (nl < 0) return fail(SCHIC_ERR_CUDA, "K1 table build failed");
+            add_launches(h, nl);
+            CU_TRY(cudaGetLastError());
+            k1t_cache_store(h, max_id, n_rows, nnz);
+            h->k1_table_state = 2;
+        }
         h->k1t_prebuilt = true;
     }
     while (c0 < n_rows) {
@@ -978,6 +1036,7 @@ static int fit_csr_device_impl(schic_mh_handle* h, int64_t n_rows, int64_t nnz, 
     ST_TRY(use_device(h));
     if (h->sliced) { CU_TRY(cudaStreamSynchronize(h->stream)); restore_fitted_signatures(h); }
     reset_stage(h, {ST_H2D, ST_SIG});
+    h->k1_table_state = 0;
     const int H = h->p.number_of_hash_functions;
     h->k1t_prebuilt = false;
     h->borrowed = true; h->b_indptr = d_indptr; h->b_feat = d_indices; h->b_val = d_data;
@@ -1278,6 +1337,13 @@ int schic_mh_stage_ms(schic_mh_handle* h, float* out, int32_t n_out) {
         sum += acc;
     }
     out[ST_COUNT] = sum;
+    return SCHIC_OK;
+}
+
+int schic_mh_k1_table_state(schic_mh_handle* h, int32_t* state_out) {
+    ST_TRY(check(h));
+    if (!state_out) return fail(SCHIC_ERR_INVALID_ARG, "null argument");
+    *state_out = h->k1_table_state;
     return SCHIC_OK;
 }
 

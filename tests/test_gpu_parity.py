@@ -488,6 +488,59 @@ def test_k1_shared_table_path(cuda, oracle, monkeypatch, H, width):
         assert np.array_equal(g.sig(), want)
 
 
+def test_k1_whole_range_table_is_kept_across_fits(cuda, oracle, monkeypatch):
+    """With the feature-range hint the shared K1 table can be built for EVERY id of the range; it then depends only on
+    (range, H, hash width), so the handle keeps it: first fit of a shape builds from its own ids (state 1), the second
+    builds the whole-range table (2), later ones -- also on DIFFERENT data of that shape -- only look up (3). Every fit
+    bit-identical to the oracle; SCHIC_K1_NO_CACHE switches the re-use off; another H or range invalidates."""
+    from schicexplorer_b200 import synth
+    import os
+    # full-length S10-like rows; the automatic table path needs >= 2 M non-zeros AND an id range <= nnz / 2
+    cfg = synth.SynthConfig(71, 1150)
+    ip, ix, dt, _ = synth.generate_csr(cfg, workers=min(16, os.cpu_count() or 1))
+    cfg2 = synth.SynthConfig(72, 1100)
+    ip2, ix2, dt2, _ = synth.generate_csr(cfg2, workers=min(16, os.cpu_count() or 1))
+    assert ip[-1] > 2 * cfg.chroms.nbins ** 2 and ip2[-1] > 2 * cfg.chroms.nbins ** 2
+    kw = dict(n_neighbors=5, fast=True, **REF_KWARGS)
+
+    def oracle_sig(a, b):
+        ho = oracle.create(number_of_cores=os.cpu_count() or 1, **kw)
+        oracle.fit_csr(ho, a, b, None, False)
+        sg = oracle.signatures(ho, 800)
+        oracle.destroy(ho)
+        return sg
+
+    want, want2 = oracle_sig(ip, ix), oracle_sig(ip2, ix2)
+    h = cuda.create(**kw)
+    cuda.set_feature_range(h, cfg.chroms.nbins ** 2)
+    states = []
+    for a, b, w in ((ip, ix, want), (ip, ix, want), (ip, ix, want), (ip2, ix2, want2), (ip, ix, want)):
+        cuda.fit_csr(h, a, b, None, False)
+        states.append(cuda.k1_table_state(h))
+        assert np.array_equal(cuda.signatures(h, 800), w)
+    # (a host fit of this size pre-builds the whole-range table while the ids upload when that is cheap enough; either
+    # way the table must be re-used from the third fit on at the latest)
+    assert states[2:] == [3, 3, 3] and states[0] in (1, 2) and states[1] in (2, 3), states
+    monkeypatch.setenv("SCHIC_K1_NO_CACHE", "1")
+    cuda.fit_csr(h, ip, ix, None, False)
+    assert cuda.k1_table_state(h) in (1, 2) and np.array_equal(cuda.signatures(h, 800), want)
+    monkeypatch.delenv("SCHIC_K1_NO_CACHE")
+    cuda.destroy(h)
+    # device-resident fits (the benchmark's loop): 1 -> 2 -> 3
+    import torch
+    dev = torch.device("cuda:0")
+    d_ip, d_ix = torch.from_numpy(ip).to(dev), torch.from_numpy(ix.view(np.int32)).to(dev)
+    h = cuda.create(**kw)
+    cuda.set_feature_range(h, cfg.chroms.nbins ** 2)
+    states = []
+    for _ in range(4):
+        cuda.fit_csr_device(h, len(ip) - 1, int(ip[-1]), d_ip.data_ptr(), d_ix.data_ptr(), None, False, indptr0=0)
+        states.append(cuda.k1_table_state(h))
+        assert np.array_equal(cuda.signatures(h, 800), want)
+    assert states == [1, 2, 3, 3], states
+    cuda.destroy(h)
+
+
 def test_async_host_fit(cuda, oracle):
     """schic_mh_fit_csr_async: returns before the value array has landed; results identical to the blocking call."""
     X = synth_csr(220, seed=33)
