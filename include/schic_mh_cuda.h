@@ -27,6 +27,18 @@ int schic_device_count(int32_t* n_out);
 int schic_mh_fit_csr_async(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
                            int32_t index_bits, const float* data, int32_t append);
 
+/* MinHash.fit straight from the arrays a scipy.sparse.csr_matrix holds (the matrix utilities.py:131 builds: float64 data,
+ * int32 or int64 indptr / indices, pageable memory): indptr_bits / index_bits = 32 | 64, data_kind = 0 float32, 1 uint16,
+ * 2 uint8, 3 float64 (data may be NULL when fast=1). A pool of host threads (params.number_of_cores, default: all) stages
+ * the arrays chunk by chunk into page-locked buffers owned by the handle -- ids as 32-bit words, values narrowed to
+ * uint8 / uint16 counts wherever a chunk holds only such integers (Hi-C counts do), else float32 -- while the calling
+ * thread uploads the chunks that are ready and queues K1 behind them: conversion, PCIe and hashing overlap, nothing is
+ * validated or copied by the Python side. async_upload != 0: return once everything is queued; the caller's arrays are
+ * no longer needed when the call returns (the staging buffers are the source of the copies). Ids >= 2^32 are refused
+ * (SCHIC_ERR_UNSUPPORTED: use schic_mh_fit_csr). */
+int schic_mh_fit_csr_host(schic_mh_handle* h, int64_t n_rows, const void* indptr, int32_t indptr_bits, const void* indices,
+                          int32_t index_bits, const void* data, int32_t data_kind, int32_t append, int32_t async_upload);
+
 /* MinHash.fit on a CSR shard already in HBM. The arrays are BORROWED (not copied) and must stay
  * valid until the next fit or destroy. d_indptr [n_rows+1] int64 (absolute positions into
  * d_indices/d_data), d_indices uint32, d_data float32 (may be NULL when fast=1). append must be 0. */

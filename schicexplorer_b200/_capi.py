@@ -60,7 +60,7 @@ CUDA_SYMBOLS = (
     "schic_mh_rerank_prep_rows", "schic_mh_set_database_prep_device", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free", "schic_mh_kneighbors_exact_device",
-    "schic_mh_fit_csr_device_at", "schic_mh_kneighbors_graph_device", "schic_mh_rerank_kernel_name", "schic_mh_k1_table_state",
+    "schic_mh_fit_csr_device_at", "schic_mh_kneighbors_graph_device", "schic_mh_rerank_kernel_name", "schic_mh_k1_table_state", "schic_mh_fit_csr_host",
 )
 
 # the dense-graph PCA post-step, CUDA library only (include/schic_pca.h)
@@ -118,6 +118,7 @@ class CApi:
             L.schic_mh_fit_csr_counts.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32]
             L.schic_mh_fit_csr_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _i32]
             L.schic_mh_kneighbors_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
+            L.schic_mh_fit_csr_host.argtypes = [_vp, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32]
             L.schic_mh_fit_csr_device_at.argtypes = [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32]
             L.schic_mh_kneighbors_graph_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
             L.schic_mh_signatures_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_i64)]
@@ -199,6 +200,27 @@ class CApi:
             data = np.ascontiguousarray(data, dtype=np.float32)
         fn = self.lib.schic_mh_fit_csr_async if async_upload else self.lib.schic_mh_fit_csr
         self.check(fn(_vp(h), len(indptr) - 1, _ptr(indptr), _ptr(indices), bits, _ptr(data), int(append)))
+
+    _HOST_KINDS = {np.dtype(np.float32): 0, np.dtype(np.uint16): 1, np.dtype(np.uint8): 2, np.dtype(np.float64): 3}
+
+    def fit_csr_host(self, h, indptr, indices, data, append: bool, async_upload: bool = True):
+        """CUDA back end: fit from scipy's own arrays (int32/int64 indptr and indices, float64/float32/uint8/uint16 data,
+        pageable memory) without a Python-side copy; staging, narrowing and upload happen inside the library on several
+        threads (include/schic_mh_cuda.h). Other dtypes are converted here first."""
+        if indptr.dtype.itemsize not in (4, 8) or indptr.dtype.kind not in "iu":
+            indptr = indptr.astype(np.int64)
+        if indices.dtype.itemsize not in (4, 8) or indices.dtype.kind not in "iu":
+            indices = indices.astype(np.int64)
+        indptr, indices = np.ascontiguousarray(indptr), np.ascontiguousarray(indices)
+        kind = -1
+        if data is not None:
+            if data.dtype not in self._HOST_KINDS:
+                data = data.astype(np.float64)
+            data = np.ascontiguousarray(data)
+            kind = self._HOST_KINDS[data.dtype]
+        self.check(self.lib.schic_mh_fit_csr_host(_vp(h), len(indptr) - 1, _ptr(indptr), indptr.dtype.itemsize * 8,
+                                                  _ptr(indices), indices.dtype.itemsize * 8, _ptr(data), kind, int(append),
+                                                  int(async_upload)))
 
     def n_fitted(self, h) -> int:
         n = _i64()

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libschic_mh.so")
 SOURCES = ["capi.cu", "k1_signatures.cu", "k1_table.cu", "k2_buckets.cu", "k3_collisions.cu", "k3_select.cu", "k4_rerank.cu", "k4c_rerank.cu", "k5_graph.cu",
-           "int_peak.cu", "pca_dense.cu"]
+           "int_peak.cu", "pca_dense.cu", "hostconv.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 # SCHIC_K1_ALL_VARIANTS=1 also compiles the 20 instruction-selection variants of K1 that
@@ -40,7 +40,7 @@ def build_cuda(force: bool = False, verbose: bool = False, variant: str = "", ex
 
     def compile_one(src):
         s = os.path.join(CSRC, src)
-        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        o = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         if force or _stale(o, [s] + headers):
             cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", s, "-o", o]
             if verbose:

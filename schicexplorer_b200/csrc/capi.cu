@@ -5,10 +5,12 @@
 // stage timing with CUDA events, and the D2H of the neighbour lists. There is no CPU compute
 // path in this file: without a usable GPU every entry point fails with SCHIC_ERR_NO_DEVICE.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>
@@ -70,7 +72,124 @@ const char* const kStageName[ST_COUNT] = {"schic:h2d", "schic:K1 signatures", "s
 
 namespace schic {
 int set_error(int code, const std::string& msg) { return fail(code, msg); }
+// hostconv.cpp
+bool narrow_f64_u8(const double* s, int64_t n, uint8_t* d);
+bool narrow_f64_u16(const double* s, int64_t n, uint16_t* d);
+bool narrow_f32_u8(const float* s, int64_t n, uint8_t* d);
+bool narrow_f32_u16(const float* s, int64_t n, uint16_t* d);
+void convert_f64_f32(const double* s, int64_t n, float* d);
+bool narrow_ids64(const uint64_t* s, int64_t n, uint32_t* lo);
 }  // namespace schic
+
+namespace {
+
+// Page-locked host buffer that can grow (contents are not kept).
+struct PinBuf {
+    unsigned char* p = nullptr;
+    size_t cap = 0;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    int reserve(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = n + n / 8;
+        if (cudaHostAlloc((void**)&p, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(SCHIC_ERR_OOM, "cudaHostAlloc of the upload staging buffer failed");
+        }
+        cap = want;
+        return 0;
+    }
+};
+
+// schic_mh_fit_csr_host: the caller's arrays are pageable and (values) float64 -- what scipy holds. A small pool of
+// worker threads stages them chunk by chunk into page-locked buffers in wire format (ids: 32-bit words; values: uint8 /
+// uint16 counts when every value of the chunk is such an integer, else float32) while the calling thread uploads the
+// chunks that are ready: staging, PCIe and K1 overlap. Work items are taken in upload order: all id chunks, then all
+// value chunks.
+struct Stager {
+    static constexpr int64_t kChunk = (int64_t)1 << 20;      // non-zeros per work item
+    const void* indices = nullptr; int index_bits = 32;
+    const void* data = nullptr; int data_kind = -1;          // -1 none, 0 f32, 1 u16, 2 u8, 3 f64
+    int64_t first = 0, nnz = 0, n_chunks = 0;
+    uint32_t* s_ids = nullptr;                               // [nnz]
+    unsigned char* s_val = nullptr;                          // 4 bytes per non-zero: chunk c starts at byte 4 * c * kChunk
+    std::vector<std::atomic<int>> ids_done, val_done;
+    std::vector<int8_t> val_kind;                            // wire kind of every value chunk: 0 f32, 1 u16, 2 u8
+    std::atomic<int64_t> next{0};
+    std::atomic<int> level{2};                               // narrowest kind still worth trying (2 u8, 1 u16, 0 f32)
+    std::atomic<bool> any_hi{false};
+    std::vector<std::thread> threads;
+
+    int64_t chunk_begin(int64_t c) const { return c * kChunk; }
+    int64_t chunk_end(int64_t c) const { return std::min(nnz, (c + 1) * kChunk); }
+
+    void stage_ids(int64_t c) {
+        const int64_t a = chunk_begin(c), b = chunk_end(c);
+        if (index_bits == 32) {
+            memcpy(s_ids + a, (const uint32_t*)indices + first + a, (size_t)(b - a) * 4);
+        } else if (schic::narrow_ids64((const uint64_t*)indices + first + a, b - a, s_ids + a)) {
+            any_hi.store(true);
+        }
+        ids_done[c].store(1, std::memory_order_release);
+    }
+    void stage_val(int64_t c) {
+        const int64_t a = chunk_begin(c), b = chunk_end(c), n = b - a;
+        unsigned char* dst = s_val + 4 * (size_t)a;
+        int kind = 0;
+        if (data_kind == 1 || data_kind == 2) {              // already narrow: copy
+            kind = data_kind;
+            const size_t w = data_kind == 1 ? 2 : 1;
+            memcpy(dst, (const unsigned char*)data + (size_t)(first + a) * w, (size_t)n * w);
+        } else {
+            const double* d64 = data_kind == 3 ? (const double*)data + first + a : nullptr;
+            const float* d32 = data_kind == 0 ? (const float*)data + first + a : nullptr;
+            int lv = level.load();
+            bool ok = false;
+            if (lv >= 2) {
+                ok = d64 ? schic::narrow_f64_u8(d64, n, dst) : schic::narrow_f32_u8(d32, n, dst);
+                if (ok) kind = 2; else { int e = 2; level.compare_exchange_strong(e, 1); lv = 1; }
+            }
+            if (!ok && lv >= 1) {
+                ok = d64 ? schic::narrow_f64_u16(d64, n, (uint16_t*)dst) : schic::narrow_f32_u16(d32, n, (uint16_t*)dst);
+                if (ok) kind = 1; else { int e = 1; level.compare_exchange_strong(e, 0); }
+            }
+            if (!ok) {
+                kind = 0;
+                if (d64) schic::convert_f64_f32(d64, n, (float*)dst); else memcpy(dst, d32, (size_t)n * 4);
+            }
+        }
+        val_kind[c] = (int8_t)kind;
+        val_done[c].store(1, std::memory_order_release);
+    }
+    void worker() {
+        const int64_t items = n_chunks * (data ? 2 : 1);
+        for (;;) {
+            const int64_t it = next.fetch_add(1);
+            if (it >= items) return;
+            if (it < n_chunks) stage_ids(it); else stage_val(it - n_chunks);
+        }
+    }
+    void start(int n_threads) {
+        n_chunks = (nnz + kChunk - 1) / kChunk;
+        ids_done = std::vector<std::atomic<int>>(n_chunks);
+        val_done = std::vector<std::atomic<int>>(n_chunks);
+        for (auto& x : ids_done) x.store(0);
+        for (auto& x : val_done) x.store(0);
+        val_kind.assign(n_chunks, 0);
+        n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, n_chunks));
+        for (int t = 0; t < n_threads; ++t) threads.emplace_back([this] { worker(); });
+    }
+    static void wait(std::atomic<int>& f) { while (!f.load(std::memory_order_acquire)) std::this_thread::yield(); }
+    void wait_ids_upto(int64_t pos) {                        // ids of positions [0, pos) are staged
+        const int64_t last = pos <= 0 ? -1 : (pos - 1) / kChunk;
+        for (int64_t c = 0; c <= last; ++c) wait(ids_done[c]);
+    }
+    void join() { for (auto& t : threads) if (t.joinable()) t.join(); threads.clear(); }
+    ~Stager() { join(); }
+};
+
+}  // namespace
 
 struct schic_mh_handle {
     schic_mh_params p{};
@@ -105,6 +224,7 @@ struct schic_mh_handle {
     int k1_table_state = 0;                   // K1 of the last fit: 0 no table, 1 built from the batch's ids, 2 whole-range table built, 3 cached table re-used
     std::vector<uint32_t> host_lo, host_hi;   // split 64-bit ids of the last fit (must outlive an async upload)
     DevBuf<unsigned char> val_stage;          // narrow (uint16 / uint8) counts as uploaded, before widening
+    PinBuf pin_ids, pin_val;                  // page-locked staging of schic_mh_fit_csr_host (ids, values in wire format)
     int64_t count_budget = 0;                 // elements of the uint16 count matrix we allow ourselves (cached)
     uint64_t feature_range = 0;               // caller's hint: all ids < feature_range (0: unknown, read the maximum back)
     DevBuf<double> norm2; int64_t norm_rows = 0; const void* norm_of = nullptr;
@@ -842,9 +962,29 @@ static int upload_values(schic_mh_handle* h, const void* data, int32_t kind, siz
 }
 
 // data_kind: 0 = float32 values, 1 = uint16 counts, 2 = uint8 counts (expanded to float32 on the device)
+// One staged value chunk (wire kind chosen by the worker that converted it) to the device behind the ids.
+static int upload_value_chunk(schic_mh_handle* h, const Stager& st, int64_t c, int64_t pos0, cudaStream_t cs) {
+    const int64_t a = st.chunk_begin(c), n = st.chunk_end(c) - a;
+    const unsigned char* src = st.s_val + 4 * (size_t)a;
+    const int kind = st.val_kind[c];
+    if (kind == 0) {
+        CU_TRY(cudaMemcpyAsync(h->val.p + pos0 + a, src, (size_t)n * 4, cudaMemcpyHostToDevice, cs));
+        return 0;
+    }
+    unsigned char* dst = h->val_stage.p + 2 * (size_t)a;      // (2 bytes per non-zero reserved: chunks never overlap)
+    CU_TRY(cudaMemcpyAsync(dst, src, (size_t)n * (kind == 1 ? 2 : 1), cudaMemcpyHostToDevice, cs));
+    add_launches(h, schic::launch_widen_counts(dst, kind == 1 ? 16 : 8, n, h->val.p + pos0 + a, cs));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// data_kind: 0 = float32 values, 1 = uint16 counts, 2 = uint8 counts (expanded to float32 on the device).
+// st != nullptr: indices / data are staged by st's worker threads (schic_mh_fit_csr_host); its data_kind may also be 3
+// (float64) and the wire kind is chosen per chunk.
 static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
-                        int32_t index_bits, const void* data, int32_t data_kind, int32_t append, bool async_upload) {
-    if (data_kind < 0 || data_kind > 2) return fail(SCHIC_ERR_INVALID_ARG, "data_kind must be 0 (f32), 1 (u16) or 2 (u8)");
+                        int32_t index_bits, const void* data, int32_t data_kind, int32_t append, bool async_upload,
+                        Stager* st = nullptr) {
+    if (!st && (data_kind < 0 || data_kind > 2)) return fail(SCHIC_ERR_INVALID_ARG, "data_kind must be 0 (f32), 1 (u16) or 2 (u8)");
     const size_t vbytes = data_kind == 0 ? 4 : (data_kind == 1 ? 2 : 1);
     ST_TRY(check(h));
     if (n_rows < 0 || !indptr) return fail(SCHIC_ERR_INVALID_ARG, "bad CSR arguments");
@@ -881,7 +1021,18 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
     std::vector<uint32_t>& lo = h->host_lo;
     std::vector<uint32_t>& hi = h->host_hi;
     bool any_hi = false;
-    if (index_bits == 32) {
+    if (st) {
+        // staged: the workers fill page-locked buffers in upload order while this thread enqueues what is ready
+        ST_TRY(h->pin_ids.reserve((size_t)std::max<int64_t>(nnz, 1) * 4));
+        if (data) ST_TRY(h->pin_val.reserve((size_t)std::max<int64_t>(nnz, 1) * 4));
+        st->indices = indices; st->index_bits = index_bits; st->data = data; st->data_kind = data ? data_kind : -1;
+        st->first = indptr[0]; st->nnz = nnz;
+        st->s_ids = (uint32_t*)h->pin_ids.p; st->s_val = h->pin_val.p;
+        int nt = h->p.number_of_cores > 0 ? h->p.number_of_cores : (int)std::thread::hardware_concurrency();
+        if (const char* e = getenv("SCHIC_STAGE_THREADS")) nt = atoi(e);
+        st->start(std::max(1, std::min(nt, 32)));
+        f32 = st->s_ids;
+    } else if (index_bits == 32) {
         f32 = (const uint32_t*)indices + indptr[0];
     } else {
         const uint64_t* f64 = (const uint64_t*)indices + indptr[0];
@@ -894,7 +1045,8 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
         f32 = lo.data();
     }
     // high words are kept from the first batch that needs them on (earlier batches are back-filled with zeros)
-    const bool want_hi = h->p.hash_width == 64 && (any_hi || (r0 > 0 && h->have_hi));
+    const bool want_hi = !st && h->p.hash_width == 64 && (any_hi || (r0 > 0 && h->have_hi));
+    if (st && r0 > 0 && h->have_hi) return fail(SCHIC_ERR_UNSUPPORTED, "staged fit cannot append to rows with ids >= 2^32");
     if (want_hi) {
         hi.assign(nnz, 0u);
         if (any_hi) {
@@ -925,7 +1077,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
     h->nnz = pos0 + nnz;
     h->have_val = want_val;
     h->have_hi = want_hi;
-    h->fit_data_kind = (r0 > 0 && h->fit_data_kind != data_kind) ? 0 : data_kind;   // appended batches: the weakest guarantee
+    if (!st) h->fit_data_kind = (r0 > 0 && h->fit_data_kind != data_kind) ? 0 : data_kind;   // appended batches: the weakest guarantee
 
     // Upload the feature ids in row-aligned chunks on the copy stream; K1 for chunk i runs on the
     // compute stream while chunk i+1 is still in flight.
@@ -972,6 +1124,10 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
         int64_t c1 = c0 + 1;
         while (c1 < n_rows && (ip[c1 + 1] - ip[c0]) <= kChunkNnz) ++c1;
         const int64_t a = ip[c0] - pos0, b = ip[c1] - pos0;
+        if (st) {
+            st->wait_ids_upto(b);
+            if (st->any_hi.load()) return fail(SCHIC_ERR_UNSUPPORTED, "feature ids >= 2^32: use schic_mh_fit_csr");
+        }
         if (b > a) {
             CU_TRY(cudaMemcpyAsync(h->feat.p + pos0 + a, f32 + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, cs));
             if (want_hi)
@@ -980,7 +1136,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
         cudaEvent_t ready = get_misc_event(h);
         if (!ready) return fail(SCHIC_ERR_CUDA, "cudaEventCreate failed");
         CU_TRY(cudaEventRecord(ready, cs));
-        if (c1 == n_rows && want_val && nnz > 0) {
+        if (c1 == n_rows && want_val && nnz > 0 && !st) {
             // the values follow the last feature chunk at once, so the copy engine stays busy while K1 runs
             // (and while the host may block on K1's id-range read-back)
             ST_TRY(upload_values(h, data, data_kind, vbytes, indptr[0], pos0, nnz, cs));
@@ -994,6 +1150,19 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
     h->k1t_prebuilt = false;      // valid for exactly this batch
     cudaEvent_t sig1 = get_event(h);
     if (sig_started && sig1) { cudaEventRecord(sig1, s); h->ev[ST_SIG].push_back({sig0, sig1}); }
+    if (want_val && nnz > 0 && st) {
+        // staged values: chunk by chunk as the workers finish them (K1 of the last id chunk is already queued)
+        ST_TRY(h->val_stage.reserve(2 * nnz, 0, cs));
+        int weakest = 2;
+        for (int64_t c = 0; c < st->n_chunks; ++c) {
+            Stager::wait(st->val_done[c]);
+            ST_TRY(upload_value_chunk(h, *st, c, pos0, cs));
+            weakest = std::min(weakest, (int)st->val_kind[c]);
+        }
+        h->fit_data_kind = (r0 > 0 && h->fit_data_kind != weakest) ? 0 : weakest;
+        val_enqueued = true;
+    }
+    if (st) st->join();
     if (want_val && nnz > 0 && !val_enqueued) ST_TRY(upload_values(h, data, data_kind, vbytes, indptr[0], pos0, nnz, cs));
     if (up0 && up1) { cudaEventRecord(up1, cs); h->ev[ST_H2D].push_back({up0, up1}); }
     // the host vectors (lo/hi) and the caller's arrays must outlive the copies; later stages use
@@ -1055,6 +1224,23 @@ static int fit_csr_device_impl(schic_mh_handle* h, int64_t n_rows, int64_t nnz, 
         ST_TRY(hash_rows(h, 0, n_rows, pos0, pos0 + nnz, h->stream));
     }
     return SCHIC_OK;
+}
+
+int schic_mh_fit_csr_host(schic_mh_handle* h, int64_t n_rows, const void* indptr, int32_t indptr_bits, const void* indices,
+                          int32_t index_bits, const void* data, int32_t data_kind, int32_t append, int32_t async_upload) {
+    ST_TRY(check(h));
+    if (n_rows < 0 || !indptr) return fail(SCHIC_ERR_INVALID_ARG, "bad CSR arguments");
+    if (indptr_bits != 32 && indptr_bits != 64) return fail(SCHIC_ERR_INVALID_ARG, "indptr_bits must be 32 or 64");
+    if (data && (data_kind < 0 || data_kind > 3)) return fail(SCHIC_ERR_INVALID_ARG, "data_kind must be 0 (f32), 1 (u16), 2 (u8) or 3 (f64)");
+    std::vector<int64_t> ip64;
+    const int64_t* ip = (const int64_t*)indptr;
+    if (indptr_bits == 32) {
+        ip64.resize(n_rows + 1);
+        for (int64_t r = 0; r <= n_rows; ++r) ip64[r] = ((const int32_t*)indptr)[r];
+        ip = ip64.data();
+    }
+    Stager st;
+    return fit_csr_impl(h, n_rows, ip, indices, index_bits, data, data_kind, append, async_upload != 0, &st);
 }
 
 int schic_mh_fit_csr_device(schic_mh_handle* h, int64_t n_rows, int64_t nnz, const int64_t* d_indptr,

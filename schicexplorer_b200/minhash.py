@@ -114,15 +114,21 @@ class MinHash:
         if append and self._n_features is not None and X.shape[1] != self._n_features:
             raise ValueError(f"partial_fit: X has {X.shape[1]} features, fitted data has {self._n_features}")
         api, h = self._ensure()
-        # values are only needed by the exact rerank; ids above 2^32 go down as 64-bit
-        data = None if self.fast else self._wire_values(X.data)
-        indices = X.indices
-        if X.shape[1] > 0xFFFFFFFF:
-            indices = indices.astype(np.int64, copy=False)
-        elif indices.dtype.itemsize != 4:
-            indices = indices.astype(np.uint32)
         api.set_feature_range(h, X.shape[1])      # ids are column indices of X: all < X.shape[1]
-        api.fit_csr(h, X.indptr, indices, data, append)
+        if getattr(api, "is_cuda", False) and X.shape[1] <= 0xFFFFFFFF:
+            # scipy's arrays go down as they are (float64 values, int32/int64 indices, pageable memory): the library
+            # stages them into page-locked memory on several threads, narrows integer counts to uint8/uint16 for the
+            # PCIe transfer and overlaps all of it with the upload and K1. Values are only needed by the exact rerank.
+            api.fit_csr_host(h, X.indptr, X.indices, None if self.fast else X.data, append)
+        else:
+            # (CPU back ends of the test-suite; ids above 2^32 go down as 64-bit through the plain entry point)
+            data = None if self.fast else self._wire_values(X.data)
+            indices = X.indices
+            if X.shape[1] > 0xFFFFFFFF:
+                indices = indices.astype(np.int64, copy=False)
+            elif indices.dtype.itemsize != 4:
+                indices = indices.astype(np.uint32)
+            api.fit_csr(h, X.indptr, indices, data, append)
         self.number_of_hash_functions = self._created_hashes()    # a fit ends any active-hash prefix
         self._n_features = X.shape[1]
         return self
@@ -193,10 +199,23 @@ class MinHash:
         api, h = self._ensure()
         k = int(n_neighbors or self.n_neighbors)
         n = api.n_fitted(h)
-        indptr, indices, data = api.kneighbors_graph(h, k, self._fast_flag(fast))
-        if mode == "connectivity":
-            data = np.ones_like(data)
-        return csr_matrix((data.astype(np.float64), indices, indptr), shape=(n, n))
+        out = None
+        if getattr(api, "is_cuda", False):
+            # page-locked result buffers, kept between calls (a fresh pageable array costs its page faults every time)
+            ke = min(k, n)
+            if getattr(self, "_graph_out", None) is None or len(self._graph_out[0]) < n + 1 or len(self._graph_out[1]) < n * ke:
+                self._graph_out = (api.pinned_empty((n + 1,), np.int64), api.pinned_empty((n * ke,), np.int32),
+                                   api.pinned_empty((n * ke,), np.float32))
+            out = self._graph_out
+            k = ke
+        indptr, indices, data = api.kneighbors_graph(h, k, self._fast_flag(fast), **({"out": out} if out is not None else {}))
+        nnz = len(data)
+        values = np.ones(nnz, dtype=np.float64) if mode == "connectivity" else data.astype(np.float64)
+        # (copies out of the reused buffers; the arrays come sorted and duplicate-free from K5)
+        g = csr_matrix((values, indices.copy(), indptr[:n + 1].copy()), shape=(n, n))
+        g.has_sorted_indices = True
+        g.has_canonical_format = True
+        return g
 
     def fit_kneighbors_graph(self, X, n_neighbors=None, mode="connectivity", fast=None):
         self.fit(X)

@@ -541,6 +541,73 @@ def test_k1_whole_range_table_is_kept_across_fits(cuda, oracle, monkeypatch):
     cuda.destroy(h)
 
 
+def test_fit_csr_host_staged_upload(cuda, oracle, monkeypatch):
+    """schic_mh_fit_csr_host: scipy's own arrays (float64 / float32 data, int32 / int64 indices and indptr, pageable) are
+    staged by worker threads, values narrowed per 2^20-element chunk to uint8 / uint16 / float32. Same answers as the
+    oracle for: integer counts (all chunks uint8), counts up to 65535 (uint16 chunks), a matrix whose later chunks hold
+    non-integer values (mixed wire kinds inside one fit), float32 input, int64 index arrays, append, 1 and many threads."""
+    from schicexplorer_b200 import synth
+    cfg = synth.SynthConfig(73, 190)                        # ~2.7 M non-zeros: three staging chunks
+    ip, ix, dt, _ = synth.generate_csr(cfg, workers=4)
+    assert ip[-1] > (2 << 20)
+    rng = np.random.default_rng(9)
+    kw = dict(n_neighbors=12, fast=False, **REF_KWARGS)
+
+    def reference(data32):
+        ho = oracle.create(**kw)
+        oracle.fit_csr(ho, ip, ix, data32, False)
+        res = oracle.kneighbors(ho, 12)
+        oracle.destroy(ho)
+        return res
+
+    variants = {}
+    variants["counts"] = dt.astype(np.float64)
+    big = dt.astype(np.float64).copy(); big[rng.choice(len(big), 5000, replace=False)] = rng.integers(256, 65536, 5000); big[:3] = [255, 256, 65535]
+    variants["u16"] = big
+    mixed = dt.astype(np.float64).copy(); mixed[(3 << 19):] *= 0.25          # from the middle of chunk 1 on: fractions
+    variants["mixed"] = mixed
+    over = dt.astype(np.float64).copy(); over[-5] = 65536.0                   # last chunk needs float32
+    variants["over"] = over
+    for name, data in variants.items():
+        want = reference(data.astype(np.float32))
+        for threads, idx_dtype, data_dtype in ((0, np.int32, np.float64), (1, np.int64, np.float64), (3, np.int32, np.float32)):
+            if data_dtype == np.float32 and not np.array_equal(data.astype(np.float32).astype(np.float64), data):
+                continue
+            if threads:
+                monkeypatch.setenv("SCHIC_STAGE_THREADS", str(threads))
+            else:
+                monkeypatch.delenv("SCHIC_STAGE_THREADS", raising=False)
+            h = cuda.create(**kw)
+            cuda.set_feature_range(h, cfg.chroms.nbins ** 2)
+            cuda.fit_csr_host(h, ip.astype(np.int32 if idx_dtype == np.int32 else np.int64), ix.astype(idx_dtype),
+                              data.astype(data_dtype), False)
+            got = cuda.kneighbors(h, 12)
+            assert_neighbours_equal_up_to_ties(*got, *want, RTOL)
+            assert cuda.rerank_kernel_name(h) == ("k4c_rerank_kernel" if name in ("counts", "u16") else "k4_rerank_window_kernel"), name
+            cuda.destroy(h)
+    # append (partial_fit) in two staged calls == one fit; fast mode without values
+    want = reference(dt)
+    h = cuda.create(**kw)
+    half = 95
+    cuda.fit_csr_host(h, ip[:half + 1], ix, dt.astype(np.float64), False)
+    cuda.fit_csr_host(h, ip[half:], ix, dt.astype(np.float64), True)
+    assert_neighbours_equal_up_to_ties(*cuda.kneighbors(h, 12), *want, RTOL)
+    cuda.destroy(h)
+    kwf = dict(kw, fast=True)
+    h, ho = cuda.create(**kwf), oracle.create(**kwf)
+    cuda.fit_csr_host(h, ip, ix.astype(np.int32), None, False)
+    oracle.fit_csr(ho, ip, ix, None, False)
+    assert np.array_equal(cuda.signatures(h, 800), oracle.signatures(ho, 800))
+    for a, b in zip(cuda.kneighbors(h, 12), oracle.kneighbors(ho, 12)):
+        assert np.array_equal(a, b)
+    cuda.destroy(h); oracle.destroy(ho)
+    # an empty batch
+    h = cuda.create(**kwf)
+    cuda.fit_csr_host(h, np.zeros(4, dtype=np.int32), np.zeros(0, dtype=np.int32), None, False)
+    assert cuda.n_fitted(h) == 3 and (cuda.signatures(h, 800) == 2147483647).all()
+    cuda.destroy(h)
+
+
 def test_async_host_fit(cuda, oracle):
     """schic_mh_fit_csr_async: returns before the value array has landed; results identical to the blocking call."""
     X = synth_csr(220, seed=33)
