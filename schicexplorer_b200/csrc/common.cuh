@@ -64,6 +64,9 @@ int launch_rename_signatures(const uint32_t* d_sig_db, int64_t ndb, int H, uint3
                              uint32_t* d_sizes /* nullable */, int64_t max_bin_size /* 0: no pruning */, cudaStream_t stream);
 int launch_collision_counts_packed(const uint16_t* d_q16, int64_t nq, const uint16_t* d_d16, int64_t ndb, int H,
                                    uint16_t* d_cnt, int64_t ld_out, cudaStream_t stream);
+// ... plus the transposed block: d_cnt_t [ndb, ld_t], cnt_t[d][q] = cnt[q][d] (what the peer rank that owns rows d needs)
+int launch_collision_counts_packed_t(const uint16_t* d_q16, int64_t nq, const uint16_t* d_d16, int64_t ndb, int H,
+                                     uint16_t* d_cnt, int64_t ld_out, uint16_t* d_cnt_t, int64_t ld_t, cudaStream_t stream);
 
 // ---- K3b: threshold + top-k select + fast distance (k3_select.cu) --------------------------
 // For each query row: candidates with cnt >= min_blocks (and > 0), ordered by (cnt desc, idx asc),

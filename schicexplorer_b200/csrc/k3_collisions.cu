@@ -209,10 +209,14 @@ k3h_prune_kernel(uint16_t* __restrict__ sig16, int64_t n, int H, int Hp, int cap
     }
 }
 
-template <bool SYM>
+// MODE 0: plain block of counts. MODE 1 (SYM): queries == database, only tiles on or above the diagonal are computed and
+// mirrored into the same matrix. MODE 2: plain block, every tile ALSO stored transposed into cnt_t [nd, ld_t] -- the
+// block a peer rank needs when the (rank x rank) blocks of a sharded symmetric count matrix are computed only once.
+template <int MODE>
 __global__ void __launch_bounds__(K3_THREADS, 2)
 k3h_collision_kernel(const uint32_t* __restrict__ q16, int64_t nq, const uint32_t* __restrict__ d16, int64_t nd, int Hw,
-                     uint16_t* __restrict__ cnt, int64_t ld_out) {
+                     uint16_t* __restrict__ cnt, int64_t ld_out, uint16_t* __restrict__ cnt_t, int64_t ld_t) {
+    constexpr bool SYM = MODE == 1;
     __shared__ __align__(16) uint32_t Qs[K3_JB][K3_LD];
     __shared__ __align__(16) uint32_t Ds[K3_JB][K3_LD];
 
@@ -283,13 +287,15 @@ k3h_collision_kernel(const uint32_t* __restrict__ q16, int64_t nq, const uint32_
                 if (d0 + tx * 8 + b < nd) dst[b] = (uint16_t)total(acc[a][b]);
         }
     }
-    if (SYM && blockIdx.x > blockIdx.y) {
-        const bool tvec_ok = ((ld_out & 7) == 0) && ((((uintptr_t)cnt) & 15) == 0) && (q0 + ty * 8 + 8 <= nq);
+    if ((SYM && blockIdx.x > blockIdx.y) || MODE == 2) {
+        uint16_t* __restrict__ mt = MODE == 2 ? cnt_t : cnt;
+        const int64_t mld = MODE == 2 ? ld_t : ld_out;
+        const bool tvec_ok = ((mld & 7) == 0) && ((((uintptr_t)mt) & 15) == 0) && (q0 + ty * 8 + 8 <= nq);
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const int64_t d = d0 + tx * 8 + b;
             if (d >= nd) continue;
-            uint16_t* dst = cnt + d * ld_out + q0 + ty * 8;
+            uint16_t* dst = mt + d * mld + q0 + ty * 8;
             if (tvec_ok) {
                 uint4 o;
                 o.x = total(acc[0][b]) | (total(acc[1][b]) << 16);
@@ -340,9 +346,21 @@ int launch_collision_counts_packed(const uint16_t* d_q16, int64_t nq, const uint
     const uint32_t* q = reinterpret_cast<const uint32_t*>(d_q16);
     const uint32_t* d = reinterpret_cast<const uint32_t*>(d_d16);
     if (d_q16 == d_d16 && nq == ndb)
-        k3h_collision_kernel<true><<<grid, K3_THREADS, 0, stream>>>(q, nq, d, ndb, Hw, d_cnt, ld_out);
+        k3h_collision_kernel<1><<<grid, K3_THREADS, 0, stream>>>(q, nq, d, ndb, Hw, d_cnt, ld_out, nullptr, 0);
     else
-        k3h_collision_kernel<false><<<grid, K3_THREADS, 0, stream>>>(q, nq, d, ndb, Hw, d_cnt, ld_out);
+        k3h_collision_kernel<0><<<grid, K3_THREADS, 0, stream>>>(q, nq, d, ndb, Hw, d_cnt, ld_out, nullptr, 0);
+    return 1;
+}
+
+// The same block with a transposed copy: d_cnt_t [ndb, ld_t] receives cnt_t[d][q] = cnt[q][d].
+int launch_collision_counts_packed_t(const uint16_t* d_q16, int64_t nq, const uint16_t* d_d16, int64_t ndb, int H,
+                                     uint16_t* d_cnt, int64_t ld_out, uint16_t* d_cnt_t, int64_t ld_t, cudaStream_t stream) {
+    if (nq <= 0 || ndb <= 0) return 0;
+    const int Hw = k3h_padded_hashes(H) / 2;
+    dim3 grid((unsigned)((ndb + K3_TILE - 1) / K3_TILE), (unsigned)((nq + K3_TILE - 1) / K3_TILE));
+    k3h_collision_kernel<2><<<grid, K3_THREADS, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_q16), nq,
+                                                             reinterpret_cast<const uint32_t*>(d_d16), ndb, Hw, d_cnt, ld_out,
+                                                             d_cnt_t, ld_t);
     return 1;
 }
 
