@@ -142,12 +142,18 @@ __device__ __noinline__ uint32_t k4c_escape_value(const uint32_t* __restrict__ q
 // Candidate order of every query for the rerank kernel: columns of the launch's candidate slice sorted by row length
 // (descending, then by column). The rerank kernel gives each slice to 8 lanes and runs four slices per warp in lock
 // step, so neighbours in this order -- rows of similar length, hence window slices of similar length -- share a warp.
-__global__ void __launch_bounds__(128)
+// lane_map != nullptr (kcand <= 128, 256 threads): additionally the lane assignment of the rerank kernel's CTA. Row
+// lengths of one query's candidates differ by an order of magnitude (log-normal depth), and with one fixed-size lane
+// group per candidate every window waits for the longest slice. Here candidate i gets gs_i lanes, a power of two
+// proportional to its row length (4..32 -- a slice's <= 3 head / tail elements need 3 lanes --, sum <= K4C_THREADS),
+// groups packed in descending size (hence aligned): lane_map[q][lane] = (sorted position << 8) | gs, 0xFFFF = spare lane.
+__global__ void __launch_bounds__(256)
 k4c_order_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ cand_idx,
                  const int32_t* __restrict__ cand_nvalid, int kcand, int P, K4Chunk ck, const uint32_t* __restrict__ flags,
-                 uint32_t esc_limit, int32_t* __restrict__ order) {
+                 uint32_t esc_limit, int32_t* __restrict__ order, uint16_t* __restrict__ lane_map) {
     if (!k4c_usable(flags, esc_limit)) return;
     extern __shared__ unsigned long long okeys[];
+    __shared__ int s_scan[40];
     const int64_t q = blockIdx.x;
     const int ncand = max(0, min((cand_idx ? cand_nvalid[q] : ck.n_all) - ck.cand_off, kcand));
     for (int c = threadIdx.x; c < P; c += blockDim.x) {
@@ -161,6 +167,31 @@ k4c_order_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
     }
     bitonic_sort_shared(okeys, P);
     for (int c = threadIdx.x; c < kcand; c += blockDim.x) order[q * (int64_t)kcand + c] = c < ncand ? (int32_t)(uint32_t)okeys[c] : -1;
+    if (!lane_map) return;
+    // proportional lane groups (blockDim.x == 256 >= P: one sorted candidate per thread)
+    const int i = threadIdx.x;
+    const uint32_t len = i < ncand ? ~(uint32_t)(okeys[i] >> 32) : 0u;
+    int total = 0;
+    block_exclusive_scan((int)min(len, 0x3FFFFFu), s_scan, &total);
+    uint32_t t = max(1u, ((uint32_t)total + K4C_THREADS - 1) / K4C_THREADS);       // non-zeros per lane to aim for
+    int gs = 0, start = 0;
+    for (int it = 0; it < 24; ++it) {
+        gs = 0;
+        if (i < ncand) {
+            const uint32_t want = (len + t - 1) / t;
+            gs = 4;
+            while (gs < 32 && (uint32_t)gs < want) gs <<= 1;
+        }
+        int sum = 0;
+        start = block_exclusive_scan(gs, s_scan, &sum);
+        if (sum <= K4C_THREADS) break;
+        t += t / 4 + 1;
+        if (it == 23) { gs = i < ncand ? 4 : 0; start = 4 * i; }    // (ncand <= 128: groups of 4 always fit)
+    }
+    uint16_t* __restrict__ m = lane_map + q * (int64_t)K4C_THREADS;
+    for (int l = threadIdx.x; l < K4C_THREADS; l += blockDim.x) m[l] = 0xFFFFu;
+    __syncthreads();
+    for (int l = 0; l < gs; ++l) m[start + l] = (uint16_t)((i << 8) | gs);
 }
 
 // One CTA = (window group g, query q); blockIdx.x = g * nq + q. dotacc [nq, kcand] uint64, zeroed by the caller.
@@ -174,13 +205,13 @@ k4c_order_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
 // query's keys of the next window, which later un-build the table from the same registers.
 // A probe is LEA.HI (table address), LDS.U8, IDP.2A (count x table byte accumulated; the id half of the word meets a
 // zero byte): three instructions per candidate non-zero.
-template <int LPS>     // lanes per slice: 8 (default) or 4
+template <int LPS>     // lanes per slice: 8 or 4 (fixed groups, candidates dealt round-robin), 0 = per-candidate group sizes from lane_map
 __global__ void __launch_bounds__(K4C_THREADS, K4C_CTAS)
 k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ packed,
                   const uint32_t* __restrict__ dir, int n_windows, int wg, int64_t q_row0, int64_t nq,
                   const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_nvalid,
-                  const int32_t* __restrict__ order, int kcand, K4Chunk ck, const uint32_t* __restrict__ flags,
-                  uint32_t esc_limit, unsigned long long* __restrict__ dotacc) {
+                  const int32_t* __restrict__ order, const uint16_t* __restrict__ lane_map, int kcand, K4Chunk ck,
+                  const uint32_t* __restrict__ flags, uint32_t esc_limit, unsigned long long* __restrict__ dotacc) {
     if (!k4c_usable(flags, esc_limit)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint8_t* tab = smem_raw;                                                            // [K4C_TAB]
@@ -197,13 +228,24 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
     const int64_t nw1 = (int64_t)n_windows + 1;
     const int wg1 = wg + 1;
     const int lane = threadIdx.x & 31;
-    const int ql = lane & (LPS - 1);                       // lane within its group of LPS
-    const int quad = threadIdx.x / LPS;                    // lane group = sorted candidate position (mod NQ)
-    constexpr int NQ = K4C_THREADS / LPS;
     constexpr int NB = 4;                                  // 16-byte words per lane and batch
-    constexpr uint32_t BATCH = (uint32_t)LPS * NB * 4u;    // non-zeros per batch (128 / 64)
-    const uint32_t qmask = (LPS == 8 ? 0xFFu : 0xFu) << (lane & ~(LPS - 1));
     const int ncand = max(0, min((cand_idx ? cand_nvalid[q] : ck.n_all) - ck.cand_off, kcand));
+    // this lane's group: gs lanes (a power of two, aligned), ql = rank in it, first_i = its first sorted candidate
+    // position (-1: spare lane), stride_i = step to its next candidate of the same window
+    int gs = LPS, first_i, stride_i;
+    if (LPS > 0) {
+        first_i = threadIdx.x / (LPS > 0 ? LPS : 1);
+        stride_i = K4C_THREADS / (LPS > 0 ? LPS : 1);
+        if (first_i >= ncand) first_i = -1;
+    } else {
+        const uint32_t m = __ldg(lane_map + q * (int64_t)K4C_THREADS + threadIdx.x);
+        gs = m == 0xFFFFu ? 4 : (int)(m & 0xFFu);
+        first_i = m == 0xFFFFu ? -1 : (int)(m >> 8);
+        stride_i = kcand + 1;                              // one candidate per group: the next one is in the next window
+    }
+    const int ql = lane & (gs - 1);
+    const uint32_t BATCH = (uint32_t)gs * NB * 4u;         // non-zeros per batch of the group
+    const uint32_t qmask = (gs == 32 ? 0xFFFFFFFFu : ((1u << gs) - 1u)) << (lane & ~(gs - 1));
 
     for (int w = threadIdx.x; w <= nwin; w += K4C_THREADS) qdir[w] = __ldg(dir + qrow * nw1 + w0 + w);
     if (threadIdx.x == 0) s_esc = 0;
@@ -243,7 +285,7 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
     // ... of every batch; words beyond B are zero and contribute nothing) plus <= 3 head and <= 3 tail elements: one
     // 32-bit load on lanes 0-2 / 4-6 of the group, probed with the slice's first batch.
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    int it_i = quad - NQ, it_j = j;                        // slice the iterator reads (advanced before use)
+    int it_i = first_i - stride_i, it_j = j;               // slice the iterator reads (advanced before use)
     uint32_t it_p = 0u, it_B = 0u;                         // next batch position / interior end of that slice
     uint4 h[NB];                                           // look-ahead batch
     uint32_t h_sx = 0u, h_tx = 0u;                         // its head / tail boundary element (first batch of a slice, else 0)
@@ -254,9 +296,9 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
         if (it_p >= it_B) {                                // open the next non-empty slice of this lane group
             uint32_t ys = 0u, ye = 0u;
             for (;;) {
-                it_i += NQ;
-                if (it_i >= ncand) { it_i = quad; it_j = next_window(it_j + 1); }
-                if (it_j >= nwin || quad >= ncand) { h_j = nwin; return; }
+                it_i += stride_i;
+                if (it_i >= ncand) { it_i = first_i; it_j = next_window(it_j + 1); }
+                if (it_j >= nwin) { h_j = nwin; return; }
                 ys = sl[it_i * wg1 + it_j]; ye = sl[it_i * wg1 + it_j + 1];
                 if (ye > ys) break;
             }
@@ -267,19 +309,14 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
         }
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
-            const uint32_t p = it_p + 4u * ql + 4u * LPS * u;
+            const uint32_t p = it_p + 4u * ql + 4u * gs * u;
             h[u] = p < it_B ? __ldg(reinterpret_cast<const uint4*>(packed + p)) : zero4;
         }
         h_i = it_i; h_j = it_j;
         it_p += BATCH;
         h_last = it_p >= it_B;
     };
-    it_j = j;
-    if (quad < ncand) {
-        // (the first call must start at window j itself: step the window back so that the wrap-around lands on it)
-        it_i = quad - NQ;
-        advance();
-    }
+    if (first_i >= 0) advance();
 
     unsigned long long acc = 0ull;
     while (j < nwin) {
@@ -342,9 +379,7 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
                     for (int u = 0; u < NB; ++u) { probe(v[u].x); probe(v[u].y); probe(v[u].z); probe(v[u].w); }
                 }
                 if (last) {
-                    acc += __shfl_xor_sync(qmask, acc, 1);
-                    acc += __shfl_xor_sync(qmask, acc, 2);
-                    if (LPS == 8) acc += __shfl_xor_sync(qmask, acc, 4);
+                    for (int o = 1; o < gs; o <<= 1) acc += __shfl_xor_sync(qmask, acc, o);
                     if (ql == 0) dotc[cur_i] += acc;       // only this lane group touches position cur_i
                     acc = 0ull;
                 }
@@ -421,8 +456,11 @@ int k4c_windows_per_group(int n_windows, int64_t db_nnz, int kcand, int64_t grou
     return (int)wg;
 }
 
-// scratch of one launch: nq * kcand uint64 dot products followed by nq * kcand int32 of candidate order
-size_t k4c_dotacc_elems(int64_t nq, int kcand) { return (size_t)nq * (size_t)kcand + ((size_t)nq * (size_t)kcand + 1) / 2; }
+// scratch of one launch (in uint64 units): nq * kcand dot products, nq * kcand int32 of candidate order, nq * K4C_THREADS
+// uint16 of lane map
+size_t k4c_dotacc_elems(int64_t nq, int kcand) {
+    return (size_t)nq * (size_t)kcand + ((size_t)nq * (size_t)kcand + 1) / 2 + ((size_t)nq * K4C_THREADS + 3) / 4 + 2;
+}
 
 // One launch (pair) over candidate columns [cand_off, cand_off + kcand); same output contract as launch_rerank.
 // d_dotacc: >= nq * kcand uint64 scratch (zeroed here). Returns launches, or -1 when kcand does not fit.
@@ -443,17 +481,21 @@ int launch_rerank_counts(const int64_t* d_indptr, const uint32_t* d_packed, cons
     if (smem > (size_t)(225 * 1024 / K4C_CTAS - 1024)) return -1;
     if (cudaMemsetAsync(d_dotacc, 0, (size_t)nq * kcand * sizeof(unsigned long long), stream) != cudaSuccess) return -1;
     int32_t* d_order = reinterpret_cast<int32_t*>(d_dotacc + (size_t)nq * kcand);
+    uint16_t* d_lane_map = reinterpret_cast<uint16_t*>(d_order + (size_t)nq * kcand);
     const int P = next_pow2(kcand);
-    k4c_order_kernel<<<(unsigned)nq, 128, (size_t)P * 8, stream>>>(d_indptr, d_cand_idx, d_cand_nvalid, kcand, P, ck, d_flags,
-                                                                   esc_limit, d_order);
-    // lanes per slice: 8 unless the lists are long enough to keep every 4-lane group busy (or SCHIC_K4_LPS says so)
+    // lanes per slice: fixed groups of 4 (8 for short lists) dealt round-robin in length-sorted order. SCHIC_K4_LPS = 4 | 8
+    // forces one; 0 = group sizes proportional to the candidates' row lengths (lists of <= 128; measured at S10:
+    // 15.7 ms against 15.1 ms for groups of 4 and 16.5 ms for groups of 8 -- the barrier structure, not the slice
+    // imbalance, is what keeps issue utilisation at ~52 %; kept as an experiment switch)
     int lps = kcand > K4C_THREADS / 8 ? 4 : 8;
-    if (const char* e = getenv("SCHIC_K4_LPS")) lps = atoi(e) == 4 ? 4 : 8;
-    auto kern = lps == 4 ? k4c_rerank_kernel<4> : k4c_rerank_kernel<8>;
+    if (const char* e = getenv("SCHIC_K4_LPS")) { const int v = atoi(e); lps = v == 8 ? 8 : (v == 4 ? 4 : (kcand <= K4C_THREADS / 4 ? 0 : 4)); }
+    k4c_order_kernel<<<(unsigned)nq, 256, (size_t)P * 8, stream>>>(d_indptr, d_cand_idx, d_cand_nvalid, kcand, P, ck, d_flags,
+                                                                   esc_limit, d_order, lps == 0 ? d_lane_map : nullptr);
+    auto kern = lps == 0 ? k4c_rerank_kernel<0> : (lps == 4 ? k4c_rerank_kernel<4> : k4c_rerank_kernel<8>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<(unsigned)(groups * nq), K4C_THREADS, smem, stream>>>(
-        d_indptr, d_packed, d_dir, n_windows, wg, q_row0, nq, d_cand_idx, d_cand_nvalid, d_order, kcand, ck, d_flags,
-        esc_limit, d_dotacc);
+        d_indptr, d_packed, d_dir, n_windows, wg, q_row0, nq, d_cand_idx, d_cand_nvalid, d_order, d_lane_map, kcand, ck,
+        d_flags, esc_limit, d_dotacc);
     k4c_finalize_kernel<<<(unsigned)nq, 256, (size_t)P * 8, stream>>>(d_flags, esc_limit, d_dotacc, d_norm2, q_row0,
                                                                       d_cand_idx, d_cand_nvalid, kcand, P, k, ck, d_idx_out,
                                                                       d_dist_out, d_nvalid_out);

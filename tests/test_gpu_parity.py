@@ -416,6 +416,11 @@ def test_counts_rerank_kernel(cuda, oracle, monkeypatch):
         else:
             monkeypatch.setenv("SCHIC_K4_GROUP_WINDOWS", wg)
         check(X, "k4c_rerank_kernel")
+    for lps in ("8", "4", "0"):                                          # lane-group variants (0: proportional to row length)
+        monkeypatch.setenv("SCHIC_K4_LPS", lps)
+        check(X, "k4c_rerank_kernel")
+        check(X[:9], "k4c_rerank_kernel", k=9)
+    monkeypatch.delenv("SCHIC_K4_LPS")
     # (a) a few large counts (escapes) in some rows, incl. the largest packable value
     Xa = X.copy()
     big = rng.choice(Xa.nnz, size=Xa.nnz // 200, replace=False)
