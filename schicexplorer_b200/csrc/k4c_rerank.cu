@@ -48,7 +48,10 @@ __device__ __forceinline__ uint32_t k4c_mac(uint32_t word, uint32_t table_byte, 
 }
 // 64 KB table (2^16-id windows): 512 threads, two CTAs per SM. Experiment build -DSCHIC_K4C_WIN_BITS=17: 128 KB table,
 // 1024 threads, one CTA per SM, counts up to 32767.
-constexpr int K4C_THREADS = K4C_WIN_BITS == 16 ? 512 : 1024;
+#ifndef K4C_THREADS_DEF
+#define K4C_THREADS_DEF (SCHIC_K4C_WIN_BITS == 16 ? 512 : 1024)
+#endif
+constexpr int K4C_THREADS = K4C_THREADS_DEF;                  // (a multiple of 32)
 #ifndef K4C_CTAS_DEF
 #define K4C_CTAS_DEF (SCHIC_K4C_WIN_BITS == 16 ? 2 : 1)
 #endif
@@ -199,8 +202,8 @@ k4c_order_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__
 // others issue. Per window three barriers (un-build | build | stream). A window's slice of one candidate (~120 non-zeros
 // at S10) is far too short to amortise a warp-wide set-up and reduction, so the unit of work is 8 lanes per slice, four
 // slices per warp, 64 per CTA, statically assigned in the length-sorted candidate order: no hand-out atomics, a 3-step
-// reduction. Every lane group walks its own sequence of BATCHES (4 x 16 bytes per lane = 128 non-zeros; a typical slice
-// is one batch) -- slice after slice, window after window -- and always holds the next batch of that sequence in
+// reduction. Every lane group walks its own sequence of BATCHES (NB x 16 bytes per lane; a typical slice is one to
+// four batches) -- slice after slice, window after window -- and always holds the next batch of that sequence in
 // registers while the current one is probed: loads cross the barriers (they do not depend on the table), as do the
 // query's keys of the next window, which later un-build the table from the same registers.
 // A probe is LEA.HI (table address), LDS.U8, IDP.2A (count x table byte accumulated; the id half of the word meets a
@@ -228,7 +231,10 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
     const int64_t nw1 = (int64_t)n_windows + 1;
     const int wg1 = wg + 1;
     const int lane = threadIdx.x & 31;
-    constexpr int NB = 4;                                  // 16-byte words per lane and batch
+#ifndef K4C_NB_DEF
+#define K4C_NB_DEF 2          // measured at S10 (groups of 4 lanes): 1 -> 16.8 ms, 2 -> 14.5 ms, 3 -> 17.2 ms, 4 -> 15.1 ms
+#endif
+    constexpr int NB = K4C_NB_DEF;                         // 16-byte words per lane and batch
     const int ncand = max(0, min((cand_idx ? cand_nvalid[q] : ck.n_all) - ck.cand_off, kcand));
     // this lane's group: gs lanes (a power of two, aligned), ql = rank in it, first_i = its first sorted candidate
     // position (-1: spare lane), stride_i = step to its next candidate of the same window
