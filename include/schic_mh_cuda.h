@@ -119,6 +119,21 @@ int schic_mh_set_database_prep_device(schic_mh_handle* h, const double* d_norm2_
                                       int64_t nnz_total);
 int schic_mh_rerank_kernel_name(schic_mh_handle* h, char* out, int32_t n_out);
 
+/* Collision counts of a BLOCK of the (database x database) count matrix, for callers that assemble the matrix
+ * themselves: rows [q_row0, q_row0 + q_rows) against columns [d_row0, d_row0 + d_rows) of the database (the external one
+ * when set, else the fitted rows), written to d_cnt[(q - q_row0) * ld + (d - d_row0)] (uint16) and -- when d_cnt_t is
+ * given -- transposed to d_cnt_t[(d - d_row0) * ld_t + (q - q_row0)]. Identical row and column ranges take the symmetric
+ * kernel (half the compares). Rule 5 (max_bin_size) is applied as in kneighbors. Needs the packed K3 (H <= 4094, <= 57 344
+ * database rows), else SCHIC_ERR_UNSUPPORTED. Asynchronous on the handle's stream.
+ * Use: the count matrix is symmetric, so in a sharded run each (rank x rank) block needs computing only once: every
+ * rank computes its diagonal block plus half of every off-diagonal block of its rows and sends the transposes to the
+ * peers that own those columns' rows -- n^2 H / (2 G) compares per rank instead of n^2 H / G.
+ * schic_mh_set_counts_device: the next kneighbors* call on the handle takes d_counts ([local rows, ld], ld a multiple of 8,
+ * 16-byte aligned) as its collision counts instead of computing them (one-shot; NULL clears). */
+int schic_mh_collision_block_device(schic_mh_handle* h, int64_t q_row0, int64_t q_rows, int64_t d_row0, int64_t d_rows,
+                                    uint16_t* d_cnt, int64_t ld, uint16_t* d_cnt_t, int64_t ld_t);
+int schic_mh_set_counts_device(schic_mh_handle* h, const uint16_t* d_counts, int64_t ld);
+
 /* Run on the caller's stream (a cudaStream_t, e.g. torch's current stream) instead of the
  * handle's own. NULL selects the legacy default stream. */
 int schic_mh_set_stream(schic_mh_handle* h, void* cuda_stream);

@@ -60,7 +60,7 @@ CUDA_SYMBOLS = (
     "schic_mh_rerank_prep_rows", "schic_mh_set_database_prep_device", "schic_mh_set_stream", "schic_mh_stage_ms",
     "schic_mh_launch_count", "schic_mh_synchronize", "schic_int32_peak", "schic_device_count",
     "schic_k1_variant_ms", "schic_pinned_alloc", "schic_pinned_free", "schic_mh_kneighbors_exact_device",
-    "schic_mh_fit_csr_device_at", "schic_mh_kneighbors_graph_device", "schic_mh_rerank_kernel_name", "schic_mh_k1_table_state", "schic_mh_fit_csr_host",
+    "schic_mh_fit_csr_device_at", "schic_mh_kneighbors_graph_device", "schic_mh_rerank_kernel_name", "schic_mh_k1_table_state", "schic_mh_fit_csr_host", "schic_mh_collision_block_device", "schic_mh_set_counts_device",
 )
 
 # the dense-graph PCA post-step, CUDA library only (include/schic_pca.h)
@@ -118,6 +118,8 @@ class CApi:
             L.schic_mh_fit_csr_counts.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _i32, _i32, _i32]
             L.schic_mh_fit_csr_device.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, _i32]
             L.schic_mh_kneighbors_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
+            L.schic_mh_collision_block_device.argtypes = [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64]
+            L.schic_mh_set_counts_device.argtypes = [_vp, _vp, _i64]
             L.schic_mh_fit_csr_host.argtypes = [_vp, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32]
             L.schic_mh_fit_csr_device_at.argtypes = [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32]
             L.schic_mh_kneighbors_graph_device.argtypes = [_vp, _i32, _i32, _vp, _vp, _vp]
@@ -383,6 +385,16 @@ class CApi:
                                  nnz_total=0):
         self.check(self.lib.schic_mh_set_database_prep_device(_vp(h), _ptr(d_norm2_all), _ptr(d_dir_all), n_windows,
                                                               _ptr(d_packed_all), _ptr(d_flags_all), int(nnz_total)))
+
+    def collision_block_device(self, h, q_row0, q_rows, d_row0, d_rows, d_cnt, ld, d_cnt_t=None, ld_t=0):
+        """Counts of database rows [q_row0, +q_rows) x [d_row0, +d_rows) into d_cnt (row stride ld), optionally also
+        transposed into d_cnt_t (row stride ld_t). Device pointers; asynchronous."""
+        self.check(self.lib.schic_mh_collision_block_device(_vp(h), q_row0, q_rows, d_row0, d_rows, _ptr(d_cnt), ld,
+                                                            _ptr(d_cnt_t), ld_t))
+
+    def set_counts_device(self, h, d_counts, ld):
+        """The next kneighbors* call uses this [local rows, ld] uint16 matrix as its collision counts."""
+        self.check(self.lib.schic_mh_set_counts_device(_vp(h), _ptr(d_counts), ld))
 
     def rerank_kernel_name(self, h) -> str:
         """Which kernel did the work of the last exact rerank (counts kernel or a generic float kernel)."""

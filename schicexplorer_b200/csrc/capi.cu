@@ -251,6 +251,9 @@ struct schic_mh_handle {
     DevBuf<uint16_t> counts; DevBuf<int32_t> cand_idx, cand_cnt, cand_nv, sel_flags, part_idx; DevBuf<float> part_dist;
     DevBuf<uint32_t> sig_masked;   // database signatures with oversized buckets blanked (K2)
     DevBuf<uint32_t> k3h_table, k3h_sizes; DevBuf<uint16_t> sig16;   // packed K3: renaming tables, bucket sizes, renamed signatures
+    const void* sig16_of = nullptr; int64_t sig16_rows = 0;          // database the renamed signatures were made from (block API)
+    const uint16_t* given_counts = nullptr; int64_t given_ld = 0;    // caller-assembled count matrix for the next kneighbors call
+    bool coll_blocks_open = false;                                   // ST_COLL holds block launches of the build in progress
     DevBuf<int32_t> out_idx, out_nv; DevBuf<float> out_dist;
     DevBuf<int64_t> g_indptr; DevBuf<int32_t> g_indices; DevBuf<float> g_data;
 
@@ -582,6 +585,7 @@ int prepare_packed_counts(schic_mh_handle* h, const uint32_t* db_sig, int64_t nd
                                                    prune ? h->k3h_sizes.p : nullptr, prune ? h->p.max_bin_size : 0, h->stream);
     if (nl < 0) return fail(SCHIC_ERR_CUDA, "signature renaming launch failed");
     add_launches(h, nl);
+    h->sig16_of = nullptr;          // (the block API re-validates what it needs)
     return 1;
 }
 
@@ -688,10 +692,16 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
         if ((!db_val || !db_feat) && !packed_db) return fail(SCHIC_ERR_INVALID_ARG, "exact rerank needs the CSR values (fit with data)");
         if (h->have_hi) return fail(SCHIC_ERR_UNSUPPORTED, "exact rerank supports 32-bit feature ids only");
     }
-    reset_stage(h, {ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_PREP});
+    // a count matrix assembled by the caller (schic_mh_set_counts_device: blocks of a sharded symmetric K3) replaces K3
+    const uint16_t* given = h->given_counts;
+    const int64_t given_ld = h->given_ld;
+    h->given_counts = nullptr;
+    if (given && h->coll_blocks_open) reset_stage(h, {ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_PREP});
+    else reset_stage(h, {ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_PREP});
+    h->coll_blocks_open = false;
     cudaStream_t s = h->stream;
     const uint32_t* q_sig = h->sig.p;
-    if (ndb >= h->p.max_bin_size && !packed_counts_possible(h, ndb)) {   // rule 5 (the packed K3 prunes while renaming)
+    if (!given && ndb >= h->p.max_bin_size && !packed_counts_possible(h, ndb)) {   // rule 5 (the packed K3 prunes while renaming)
         StageTimer t(h, ST_COLL, s);
         ST_TRY(prune_buckets(h, db_sig, ndb));
         db_sig = h->sig_masked.p;
@@ -710,7 +720,7 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
     }
 
     // query blocking: the uint16 count matrix is produced and consumed in row blocks of <= 2 GiB
-    const int64_t ld = (ndb + 7) & ~(int64_t)7;
+    const int64_t ld = given ? given_ld : ((ndb + 7) & ~(int64_t)7);
     // budget: a quarter of the free HBM, at least 2 GiB, at most 32 GiB (the all-rows-in-one-block case also
     // lets K3 use the symmetry of the counts)
     if (const char* forced = getenv("SCHIC_COUNT_BUDGET")) {     // tests: force several query blocks on small inputs
@@ -727,17 +737,19 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
                                                               : std::max<int64_t>(h->count_budget, h->counts.cap);   // never below what is already held
     int64_t qb = std::max<int64_t>(128, budget_elems / ld);
     qb = std::min<int64_t>((qb / 128) * 128, (nq + 127) / 128 * 128);
-    ST_TRY(h->counts.reserve(qb * ld, 0, s));
+    if (given) qb = nq;
+    else ST_TRY(h->counts.reserve(qb * ld, 0, s));
     int packed = 0;
-    {
+    if (!given) {
         StageTimer t(h, ST_COLL, s);
         packed = prepare_packed_counts(h, db_sig, ndb);
         if (packed < 0) return packed;
     }
+    const uint16_t* counts_in = given ? given : h->counts.p;
     const int64_t Hp = schic::k3h_padded_hashes(H);
     for (int64_t q0 = 0; q0 < nq; q0 += qb) {
         const int64_t q1 = std::min(nq, q0 + qb);
-        {
+        if (!given) {
             StageTimer t(h, ST_COLL, s);
             if (packed)
                 add_launches(h, schic::launch_collision_counts_packed(h->sig16.p + (row0 + q0) * Hp, q1 - q0,
@@ -748,7 +760,7 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
         }
         {
             StageTimer t(h, ST_SELECT, s);
-            const int nl = schic::launch_select_topk(h->counts.p, q1 - q0, ndb, ld, H, h->p.minimal_blocks_in_common,
+            const int nl = schic::launch_select_topk(counts_in, q1 - q0, ndb, ld, H, h->p.minimal_blocks_in_common,
                                                      kcand, h->cand_idx.p + q0 * kcand, h->cand_cnt.p + q0 * kcand,
                                                      h->cand_nv.p + q0, h->sel_flags.p, s);
             if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k * excess_factor too large for the in-shared-memory select");
@@ -1005,6 +1017,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
     }
     reset_stage(h, {ST_H2D, ST_SIG});
     h->k1_table_state = 0;
+    h->sig16_of = nullptr; h->given_counts = nullptr;
     for (cudaEvent_t e : h->misc_ev) h->free_ev.push_back(e);
     h->misc_ev.clear();
     h->val_done = nullptr;
@@ -1206,6 +1219,7 @@ static int fit_csr_device_impl(schic_mh_handle* h, int64_t n_rows, int64_t nnz, 
     if (h->sliced) { CU_TRY(cudaStreamSynchronize(h->stream)); restore_fitted_signatures(h); }
     reset_stage(h, {ST_H2D, ST_SIG});
     h->k1_table_state = 0;
+    h->sig16_of = nullptr; h->given_counts = nullptr;
     const int H = h->p.number_of_hash_functions;
     h->k1t_prebuilt = false;
     h->borrowed = true; h->b_indptr = d_indptr; h->b_feat = d_indices; h->b_val = d_data;
@@ -1298,6 +1312,7 @@ int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t ro
     h->db_ready = nullptr;
     h->ext_norm2 = nullptr; h->ext_dir = nullptr; h->ext_nw = 0;
     h->ext_packed = nullptr; h->ext_flags = nullptr; h->ext_nnz = 0;
+    h->sig16_of = nullptr; h->given_counts = nullptr;
     if (!d_sig_all) { h->ext = false; h->norm_of = nullptr; return SCHIC_OK; }
     if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "fit the local shard first");
     if (h->sliced) return fail(SCHIC_ERR_UNSUPPORTED, "external database while an active-hash prefix is set");
@@ -1408,6 +1423,50 @@ int schic_mh_collision_counts(schic_mh_handle* h, int64_t row0, int64_t row1, ui
     CU_TRY(cudaMemcpy2DAsync(out, (size_t)ndb * 2, h->counts.p, (size_t)ld * 2, (size_t)ndb * 2, (size_t)nq,
                              cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
+    return SCHIC_OK;
+}
+
+int schic_mh_collision_block_device(schic_mh_handle* h, int64_t q_row0, int64_t q_rows, int64_t d_row0, int64_t d_rows,
+                                    uint16_t* d_cnt, int64_t ld, uint16_t* d_cnt_t, int64_t ld_t) {
+    ST_TRY(check(h));
+    if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "no rows fitted");
+    ST_TRY(use_device(h));
+    const int H = h->p.number_of_hash_functions;
+    const int64_t ndb = h->ext ? h->db_n : h->n;
+    const uint32_t* db_sig = h->ext ? h->db_sig : h->sig.p;
+    if (q_row0 < 0 || d_row0 < 0 || q_rows < 0 || d_rows < 0 || q_row0 + q_rows > ndb || d_row0 + d_rows > ndb || !d_cnt || ld < d_rows ||
+        (d_cnt_t && ld_t < q_rows))
+        return fail(SCHIC_ERR_INVALID_ARG, "bad block arguments");
+    if (!packed_counts_possible(h, ndb)) return fail(SCHIC_ERR_UNSUPPORTED, "the block entry point needs the packed K3 (H <= 4094, <= 57344 database rows)");
+    cudaStream_t s = h->stream;
+    if (!h->coll_blocks_open) { reset_stage(h, {ST_COLL}); h->coll_blocks_open = true; }
+    StageTimer t(h, ST_COLL, s);
+    if (h->sig16_of != (const void*)db_sig || h->sig16_rows != ndb) {      // rename once per database
+        const int r = prepare_packed_counts(h, db_sig, ndb);
+        if (r <= 0) return r < 0 ? r : fail(SCHIC_ERR_UNSUPPORTED, "packed K3 not applicable");
+        h->sig16_of = db_sig; h->sig16_rows = ndb;
+    }
+    if (q_rows == 0 || d_rows == 0) return SCHIC_OK;
+    const int64_t Hp = schic::k3h_padded_hashes(H);
+    const uint16_t* q16 = h->sig16.p + q_row0 * Hp;
+    const uint16_t* d16 = h->sig16.p + d_row0 * Hp;
+    int nl;
+    if (d_cnt_t && !(q_row0 == d_row0 && q_rows == d_rows))
+        nl = schic::launch_collision_counts_packed_t(q16, q_rows, d16, d_rows, H, d_cnt, ld, d_cnt_t, ld_t, s);
+    else
+        nl = schic::launch_collision_counts_packed(q16, q_rows, d16, d_rows, H, d_cnt, ld, s);   // (same rows twice: symmetric kernel)
+    add_launches(h, nl);
+    CU_TRY(cudaGetLastError());
+    return SCHIC_OK;
+}
+
+int schic_mh_set_counts_device(schic_mh_handle* h, const uint16_t* d_counts, int64_t ld) {
+    ST_TRY(check(h));
+    const int64_t ndb = h->ext ? h->db_n : h->n;
+    if (d_counts && (ld < ndb || (ld & 7) != 0 || ((uintptr_t)d_counts & 15u)))
+        return fail(SCHIC_ERR_INVALID_ARG, "the count matrix needs a 16-byte aligned base and a row stride >= database rows that is a multiple of 8");
+    h->given_counts = d_counts;
+    h->given_ld = ld;
     return SCHIC_OK;
 }
 

@@ -330,13 +330,86 @@ class ShardedMinHash:
                 self.api.set_database_prep_device(self.h, norms_all.data_ptr(), dir_all.data_ptr(), self._nw,
                                                   packed_all.data_ptr(), flags_all.data_ptr(), nnz_total)
 
+    # -- step 2b: collision counts of a sharded run, every (rank x rank) block computed once -------------------------
+    def _symmetric_counts_possible(self) -> bool:
+        import os
+        return (self.world > 1 and self.device.type == "cuda" and hasattr(self.api, "collision_block_device")
+                and self.H <= 4094 and self.n_total <= 57344 and os.environ.get("SCHIC_K3_SHARDING", "symmetric") == "symmetric")
+
+    def _symmetric_counts(self):
+        """The count matrix is symmetric. With rows sharded, rank r needs block row r of it; computing that row alone
+        costs n^2 H / G compares per rank although every off-diagonal block (r, s) is the transpose of (s, r). Here rank r
+        computes its diagonal block with the symmetric kernel and HALF of every off-diagonal block of its rows -- for
+        s > r the columns of the first half of shard s, for s < r the rows of the second half of its own shard -- and
+        the kernel stores each such piece a second time, transposed, into a send buffer: exactly the piece rank s is
+        not computing. One point-to-point exchange (NCCL send/recv, ~(n/G)^2 bytes per peer) completes every rank's
+        block row: n^2 H / (2 G) compares per rank. Returns the [n_local, ld] uint16 matrix (as int16 tensor)."""
+        G, r, b = self.world, self.rank, self.bounds
+        nl = self.n_local
+        ld = (self.n_total + 7) // 8 * 8
+        counts = self._keep.get("counts")
+        if counts is None or counts.shape != (nl, ld):
+            counts = torch.empty((nl, ld), dtype=torch.int16, device=self.device)
+            self._keep["counts"] = counts
+        base, esz = counts.data_ptr(), 2
+
+        def half(s):                       # shard s = [lo, mid) + [mid, hi)
+            lo, hi = b[s], b[s + 1]
+            return lo, lo + (hi - lo + 1) // 2, hi
+
+        my_lo, my_mid, my_hi = half(r)
+        self.api.collision_block_device(self.h, my_lo, nl, my_lo, nl, base + my_lo * esz, ld)          # diagonal block
+        sends, recvs, ops = {}, {}, []
+        for s in range(G):
+            if s == r:
+                continue
+            s_lo, s_mid, s_hi = half(s)
+            if r < s:      # all my rows x first half of shard s; its transpose is what s lacks
+                rows0, nrows, cols0, ncols = my_lo, nl, s_lo, s_mid - s_lo
+                rshape = (nl, s_hi - s_mid)                   # from s: my rows x second half of shard s
+            else:          # second half of my rows x all of shard s
+                rows0, nrows, cols0, ncols = my_mid, my_hi - my_mid, s_lo, s_hi - s_lo
+                rshape = (my_mid - my_lo, s_hi - s_lo)        # from s: first half of my rows x shard s
+            ld_t = (nrows + 7) // 8 * 8
+            snd = torch.empty((ncols, ld_t), dtype=torch.int16, device=self.device)
+            self.api.collision_block_device(self.h, rows0, nrows, cols0, ncols,
+                                            base + ((rows0 - my_lo) * ld + cols0) * esz, ld, snd.data_ptr(), ld_t)
+            # what s sends has ITS row stride: rows = rshape[0] (mine), padded to a multiple of 8
+            sends[s] = snd
+            recvs[s] = torch.empty((rshape[0], (rshape[1] + 7) // 8 * 8), dtype=torch.int16, device=self.device)
+        # the piece s computed for me is [its columns = my rows] transposed: it arrives as [my rows, its rows (padded)]
+        for s in range(G):
+            if s == r:
+                continue
+            ops.append(dist.P2POp(dist.isend, sends[s].view(torch.uint8), s, group=self.group))     # (NCCL has no 16-bit integer type)
+            ops.append(dist.P2POp(dist.irecv, recvs[s].view(torch.uint8), s, group=self.group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for s in range(G):
+            if s == r:
+                continue
+            s_lo, s_mid, s_hi = half(s)
+            rv = recvs[s]
+            if r < s:      # my rows x second half of shard s
+                counts[:, s_mid:s_hi].copy_(rv[:, :s_hi - s_mid])
+            else:          # first half of my rows x shard s
+                counts[:my_mid - my_lo, s_lo:s_hi].copy_(rv[:, :s_hi - s_lo])
+        self._keep["k3_sends"] = (sends, recvs)        # keep the buffers alive until the stream has used them
+        return counts, ld
+
     # -- step 3: local queries -------------------------------------------------------------------
+    def _counts_for_queries(self):
+        if self._symmetric_counts_possible() and "sig_all" in self._keep:
+            counts, ld = self._symmetric_counts()
+            self.api.set_counts_device(self.h, counts.data_ptr(), ld)
+
     def kneighbors_local(self, k: int, out=None):
         if out is None:
             out = (torch.empty((self.n_local, k), dtype=torch.int32, device=self.device),
                    torch.empty((self.n_local, k), dtype=torch.float32, device=self.device),
                    torch.empty(self.n_local, dtype=torch.int32, device=self.device))
         idx, dst, nv = out
+        self._counts_for_queries()
         self.api.kneighbors_device(self.h, k, -1, idx.data_ptr(), dst.data_ptr(), nv.data_ptr())
         return out
 
@@ -349,6 +422,7 @@ class ShardedMinHash:
                    torch.empty(self.n_local * k, dtype=torch.int32, device=self.device),
                    torch.empty(self.n_local * k, dtype=torch.float32, device=self.device))
         ip, ix, dt = out
+        self._counts_for_queries()
         self.api.kneighbors_graph_device(self.h, k, -1, ip.data_ptr(), ix.data_ptr(), dt.data_ptr())
         return out
 

@@ -613,6 +613,49 @@ def test_fit_csr_host_staged_upload(cuda, oracle, monkeypatch):
     cuda.destroy(h)
 
 
+def test_collision_blocks_and_given_counts(cuda, oracle):
+    """schic_mh_collision_block_device / schic_mh_set_counts_device (the pieces of the sharded symmetric K3): arbitrary
+    blocks of the count matrix, with and without the transposed copy, equal the corresponding part of the full matrix
+    (= the oracle's); a count matrix assembled from blocks and handed back gives the same neighbours as the built-in K3,
+    also with bucket pruning (max_bin_size) active."""
+    import torch
+    X = synth_csr(300, seed=51)
+    n = X.shape[0]
+    dev = torch.device("cuda:0")
+    for extra in ({}, {"max_bin_size": 40, "minimal_blocks_in_common": 20}):
+        kw = dict(fast=True, n_neighbors=15, **extra)
+        with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
+            cuda.set_stream(g.h, torch.cuda.current_stream().cuda_stream)
+            full = oracle.collision_counts(o.h).astype(np.int64)
+            want = oracle.kneighbors(o.h, 15)
+            for (q0, qn, d0, dn) in ((0, n, 0, n), (17, 100, 130, 77), (130, 77, 17, 100), (5, 1, 0, n), (40, 128, 40, 128), (0, 0, 0, 10)):
+                ld, ldt = (dn + 7) // 8 * 8 + 8, (qn + 7) // 8 * 8
+                c = torch.full((max(qn, 1), ld), -1, dtype=torch.int16, device=dev)
+                ct = torch.full((max(dn, 1), max(ldt, 8)), -1, dtype=torch.int16, device=dev)
+                cuda.collision_block_device(g.h, q0, qn, d0, dn, c.data_ptr(), ld, ct.data_ptr(), max(ldt, 8))
+                torch.cuda.synchronize()
+                got = c.cpu().numpy().view(np.uint16)[:qn, :dn].astype(np.int64)
+                assert np.array_equal(got, full[q0:q0 + qn, d0:d0 + dn])
+                if not (q0 == d0 and qn == dn) and qn and dn:
+                    got_t = ct.cpu().numpy().view(np.uint16)[:dn, :qn].astype(np.int64)
+                    assert np.array_equal(got_t, full[q0:q0 + qn, d0:d0 + dn].T)
+            # assemble the whole matrix from a 2 x 2 split computed "once per pair" and hand it back
+            ld = (n + 7) // 8 * 8
+            m = torch.zeros((n, ld), dtype=torch.int16, device=dev)
+            h1 = 137
+            cuda.collision_block_device(g.h, 0, h1, 0, h1, m.data_ptr(), ld)
+            cuda.collision_block_device(g.h, h1, n - h1, h1, n - h1, m.data_ptr() + (h1 * ld + h1) * 2, ld)
+            tr = torch.zeros((n - h1, (h1 + 7) // 8 * 8), dtype=torch.int16, device=dev)
+            cuda.collision_block_device(g.h, 0, h1, h1, n - h1, m.data_ptr() + h1 * 2, ld, tr.data_ptr(), tr.shape[1])
+            m[h1:, :h1].copy_(tr[:, :h1])
+            cuda.set_counts_device(g.h, m.data_ptr(), ld)
+            got = cuda.kneighbors(g.h, 15)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b)
+            for a, b in zip(cuda.kneighbors(g.h, 15), want):          # one-shot: the next call computes K3 itself again
+                assert np.array_equal(a, b)
+
+
 def test_async_host_fit(cuda, oracle):
     """schic_mh_fit_csr_async: returns before the value array has landed; results identical to the blocking call."""
     X = synth_csr(220, seed=33)
