@@ -254,6 +254,9 @@ struct schic_mh_handle {
     const void* sig16_of = nullptr; int64_t sig16_rows = 0;          // database the renamed signatures were made from (block API)
     const uint16_t* given_counts = nullptr; int64_t given_ld = 0;    // caller-assembled count matrix for the next kneighbors call
     bool coll_blocks_open = false;                                   // ST_COLL holds block launches of the build in progress
+    DevBuf<unsigned long long> long_keys;                            // rows beyond the shared-memory sorts (k6_longrows.cu)
+    DevBuf<uint32_t> feat_rank; DevBuf<unsigned char> rank_scratch;  // ids >= 2^32: rank of every id among the distinct ids
+    bool rank_valid = false; uint32_t rank_max = 0;
     DevBuf<int32_t> out_idx, out_nv; DevBuf<float> out_dist;
     DevBuf<int64_t> g_indptr; DevBuf<int32_t> g_indices; DevBuf<float> g_data;
 
@@ -514,6 +517,29 @@ int prune_buckets(schic_mh_handle* h, const uint32_t* db_sig, int64_t ndb) {
     return 0;
 }
 
+// Feature ids beyond 32 bits: the rerank runs on the rank of every id among the distinct ids of the fitted rows (a
+// monotone relabelling, so equality and the order inside a row are preserved). Once per fit; one read-back (the number
+// of distinct ids sizes the window directory).
+int ensure_rank_labels(schic_mh_handle* h) {
+    if (h->rank_valid) return 0;
+    if (h->nnz > INT32_MAX) return fail(SCHIC_ERR_UNSUPPORTED, "exact rerank with ids >= 2^32 supports up to 2^31 non-zeros");
+    cudaStream_t s = h->stream;
+    CU_TRY(cudaStreamSynchronize(h->copy_stream));
+    const size_t need = schic::relabel_scratch_bytes(h->nnz);
+    ST_TRY(h->feat_rank.reserve(h->nnz + 4, 0, s));
+    ST_TRY(h->rank_scratch.reserve((int64_t)need, 0, s));
+    ST_TRY(h->max_feat.reserve(1, 0, s));
+    const int nl = schic::launch_relabel_ids(h->feat.p, h->feat_hi.p, h->nnz, h->feat_rank.p, h->max_feat.p, h->rank_scratch.p,
+                                             need, s);
+    if (nl < 0) return fail(SCHIC_ERR_CUDA, "id relabelling failed");
+    add_launches(h, nl);
+    CU_TRY(cudaMemcpyAsync(&h->rank_max, h->max_feat.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    h->rank_scratch.release();
+    h->rank_valid = true;
+    return 0;
+}
+
 // Per-database preparation of the exact rerank, cached until the next fit -- ONE pass over ids + values
 // (k4c_prep_kernel): fp64 row norms and, when the id range spans at most kMaxWindows windows of 2^16 ids, the window
 // directory, the packed stream of the counts kernel and the flags that say whether the data is packable.
@@ -535,7 +561,9 @@ int ensure_norms(schic_mh_handle* h, const int64_t* indptr, const uint32_t* feat
     int nw = 0;
     if (!(mode && strcmp(mode, "hash") == 0)) {
         uint32_t mx = 0;
-        if (h->feature_range > 0 && h->feature_range <= 0xFFFFFFFFull) {
+        if (h->have_hi && !h->ext && h->rank_valid) {
+            mx = h->rank_max;                      // ids were replaced by their ranks
+        } else if (h->feature_range > 0 && h->feature_range <= 0xFFFFFFFFull) {
             mx = (uint32_t)(h->feature_range - 1);
         } else {
             ST_TRY(h->max_feat.reserve(1, 0, s));
@@ -587,6 +615,19 @@ int prepare_packed_counts(schic_mh_handle* h, const uint32_t* db_sig, int64_t nd
     add_launches(h, nl);
     h->sig16_of = nullptr;          // (the block API re-validates what it needs)
     return 1;
+}
+
+// SCHIC_FORCE_LONGROWS=1 (tests): take the global-memory row sorts even when a row fits in shared memory
+bool force_longrows() { const char* e = getenv("SCHIC_FORCE_LONGROWS"); return e && atoi(e) != 0; }
+
+// scratch of the global-memory row sorts: rows per pass for rows of `row_len` keys (<= 1 GiB of keys at a time)
+int64_t long_rows_per_pass(int64_t row_len, int64_t nq) {
+    const int64_t P = schic::longrow_pow2(row_len);
+    return std::max<int64_t>(1, std::min<int64_t>(nq, ((int64_t)1 << 27) / P));
+}
+int reserve_long_keys(schic_mh_handle* h, int64_t row_len, int64_t nq, int64_t* rows_per_pass) {
+    *rows_per_pass = long_rows_per_pass(row_len, nq);
+    return h->long_keys.reserve(*rows_per_pass * (int64_t)schic::longrow_pow2(row_len), 0, h->stream);
 }
 
 // K4 over candidate lists [nq, kcand] (cand_idx == nullptr: brute force, every database row is a candidate of every
@@ -650,7 +691,7 @@ int rerank_lists(schic_mh_handle* h, const int64_t* db_indptr, const uint32_t* d
         const int kc = (int)std::min<int64_t>((int64_t)k + (exclude_self ? 1 : 0), RERANK_CHUNK);
         const int nchunks = (kcand + RERANK_CHUNK - 1) / RERANK_CHUNK;
         const int64_t stride = (int64_t)nchunks * kc;
-        if (stride > 16384) return fail(SCHIC_ERR_UNSUPPORTED, "rerank: candidate lists too long for the per-row merge (chunks * min(k, 1024) > 16384)");
+        if (stride > INT32_MAX / 2) return fail(SCHIC_ERR_UNSUPPORTED, "rerank: candidate lists too long");
         ST_TRY(h->part_idx.reserve(nq * stride, 0, s));
         ST_TRY(h->part_dist.reserve(nq * stride, 0, s));
         nl = 0;
@@ -660,9 +701,16 @@ int rerank_lists(schic_mh_handle* h, const int64_t* db_indptr, const uint32_t* d
             if (r < 0) return fail(SCHIC_ERR_UNSUPPORTED, "rerank: chunk does not fit in shared memory");
             nl += r;
         }
-        const int r = schic::launch_rerank_merge(h->part_idx.p, h->part_dist.p, (int)stride, cand_idx ? cand_nv : nullptr,
-                                                 kcand, (int)ndb, exclude_self ? row0 : -1, nq, k, d_idx, d_dist, d_nv, s);
-        if (r < 0) return fail(SCHIC_ERR_UNSUPPORTED, "rerank: merge does not fit in shared memory");
+        int r = (stride > 16384 || force_longrows()) ? -1
+                               : schic::launch_rerank_merge(h->part_idx.p, h->part_dist.p, (int)stride, cand_idx ? cand_nv : nullptr,
+                                                            kcand, (int)ndb, exclude_self ? row0 : -1, nq, k, d_idx, d_dist, d_nv, s);
+        if (r < 0) {           // more partial results per row than one CTA's shared memory sorts: global sort
+            int64_t per = 0;
+            ST_TRY(reserve_long_keys(h, stride, nq, &per));
+            r = schic::launch_rerank_merge_long(h->part_idx.p, h->part_dist.p, (int)stride, cand_idx ? cand_nv : nullptr, kcand,
+                                                (int)ndb, exclude_self ? row0 : -1, nq, k, d_idx, d_dist, d_nv, h->long_keys.p,
+                                                per, s);
+        }
         nl += r;
     }
     add_launches(h, nl);
@@ -682,7 +730,8 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
     const int64_t row0 = h->ext ? h->db_row0 : 0;
     const uint32_t* db_sig = h->ext ? h->db_sig : h->sig.p;
     const int64_t* db_indptr = h->ext ? h->db_indptr : h->d_indptr();
-    const uint32_t* db_feat = h->ext ? h->db_feat : h->d_feat();
+    const uint32_t* db_feat_in = h->ext ? h->db_feat : h->d_feat();
+    const uint32_t* db_feat = db_feat_in;      // (replaced by the ids' ranks when ids need more than 32 bits)
     const float* db_val = h->ext ? h->db_val : h->d_val();
     if (k > ndb) k = (int)ndb;   // cannot have more neighbours than fitted rows; outputs keep stride k
     const int64_t kc64 = fast ? (int64_t)k : std::min<int64_t>((int64_t)k * std::max(1, h->p.excess_factor), ndb);
@@ -690,7 +739,11 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
     const bool packed_db = h->ext && h->ext_packed && h->ext_flags && h->ext_norm2 && h->ext_dir && h->ext_nw > 0;
     if (!fast) {
         if ((!db_val || !db_feat) && !packed_db) return fail(SCHIC_ERR_INVALID_ARG, "exact rerank needs the CSR values (fit with data)");
-        if (h->have_hi) return fail(SCHIC_ERR_UNSUPPORTED, "exact rerank supports 32-bit feature ids only");
+        if (h->have_hi) {
+            if (h->ext || h->borrowed) return fail(SCHIC_ERR_UNSUPPORTED, "exact rerank with ids >= 2^32 needs the rows fitted through the host entry points");
+            ST_TRY(ensure_rank_labels(h));
+            db_feat = h->feat_rank.p;
+        }
     }
     // a count matrix assembled by the caller (schic_mh_set_counts_device: blocks of a sharded symmetric K3) replaces K3
     const uint16_t* given = h->given_counts;
@@ -760,10 +813,17 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
         }
         {
             StageTimer t(h, ST_SELECT, s);
-            const int nl = schic::launch_select_topk(counts_in, q1 - q0, ndb, ld, H, h->p.minimal_blocks_in_common,
-                                                     kcand, h->cand_idx.p + q0 * kcand, h->cand_cnt.p + q0 * kcand,
-                                                     h->cand_nv.p + q0, h->sel_flags.p, s);
-            if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k * excess_factor too large for the in-shared-memory select");
+            int nl = force_longrows() ? -1
+                                      : schic::launch_select_topk(counts_in, q1 - q0, ndb, ld, H, h->p.minimal_blocks_in_common,
+                                                                  kcand, h->cand_idx.p + q0 * kcand, h->cand_cnt.p + q0 * kcand,
+                                                                  h->cand_nv.p + q0, h->sel_flags.p, s);
+            if (nl < 0) {      // lists too long for the shared-memory select (e.g. the tool's default k = n): global sort
+                int64_t per = 0;
+                ST_TRY(reserve_long_keys(h, ndb, q1 - q0, &per));
+                nl = schic::launch_select_topk_long(counts_in, q1 - q0, ndb, ld, H, h->p.minimal_blocks_in_common, kcand,
+                                                    h->cand_idx.p + q0 * kcand, h->cand_cnt.p + q0 * kcand, h->cand_nv.p + q0,
+                                                    h->long_keys.p, per, s);
+            }
             add_launches(h, nl);
         }
         CU_TRY(cudaGetLastError());
@@ -795,11 +855,16 @@ int exact_knn_on_device(schic_mh_handle* h, int k, bool include_self, int32_t* d
     const int64_t ndb = h->ext ? h->db_n : h->n;
     const int64_t row0 = h->ext ? h->db_row0 : 0;
     const int64_t* db_indptr = h->ext ? h->db_indptr : h->d_indptr();
-    const uint32_t* db_feat = h->ext ? h->db_feat : h->d_feat();
+    const uint32_t* db_feat_in = h->ext ? h->db_feat : h->d_feat();
+    const uint32_t* db_feat = db_feat_in;      // (replaced by the ids' ranks when ids need more than 32 bits)
     const float* db_val = h->ext ? h->db_val : h->d_val();
     const bool packed_db = h->ext && h->ext_packed && h->ext_flags && h->ext_norm2 && h->ext_dir && h->ext_nw > 0;
     if ((!db_val || !db_feat) && !packed_db) return fail(SCHIC_ERR_INVALID_ARG, "exact kNN needs the CSR values (fit with data)");
-    if (h->have_hi) return fail(SCHIC_ERR_UNSUPPORTED, "exact kNN supports 32-bit feature ids only");
+    if (h->have_hi) {
+        if (h->ext || h->borrowed) return fail(SCHIC_ERR_UNSUPPORTED, "exact kNN with ids >= 2^32 needs the rows fitted through the host entry points");
+        ST_TRY(ensure_rank_labels(h));
+        db_feat = h->feat_rank.p;
+    }
     if (ndb > INT32_MAX) return fail(SCHIC_ERR_UNSUPPORTED, "too many rows");
     reset_stage(h, {ST_COLL, ST_SELECT, ST_RERANK, ST_GRAPH, ST_D2H, ST_PREP});
     cudaStream_t s = h->stream;
@@ -847,9 +912,14 @@ int graph_to_host(schic_mh_handle* h, int ke, int64_t* indptr, int32_t* indices,
     ST_TRY(h->g_data.reserve(n * ke, 0, s));
     {
         StageTimer t(h, ST_GRAPH, s);
-        const int nl = schic::launch_graph_emit(h->out_idx.p, h->out_dist.p, h->out_nv.p, n, ke, h->g_indptr.p,
-                                                h->g_indices.p, h->g_data.p, s);
-        if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k too large for the in-shared-memory graph emit");
+        int nl = force_longrows() ? -1 : schic::launch_graph_emit(h->out_idx.p, h->out_dist.p, h->out_nv.p, n, ke, h->g_indptr.p,
+                                                                  h->g_indices.p, h->g_data.p, s);
+        if (nl < 0) {          // rows longer than the shared-memory sort (dense graphs of > 16 384 cells): global sort
+            int64_t per = 0;
+            ST_TRY(reserve_long_keys(h, ke, n, &per));
+            nl = schic::launch_graph_emit_long(h->out_idx.p, h->out_dist.p, h->out_nv.p, n, ke, h->g_indptr.p, h->g_indices.p,
+                                               h->g_data.p, h->long_keys.p, per, s);
+        }
         add_launches(h, nl);
     }
     CU_TRY(cudaGetLastError());
@@ -1017,7 +1087,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
     }
     reset_stage(h, {ST_H2D, ST_SIG});
     h->k1_table_state = 0;
-    h->sig16_of = nullptr; h->given_counts = nullptr;
+    h->sig16_of = nullptr; h->given_counts = nullptr; h->rank_valid = false;
     for (cudaEvent_t e : h->misc_ev) h->free_ev.push_back(e);
     h->misc_ev.clear();
     h->val_done = nullptr;
@@ -1054,11 +1124,11 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
             lo[e] = (uint32_t)f64[e];
             any_hi = any_hi || (f64[e] >> 32) != 0;
         }
-        if (any_hi && !h->p.fast) return fail(SCHIC_ERR_UNSUPPORTED, "exact rerank supports feature ids < 2^32 only");
         f32 = lo.data();
     }
     // high words are kept from the first batch that needs them on (earlier batches are back-filled with zeros)
-    const bool want_hi = !st && h->p.hash_width == 64 && (any_hi || (r0 > 0 && h->have_hi));
+    // (the width-64 hash needs them; so does the exact rerank, which runs on the ranks of the full ids: k7_relabel.cu)
+    const bool want_hi = !st && (h->p.hash_width == 64 || !h->p.fast) && (any_hi || (r0 > 0 && h->have_hi));
     if (st && r0 > 0 && h->have_hi) return fail(SCHIC_ERR_UNSUPPORTED, "staged fit cannot append to rows with ids >= 2^32");
     if (want_hi) {
         hi.assign(nnz, 0u);
@@ -1507,9 +1577,14 @@ int schic_mh_kneighbors_graph_device(schic_mh_handle* h, int32_t k, int32_t fast
     const int ke = effective_k(h, k);
     ST_TRY(kneighbors_on_device(h, ke, fast, nullptr, nullptr, nullptr));
     StageTimer t(h, ST_GRAPH, h->stream);
-    const int nl = schic::launch_graph_emit(h->out_idx.p, h->out_dist.p, h->out_nv.p, h->n, ke, d_indptr, d_indices, d_data,
-                                            h->stream);
-    if (nl < 0) return fail(SCHIC_ERR_UNSUPPORTED, "k too large for the in-shared-memory graph emit");
+    int nl = force_longrows() ? -1 : schic::launch_graph_emit(h->out_idx.p, h->out_dist.p, h->out_nv.p, h->n, ke, d_indptr,
+                                                              d_indices, d_data, h->stream);
+    if (nl < 0) {
+        int64_t per = 0;
+        ST_TRY(reserve_long_keys(h, ke, h->n, &per));
+        nl = schic::launch_graph_emit_long(h->out_idx.p, h->out_dist.p, h->out_nv.p, h->n, ke, d_indptr, d_indices, d_data,
+                                           h->long_keys.p, per, h->stream);
+    }
     add_launches(h, nl);
     CU_TRY(cudaGetLastError());
     return SCHIC_OK;

@@ -138,6 +138,27 @@ int launch_rerank_merge(const int32_t* d_part_idx, const float* d_part_dist, int
 int launch_graph_emit(const int32_t* d_idx, const float* d_dist, const int32_t* d_nvalid, int64_t nq, int k,
                       int64_t* d_indptr, int32_t* d_indices, float* d_data, cudaStream_t stream);
 
+int launch_scan_nvalid(const int32_t* d_nvalid, int64_t nq, int64_t* d_indptr, cudaStream_t stream);
+
+// ---- rows beyond the shared-memory sorts (k6_longrows.cu): same contracts as launch_select_topk / launch_graph_emit /
+// launch_rerank_merge, ordered by a global-memory bitonic sort. d_keys: nq_block * longrow_pow2(row length) uint64.
+int longrow_pow2(int64_t n);
+int launch_select_topk_long(const uint16_t* d_cnt, int64_t nq, int64_t ndb, int64_t ld_cnt, int H, int min_blocks, int kcand,
+                            int32_t* d_idx, int32_t* d_cntsel, int32_t* d_nvalid, unsigned long long* d_keys,
+                            int64_t nq_block, cudaStream_t stream);
+int launch_graph_emit_long(const int32_t* d_idx, const float* d_dist, const int32_t* d_nvalid, int64_t nq, int k,
+                           int64_t* d_indptr, int32_t* d_indices, float* d_data, unsigned long long* d_keys,
+                           int64_t nq_block, cudaStream_t stream);
+int launch_rerank_merge_long(const int32_t* d_part_idx, const float* d_part_dist, int part_stride, const int32_t* d_cand_nvalid,
+                             int kcand, int n_all, int64_t exclude_row0, int64_t nq, int k, int32_t* d_idx_out,
+                             float* d_dist_out, int32_t* d_nvalid_out, unsigned long long* d_keys, int64_t nq_block,
+                             cudaStream_t stream);
+
+// ---- ids beyond 32 bits for the rerank (k7_relabel.cu): labels[i] = rank of (hi[i] << 32 | lo[i]) among the distinct ids
+size_t relabel_scratch_bytes(int64_t n);
+int launch_relabel_ids(const uint32_t* d_lo, const uint32_t* d_hi, int64_t n, uint32_t* d_labels, uint32_t* d_max_label,
+                       void* d_scratch, size_t scratch_bytes, cudaStream_t stream);
+
 // ---- INT32 throughput micro-benchmark (int_peak.cu) -----------------------------------------
 // out[0] ALU-pipe (LOP3/SHF/IADD3) Tint-op/s, out[1] FMA-pipe (IMAD), out[2] 1:1 mix, out[3] SM MHz.
 int run_int32_peak(int iters, double* out4, cudaStream_t stream);

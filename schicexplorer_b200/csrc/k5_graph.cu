@@ -47,6 +47,11 @@ graph_emit_kernel(const int32_t* __restrict__ idx, const float* __restrict__ dis
     }
 }
 
+int launch_scan_nvalid(const int32_t* d_nvalid, int64_t nq, int64_t* d_indptr, cudaStream_t stream) {
+    scan_nvalid_kernel<<<1, 1024, 0, stream>>>(d_nvalid, nq, d_indptr);
+    return 1;
+}
+
 int launch_graph_emit(const int32_t* d_idx, const float* d_dist, const int32_t* d_nvalid, int64_t nq, int k,
                       int64_t* d_indptr, int32_t* d_indices, float* d_data, cudaStream_t stream) {
     if (nq <= 0) return 0;

@@ -148,6 +148,47 @@ def test_ids_beyond_32_bits(cuda, oracle, width):
         assert np.array_equal(g.sig(), want_sig)
 
 
+@pytest.mark.parametrize("width", [32, 64])
+def test_exact_rerank_with_ids_beyond_32_bits(cuda, oracle, width):
+    """-em at high resolution (10 kb: bins^2 ~ 7e10 feature ids): the rerank and the exact kNN run on the ranks of the
+    64-bit ids (k7_relabel.cu). Ids that differ only in the HIGH word must stay different features; integer counts take
+    the counts kernel, fractional values the generic one; partial_fit re-ranks over all fitted rows; the Python class
+    takes the same route for a matrix with more than 2^32 columns."""
+    rng = np.random.default_rng(40 + width)
+    ncols = 1 << 40
+    low = np.unique(rng.integers(0, 1 << 20, size=600))
+    pool = np.unique(np.concatenate([low, low + (1 << 32), low + (5 << 32), rng.integers(1 << 33, ncols, size=500)]))
+    rows, cols, vals = [], [], []
+    for r in range(80):
+        c = np.sort(rng.choice(pool, size=int(rng.integers(20, 700)), replace=False))
+        rows.append(np.full(len(c), r)); cols.append(c); vals.append(rng.integers(1, 30, size=len(c)).astype(np.float64))
+    X = csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(80, ncols))
+    X.indices = X.indices.astype(np.int64)
+    X.indptr = X.indptr.astype(np.int64)
+    for scale, kernel in ((1.0, "k4c_rerank_kernel"), (0.5, "k4_rerank_window_kernel")):
+        Xs = X.copy(); Xs.data = Xs.data * scale
+        kw = dict(number_of_hash_functions=128, minimal_blocks_in_common=1, hash_width=width, fast=False, n_neighbors=12, excess_factor=2)
+        with Fitted(oracle, Xs, **kw) as o, Fitted(cuda, Xs, **kw) as g:
+            want = oracle.kneighbors(o.h, 12)
+            assert_neighbours_equal_up_to_ties(*cuda.kneighbors(g.h, 12), *want, RTOL)
+            assert cuda.rerank_kernel_name(g.h) == kernel
+            assert_neighbours_equal_up_to_ties(*cuda.kneighbors_exact(g.h, 7, False), *oracle.kneighbors_exact(o.h, 7, False), RTOL)
+            a, b = Xs[:30], Xs[30:]
+            cuda.fit_csr(g.h, a.indptr, a.indices, a.data.astype(np.float32), False)
+            cuda.fit_csr(g.h, b.indptr, b.indices, b.data.astype(np.float32), True)
+            assert_neighbours_equal_up_to_ties(*cuda.kneighbors(g.h, 12), *want, RTOL)
+    from schicexplorer_b200 import MinHash
+    kwc = dict(number_of_hash_functions=128, minimal_blocks_in_common=1, hash_width=width, fast=False, n_neighbors=12, excess_factor=2,
+               max_bin_size=100000)
+    mh = MinHash(device=0, **kwc)
+    graph = mh.fit(X).kneighbors_graph(mode="distance")
+    mh.close()
+    with Fitted(oracle, X, **dict(kw, fast=False)) as o:
+        oi, oc, od = oracle.kneighbors_graph(o.h, 12)
+    assert np.array_equal(graph.indptr, oi) and np.array_equal(graph.indices, oc)
+    np.testing.assert_allclose(graph.data, od, rtol=RTOL)
+
+
 @pytest.mark.parametrize("seed", range(6))
 @pytest.mark.parametrize("exchange", ["csr", "csr+packed", "packed"])
 def test_sharded_query_path_on_one_gpu(cuda, oracle, seed, exchange):

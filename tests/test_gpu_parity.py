@@ -656,6 +656,46 @@ def test_collision_blocks_and_given_counts(cuda, oracle):
                 assert np.array_equal(a, b)
 
 
+def test_long_row_fallbacks(cuda, oracle, monkeypatch):
+    """k6_longrows.cu: select, graph emit and rerank merge through the global-memory row sort (what a dense graph of more
+    than 16 384 cells takes -- the tool's default k = n), forced on small inputs with SCHIC_FORCE_LONGROWS: identical
+    to the oracle in fast and exact mode, k = n and k < n, with excess candidates, chunked rerank lists and the
+    brute-force exact kNN; and once for real on rows longer than the shared-memory limit."""
+    monkeypatch.setenv("SCHIC_FORCE_LONGROWS", "1")
+    X = synth_csr(210, seed=61)
+    n = X.shape[0]
+    for fast, k, ef in ((True, n, 1), (True, 17, 3), (False, n, 1), (False, 30, 2)):
+        kw = dict(fast=fast, n_neighbors=k, excess_factor=ef, minimal_blocks_in_common=40)
+        with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
+            a, b = cuda.kneighbors(g.h, k), oracle.kneighbors(o.h, k)
+            assert_neighbours_equal_up_to_ties(*a, *b, 0 if fast else RTOL)
+            gi, gc, gd = cuda.kneighbors_graph(g.h, k)
+            oi, oc, od = oracle.kneighbors_graph(o.h, k)
+            assert np.array_equal(gi, oi) and np.array_equal(gc, oc)
+            np.testing.assert_allclose(gd, od, rtol=0 if fast else RTOL)
+    # chunked rerank (lists longer than 1024) + merge, and the brute-force exact kNN, through the global merge
+    Xl = synth_csr(1300, seed=62, median_nnz=300, min_nnz=60, max_nnz=900)
+    kw = dict(fast=False, n_neighbors=1300, minimal_blocks_in_common=1, number_of_hash_functions=64)
+    with Fitted(cuda, Xl, **kw) as g, Fitted(oracle, Xl, **kw) as o:
+        assert_neighbours_equal_up_to_ties(*cuda.kneighbors(g.h, 1300), *oracle.kneighbors(o.h, 1300), RTOL)
+        a, b = cuda.kneighbors_exact(g.h, 25, False), oracle.kneighbors_exact(o.h, 25, False)
+        assert_neighbours_equal_up_to_ties(*a, *b, RTOL)
+    monkeypatch.delenv("SCHIC_FORCE_LONGROWS")
+    # for real: 17 000 tiny cells, dense graph (k = n > 16 384), fast distances -- graph identical to the oracle's
+    rng = np.random.default_rng(63)
+    nbig, ncols = 17000, 50000
+    pool = rng.choice(ncols, size=400, replace=False)
+    rows = np.repeat(np.arange(nbig), 12)
+    cols = np.concatenate([np.sort(rng.choice(pool, size=12, replace=False)) for _ in range(nbig)])
+    Xb = csr_matrix((np.ones(len(cols)), (rows, cols)), shape=(nbig, ncols))
+    kw = dict(fast=True, n_neighbors=nbig, number_of_hash_functions=32, minimal_blocks_in_common=8)
+    with Fitted(cuda, Xb, **kw) as g, Fitted(oracle, Xb, **kw) as o:
+        gi, gc, gd = cuda.kneighbors_graph(g.h, nbig)
+        oi, oc, od = oracle.kneighbors_graph(o.h, nbig)
+        assert np.array_equal(gi, oi) and np.array_equal(gc, oc) and np.array_equal(gd, od)
+        assert gi[-1] > 5 * nbig
+
+
 def test_async_host_fit(cuda, oracle):
     """schic_mh_fit_csr_async: returns before the value array has landed; results identical to the blocking call."""
     X = synth_csr(220, seed=33)
