@@ -252,6 +252,8 @@ struct schic_mh_handle {
     DevBuf<uint32_t> sig_masked;   // database signatures with oversized buckets blanked (K2)
     DevBuf<uint32_t> k3h_table, k3h_sizes; DevBuf<uint16_t> sig16;   // packed K3: renaming tables, bucket sizes, renamed signatures
     const void* sig16_of = nullptr; int64_t sig16_rows = 0;          // database the renamed signatures were made from (block API)
+    DevBuf<uint32_t> sig16T;                                         // the same, transposed, for the TMA-staged K3
+    alignas(64) unsigned char k3_tmap[128]; bool k3_tma = false;     // tensor map over sig16T (valid for the last rename)
     const uint16_t* given_counts = nullptr; int64_t given_ld = 0;    // caller-assembled count matrix for the next kneighbors call
     bool coll_blocks_open = false;                                   // ST_COLL holds block launches of the build in progress
     DevBuf<unsigned long long> long_keys;                            // rows beyond the shared-memory sorts (k6_longrows.cu)
@@ -601,6 +603,21 @@ bool packed_counts_possible(const schic_mh_handle* h, int64_t ndb) {
     return !(mode && strcmp(mode, "plain") == 0) && schic::k3h_applicable(ndb, h->p.number_of_hash_functions);
 }
 
+// Packed K3 on database rows [q_row0, +nq) x [d_row0, +nd) of the renamed signatures (TMA-staged when available)
+int launch_k3_packed(schic_mh_handle* h, int64_t q_row0, int64_t nq, int64_t d_row0, int64_t nd, uint16_t* cnt, int64_t ld,
+                     uint16_t* cnt_t, int64_t ld_t) {
+    const int H = h->p.number_of_hash_functions;
+    // (a TMA box must start on a 16-byte boundary of the row axis: row offsets that are not multiples of 4 take the LDG kernel)
+    if (h->k3_tma && (q_row0 & 3) == 0 && (d_row0 & 3) == 0)
+        return schic::launch_collision_counts_tma(h->k3_tmap, q_row0, nq, d_row0, nd, H, cnt, ld, cnt_t, ld_t, h->stream);
+    const int64_t Hp = schic::k3h_padded_hashes(H);
+    const uint16_t* q16 = h->sig16.p + q_row0 * Hp;
+    const uint16_t* d16 = h->sig16.p + d_row0 * Hp;
+    if (cnt_t && !(q_row0 == d_row0 && nq == nd))
+        return schic::launch_collision_counts_packed_t(q16, nq, d16, nd, H, cnt, ld, cnt_t, ld_t, h->stream);
+    return schic::launch_collision_counts_packed(q16, nq, d16, nd, H, cnt, ld, h->stream);
+}
+
 // db_sig: the UNPRUNED database signatures; buckets with >= max_bin_size members are blanked here when ndb reaches it
 int prepare_packed_counts(schic_mh_handle* h, const uint32_t* db_sig, int64_t ndb) {
     const int H = h->p.number_of_hash_functions;
@@ -614,6 +631,16 @@ int prepare_packed_counts(schic_mh_handle* h, const uint32_t* db_sig, int64_t nd
     if (nl < 0) return fail(SCHIC_ERR_CUDA, "signature renaming launch failed");
     add_launches(h, nl);
     h->sig16_of = nullptr;          // (the block API re-validates what it needs)
+    // TMA-staged K3 (default; SCHIC_K3_TMA=0: LDG-staged kernel): transposed copy + tensor map
+    h->k3_tma = false;
+    const char* tma = getenv("SCHIC_K3_TMA");
+    if (!(tma && atoi(tma) == 0) && ndb < INT32_MAX) {
+        ST_TRY(h->sig16T.reserve((int64_t)schic::k3t_transposed_elems(ndb, H), 0, h->stream));
+        if (schic::k3t_make_tensor_map(h->sig16T.p, ndb, H, h->k3_tmap) == 0) {
+            add_launches(h, schic::launch_transpose_signatures(h->sig16.p, ndb, H, h->sig16T.p, h->stream));
+            h->k3_tma = true;
+        }
+    }
     return 1;
 }
 
@@ -805,8 +832,7 @@ int kneighbors_on_device(schic_mh_handle* h, int k, int fast_arg, int32_t* d_idx
         if (!given) {
             StageTimer t(h, ST_COLL, s);
             if (packed)
-                add_launches(h, schic::launch_collision_counts_packed(h->sig16.p + (row0 + q0) * Hp, q1 - q0,
-                                                                     h->sig16.p, ndb, H, h->counts.p, ld, s));
+                add_launches(h, launch_k3_packed(h, row0 + q0, q1 - q0, 0, ndb, h->counts.p, ld, nullptr, 0));
             else
                 add_launches(h, schic::launch_collision_counts(q_sig + q0 * (int64_t)H, q1 - q0, db_sig, ndb, H,
                                                               h->counts.p, ld, s));
@@ -1482,10 +1508,8 @@ int schic_mh_collision_counts(schic_mh_handle* h, int64_t row0, int64_t row1, ui
     const int packed = prepare_packed_counts(h, db_sig, ndb);
     if (packed < 0) return packed;
     if (packed) {
-        const int64_t Hp = schic::k3h_padded_hashes(H);
         const int64_t first = (h->ext ? h->db_row0 : 0) + row0;     // the query rows are database rows
-        add_launches(h, schic::launch_collision_counts_packed(h->sig16.p + first * Hp, nq, h->sig16.p, ndb, H,
-                                                             h->counts.p, ld, h->stream));
+        add_launches(h, launch_k3_packed(h, first, nq, 0, ndb, h->counts.p, ld, nullptr, 0));
     } else {
         add_launches(h, schic::launch_collision_counts(q_sig + row0 * (int64_t)H, nq, db_sig, ndb, H, h->counts.p, ld, h->stream));
     }
@@ -1517,15 +1541,8 @@ int schic_mh_collision_block_device(schic_mh_handle* h, int64_t q_row0, int64_t 
         h->sig16_of = db_sig; h->sig16_rows = ndb;
     }
     if (q_rows == 0 || d_rows == 0) return SCHIC_OK;
-    const int64_t Hp = schic::k3h_padded_hashes(H);
-    const uint16_t* q16 = h->sig16.p + q_row0 * Hp;
-    const uint16_t* d16 = h->sig16.p + d_row0 * Hp;
-    int nl;
-    if (d_cnt_t && !(q_row0 == d_row0 && q_rows == d_rows))
-        nl = schic::launch_collision_counts_packed_t(q16, q_rows, d16, d_rows, H, d_cnt, ld, d_cnt_t, ld_t, s);
-    else
-        nl = schic::launch_collision_counts_packed(q16, q_rows, d16, d_rows, H, d_cnt, ld, s);   // (same rows twice: symmetric kernel)
-    add_launches(h, nl);
+    const bool same = q_row0 == d_row0 && q_rows == d_rows;          // same rows twice: symmetric kernel, no transposed copy
+    add_launches(h, launch_k3_packed(h, q_row0, q_rows, d_row0, d_rows, d_cnt, ld, same ? nullptr : d_cnt_t, ld_t));
     CU_TRY(cudaGetLastError());
     return SCHIC_OK;
 }

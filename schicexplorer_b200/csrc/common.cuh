@@ -68,6 +68,14 @@ int launch_collision_counts_packed(const uint16_t* d_q16, int64_t nq, const uint
 int launch_collision_counts_packed_t(const uint16_t* d_q16, int64_t nq, const uint16_t* d_d16, int64_t ndb, int H,
                                      uint16_t* d_cnt, int64_t ld_out, uint16_t* d_cnt_t, int64_t ld_t, cudaStream_t stream);
 
+// TMA-staged variant: the renamed signatures transposed (sig16T, k3t_transposed_elems uint32), a tensor map over them
+// (128 bytes, 64-byte aligned host memory), counts of database rows [q_row0, +nq) x [d_row0, +ndb).
+size_t k3t_transposed_elems(int64_t n, int H);
+int launch_transpose_signatures(const uint16_t* d_sig16, int64_t n, int H, uint32_t* d_sig16T, cudaStream_t stream);
+int k3t_make_tensor_map(const uint32_t* d_sig16T, int64_t n, int H, void* out_map);
+int launch_collision_counts_tma(const void* map, int64_t q_row0, int64_t nq, int64_t d_row0, int64_t ndb, int H, uint16_t* d_cnt,
+                                int64_t ld_out, uint16_t* d_cnt_t, int64_t ld_t, cudaStream_t stream);
+
 // ---- K3b: threshold + top-k select + fast distance (k3_select.cu) --------------------------
 // For each query row: candidates with cnt >= min_blocks (and > 0), ordered by (cnt desc, idx asc),
 // first kcand kept. Writes idx [nq,kcand] (-1 padded), cnt [nq,kcand], n_valid [nq].

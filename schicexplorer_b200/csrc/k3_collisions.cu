@@ -12,6 +12,7 @@
 // in shared memory so every operand fetch is a conflict-free LDS.128. Non-admissible values
 // (0, the sentinel M, padding) are rewritten while staging to two patterns that can never be
 // equal, so the inner loop has no validity test.
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -310,6 +311,234 @@ k3h_collision_kernel(const uint32_t* __restrict__ q16, int64_t nq, const uint32_
             }
         }
     }
+}
+
+// =================================================================================================
+// TMA-staged variant of the packed kernel (Blackwell bulk-tensor copies + mbarrier).
+//
+// The kernels above stage every 128 x 32 operand tile with LDG + transposed STS by all 256 threads and two barriers per
+// step. Here the renamed signatures are ALSO kept transposed -- sig16T [Hw_pad][n_pad] uint32, row index contiguous
+// (k3h_transpose_kernel) -- so that an operand tile [32 words][128 rows] is one 2-D box of a tensor map: one elected
+// thread issues two cp.async.bulk.tensor.2d loads (query tile, database tile: 32 KB) per step into a double-buffered
+// stage and arms an mbarrier with the byte count; the other threads only wait on the barrier's phase. Loads for step
+// s + 1 are in flight while step s is compared, the compare warps issue no staging instructions at all, and one
+// __syncthreads per step (stage reuse) remains instead of two. Row offsets must be multiples of 4 (a box starts on a
+// 16-byte boundary; other offsets take the LDG kernel), rows past the end read as zero -- such rows and columns are never stored -- and the padding words
+// (Hw .. Hw_pad) hold the never-equal NaN pattern.
+// =================================================================================================
+constexpr int K3T_STAGE_WORDS = 2 * K3_JB * K3_TILE;        // query tile + database tile, uint32
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "K3T_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra K3T_DONE;\n"
+        "bra K3T_WAIT;\n"
+        "K3T_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+// sig16 [n][Hp] uint16 (row major, Hp even) -> sig16T [Hw_pad][n_pad] uint32; padding = NaN pattern
+__global__ void __launch_bounds__(256)
+k3h_transpose_kernel(const uint32_t* __restrict__ sig16w, int64_t n, int Hw, int Hw_pad, int64_t n_pad,
+                     uint32_t* __restrict__ sig16T) {
+    __shared__ uint32_t tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 8 x 32
+    for (int a = ty; a < 32; a += 8) {
+        const int64_t r = r0 + a;
+        const int j = j0 + tx;
+        tile[a][tx] = (r < n && j < Hw) ? __ldg(sig16w + r * (int64_t)Hw + j) : 0x7E007E00u;
+    }
+    __syncthreads();
+    for (int a = ty; a < 32; a += 8) {
+        const int j = j0 + a;
+        const int64_t r = r0 + tx;
+        if (j < Hw_pad && r < n_pad) sig16T[(int64_t)j * n_pad + r] = tile[tx][a];
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(K3_THREADS, 2)
+k3t_collision_kernel(const __grid_constant__ CUtensorMap tmap, int q_row0, int64_t nq, int d_row0, int64_t nd, int Hw_pad,
+                     uint16_t* __restrict__ cnt, int64_t ld_out, uint16_t* __restrict__ cnt_t, int64_t ld_t) {
+    constexpr bool SYM = MODE == 1;
+    extern __shared__ __align__(1024) unsigned char k3t_smem[];
+    uint32_t* stage_base = reinterpret_cast<uint32_t*>(k3t_smem);                       // [2][K3T_STAGE_WORDS]
+    __shared__ __align__(8) uint64_t full_bar[2];
+
+    if (SYM && blockIdx.x < blockIdx.y) return;
+    const int64_t q0 = (int64_t)blockIdx.y * K3_TILE;
+    const int64_t d0 = (int64_t)blockIdx.x * K3_TILE;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int steps = Hw_pad / K3_JB;
+    auto issue = [&](int s) {
+        uint32_t* st = stage_base + (s & 1) * K3T_STAGE_WORDS;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic-proxy reads of this stage are done
+        mbar_expect_tx(&full_bar[s & 1], K3T_STAGE_WORDS * 4);
+        tma_load_2d(st, &tmap, (int)(q_row0 + q0), s * K3_JB, &full_bar[s & 1]);
+        tma_load_2d(st + K3_JB * K3_TILE, &tmap, (int)(d_row0 + d0), s * K3_JB, &full_bar[s & 1]);
+    };
+    if (threadIdx.x == 0) issue(0);
+
+    uint32_t acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0u;
+
+    for (int s = 0; s < steps; ++s) {
+        if (threadIdx.x == 0 && s + 1 < steps) issue(s + 1);        // its stage was released by the barrier ending step s - 1
+        mbar_wait(&full_bar[s & 1], (uint32_t)((s >> 1) & 1));
+        const uint32_t* Qs = stage_base + (s & 1) * K3T_STAGE_WORDS;
+        const uint32_t* Ds = Qs + K3_JB * K3_TILE;
+#pragma unroll 2
+        for (int jj = 0; jj < K3_JB; ++jj) {
+            const uint4 qa = *reinterpret_cast<const uint4*>(Qs + jj * K3_TILE + ty * 8);
+            const uint4 qb = *reinterpret_cast<const uint4*>(Qs + jj * K3_TILE + ty * 8 + 4);
+            const uint4 da = *reinterpret_cast<const uint4*>(Ds + jj * K3_TILE + tx * 8);
+            const uint4 db = *reinterpret_cast<const uint4*>(Ds + jj * K3_TILE + tx * 8 + 4);
+            const uint32_t q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+            const uint32_t d[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b)
+                    asm("{ .reg .b32 e; set.eq.f16x2.f16x2 e, %1, %2; add.f16x2 %0, %0, e; }"
+                        : "+r"(acc[a][b]) : "r"(q[a]), "r"(d[b]));
+        }
+        __syncthreads();                                             // stage s & 1 may be refilled (by the issue of step s + 2)
+    }
+
+    auto total = [](uint32_t h2) -> uint32_t {
+        const __half2 v = *reinterpret_cast<const __half2*>(&h2);
+        return (uint32_t)(__low2float(v) + __high2float(v));
+    };
+    const bool vec_ok = ((ld_out & 7) == 0) && ((((uintptr_t)cnt) & 15) == 0) && (d0 + tx * 8 + 8 <= nd);
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int64_t q = q0 + ty * 8 + a;
+        if (q >= nq) continue;
+        uint16_t* dst = cnt + q * ld_out + d0 + tx * 8;
+        if (vec_ok) {
+            uint4 o;
+            o.x = total(acc[a][0]) | (total(acc[a][1]) << 16);
+            o.y = total(acc[a][2]) | (total(acc[a][3]) << 16);
+            o.z = total(acc[a][4]) | (total(acc[a][5]) << 16);
+            o.w = total(acc[a][6]) | (total(acc[a][7]) << 16);
+            *reinterpret_cast<uint4*>(dst) = o;
+        } else {
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+                if (d0 + tx * 8 + b < nd) dst[b] = (uint16_t)total(acc[a][b]);
+        }
+    }
+    if ((SYM && blockIdx.x > blockIdx.y) || MODE == 2) {
+        uint16_t* __restrict__ mt = MODE == 2 ? cnt_t : cnt;
+        const int64_t mld = MODE == 2 ? ld_t : ld_out;
+        const bool tvec_ok = ((mld & 7) == 0) && ((((uintptr_t)mt) & 15) == 0) && (q0 + ty * 8 + 8 <= nq);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int64_t d = d0 + tx * 8 + b;
+            if (d >= nd) continue;
+            uint16_t* dst = mt + d * mld + q0 + ty * 8;
+            if (tvec_ok) {
+                uint4 o;
+                o.x = total(acc[0][b]) | (total(acc[1][b]) << 16);
+                o.y = total(acc[2][b]) | (total(acc[3][b]) << 16);
+                o.z = total(acc[4][b]) | (total(acc[5][b]) << 16);
+                o.w = total(acc[6][b]) | (total(acc[7][b]) << 16);
+                *reinterpret_cast<uint4*>(dst) = o;
+            } else {
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+                    if (q0 + ty * 8 + a < nq) dst[a] = (uint16_t)total(acc[a][b]);
+            }
+        }
+    }
+}
+
+int k3t_padded_words(int H) { return ((k3h_padded_hashes(H) / 2) + K3_JB - 1) / K3_JB * K3_JB; }
+int64_t k3t_padded_rows(int64_t n) { return (n + 3) & ~(int64_t)3; }
+size_t k3t_transposed_elems(int64_t n, int H) { return (size_t)k3t_padded_words(H) * (size_t)k3t_padded_rows(n); }
+
+// The tensor map over sig16T (driver entry point resolved through the runtime: no link against libcuda).
+// out_map: 128 bytes (CUtensorMap). Returns 0 on success.
+int k3t_make_tensor_map(const uint32_t* d_sig16T, int64_t n, int H, void* out_map) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            cudaGetLastError();
+            return -1;
+        }
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)k3t_padded_rows(n), (cuuint64_t)k3t_padded_words(H)};
+    const cuuint64_t strides[1] = {(cuuint64_t)k3t_padded_rows(n) * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)K3_TILE, (cuuint32_t)K3_JB};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)d_sig16T, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+
+int launch_transpose_signatures(const uint16_t* d_sig16, int64_t n, int H, uint32_t* d_sig16T, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    const int Hw = k3h_padded_hashes(H) / 2, Hw_pad = k3t_padded_words(H);
+    const int64_t n_pad = k3t_padded_rows(n);
+    dim3 grid((unsigned)((n_pad + 31) / 32), (unsigned)(Hw_pad / 32));
+    k3h_transpose_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_sig16), n, Hw, Hw_pad, n_pad, d_sig16T);
+    return 1;
+}
+
+// Counts of database rows [q_row0, +nq) x [d_row0, +ndb) from the transposed renamed signatures behind `map`.
+// Same rows twice (q_row0 == d_row0, nq == ndb, no transposed output): symmetric kernel.
+int launch_collision_counts_tma(const void* map, int64_t q_row0, int64_t nq, int64_t d_row0, int64_t ndb, int H, uint16_t* d_cnt,
+                                int64_t ld_out, uint16_t* d_cnt_t, int64_t ld_t, cudaStream_t stream) {
+    if (nq <= 0 || ndb <= 0) return 0;
+    const int Hw_pad = k3t_padded_words(H);
+    dim3 grid((unsigned)((ndb + K3_TILE - 1) / K3_TILE), (unsigned)((nq + K3_TILE - 1) / K3_TILE));
+    const size_t smem = (size_t)2 * K3T_STAGE_WORDS * 4 + 1024;
+    const CUtensorMap& tm = *reinterpret_cast<const CUtensorMap*>(map);
+    const bool sym = q_row0 == d_row0 && nq == ndb && !d_cnt_t;
+    if (sym) {
+        cudaFuncSetAttribute(k3t_collision_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k3t_collision_kernel<1><<<grid, K3_THREADS, smem, stream>>>(tm, (int)q_row0, nq, (int)d_row0, ndb, Hw_pad, d_cnt, ld_out, nullptr, 0);
+    } else if (d_cnt_t) {
+        cudaFuncSetAttribute(k3t_collision_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k3t_collision_kernel<2><<<grid, K3_THREADS, smem, stream>>>(tm, (int)q_row0, nq, (int)d_row0, ndb, Hw_pad, d_cnt, ld_out, d_cnt_t, ld_t);
+    } else {
+        cudaFuncSetAttribute(k3t_collision_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k3t_collision_kernel<0><<<grid, K3_THREADS, smem, stream>>>(tm, (int)q_row0, nq, (int)d_row0, ndb, Hw_pad, d_cnt, ld_out, nullptr, 0);
+    }
+    return 1;
 }
 
 bool k3h_applicable(int64_t ndb, int H) { return H <= 4094 && ndb <= K3H_MAX_ROWS && ndb > 0; }
