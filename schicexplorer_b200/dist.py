@@ -68,6 +68,33 @@ def _gather_padded(local: torch.Tensor, counts: list, group, tail_pad: int = 0) 
     return out[:total]
 
 
+def _gather_var(local: torch.Tensor, counts: list, group, tail_pad: int = 0) -> torch.Tensor:
+    """All-gather of unequal first-dimension shards WITHOUT padding or compaction: every rank receives each peer's shard
+    straight into its place of the result (one grouped round of NCCL send / recv). For the big arrays of the exchange
+    (packed stream, ids, values), where pad + all-gather + concatenate would move the data twice."""
+    world, rank = len(counts), dist.get_rank(group)
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + int(c))
+    tail = tuple(local.shape[1:])
+    out = torch.empty((offs[-1] + tail_pad,) + tail, dtype=local.dtype, device=local.device)
+    local = local.contiguous()
+    assert local.shape[0] == counts[rank]
+    if counts[rank]:
+        out[offs[rank]:offs[rank + 1]].copy_(local)
+    ops = []
+    for step in range(1, world):
+        dst, src = (rank + step) % world, (rank - step) % world
+        if counts[rank]:
+            ops.append(dist.P2POp(dist.isend, local, dst, group=group))
+        if counts[src]:
+            ops.append(dist.P2POp(dist.irecv, out[offs[src]:offs[src + 1]], src, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out[:offs[-1]]
+
+
 class PeerExchange:
     """CSR exchange over NVLink peer memory instead of an NCCL all-gather (experimental, opt-in: see the note in
     ShardedMinHash.__init__ -- correct, but slower than NCCL where legacy CUDA IPC mappings do not get NVLink DMA).
@@ -255,33 +282,49 @@ class ShardedMinHash:
             dist.all_gather_into_tensor(nnz_all, nnz_local, group=group)
             nnzs = [int(x) for x in nnz_all.tolist()]
         ev = None
+        gather_big = _gather_var if self.device.type == "cuda" else _gather_padded
         packed_only = "prep_local" in self._keep and self._keep["prep_local"][3] is not None
         if packed_only:
             ix_all = dt_all = None            # the packed stream (gathered below) is all the rerank reads
         elif self._peer is not None:
             ix_all, dt_all, ev = self._peer.exchange(d_indices, d_data)
         else:
-            ix_all = _gather_padded(d_indices, nnzs, group)
-            dt_all = _gather_padded(d_data, nnzs, group)
-        # row lengths -> global indptr
+            ix_all = gather_big(d_indices, nnzs, group)
+            dt_all = gather_big(d_data, nnzs, group)
         lens = (d_indptr[1:] - d_indptr[:-1]).contiguous()
-        lens_all = _gather_padded(lens, counts, group)
+        self._keep.pop("prep_all", None)
+        if "prep_local" in self._keep:
+            norms, wdir, flags, packed = self._keep["prep_local"]
+            packed_all = None
+            if packed is not None:
+                # (16 readable bytes behind the stream: the counts kernel reads slices as aligned 16-byte words)
+                packed_all = gather_big(packed, nnzs, group, tail_pad=4)
+            # the small per-row arrays travel in ONE collective: [lens | norms | directory | flags] per rank, padded to the
+            # largest shard (row lengths as int64, norms as float64, both viewed as bytes)
+            mx, nw1 = max(counts), self._nw + 1
+            seg = [(x + 15) // 16 * 16 for x in (mx * 8, mx * 8, mx * nw1 * 4, 16)]      # 16-byte aligned segments
+            buf = torch.zeros(sum(seg), dtype=torch.uint8, device=self.device)
+            nl = self.n_local
+            buf[:nl * 8].copy_(lens.view(torch.uint8))
+            buf[seg[0]:seg[0] + nl * 8].copy_(norms.view(torch.uint8))
+            buf[seg[0] + seg[1]:seg[0] + seg[1] + nl * nw1 * 4].copy_(wdir.reshape(-1).view(torch.uint8))
+            buf[seg[0] + seg[1] + seg[2]:].copy_(flags.view(torch.uint8))
+            allb = torch.empty((self.world, sum(seg)), dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allb.view(-1), buf, group=group)
+            o1, o2, o3 = seg[0], seg[0] + seg[1], seg[0] + seg[1] + seg[2]
+            lens_all = torch.cat([allb[r, :counts[r] * 8].view(torch.int64) for r in range(self.world)])
+            norms_all = torch.cat([allb[r, o1:o1 + counts[r] * 8].view(torch.float64) for r in range(self.world)])
+            dir_all = torch.cat([allb[r, o2:o2 + counts[r] * nw1 * 4].view(torch.int32).view(counts[r], nw1)
+                                 for r in range(self.world)])
+            flags_all = allb[:, o3:].contiguous().view(torch.int32).view(self.world, 4).sum(dim=0).to(torch.int32)   # 0/1 flags and one count: a sum combines them
+            self._keep["prep_all"] = (norms_all, dir_all, flags_all, packed_all, sum(nnzs))
+        else:
+            lens_all = _gather_padded(lens, counts, group)
+        # row lengths -> global indptr
         ip_all = torch.zeros(self.n_total + 1, dtype=torch.int64, device=self.device)
         torch.cumsum(lens_all, 0, out=ip_all[1:])
         if ev is not None:
             torch.cuda.current_stream(self.device).wait_event(ev)
-        self._keep.pop("prep_all", None)
-        if "prep_local" in self._keep:
-            norms, wdir, flags, packed = self._keep["prep_local"]
-            flags_all = torch.empty(self.world * 4, dtype=torch.int32, device=self.device)
-            dist.all_gather_into_tensor(flags_all, flags, group=group)
-            flags_all = flags_all.view(self.world, 4).sum(dim=0).to(torch.int32)     # 0/1 flags and one count: a sum combines them
-            packed_all = None
-            if packed is not None:
-                # (16 readable bytes behind the stream: the counts kernel reads slices as aligned 16-byte words)
-                packed_all = _gather_padded(packed, nnzs, group, tail_pad=4)
-            self._keep["prep_all"] = (_gather_padded(norms, counts, group), _gather_padded(wdir, counts, group), flags_all,
-                                      packed_all, sum(nnzs))
         return ip_all, ix_all, dt_all
 
     def _start_csr_gather(self):
