@@ -327,6 +327,7 @@ k3h_collision_kernel(const uint32_t* __restrict__ q16, int64_t nq, const uint32_
 // (Hw .. Hw_pad) hold the never-equal NaN pattern.
 // =================================================================================================
 constexpr int K3T_STAGE_WORDS = 2 * K3_JB * K3_TILE;        // query tile + database tile, uint32
+constexpr int K3T_MAX_BLOCKS = 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -372,18 +373,15 @@ k3h_transpose_kernel(const uint32_t* __restrict__ sig16w, int64_t n, int Hw, int
     }
 }
 
+// One 128 x 128 tile (tile_x, tile_y) of the block [q_row0, +nq) x [d_row0, +nd). MODE as in k3h_collision_kernel.
 template <int MODE>
-__global__ void __launch_bounds__(K3_THREADS, 2)
-k3t_collision_kernel(const __grid_constant__ CUtensorMap tmap, int q_row0, int64_t nq, int d_row0, int64_t nd, int Hw_pad,
-                     uint16_t* __restrict__ cnt, int64_t ld_out, uint16_t* __restrict__ cnt_t, int64_t ld_t) {
+__device__ __forceinline__ void k3t_tile(const CUtensorMap& tmap, int q_row0, int64_t nq, int d_row0, int64_t nd, int Hw_pad,
+                                         uint16_t* __restrict__ cnt, int64_t ld_out, uint16_t* __restrict__ cnt_t, int64_t ld_t,
+                                         int tile_x, int tile_y, uint32_t* stage_base, uint64_t* full_bar) {
     constexpr bool SYM = MODE == 1;
-    extern __shared__ __align__(1024) unsigned char k3t_smem[];
-    uint32_t* stage_base = reinterpret_cast<uint32_t*>(k3t_smem);                       // [2][K3T_STAGE_WORDS]
-    __shared__ __align__(8) uint64_t full_bar[2];
-
-    if (SYM && blockIdx.x < blockIdx.y) return;
-    const int64_t q0 = (int64_t)blockIdx.y * K3_TILE;
-    const int64_t d0 = (int64_t)blockIdx.x * K3_TILE;
+    if (SYM && tile_x < tile_y) return;
+    const int64_t q0 = (int64_t)tile_y * K3_TILE;
+    const int64_t d0 = (int64_t)tile_x * K3_TILE;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 
     if (threadIdx.x == 0) {
@@ -454,7 +452,7 @@ k3t_collision_kernel(const __grid_constant__ CUtensorMap tmap, int q_row0, int64
                 if (d0 + tx * 8 + b < nd) dst[b] = (uint16_t)total(acc[a][b]);
         }
     }
-    if ((SYM && blockIdx.x > blockIdx.y) || MODE == 2) {
+    if ((SYM && tile_x > tile_y) || MODE == 2) {
         uint16_t* __restrict__ mt = MODE == 2 ? cnt_t : cnt;
         const int64_t mld = MODE == 2 ? ld_t : ld_out;
         const bool tvec_ok = ((mld & 7) == 0) && ((((uintptr_t)mt) & 15) == 0) && (q0 + ty * 8 + 8 <= nq);
@@ -477,6 +475,45 @@ k3t_collision_kernel(const __grid_constant__ CUtensorMap tmap, int q_row0, int64
             }
         }
     }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(K3_THREADS, 2)
+k3t_collision_kernel(const __grid_constant__ CUtensorMap tmap, int q_row0, int64_t nq, int d_row0, int64_t nd, int Hw_pad,
+                     uint16_t* __restrict__ cnt, int64_t ld_out, uint16_t* __restrict__ cnt_t, int64_t ld_t) {
+    extern __shared__ __align__(1024) unsigned char k3t_smem[];
+    __shared__ __align__(8) uint64_t full_bar[2];
+    k3t_tile<MODE>(tmap, q_row0, nq, d_row0, nd, Hw_pad, cnt, ld_out, cnt_t, ld_t, (int)blockIdx.x, (int)blockIdx.y,
+                   reinterpret_cast<uint32_t*>(k3t_smem), full_bar);
+}
+
+// Several blocks in ONE launch (the pieces of a sharded symmetric count matrix: each is less than a wave of tiles, so
+// separate launches leave most of the GPU idle). Block i owns tiles [tile_begin[i], tile_begin[i + 1]) of a 1-D grid.
+struct K3TBlocks {
+    int n;
+    int q_row0[K3T_MAX_BLOCKS], nq[K3T_MAX_BLOCKS], d_row0[K3T_MAX_BLOCKS], nd[K3T_MAX_BLOCKS], tile_begin[K3T_MAX_BLOCKS + 1];
+    uint16_t* cnt[K3T_MAX_BLOCKS];
+    uint16_t* cnt_t[K3T_MAX_BLOCKS];
+    int64_t ld[K3T_MAX_BLOCKS], ld_t[K3T_MAX_BLOCKS];
+};
+
+__global__ void __launch_bounds__(K3_THREADS, 2)
+k3t_blocks_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K3TBlocks bl, int Hw_pad) {
+    extern __shared__ __align__(1024) unsigned char k3t_smem[];
+    __shared__ __align__(8) uint64_t full_bar[2];
+    int i = 0;
+    while (i + 1 < bl.n && (int)blockIdx.x >= bl.tile_begin[i + 1]) ++i;
+    const int t = (int)blockIdx.x - bl.tile_begin[i];
+    const int tiles_x = (bl.nd[i] + K3_TILE - 1) / K3_TILE;
+    const int tile_y = t / tiles_x, tile_x = t - tile_y * tiles_x;
+    uint32_t* stage = reinterpret_cast<uint32_t*>(k3t_smem);
+    const bool same = bl.q_row0[i] == bl.d_row0[i] && bl.nq[i] == bl.nd[i];
+    if (same)
+        k3t_tile<1>(tmap, bl.q_row0[i], bl.nq[i], bl.d_row0[i], bl.nd[i], Hw_pad, bl.cnt[i], bl.ld[i], nullptr, 0, tile_x, tile_y, stage, full_bar);
+    else if (bl.cnt_t[i])
+        k3t_tile<2>(tmap, bl.q_row0[i], bl.nq[i], bl.d_row0[i], bl.nd[i], Hw_pad, bl.cnt[i], bl.ld[i], bl.cnt_t[i], bl.ld_t[i], tile_x, tile_y, stage, full_bar);
+    else
+        k3t_tile<0>(tmap, bl.q_row0[i], bl.nq[i], bl.d_row0[i], bl.nd[i], Hw_pad, bl.cnt[i], bl.ld[i], nullptr, 0, tile_x, tile_y, stage, full_bar);
 }
 
 int k3t_padded_words(int H) { return ((k3h_padded_hashes(H) / 2) + K3_JB - 1) / K3_JB * K3_JB; }
@@ -538,6 +575,31 @@ int launch_collision_counts_tma(const void* map, int64_t q_row0, int64_t nq, int
         cudaFuncSetAttribute(k3t_collision_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k3t_collision_kernel<0><<<grid, K3_THREADS, smem, stream>>>(tm, (int)q_row0, nq, (int)d_row0, ndb, Hw_pad, d_cnt, ld_out, nullptr, 0);
     }
+    return 1;
+}
+
+// n blocks in one launch; every row offset must be a multiple of 4 (TMA box alignment). Arrays of length n.
+int launch_collision_blocks_tma(const void* map, int n, const int64_t* q_row0, const int64_t* nq, const int64_t* d_row0,
+                                const int64_t* nd, uint16_t* const* cnt, const int64_t* ld, uint16_t* const* cnt_t,
+                                const int64_t* ld_t, int H, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    if (n > K3T_MAX_BLOCKS) return -1;
+    K3TBlocks bl;
+    bl.n = 0;
+    int tiles = 0;
+    for (int i = 0; i < n; ++i) {
+        if (nq[i] <= 0 || nd[i] <= 0) continue;
+        const int k = bl.n++;
+        bl.q_row0[k] = (int)q_row0[i]; bl.nq[k] = (int)nq[i]; bl.d_row0[k] = (int)d_row0[i]; bl.nd[k] = (int)nd[i];
+        bl.cnt[k] = cnt[i]; bl.ld[k] = ld[i]; bl.cnt_t[k] = cnt_t ? cnt_t[i] : nullptr; bl.ld_t[k] = ld_t ? ld_t[i] : 0;
+        bl.tile_begin[k] = tiles;
+        tiles += (int)(((nq[i] + K3_TILE - 1) / K3_TILE) * ((nd[i] + K3_TILE - 1) / K3_TILE));
+    }
+    if (bl.n == 0) return 0;
+    bl.tile_begin[bl.n] = tiles;
+    const size_t smem = (size_t)2 * K3T_STAGE_WORDS * 4 + 1024;
+    cudaFuncSetAttribute(k3t_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k3t_blocks_kernel<<<(unsigned)tiles, K3_THREADS, smem, stream>>>(*reinterpret_cast<const CUtensorMap*>(map), bl, k3t_padded_words(H));
     return 1;
 }
 

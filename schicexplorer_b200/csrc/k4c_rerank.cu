@@ -295,10 +295,11 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
     uint32_t it_p = 0u, it_B = 0u;                         // next batch position / interior end of that slice
     uint4 h[NB];                                           // look-ahead batch
     uint32_t h_sx = 0u, h_tx = 0u;                         // its head / tail boundary element (first batch of a slice, else 0)
+    uint32_t h_sx2 = 0u, h_tx2 = 0u;                       // groups of 2 lanes: the third boundary element goes to lane 0
     int h_i = 0, h_j = nwin;                               // its slice; h_j == nwin: the sequence is exhausted
     bool h_last = false;
     auto advance = [&]() {
-        h_sx = 0u; h_tx = 0u;
+        h_sx = 0u; h_tx = 0u; h_sx2 = 0u; h_tx2 = 0u;
         if (it_p >= it_B) {                                // open the next non-empty slice of this lane group
             uint32_t ys = 0u, ye = 0u;
             for (;;) {
@@ -312,6 +313,10 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
             it_B = max(it_p, ye & ~3u);
             if (ql < (int)(it_p - ys)) h_sx = __ldg(packed + ys + ql);           // <= 3 elements before the interior
             if (ql < (int)(ye - it_B)) h_tx = __ldg(packed + it_B + ql);         // <= 3 elements behind it
+            if (LPS == 2) {
+                if (ql + 2 < (int)(it_p - ys)) h_sx2 = __ldg(packed + ys + ql + 2);
+                if (ql + 2 < (int)(ye - it_B)) h_tx2 = __ldg(packed + it_B + ql + 2);
+            }
         }
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
@@ -355,13 +360,17 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
                 uint4 v[NB];
 #pragma unroll
                 for (int u = 0; u < NB; ++u) v[u] = h[u];
-                const uint32_t sx = h_sx, tx = h_tx;
+                const uint32_t sx = h_sx, tx = h_tx, sx2 = h_sx2, tx2 = h_tx2;
                 const int cur_i = h_i;
                 const bool last = h_last;
                 advance();                                 // next batch in flight while this one is probed
                 if (!esc) {
                     uint32_t a32 = k4c_mac(sx, (uint32_t)tab[sx >> K4C_CNT_BITS], 0u);   // <= 18 products < 2^24 each
                     a32 = k4c_mac(tx, (uint32_t)tab[tx >> K4C_CNT_BITS], a32);
+                    if (LPS == 2) {
+                        a32 = k4c_mac(sx2, (uint32_t)tab[sx2 >> K4C_CNT_BITS], a32);
+                        a32 = k4c_mac(tx2, (uint32_t)tab[tx2 >> K4C_CNT_BITS], a32);
+                    }
 #pragma unroll
                     for (int u = 0; u < NB; ++u) {
                         a32 = k4c_mac(v[u].x, (uint32_t)tab[v[u].x >> K4C_CNT_BITS], a32);
@@ -381,6 +390,7 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
                     };
                     probe(sx);
                     probe(tx);
+                    if (LPS == 2) { probe(sx2); probe(tx2); }
 #pragma unroll
                     for (int u = 0; u < NB; ++u) { probe(v[u].x); probe(v[u].y); probe(v[u].z); probe(v[u].w); }
                 }
@@ -494,10 +504,10 @@ int launch_rerank_counts(const int64_t* d_indptr, const uint32_t* d_packed, cons
     // 15.7 ms against 15.1 ms for groups of 4 and 16.5 ms for groups of 8 -- the barrier structure, not the slice
     // imbalance, is what keeps issue utilisation at ~52 %; kept as an experiment switch)
     int lps = kcand > K4C_THREADS / 8 ? 4 : 8;
-    if (const char* e = getenv("SCHIC_K4_LPS")) { const int v = atoi(e); lps = v == 8 ? 8 : (v == 4 ? 4 : (kcand <= K4C_THREADS / 4 ? 0 : 4)); }
+    if (const char* e = getenv("SCHIC_K4_LPS")) { const int v = atoi(e); lps = v == 8 ? 8 : (v == 4 ? 4 : (v == 2 ? 2 : (kcand <= K4C_THREADS / 4 ? 0 : 4))); }
     k4c_order_kernel<<<(unsigned)nq, 256, (size_t)P * 8, stream>>>(d_indptr, d_cand_idx, d_cand_nvalid, kcand, P, ck, d_flags,
                                                                    esc_limit, d_order, lps == 0 ? d_lane_map : nullptr);
-    auto kern = lps == 0 ? k4c_rerank_kernel<0> : (lps == 4 ? k4c_rerank_kernel<4> : k4c_rerank_kernel<8>);
+    auto kern = lps == 0 ? k4c_rerank_kernel<0> : (lps == 2 ? k4c_rerank_kernel<2> : (lps == 4 ? k4c_rerank_kernel<4> : k4c_rerank_kernel<8>));
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<(unsigned)(groups * nq), K4C_THREADS, smem, stream>>>(
         d_indptr, d_packed, d_dir, n_windows, wg, q_row0, nq, d_cand_idx, d_cand_nvalid, d_order, d_lane_map, kcand, ck,
