@@ -1474,14 +1474,14 @@ int schic_mh_rerank_kernel_name(schic_mh_handle* h, char* out, int32_t n_out) {
     if (h->rerank_path == 3) {
         name = h->n_windows > 0 || (h->ext && h->ext_nw > 0) ? "k4_rerank_window_kernel" : "k4_rerank_kernel";
     } else if (h->rerank_path == 1) {
-        name = "k4c_rerank_kernel";
+        name = schic::k4c_kernel_name();
     } else if (h->rerank_path == 2) {      // both were launched: the flags on the device say which one did the work
         const uint32_t* fl = (h->ext && h->ext_flags) ? h->ext_flags : h->k4_flags.p;
         const int64_t nnz = (h->ext && h->ext_flags) ? h->ext_nnz : h->prep_nnz;
         uint32_t f[4] = {0, 0, 0, 0};
         CU_TRY(cudaMemcpyAsync(f, fl, sizeof(f), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
-        name = (f[0] == 0 && f[1] <= esc_limit_for(nnz)) ? "k4c_rerank_kernel" : "k4_rerank_window_kernel";
+        name = (f[0] == 0 && f[1] <= esc_limit_for(nnz)) ? schic::k4c_kernel_name() : "k4_rerank_window_kernel";
     }
     snprintf(out, (size_t)n_out, "%s", name);
     return SCHIC_OK;

@@ -108,6 +108,8 @@ int launch_rerank_prep(const int64_t* d_indptr, const uint32_t* d_feat, const fl
 // d_dotacc: k4c_dotacc_elems(nq, kcand) uint64 of scratch. group_bytes: share of the packed stream one window group
 // may span (sized for L2; <= 0: one group). Returns the number of launches, -1 when kcand does not fit.
 size_t k4c_dotacc_elems(int64_t nq, int kcand);
+bool k4c_direct_selected();
+const char* k4c_kernel_name();   // "k4c_rerank_direct_kernel" | "k4c_rerank_kernel" (SCHIC_K4_KERNEL=iter)
 int launch_rerank_counts(const int64_t* d_indptr, const uint32_t* d_packed, const double* d_norm2, const uint32_t* d_dir,
                          int n_windows, int64_t db_nnz, int64_t group_bytes, int64_t q_row0, int64_t nq,
                          const int32_t* d_cand_idx, const int32_t* d_cand_nvalid, int cand_stride, int cand_off, int kcand,

@@ -26,6 +26,7 @@
 // float kernels of k4_rerank.cu, launched behind them with the same flag, do the work. No host round trip decides.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "sort.cuh"
@@ -416,6 +417,205 @@ k4c_rerank_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict
         if (dotc[i] != 0ull) atomicAdd(&dotacc[q * (int64_t)kcand + __ldg(order + q * (int64_t)kcand + i)], dotc[i]);
 }
 
+// ---- direct variant: no batch iterator ----------------------------------------------------------------------------
+// Same CTA = (window group, query), same table, same shared-memory layout and the same three barriers per window as
+// k4c_rerank_kernel, but the streaming phase is a plain loop: lane group gi (LPS lanes) owns the candidates at sorted
+// positions gi, gi + NG, ...; in one window it reads such a candidate's slice as ALIGNED 16-byte chunks, a round of
+// U chunks per lane issued back to back (LPS * U * 4 non-zeros; one round covers the typical slice), then probes them.
+// No head / tail special cases inside the loop: an aligned chunk that straddles the slice's start or end carries <= 3
+// foreign non-zeros (of the neighbouring window or row); those are probed like the rest and their products are
+// subtracted again -- <= 3 + 3 single-word loads per slice on lanes 0-2 of the group, exact in modular arithmetic
+// (the stream is allocated with 4 words of slack behind its end). Round 0 of the group's first slice of the NEXT
+// window is requested right after the probes of this window, so those loads are in flight across un-build, the
+// barriers and the next build: the latency hiding of the batch iterator without its ~280 instructions of per-window
+// bookkeeping per warp (ncu r02n: 76 % of the 8.9e9 issued instructions of k4c_rerank_kernel were not probes).
+// T = threads per CTA: NG = T / LPS lane groups should cover the candidate list (warps without a candidate still pay
+// for the three barriers per window: 100 candidates x 4 lanes on 416 threads 10.4 ms, on 512 threads 11.2 ms at S10).
+template <int LPS, int U, int T>
+__global__ void __launch_bounds__(T, K4C_CTAS)
+k4c_rerank_direct_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ packed,
+                         const uint32_t* __restrict__ dir, int n_windows, int wg, int64_t q_row0, int64_t nq,
+                         const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_nvalid,
+                         const int32_t* __restrict__ order, int kcand, K4Chunk ck,
+                         const uint32_t* __restrict__ flags, uint32_t esc_limit, unsigned long long* __restrict__ dotacc) {
+    static_assert(LPS >= 4 && LPS <= 32 && (LPS & (LPS - 1)) == 0, "<= 3 foreign elements per end go to lanes 0-2 of a group");
+    if (!k4c_usable(flags, esc_limit)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint8_t* tab = smem_raw;                                                            // [K4C_TAB]
+    unsigned long long* dotc = reinterpret_cast<unsigned long long*>(smem_raw + K4C_TAB);   // [kcand] by sorted position
+    uint32_t* sl = reinterpret_cast<uint32_t*>(dotc + kcand);                           // [kcand][sls] absolute positions
+    const int sls = (wg + 1) | 1;                          // odd row stride: the 8 groups of a warp read 8 banks
+    uint32_t* qdir = sl + (size_t)kcand * sls;                                          // [wg + 1]
+    __shared__ int s_esc;
+
+    const int64_t g = blockIdx.x / nq;
+    const int64_t q = blockIdx.x - g * nq;
+    const int64_t qrow = q_row0 + q;
+    const int w0 = (int)g * wg;
+    const int nwin = min(wg, n_windows - w0);
+    const int64_t nw1 = (int64_t)n_windows + 1;
+    const int lane = threadIdx.x & 31;
+    constexpr int NG = T / LPS;                  // lane groups per CTA
+    constexpr uint32_t ROUND = 4u * LPS * U;               // non-zeros per round of a lane group
+    const int ncand = max(0, min((cand_idx ? cand_nvalid[q] : ck.n_all) - ck.cand_off, kcand));
+    const int gi = threadIdx.x / LPS;
+    const int ql = lane & (LPS - 1);
+    const int gw = (threadIdx.x >> 5) * (32 / LPS);        // first lane group of this warp
+
+    for (int w = threadIdx.x; w <= nwin; w += T) qdir[w] = __ldg(dir + qrow * nw1 + w0 + w);
+    if (threadIdx.x == 0) s_esc = 0;
+    __syncthreads();
+    if (qdir[0] == qdir[nwin] || ncand == 0) return;       // the query row is empty in this whole group (uniform)
+
+    const int64_t xb = indptr[qrow];
+    auto next_window = [&](int j) { while (j < nwin && qdir[j + 1] == qdir[j]) ++j; return j; };
+    uint32_t qn0 = 0u, qn1 = 0u;
+    auto prefetch_keys = [&](int j) {
+        if (j >= nwin) return;
+        const uint32_t i0 = qdir[j] + threadIdx.x, e = qdir[j + 1];
+        if (i0 < e) qn0 = __ldg(packed + xb + i0);
+        if (i0 + T < e) qn1 = __ldg(packed + xb + i0 + T);
+    };
+    int j = next_window(0);
+    prefetch_keys(j);
+
+    for (int c = threadIdx.x; c < ncand; c += T) dotc[c] = 0ull;
+    {
+        const int per = nwin + 1, total = ncand * per;
+        for (int x = threadIdx.x; x < total; x += T) {
+            const int i = x / per, jj = x - i * per;
+            const int c = __ldg(order + q * (int64_t)kcand + i);
+            const int32_t d = cand_idx ? cand_idx[q * ck.cand_stride + ck.cand_off + c] : ck.cand_off + c;
+            sl[i * sls + jj] = (uint32_t)(indptr[d] + (int64_t)__ldg(dir + (int64_t)d * nw1 + w0 + jj));
+        }
+    }
+    for (int i = threadIdx.x; i < K4C_TAB / 16; i += T)
+        reinterpret_cast<uint4*>(tab)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();                                       // sl complete
+
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    uint4 v[U];                                            // one round of this lane
+    uint32_t s_ys = 0u, s_ye = 0u, s_hw = 0u, s_tw = 0u;   // the slice v belongs to; its foreign head / tail word on this lane
+    // one round: chunks bp[0], bp[LPS], ... of this lane while they start inside the slice (rem = non-zeros from this
+    // lane's first chunk to the slice end; <= 0: nothing)
+    auto load_round = [&](const uint4* __restrict__ bp, int rem) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = rem > 4 * LPS * u ? __ldg(bp + LPS * u) : zero4;
+    };
+    // slice of sorted candidate i in window jw: bounds, foreign words, round 0 (nothing is read for an empty slice)
+    auto open_slice = [&](int i, int jw) {
+        s_ys = 0u; s_ye = 0u; s_hw = 0u; s_tw = 0u;
+        if (i < ncand && jw < nwin) {
+            const uint32_t ys = sl[i * sls + jw], ye = sl[i * sls + jw + 1];
+            if (ye > ys) { s_ys = ys; s_ye = ye; }
+        }
+        const uint32_t a0 = s_ys & ~3u;
+        if (ql < (int)(s_ys - a0)) s_hw = __ldg(packed + a0 + ql);                 // in the first chunk, before the slice
+        if (ql < (int)((0u - s_ye) & 3u)) s_tw = __ldg(packed + s_ye + ql);         // in the last chunk, behind the slice
+        const uint32_t p0 = a0 + 4u * ql;
+        load_round(reinterpret_cast<const uint4*>(packed + p0), (int)(s_ye - p0));
+    };
+    open_slice(gi, j);
+
+    while (j < nwin) {
+        const uint32_t k0 = qdir[j], k1 = qdir[j + 1];
+        const uint32_t qc0 = qn0, qc1 = qn1;               // this window's keys (prefetched)
+        __syncthreads();                                   // table clear / previous un-build done
+        bool any_big = false;
+        {
+            const uint32_t i0 = k0 + threadIdx.x;
+            if (i0 < k1) { const uint32_t x = qc0 & K4C_CNT_MASK; tab[qc0 >> K4C_CNT_BITS] = (uint8_t)min(x, 255u); any_big |= x >= 255u; }
+            if (i0 + T < k1) { const uint32_t x = qc1 & K4C_CNT_MASK; tab[qc1 >> K4C_CNT_BITS] = (uint8_t)min(x, 255u); any_big |= x >= 255u; }
+            for (uint32_t i = i0 + 2 * T; i < k1; i += T) {
+                const uint32_t p = __ldg(packed + xb + i);
+                const uint32_t x = p & K4C_CNT_MASK;
+                tab[p >> K4C_CNT_BITS] = (uint8_t)min(x, 255u);
+                any_big |= x >= 255u;
+            }
+        }
+        if (any_big) s_esc = j + 1;                        // (j + 1 never repeats within a CTA: no reset needed)
+        const int jn = next_window(j + 1);
+        prefetch_keys(jn);                                 // consumed at the top of the next iteration
+        __syncthreads();
+        // ---- stream ---------------------------------------------------------------------------------------------
+        {
+            const bool esc = s_esc == j + 1;
+            for (int ib = gw; ib < ncand; ib += NG) {      // warp-uniform trip count: the reduction below is warp-wide
+                const int i = ib + (lane / LPS);
+                if (ib != gw) open_slice(i, j);            // (only lists longer than NG candidates)
+                unsigned long long acc = 0ull;
+                const bool live = s_ye > s_ys;             // uniform in the lane group
+                if (live) {
+                    if (!esc) {
+                        uint32_t a32 = 0u;                 // <= 4 U products < 2^24 each
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            a32 = k4c_mac(v[u].x, (uint32_t)tab[v[u].x >> K4C_CNT_BITS], a32);
+                            a32 = k4c_mac(v[u].y, (uint32_t)tab[v[u].y >> K4C_CNT_BITS], a32);
+                            a32 = k4c_mac(v[u].z, (uint32_t)tab[v[u].z >> K4C_CNT_BITS], a32);
+                            a32 = k4c_mac(v[u].w, (uint32_t)tab[v[u].w >> K4C_CNT_BITS], a32);
+                        }
+                        acc = a32;
+                        const uint32_t p0 = (s_ys & ~3u) + 4u * ql;
+                        const uint4* __restrict__ bp = reinterpret_cast<const uint4*>(packed + p0);
+                        int rem = (int)(s_ye - p0);
+                        // further rounds while the slice goes on (group-uniform). NOT unrolled: nvcc 12.9 unrolled the <8, 2>
+                        // instance of an earlier form of this loop (condition on rem + 4 * ql) by four with the lane term's sign
+                        // flipped in the unrolled exit test, and lanes 1.. of a group lost rounds.
+#pragma unroll 1
+                        for (uint32_t left = s_ye - (s_ys & ~3u); left > ROUND; left -= ROUND) {
+                            bp += LPS * U;
+                            rem -= (int)ROUND;
+                            load_round(bp, rem);
+                            a32 = 0u;
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                a32 = k4c_mac(v[u].x, (uint32_t)tab[v[u].x >> K4C_CNT_BITS], a32);
+                                a32 = k4c_mac(v[u].y, (uint32_t)tab[v[u].y >> K4C_CNT_BITS], a32);
+                                a32 = k4c_mac(v[u].z, (uint32_t)tab[v[u].z >> K4C_CNT_BITS], a32);
+                                a32 = k4c_mac(v[u].w, (uint32_t)tab[v[u].w >> K4C_CNT_BITS], a32);
+                            }
+                            acc += a32;
+                        }
+                        uint32_t f32 = k4c_mac(s_hw, (uint32_t)tab[s_hw >> K4C_CNT_BITS], 0u);   // the foreign non-zeros again
+                        f32 = k4c_mac(s_tw, (uint32_t)tab[s_tw >> K4C_CNT_BITS], f32);
+                        acc -= f32;                        // (per lane this may wrap; the group's sum is exact mod 2^64)
+                    } else {
+                        // this window of the query holds counts >= 255: element-wise over the exact slice, table bytes of
+                        // 255 looked up exactly (rare; v is not used)
+                        const uint32_t* __restrict__ qp = packed + xb + k0;
+                        const int qn = (int)(k1 - k0);
+                        for (uint32_t p = s_ys + ql; p < s_ye; p += LPS) {
+                            const uint32_t w = __ldg(packed + p);
+                            const uint32_t t = w >> K4C_CNT_BITS, cnt = w & K4C_CNT_MASK;
+                            const uint32_t tv = tab[t];
+                            acc += (unsigned long long)(tv * cnt);
+                            if (tv == 255u && cnt != 0u)
+                                acc += (unsigned long long)(k4c_escape_value(qp, qn, t) - 255u) * (unsigned long long)cnt;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 1; o < LPS; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (ql == 0 && live) dotc[i] += acc;       // only this lane group touches position i
+            }
+            open_slice(gi, jn);                            // in flight across un-build, the barriers and the next build
+        }
+        // ---- un-build: zero exactly the bytes this window set ----------------------------------------------------
+        __syncthreads();
+        {
+            const uint32_t i0 = k0 + threadIdx.x;
+            if (i0 < k1) tab[qc0 >> K4C_CNT_BITS] = 0;
+            if (i0 + T < k1) tab[qc1 >> K4C_CNT_BITS] = 0;
+            for (uint32_t i = i0 + 2 * T; i < k1; i += T) tab[__ldg(packed + xb + i) >> K4C_CNT_BITS] = 0;
+        }
+        j = jn;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncand; i += T)
+        if (dotc[i] != 0ull) atomicAdd(&dotacc[q * (int64_t)kcand + __ldg(order + q * (int64_t)kcand + i)], dotc[i]);
+}
+
 // distances from the exact integer dot products, (distance asc, index asc) order, keep k
 __global__ void __launch_bounds__(256)
 k4c_finalize_kernel(const uint32_t* __restrict__ flags, uint32_t esc_limit, const unsigned long long* __restrict__ dotacc,
@@ -461,8 +661,8 @@ k4c_finalize_kernel(const uint32_t* __restrict__ flags, uint32_t esc_limit, cons
 int k4c_windows_per_group(int n_windows, int64_t db_nnz, int kcand, int64_t group_bytes) {
     const int64_t smem_left = (int64_t)(225 * 1024 / K4C_CTAS - 1024) - K4C_TAB - (int64_t)kcand * 8 - 64;
     if (smem_left < (int64_t)kcand * 8) return -1;
-    int64_t wg_smem = smem_left / ((int64_t)kcand * 4) - 1;                  // (wg + 1) * 4 * kcand + (wg + 1) * 4 <= left
-    while (wg_smem > 1 && (wg_smem + 1) * 4 * ((int64_t)kcand + 1) > smem_left) --wg_smem;
+    int64_t wg_smem = smem_left / ((int64_t)kcand * 4) - 2;                  // (wg + 2) * 4 * kcand + (wg + 1) * 4 <= left
+    while (wg_smem > 1 && (wg_smem + 2) * 4 * (int64_t)kcand + (wg_smem + 1) * 4 > smem_left) --wg_smem;
     if (wg_smem < 1) return -1;
     int64_t wg = n_windows;
     const int64_t stream_bytes = 4 * std::max<int64_t>(db_nnz, 1);
@@ -477,6 +677,16 @@ int k4c_windows_per_group(int n_windows, int64_t db_nnz, int kcand, int64_t grou
 size_t k4c_dotacc_elems(int64_t nq, int kcand) {
     return (size_t)nq * (size_t)kcand + ((size_t)nq * (size_t)kcand + 1) / 2 + ((size_t)nq * K4C_THREADS + 3) / 4 + 2;
 }
+
+// which of the two counts kernels launch_rerank_counts uses (SCHIC_K4_KERNEL = direct | iter; lane-group experiments
+// SCHIC_K4_LPS = 0 | 2 exist in the iterator kernel only)
+bool k4c_direct_selected() {
+    const char* kk = getenv("SCHIC_K4_KERNEL");
+    if (kk && strcmp(kk, "iter") == 0) return false;
+    if (const char* e = getenv("SCHIC_K4_LPS")) { const int v = atoi(e); if (v != 4 && v != 8) return false; }
+    return true;
+}
+const char* k4c_kernel_name() { return k4c_direct_selected() ? "k4c_rerank_direct_kernel" : "k4c_rerank_kernel"; }
 
 // One launch (pair) over candidate columns [cand_off, cand_off + kcand); same output contract as launch_rerank.
 // d_dotacc: >= nq * kcand uint64 scratch (zeroed here). Returns launches, or -1 when kcand does not fit.
@@ -493,7 +703,8 @@ int launch_rerank_counts(const int64_t* d_indptr, const uint32_t* d_packed, cons
     const int64_t groups = (n_windows + wg - 1) / wg;
     if (groups * nq > 0x7FFFFFFFll) return -1;
     const K4Chunk ck{cand_stride, cand_off, out_stride, out_off, final, n_all};
-    const size_t smem = (size_t)K4C_TAB + (size_t)kcand * 8 + (size_t)kcand * (wg + 1) * 4 + (size_t)(wg + 1) * 4 + 16;
+    // (the direct kernel pads the rows of the slice table to an odd stride: wg + 2 words at most)
+    const size_t smem = (size_t)K4C_TAB + (size_t)kcand * 8 + (size_t)kcand * (wg + 2) * 4 + (size_t)(wg + 1) * 4 + 16;
     if (smem > (size_t)(225 * 1024 / K4C_CTAS - 1024)) return -1;
     if (cudaMemsetAsync(d_dotacc, 0, (size_t)nq * kcand * sizeof(unsigned long long), stream) != cudaSuccess) return -1;
     int32_t* d_order = reinterpret_cast<int32_t*>(d_dotacc + (size_t)nq * kcand);
@@ -507,11 +718,35 @@ int launch_rerank_counts(const int64_t* d_indptr, const uint32_t* d_packed, cons
     if (const char* e = getenv("SCHIC_K4_LPS")) { const int v = atoi(e); lps = v == 8 ? 8 : (v == 4 ? 4 : (v == 2 ? 2 : (kcand <= K4C_THREADS / 4 ? 0 : 4))); }
     k4c_order_kernel<<<(unsigned)nq, 256, (size_t)P * 8, stream>>>(d_indptr, d_cand_idx, d_cand_nvalid, kcand, P, ck, d_flags,
                                                                    esc_limit, d_order, lps == 0 ? d_lane_map : nullptr);
-    auto kern = lps == 0 ? k4c_rerank_kernel<0> : (lps == 2 ? k4c_rerank_kernel<2> : (lps == 4 ? k4c_rerank_kernel<4> : k4c_rerank_kernel<8>));
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<(unsigned)(groups * nq), K4C_THREADS, smem, stream>>>(
-        d_indptr, d_packed, d_dir, n_windows, wg, q_row0, nq, d_cand_idx, d_cand_nvalid, d_order, d_lane_map, kcand, ck,
-        d_flags, esc_limit, d_dotacc);
+    // SCHIC_K4_KERNEL = direct (default) | iter (the batch-iterator kernel); SCHIC_K4_U = chunks per lane and round
+    const bool direct = k4c_direct_selected() && lps >= 4;
+    if (direct) {
+        // chunks per lane and round: 4 x 4 lanes x 4 = 64 non-zeros cover most S10 slices in one or two rounds (measured
+        // 3 / 4 / 5 / 6 / 8 chunks: 11.6 / 10.4 / 10.4 / 10.6 / 13.0 ms); threads: the smallest build that gives every
+        // candidate its lane group
+        int u = lps == 8 ? 3 : 4;
+        if (const char* e = getenv("SCHIC_K4_U")) u = atoi(e);
+        int threads = kcand * lps <= 416 ? 416 : 512;
+        if (const char* e = getenv("SCHIC_K4_THREADS")) threads = atoi(e) == 416 ? 416 : 512;
+        void (*kern)(const int64_t*, const uint32_t*, const uint32_t*, int, int, int64_t, int64_t, const int32_t*, const int32_t*,
+                     const int32_t*, int, K4Chunk, const uint32_t*, uint32_t, unsigned long long*);
+        if (threads == 416)
+            kern = lps == 8 ? (u <= 2 ? k4c_rerank_direct_kernel<8, 2, 416> : k4c_rerank_direct_kernel<8, 3, 416>)
+                            : (u <= 4 ? k4c_rerank_direct_kernel<4, 4, 416> : k4c_rerank_direct_kernel<4, 6, 416>);
+        else
+            kern = lps == 8 ? (u <= 2 ? k4c_rerank_direct_kernel<8, 2, 512> : k4c_rerank_direct_kernel<8, 3, 512>)
+                            : (u <= 4 ? k4c_rerank_direct_kernel<4, 4, 512> : k4c_rerank_direct_kernel<4, 6, 512>);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<(unsigned)(groups * nq), threads, smem, stream>>>(
+            d_indptr, d_packed, d_dir, n_windows, wg, q_row0, nq, d_cand_idx, d_cand_nvalid, d_order, kcand, ck,
+            d_flags, esc_limit, d_dotacc);
+    } else {
+        auto kern = lps == 0 ? k4c_rerank_kernel<0> : (lps == 2 ? k4c_rerank_kernel<2> : (lps == 4 ? k4c_rerank_kernel<4> : k4c_rerank_kernel<8>));
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<(unsigned)(groups * nq), K4C_THREADS, smem, stream>>>(
+            d_indptr, d_packed, d_dir, n_windows, wg, q_row0, nq, d_cand_idx, d_cand_nvalid, d_order, d_lane_map, kcand, ck,
+            d_flags, esc_limit, d_dotacc);
+    }
     k4c_finalize_kernel<<<(unsigned)nq, 256, (size_t)P * 8, stream>>>(d_flags, esc_limit, d_dotacc, d_norm2, q_row0,
                                                                       d_cand_idx, d_cand_nvalid, kcand, P, k, ck, d_idx_out,
                                                                       d_dist_out, d_nvalid_out);

@@ -165,7 +165,7 @@ def test_exact_rerank_with_ids_beyond_32_bits(cuda, oracle, width):
     X = csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(80, ncols))
     X.indices = X.indices.astype(np.int64)
     X.indptr = X.indptr.astype(np.int64)
-    for scale, kernel in ((1.0, "k4c_rerank_kernel"), (0.5, "k4_rerank_window_kernel")):
+    for scale, kernel in ((1.0, "k4c_rerank_direct_kernel"), (0.5, "k4_rerank_window_kernel")):
         Xs = X.copy(); Xs.data = Xs.data * scale
         kw = dict(number_of_hash_functions=128, minimal_blocks_in_common=1, hash_width=width, fast=False, n_neighbors=12, excess_factor=2)
         with Fitted(oracle, Xs, **kw) as o, Fitted(cuda, Xs, **kw) as g:
@@ -254,7 +254,7 @@ def test_sharded_query_path_on_one_gpu(cuda, oracle, seed, exchange):
                                           flags_all.data_ptr(), int(ip[-1]))
         idx, dist, nv = cuda.kneighbors(h, k, n_rows=b - a)
         assert_neighbours_equal_up_to_ties(idx, dist, nv, ref[0][a:b], ref[1][a:b], ref[2][a:b], RTOL)
-        assert cuda.rerank_kernel_name(h) == ("k4_rerank_window_kernel" if packed_all is None else "k4c_rerank_kernel")
+        assert cuda.rerank_kernel_name(h) == ("k4_rerank_window_kernel" if packed_all is None else "k4c_rerank_direct_kernel")
         cuda.destroy(h)
 
 

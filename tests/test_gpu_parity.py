@@ -10,6 +10,8 @@ from schicexplorer_b200 import synth
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5   # north_star: "reranked distances within 1e-5 relative"
+# the two counts kernels of k4c_rerank.cu (direct: default; batch iterator: SCHIC_K4_KERNEL=iter or SCHIC_K4_LPS=0|2)
+COUNTS_KERNELS = ("k4c_rerank_direct_kernel", "k4c_rerank_kernel")
 
 
 def synth_csr(n, seed=11, **kw):
@@ -349,7 +351,7 @@ def test_rerank_kernel_variants(cuda, oracle, monkeypatch, mode):
     with Fitted(cuda, X, **kw) as g, Fitted(oracle, X, **kw) as o:
         a, b = cuda.kneighbors(g.h, 20), oracle.kneighbors(o.h, 20)
         assert_neighbours_equal_up_to_ties(*a, *b, RTOL)
-        assert cuda.rerank_kernel_name(g.h) == {"counts": "k4c_rerank_kernel", "hash": "k4_rerank_kernel"}.get(mode, "k4_rerank_window_kernel")
+        assert cuda.rerank_kernel_name(g.h) in {"counts": COUNTS_KERNELS, "hash": ("k4_rerank_kernel",)}.get(mode, ("k4_rerank_window_kernel",))
     # realistic clustered cells, k*excess_factor candidates
     Xs = synth_csr(200, seed=21)
     kw = dict(fast=False, n_neighbors=15, excess_factor=2, minimal_blocks_in_common=30)
@@ -383,6 +385,14 @@ def _count_rows(rng, n_rows, ncols, lens, hi=40, pool=None):
     return csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n_rows, ncols))
 
 
+def Xa_early(X, rng):
+    """X with a few counts >= 255 (escape windows) and slices that start / end on every alignment."""
+    Xa = X.copy()
+    big = rng.choice(Xa.nnz, size=Xa.nnz // 300, replace=False)
+    Xa.data[big] = rng.integers(255, 65536, size=len(big)).astype(np.float64)
+    return Xa
+
+
 def test_counts_rerank_kernel(cuda, oracle, monkeypatch):
     """The counts kernel (k4c_rerank.cu) on its own edge cases, always against the oracle:
     (a) counts >= 255 in query rows (table bytes saturate at 255, resolved by the escape search), up to the largest
@@ -407,7 +417,7 @@ def test_counts_rerank_kernel(cuda, oracle, monkeypatch):
             cuda.set_feature_range(g.h, M.shape[1])
             a, b = cuda.kneighbors(g.h, k), oracle.kneighbors(o.h, k)
             assert_neighbours_equal_up_to_ties(*a, *b, RTOL)
-            assert cuda.rerank_kernel_name(g.h) == want_kernel
+            assert cuda.rerank_kernel_name(g.h) in ((want_kernel,) if isinstance(want_kernel, str) else want_kernel)
             return a
 
     for wg in ("1", "3", "100000", None):                                # (c): one window per group ... one group / default
@@ -415,18 +425,31 @@ def test_counts_rerank_kernel(cuda, oracle, monkeypatch):
             monkeypatch.delenv("SCHIC_K4_GROUP_WINDOWS", raising=False)
         else:
             monkeypatch.setenv("SCHIC_K4_GROUP_WINDOWS", wg)
-        check(X, "k4c_rerank_kernel")
-    for lps in ("8", "4", "0"):                                          # lane-group variants (0: proportional to row length)
+        check(X, COUNTS_KERNELS)
+    for lps in ("8", "4", "0", "2"):                                     # lane-group variants (0: proportional to row length)
         monkeypatch.setenv("SCHIC_K4_LPS", lps)
-        check(X, "k4c_rerank_kernel")
-        check(X[:9], "k4c_rerank_kernel", k=9)
+        for kern in ("direct", "iter"):                                  # (direct exists for groups of 4 and 8 lanes)
+            monkeypatch.setenv("SCHIC_K4_KERNEL", kern)
+            want = "k4c_rerank_direct_kernel" if kern == "direct" and lps in ("8", "4") else "k4c_rerank_kernel"
+            check(X, want)
+            check(X[:9], want, k=9)
     monkeypatch.delenv("SCHIC_K4_LPS")
+    for lps, u in (("8", "2"), ("8", "3"), ("4", "4"), ("4", "6")):      # direct kernel: every (lanes, chunks per round, threads) build
+        for threads in ("416", "512"):
+            monkeypatch.setenv("SCHIC_K4_KERNEL", "direct")
+            monkeypatch.setenv("SCHIC_K4_U", u)
+            monkeypatch.setenv("SCHIC_K4_LPS", lps)
+            monkeypatch.setenv("SCHIC_K4_THREADS", threads)
+            check(X, "k4c_rerank_direct_kernel")
+            check(Xa_early(X, rng), "k4c_rerank_direct_kernel")
+    for name in ("SCHIC_K4_U", "SCHIC_K4_LPS", "SCHIC_K4_KERNEL", "SCHIC_K4_THREADS"):
+        monkeypatch.delenv(name)
     # (a) a few large counts (escapes) in some rows, incl. the largest packable value
     Xa = X.copy()
     big = rng.choice(Xa.nnz, size=Xa.nnz // 200, replace=False)
     Xa.data[big] = rng.integers(255, 65536, size=len(big)).astype(np.float64)
     Xa.data[big[:3]] = [255.0, 256.0, 65535.0]
-    check(Xa, "k4c_rerank_kernel")
+    check(Xa, COUNTS_KERNELS)
     # (d) not packable: every variant must come out of the generic kernel, same answers as the oracle
     Xf = X.copy(); Xf.data = Xf.data * 0.5                               # non-integer values
     check(Xf, "k4_rerank_window_kernel")
@@ -440,7 +463,7 @@ def test_counts_rerank_kernel(cuda, oracle, monkeypatch):
     with Fitted(cuda, Xa, **kw) as g, Fitted(oracle, Xa, **kw) as o:
         gi, gd, gn = cuda.kneighbors_exact(g.h, 10, False)
         oi, od, on = oracle.kneighbors_exact(o.h, 10, False)
-        assert cuda.rerank_kernel_name(g.h) == "k4c_rerank_kernel"
+        assert cuda.rerank_kernel_name(g.h) in COUNTS_KERNELS
         assert_neighbours_equal_up_to_ties(gi, gd, gn, oi, od, on, RTOL)
         monkeypatch.setenv("SCHIC_K4_MODE", "window")
     with Fitted(cuda, Xa, **kw) as g:
@@ -588,7 +611,7 @@ def test_fit_csr_host_staged_upload(cuda, oracle, monkeypatch):
                               data.astype(data_dtype), False)
             got = cuda.kneighbors(h, 12)
             assert_neighbours_equal_up_to_ties(*got, *want, RTOL)
-            assert cuda.rerank_kernel_name(h) == ("k4c_rerank_kernel" if name in ("counts", "u16") else "k4_rerank_window_kernel"), name
+            assert cuda.rerank_kernel_name(h) in (COUNTS_KERNELS if name in ("counts", "u16") else ("k4_rerank_window_kernel",)), name
             cuda.destroy(h)
     # append (partial_fit) in two staged calls == one fit; fast mode without values
     want = reference(dt)

@@ -69,7 +69,7 @@ def main():
                     and np.array_equal(env.cpu().numpy(), xnv[lo:hi]))
         api.destroy(h)
         if exchange == "packed":
-            same = same and api.rerank_kernel_name(sh.h) == "k4c_rerank_kernel"
+            same = same and api.rerank_kernel_name(sh.h) in ("k4c_rerank_direct_kernel", "k4c_rerank_kernel")
         # ... and against the CPU oracle (rank 0 computes it once per mode, everybody compares its own rows)
         if fast not in oracle_ref:
             from oracle import oracle_api
