@@ -547,35 +547,33 @@ k4c_rerank_direct_kernel(const int64_t* __restrict__ indptr, const uint32_t* __r
                 const bool live = s_ye > s_ys;             // uniform in the lane group
                 if (live) {
                     if (!esc) {
-                        uint32_t a32 = 0u;                 // <= 4 U products < 2^24 each
+                        auto probe_round = [&](const uint4 (&x)[U]) {   // <= 4 U products < 2^24 each
+                            uint32_t a32 = 0u;
 #pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            a32 = k4c_mac(v[u].x, (uint32_t)tab[v[u].x >> K4C_CNT_BITS], a32);
-                            a32 = k4c_mac(v[u].y, (uint32_t)tab[v[u].y >> K4C_CNT_BITS], a32);
-                            a32 = k4c_mac(v[u].z, (uint32_t)tab[v[u].z >> K4C_CNT_BITS], a32);
-                            a32 = k4c_mac(v[u].w, (uint32_t)tab[v[u].w >> K4C_CNT_BITS], a32);
-                        }
-                        acc = a32;
+                            for (int u = 0; u < U; ++u) {
+                                a32 = k4c_mac(x[u].x, (uint32_t)tab[x[u].x >> K4C_CNT_BITS], a32);
+                                a32 = k4c_mac(x[u].y, (uint32_t)tab[x[u].y >> K4C_CNT_BITS], a32);
+                                a32 = k4c_mac(x[u].z, (uint32_t)tab[x[u].z >> K4C_CNT_BITS], a32);
+                                a32 = k4c_mac(x[u].w, (uint32_t)tab[x[u].w >> K4C_CNT_BITS], a32);
+                            }
+                            return a32;
+                        };
                         const uint32_t p0 = (s_ys & ~3u) + 4u * ql;
                         const uint4* __restrict__ bp = reinterpret_cast<const uint4*>(packed + p0);
                         int rem = (int)(s_ye - p0);
-                        // further rounds while the slice goes on (group-uniform). NOT unrolled: nvcc 12.9 unrolled the <8, 2>
-                        // instance of an earlier form of this loop (condition on rem + 4 * ql) by four with the lane term's sign
-                        // flipped in the unrolled exit test, and lanes 1.. of a group lost rounds.
+                        uint32_t left = s_ye - (s_ys & ~3u);           // non-zeros from the aligned start (group-uniform)
+                        // Further rounds while the slice goes on. The loops are NOT unrolled: nvcc 12.9 unrolled the <8, 2>
+                        // instance of an earlier form (loop condition on rem + 4 * ql) by four with the lane term's sign flipped
+                        // in the unrolled exit test, and lanes 1.. of a group lost rounds.
+                        // (a second register set that requests round r + 1 before round r is probed was measured: 10.7 ms
+                        // against 10.4 ms -- the kernel is bound by L1 wavefronts, not by the latency of these loads)
+                        acc = probe_round(v);
 #pragma unroll 1
-                        for (uint32_t left = s_ye - (s_ys & ~3u); left > ROUND; left -= ROUND) {
+                        for (; left > ROUND; left -= ROUND) {
                             bp += LPS * U;
                             rem -= (int)ROUND;
                             load_round(bp, rem);
-                            a32 = 0u;
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                a32 = k4c_mac(v[u].x, (uint32_t)tab[v[u].x >> K4C_CNT_BITS], a32);
-                                a32 = k4c_mac(v[u].y, (uint32_t)tab[v[u].y >> K4C_CNT_BITS], a32);
-                                a32 = k4c_mac(v[u].z, (uint32_t)tab[v[u].z >> K4C_CNT_BITS], a32);
-                                a32 = k4c_mac(v[u].w, (uint32_t)tab[v[u].w >> K4C_CNT_BITS], a32);
-                            }
-                            acc += a32;
+                            acc += probe_round(v);
                         }
                         uint32_t f32 = k4c_mac(s_hw, (uint32_t)tab[s_hw >> K4C_CNT_BITS], 0u);   // the foreign non-zeros again
                         f32 = k4c_mac(s_tw, (uint32_t)tab[s_tw >> K4C_CNT_BITS], f32);

@@ -434,7 +434,8 @@ def test_counts_rerank_kernel(cuda, oracle, monkeypatch):
             check(X, want)
             check(X[:9], want, k=9)
     monkeypatch.delenv("SCHIC_K4_LPS")
-    for lps, u in (("8", "2"), ("8", "3"), ("4", "4"), ("4", "6")):      # direct kernel: every (lanes, chunks per round, threads) build
+    # direct kernel: every (lanes, chunks per round, threads) build
+    for lps, u in (("8", "2"), ("8", "3"), ("4", "4"), ("4", "6")):
         for threads in ("416", "512"):
             monkeypatch.setenv("SCHIC_K4_KERNEL", "direct")
             monkeypatch.setenv("SCHIC_K4_U", u)
