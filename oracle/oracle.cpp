@@ -68,6 +68,22 @@ inline uint32_t hash64(uint64_t f, uint32_t j) {
     return (uint32_t)(k % M);
 }
 
+// Rule 4 (block combine, "shingle"; decision point D2 -- OFF unless schic_mh_params.shingle != 0): the minima of
+// `shingle_size` consecutive hash functions are folded into ONE key, key = sig[b*s]; key = h'(sig[b*s+t] + 1, key + 1)
+// for t = 1..s-1, which leaves H / s tables. h' is the hash family's own mix applied to the product of its two
+// arguments (SURVEY leaves h' open; this is the restatement's choice, recorded with the HashSpec).
+inline uint32_t combine32(uint32_t v, uint32_t key) { return wang32((v + 1u) * (key + 1u)) % M; }
+inline uint32_t combine64(uint32_t v, uint32_t key) {
+    uint64_t k = ((uint64_t)v + 1) * ((uint64_t)key + 1);
+    k = ~k + (k << 15);
+    k ^= k >> 12;
+    k += k << 2;
+    k ^= k >> 4;
+    k *= 2057u;
+    k ^= k >> 16;
+    return (uint32_t)(k % M);
+}
+
 }  // namespace
 
 struct schic_mh_handle {
@@ -77,7 +93,8 @@ struct schic_mh_handle {
     std::vector<uint64_t> idx;
     std::vector<float> val;
     std::vector<uint32_t> sig;  // [n, H]
-    int H_created = 0;          // hash count the handle was created with (schic_mh_set_active_hashes changes p's)
+    int H_created = 0;          // table count the handle was created with (schic_mh_set_active_hashes changes p's)
+    int H_raw = 0, block = 1;   // hash functions evaluated per row; minima folded per table (1: block combine off)
     // inverse index (rule 5), rebuilt lazily after every fit
     bool index_ok = false;
     std::vector<int32_t> order;        // [H, n] cells of table j sorted by (value, cell)
@@ -120,16 +137,36 @@ void sig_row64(const uint64_t* f, int64_t nnz, int H, uint32_t* s) {
 
 // Rules 2-3: signature of the rows [r0, r1) of the handle's CSR.
 void compute_signatures(schic_mh_handle* h, int64_t r0, int64_t r1) {
-    const int H = h->p.number_of_hash_functions;
+    const int H = h->p.number_of_hash_functions;     // tables = columns of sig
     const bool w64 = h->p.hash_width == 64;
     h->sig.resize((size_t)r1 * H);
+    if (h->block <= 1) {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads(h))
+        for (int64_t c = r0; c < r1; ++c) {
+            uint32_t* s = h->sig.data() + (size_t)c * H;
+            for (int j = 0; j < H; ++j) s[j] = M;  // empty row => sentinel M
+            const uint64_t* f = h->idx.data() + h->indptr[c];
+            const int64_t nnz = h->indptr[c + 1] - h->indptr[c];
+            if (w64) sig_row64(f, nnz, H, s); else sig_row32(f, nnz, H, s);
+        }
+        return;
+    }
+    // rule 4: H_raw minima per row, folded block by block into H keys; an empty row keeps the sentinel
+    const int Hr = h->H_raw, bs = h->block;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads(h))
     for (int64_t c = r0; c < r1; ++c) {
-        uint32_t* s = h->sig.data() + (size_t)c * H;
-        for (int j = 0; j < H; ++j) s[j] = M;  // empty row => sentinel M
+        std::vector<uint32_t> raw((size_t)Hr, M);
         const uint64_t* f = h->idx.data() + h->indptr[c];
         const int64_t nnz = h->indptr[c + 1] - h->indptr[c];
-        if (w64) sig_row64(f, nnz, H, s); else sig_row32(f, nnz, H, s);
+        if (w64) sig_row64(f, nnz, Hr, raw.data()); else sig_row32(f, nnz, Hr, raw.data());
+        uint32_t* s = h->sig.data() + (size_t)c * H;
+        for (int b = 0; b < H; ++b) {
+            uint32_t key = raw[(size_t)b * bs];
+            if (nnz > 0)
+                for (int t = 1; t < bs; ++t)
+                    key = w64 ? combine64(raw[(size_t)b * bs + t], key) : combine32(raw[(size_t)b * bs + t], key);
+            s[b] = nnz > 0 ? key : M;
+        }
     }
 }
 
@@ -258,12 +295,17 @@ int schic_mh_create(const schic_mh_params* p, schic_mh_handle** out) {
         return fail(SCHIC_ERR_INVALID_ARG, "number_of_hash_functions must be in [1, 65535]");
     if (p->hash_width != 32 && p->hash_width != 64)
         return fail(SCHIC_ERR_INVALID_ARG, "hash_width must be 32 or 64");
-    if (p->shingle != 0)
-        return fail(SCHIC_ERR_UNSUPPORTED, "block combine (shingle) is off in the default HashSpec");
+    if (p->shingle != 0 && (p->shingle_size < 1 || p->number_of_hash_functions / p->shingle_size < 1))
+        return fail(SCHIC_ERR_INVALID_ARG, "block combine needs 1 <= shingle_size <= number_of_hash_functions");
     if (p->n_neighbors < 1) return fail(SCHIC_ERR_INVALID_ARG, "n_neighbors must be >= 1");
     auto* h = new schic_mh_handle();
     h->p = *p;
-    h->H_created = p->number_of_hash_functions;
+    h->H_raw = p->number_of_hash_functions;
+    if (p->shingle != 0 && p->shingle_size > 1) {   // rule 4: everything behind the signatures sees H / s tables
+        h->block = p->shingle_size;
+        h->p.number_of_hash_functions = h->H_raw / h->block;
+    }
+    h->H_created = h->p.number_of_hash_functions;
     if (h->p.excess_factor < 1) h->p.excess_factor = 1;
     if (h->p.max_bin_size < 1) h->p.max_bin_size = std::numeric_limits<int64_t>::max();
     *out = h;
@@ -431,6 +473,7 @@ int schic_mh_kneighbors_exact(schic_mh_handle* h, int32_t k, int32_t include_sel
 // re-hashes every fitted row with n_hashes functions.
 int schic_mh_set_active_hashes(schic_mh_handle* h, int32_t n_hashes) {
     if (int e = check_handle(h)) return e;
+    if (h->block > 1) return fail(SCHIC_ERR_UNSUPPORTED, "active-hash prefix with block combine (shingle)");
     if (n_hashes < 1 || n_hashes > h->H_created)
         return fail(SCHIC_ERR_INVALID_ARG, "n_hashes must be in [1, number_of_hash_functions as created]");
     if (n_hashes == h->p.number_of_hash_functions) return SCHIC_OK;

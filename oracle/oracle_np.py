@@ -55,6 +55,29 @@ def signatures(X, n_hash, width=32, block=64):
     return sig
 
 
+def combine(sig, block, width=32, empty_rows=None):
+    """Rule 4 (block combine / "shingle", decision point D2; off unless asked for): fold the minima of `block`
+    consecutive hash functions into one key, key = sig[b*s]; key = h'(sig[b*s+t] + 1, key + 1), t = 1..s-1, where h' is
+    the family's mix of the product of its arguments. [n, H] -> [n, H // block]; empty rows keep the sentinel M."""
+    n, H = sig.shape
+    T = H // block
+    out = np.empty((n, T), dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        for b in range(T):
+            key = sig[:, b * block].astype(np.uint32)
+            for t in range(1, block):
+                v = sig[:, b * block + t]
+                if width == 32:
+                    key = wang32((v + np.uint32(1)) * (key + np.uint32(1))) % M
+                else:
+                    k = (v.astype(np.uint64) + np.uint64(1)) * (key.astype(np.uint64) + np.uint64(1))
+                    key = (wang64(k) % np.uint64(M)).astype(np.uint32)
+            out[:, b] = key
+    if empty_rows is not None:
+        out[empty_rows] = M
+    return out
+
+
 def collision_counts(sig, max_bin_size=None):
     """Rules 5-6, all pairs: cnt[c][d] = #{j: sig[c][j] == sig[d][j], value admissible}."""
     n, H = sig.shape
