@@ -53,8 +53,13 @@ typedef struct schic_mh_params {
     int32_t minimal_blocks_in_common; /* minimal_blocks_in_common= (100 at :404) */
     int32_t excess_factor;            /* excess_factor= (1 at :404) */
     int64_t max_bin_size;             /* max_bin_size= (100000 at :403); buckets >= this are skipped */
-    int32_t shingle_size;             /* accepted; block combine is OFF in the default HashSpec (D2) */
-    int32_t shingle;                  /* must be 0 */
+    int32_t shingle_size;             /* minima folded per table when shingle != 0; otherwise accepted and unused (D2) */
+    int32_t shingle;                  /* 0 (default HashSpec): one table per hash function. != 0: block combine (SURVEY 8(c)
+                                         rule 4) -- K1 evaluates number_of_hash_functions minima per row, K2 folds every
+                                         shingle_size consecutive ones into a key, and everything behind the signatures
+                                         (signature accessors, counts, thresholds, 1 - cnt/H) sees
+                                         number_of_hash_functions / shingle_size tables. Not available together with
+                                         schic_mh_set_active_hashes or an external (sharded) database. */
     int32_t number_of_cores;          /* oracle: OpenMP threads (<=0: all); CUDA: ignored */
     int32_t device;                   /* CUDA ordinal, -1 = current device; oracle: ignored */
 } schic_mh_params;

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libschic_mh.so")
-SOURCES = ["capi.cu", "k1_signatures.cu", "k1_table.cu", "k2_buckets.cu", "k3_collisions.cu", "k3_select.cu", "k4_rerank.cu", "k4c_rerank.cu", "k5_graph.cu", "k6_longrows.cu", "k7_relabel.cu",
+SOURCES = ["capi.cu", "k1_signatures.cu", "k1_table.cu", "k2_buckets.cu", "k2_combine.cu", "k3_collisions.cu", "k3_select.cu", "k4_rerank.cu", "k4c_rerank.cu", "k5_graph.cu", "k6_longrows.cu", "k7_relabel.cu",
            "int_peak.cu", "pca_dense.cu", "hostconv.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]

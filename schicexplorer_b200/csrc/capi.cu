@@ -210,6 +210,10 @@ struct schic_mh_handle {
     // signature matrix of a smaller hash count. While a prefix is active, sig holds the compacted [n, H_active] copy,
     // sig_fit the fitted [n, H_fit] matrix, and p.number_of_hash_functions == H_active.
     DevBuf<uint32_t> sig_fit; int H_fit = 0; bool sliced = false;
+    // block combine ("shingle", SURVEY 8(c) rule 4; off unless params.shingle != 0): K1 fills the raw [n, H] matrix, the
+    // combine kernel folds `block` minima per table into sig [n, H / block] and the handle then looks like one created
+    // with H / block hash functions -- the same two-buffer state as an active-hash prefix (sliced), undone by the next fit.
+    int block = 1;
     DevBuf<unsigned char> k1_scratch;    // work-item list of the filtered / table K1 kernels
     // shared-table K1 (k1_table.cu): per-id presence bytes and slots, hit entries, {entries used, overflow, max id}
     DevBuf<unsigned char> k1t_present; DevBuf<unsigned long long> k1t_slot; DevBuf<uint16_t> k1t_entries;
@@ -502,6 +506,7 @@ int hash_rows(schic_mh_handle* h, int64_t r0, int64_t r1, int64_t pos0, int64_t 
     return 0;
 }
 
+int apply_block_combine(schic_mh_handle* h);
 // Undo schic_mh_set_active_hashes: the fitted [n, H_fit] matrix becomes the live one again.
 void restore_fitted_signatures(schic_mh_handle* h) {
     if (!h->sliced) return;
@@ -509,6 +514,25 @@ void restore_fitted_signatures(schic_mh_handle* h) {
     std::swap(h->sig.cap, h->sig_fit.cap);
     h->p.number_of_hash_functions = h->H_fit;
     h->sliced = false;
+}
+
+// End of every fit when block combine is on: fold the raw minima (K2) and switch the handle to the H / block tables.
+int apply_block_combine(schic_mh_handle* h) {
+    if (h->block <= 1 || h->sliced) return SCHIC_OK;
+    const int H_raw = h->p.number_of_hash_functions, T = H_raw / h->block;
+    cudaStream_t s = h->stream;
+    ST_TRY(h->sig_fit.reserve(std::max<int64_t>(1, h->n * (int64_t)T), 0, s));
+    {
+        StageTimer t(h, ST_SIG, s);
+        add_launches(h, schic::launch_block_combine(h->p.hash_width, h->sig.p, h->n, H_raw, h->block, h->sig_fit.p, s));
+    }
+    CU_TRY(cudaGetLastError());
+    h->H_fit = H_raw;
+    std::swap(h->sig.p, h->sig_fit.p);      // sig: the keys [n, T]; sig_fit: the raw matrix (restored by the next fit)
+    std::swap(h->sig.cap, h->sig_fit.cap);
+    h->sliced = true;
+    h->p.number_of_hash_functions = T;
+    return SCHIC_OK;
 }
 
 int prune_buckets(schic_mh_handle* h, const uint32_t* db_sig, int64_t ndb) {
@@ -990,7 +1014,8 @@ int schic_mh_create(const schic_mh_params* p, schic_mh_handle** out) {
     if (p->number_of_hash_functions < 1 || p->number_of_hash_functions > 65535)
         return fail(SCHIC_ERR_INVALID_ARG, "number_of_hash_functions must be in [1, 65535]");
     if (p->hash_width != 32 && p->hash_width != 64) return fail(SCHIC_ERR_INVALID_ARG, "hash_width must be 32 or 64");
-    if (p->shingle != 0) return fail(SCHIC_ERR_UNSUPPORTED, "block combine (shingle) is off in the default HashSpec");
+    if (p->shingle != 0 && (p->shingle_size < 1 || p->number_of_hash_functions / p->shingle_size < 1))
+        return fail(SCHIC_ERR_INVALID_ARG, "block combine needs 1 <= shingle_size <= number_of_hash_functions");
     if (p->n_neighbors < 1) return fail(SCHIC_ERR_INVALID_ARG, "n_neighbors must be >= 1");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -1009,6 +1034,7 @@ int schic_mh_create(const schic_mh_params* p, schic_mh_handle** out) {
     h->p = *p;
     if (h->p.excess_factor < 1) h->p.excess_factor = 1;
     if (h->p.max_bin_size < 1) h->p.max_bin_size = INT64_MAX;
+    if (p->shingle != 0 && p->shingle_size > 1) h->block = p->shingle_size;
     h->device = dev;
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1285,7 +1311,7 @@ static int fit_csr_impl(schic_mh_handle* h, int64_t n_rows, const int64_t* indpt
         CU_TRY(cudaStreamWaitEvent(s, done, 0));
         CU_TRY(cudaStreamSynchronize(cs));
     }
-    return SCHIC_OK;
+    return apply_block_combine(h);
 }
 
 int schic_mh_fit_csr(schic_mh_handle* h, int64_t n_rows, const int64_t* indptr, const void* indices,
@@ -1333,7 +1359,7 @@ static int fit_csr_device_impl(schic_mh_handle* h, int64_t n_rows, int64_t nnz, 
         StageTimer t(h, ST_SIG, h->stream);
         ST_TRY(hash_rows(h, 0, n_rows, pos0, pos0 + nnz, h->stream));
     }
-    return SCHIC_OK;
+    return apply_block_combine(h);
 }
 
 int schic_mh_fit_csr_host(schic_mh_handle* h, int64_t n_rows, const void* indptr, int32_t indptr_bits, const void* indices,
@@ -1411,7 +1437,7 @@ int schic_mh_set_database_device(schic_mh_handle* h, int64_t n_total, int64_t ro
     h->sig16_of = nullptr; h->given_counts = nullptr;
     if (!d_sig_all) { h->ext = false; h->norm_of = nullptr; return SCHIC_OK; }
     if (h->n == 0) return fail(SCHIC_ERR_NOT_FITTED, "fit the local shard first");
-    if (h->sliced) return fail(SCHIC_ERR_UNSUPPORTED, "external database while an active-hash prefix is set");
+    if (h->sliced) return fail(SCHIC_ERR_UNSUPPORTED, "external database while an active-hash prefix or block combine (shingle) is set");
     if (row0 < 0 || row0 + h->n > n_total) return fail(SCHIC_ERR_INVALID_ARG, "local rows do not fit in the database");
     h->ext = true; h->db_n = n_total; h->db_row0 = row0; h->db_sig = d_sig_all;
     h->db_indptr = d_indptr_all; h->db_feat = d_indices_all; h->db_val = d_data_all;
@@ -1638,6 +1664,7 @@ int schic_mh_kneighbors_exact_device(schic_mh_handle* h, int32_t k, int32_t incl
 int schic_mh_set_active_hashes(schic_mh_handle* h, int32_t n_hashes) {
     ST_TRY(check(h));
     ST_TRY(use_device(h));
+    if (h->block > 1) return fail(SCHIC_ERR_UNSUPPORTED, "active-hash prefix with block combine (shingle)");
     const int H_fit = h->sliced ? h->H_fit : h->p.number_of_hash_functions;
     if (n_hashes < 1 || n_hashes > H_fit) return fail(SCHIC_ERR_INVALID_ARG, "n_hashes must be in [1, number_of_hash_functions as created]");
     if (h->ext) return fail(SCHIC_ERR_UNSUPPORTED, "active-hash prefix with an external database");

@@ -45,7 +45,11 @@ int launch_signatures64(const int64_t* d_indptr, const uint32_t* d_feat_lo, cons
                         int64_t n_rows, int64_t nnz, int64_t indptr0, int H, uint32_t* d_sig,
                         cudaStream_t stream);
 
-// ---- K2: max_bin_size bucket pruning (k2_buckets.cu) ------------------------------------------
+// ---- K2: optional block combine ("shingle", k2_combine.cu) ------------------------------------
+// keys[r][b] = fold of raw[r][b*block .. b*block+block-1] (rule 4); raw [n, H_raw] -> keys [n, H_raw / block].
+int launch_block_combine(int width, const uint32_t* d_raw, int64_t n, int H_raw, int block, uint32_t* d_keys, cudaStream_t stream);
+
+// ---- K2b: max_bin_size bucket pruning (k2_buckets.cu) -----------------------------------------
 // out[c][j] = sig[c][j] unless its bucket {d : sig[d][j] == sig[c][j]} has >= max_bin_size members, then 0.
 int launch_bucket_mask(const uint32_t* d_sig, int64_t n, int H, int64_t max_bin_size, uint32_t* d_out,
                        cudaStream_t stream);

@@ -170,6 +170,8 @@ class ShardedMinHash:
         self.bounds = list(row_bounds)
         self.row0, self.n_local = self.bounds[self.rank], self.bounds[self.rank + 1] - self.bounds[self.rank]
         self.kw = dict(minhash_kwargs)
+        if self.kw.get("shingle"):
+            raise NotImplementedError("block combine (shingle=1) is a single-GPU option: the sharded layer exchanges raw signatures")
         self.H = int(self.kw["number_of_hash_functions"])
         self.fast = bool(self.kw.get("fast", True))
         dev_index = device.index if device.type == "cuda" else -1

@@ -156,6 +156,8 @@ class MinHash:
         ``n_hashes`` must not exceed the value the object was constructed with. The next fit switches back."""
         api, h = self._ensure()
         n_hashes = int(n_hashes)
+        if self.shingle and self.shingle_size > 1:
+            raise ValueError("set_number_of_hash_functions is not available with block combine (shingle=1)")
         if not 1 <= n_hashes <= self._created_hashes():
             raise ValueError(f"n_hashes must be in [1, {self._created_hashes()}]")
         api.set_active_hashes(h, n_hashes)
@@ -167,10 +169,17 @@ class MinHash:
             self._n_hashes_created = self.number_of_hash_functions
         return self._n_hashes_created
 
+    def _tables(self) -> int:
+        """Columns of the signature matrix: the hash functions, or -- with block combine (``shingle=1``, SURVEY 8(c)
+        rule 4; off by default) -- one key per ``shingle_size`` consecutive hash functions."""
+        if self.shingle and self.shingle_size > 1:
+            return self._created_hashes() // self.shingle_size
+        return self.number_of_hash_functions
+
     # ---- parity hooks --------------------------------------------------------------------------
     def signatures(self) -> np.ndarray:
         api, h = self._ensure()
-        return api.signatures(h, self.number_of_hash_functions)
+        return api.signatures(h, self._tables())
 
     def collision_counts(self, row0=0, row1=None) -> np.ndarray:
         api, h = self._ensure()

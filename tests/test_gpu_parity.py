@@ -183,6 +183,59 @@ def test_minhash_class_runs_on_the_gpu(cuda, fixture20, golden20):
     mh.close()
 
 
+@pytest.mark.parametrize("width", [32, 64])
+def test_block_combine_shingle(cuda, oracle, fixture20, width):
+    """K2 (k2_combine.cu), the optional block combine behind schic_mh_params.shingle (SURVEY 8(c) rule 4, off by default):
+    keys, counts, fast and exact neighbours equal the oracle's for both HashSpecs; empty rows keep the sentinel;
+    partial_fit == fit; the device-resident fit entry point; the reference-facing class; the prefix switch is refused."""
+    import torch
+    from schicexplorer_b200 import MinHash
+    from schicexplorer_b200._capi import SchicError
+    X = fixture20[0]
+    Xe = vstack([X[:9], csr_matrix((1, X.shape[1])), X[9:]]).tocsr()
+    H, s = 803, 5
+    T = H // s
+    kw = dict(number_of_hash_functions=H, shingle=1, shingle_size=s, minimal_blocks_in_common=3, hash_width=width)
+    o = oracle.create(n_neighbors=20, fast=False, **kw)
+    oracle.fit_csr(o, Xe.indptr, Xe.indices, Xe.data.astype(np.float32), False)
+    keys, counts = oracle.signatures(o, T), oracle.collision_counts(o)
+    assert (keys[9] == 2147483647).all()
+    g = cuda.create(n_neighbors=20, fast=False, **kw)
+    cuda.fit_csr(g, Xe.indptr, Xe.indices, Xe.data.astype(np.float32), False)
+    assert np.array_equal(cuda.signatures(g, T), keys)
+    assert np.array_equal(cuda.collision_counts(g), counts)
+    for fast in (1, 0):
+        assert_neighbours_equal_up_to_ties(*cuda.kneighbors(g, 6, fast), *oracle.kneighbors(o, 6, fast), RTOL)
+    with pytest.raises(SchicError):
+        cuda.set_active_hashes(g, 100)
+    # a second fit on the same handle (raw matrix restored, combined again), then partial fits
+    cuda.fit_csr(g, Xe.indptr, Xe.indices, Xe.data.astype(np.float32), False)
+    assert np.array_equal(cuda.signatures(g, T), keys)
+    for a, b, app in ((0, 8, False), (8, 15, True), (15, 21, True)):
+        P = Xe[a:b]
+        cuda.fit_csr(g, P.indptr, P.indices, P.data.astype(np.float32), app)
+    assert cuda.n_fitted(g) == 21 and np.array_equal(cuda.signatures(g, T), keys)
+    assert_neighbours_equal_up_to_ties(*cuda.kneighbors(g, 6, 0), *oracle.kneighbors(o, 6, 0), RTOL)
+    cuda.destroy(g)
+    # device-resident CSR
+    dev = torch.device("cuda:0")
+    ip = torch.from_numpy(Xe.indptr.astype(np.int64)).to(dev)
+    ix = torch.from_numpy(Xe.indices.astype(np.int32)).to(dev)
+    dt = torch.from_numpy(Xe.data.astype(np.float32)).to(dev)
+    g = cuda.create(n_neighbors=20, fast=False, device=0, **kw)
+    cuda.fit_csr_device(g, Xe.shape[0], Xe.nnz, ip.data_ptr(), ix.data_ptr(), dt.data_ptr(), False)
+    assert np.array_equal(cuda.signatures(g, T), keys)
+    cuda.destroy(g)
+    oracle.destroy(o)
+    # the class: signatures() has one column per table
+    mh = MinHash(n_neighbors=20, fast=True, **kw)
+    mh.fit(Xe)
+    assert mh.signatures().shape == (21, T) and np.array_equal(mh.signatures(), keys)
+    with pytest.raises(ValueError):
+        mh.set_number_of_hash_functions(100)
+    mh.close()
+
+
 def test_device_resident_entry_points(cuda, oracle):
     import torch
     X = synth_csr(200, seed=8)

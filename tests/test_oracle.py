@@ -153,9 +153,52 @@ def test_error_reporting(oracle):
     with pytest.raises(SchicError):
         oracle.create(n_neighbors=5, number_of_hash_functions=0)
     with pytest.raises(SchicError):
-        oracle.create(n_neighbors=5, shingle=1)
+        oracle.create(n_neighbors=5, number_of_hash_functions=8, shingle=1, shingle_size=9)   # no table left
     h = oracle.create(n_neighbors=5)
     with pytest.raises(SchicError) as e:
         oracle.kneighbors(h, 5, n_rows=1)
     assert e.value.status == -2   # SCHIC_ERR_NOT_FITTED
     oracle.destroy(h)
+
+
+@pytest.mark.parametrize("width", [32, 64])
+def test_block_combine_shingle(oracle, fixture20, width):
+    """SURVEY 8(c) rule 4 (decision point D2, off by default): with shingle=1 the minima of shingle_size consecutive
+    hash functions are folded into one key. The C++ oracle against the numpy restatement: keys, counts, neighbours;
+    empty rows keep the sentinel; partial_fit == fit; the active-hash prefix is refused."""
+    from schicexplorer_b200._capi import SchicError
+    X = fixture20[0]
+    empty = csr_matrix((1, X.shape[1]))
+    Xe = vstack([X[:9], empty, X[9:]]).tocsr()
+    H, s = 803, 5                                   # 160 tables, 3 left-over minima unused
+    kw = dict(number_of_hash_functions=H, shingle=1, shingle_size=s, minimal_blocks_in_common=3, hash_width=width)
+    T = H // s
+    raw = oracle_np.signatures(Xe, H, width=width)
+    keys = oracle_np.combine(raw, s, width=width, empty_rows=np.diff(Xe.indptr) == 0)
+    assert keys.shape == (21, T) and (keys[9] == 2147483647).all()
+    h = oracle.create(n_neighbors=20, fast=False, **kw)
+    oracle.fit_csr(h, Xe.indptr, Xe.indices, Xe.data.astype(np.float32), False)
+    assert np.array_equal(oracle.signatures(h, T), keys)
+    assert np.array_equal(oracle.collision_counts(h).astype(np.int64), oracle_np.collision_counts(keys))
+    for fast in (1, 0):
+        idx, dist, nv = oracle.kneighbors(h, 6, fast)
+        i2, d2, n2 = oracle_np.kneighbors(Xe, keys, 6, fast=bool(fast), min_blocks=3)
+        assert np.array_equal(nv, n2) and np.array_equal(idx, i2)
+        fin = np.isfinite(d2)
+        np.testing.assert_allclose(dist[fin], d2[fin], rtol=1e-6)
+    with pytest.raises(SchicError):
+        oracle.set_active_hashes(h, 100)
+    ref = oracle.kneighbors(h, 6, 0)
+    oracle.destroy(h)
+    h = oracle.create(n_neighbors=20, fast=False, **kw)
+    for a, b, app in ((0, 8, False), (8, 15, True), (15, 21, True)):
+        P = Xe[a:b]
+        oracle.fit_csr(h, P.indptr, P.indices, P.data.astype(np.float32), app)
+    assert np.array_equal(oracle.signatures(h, T), keys)
+    got = oracle.kneighbors(h, 6, 0)
+    assert all(np.array_equal(x, y) for x, y in zip(got, ref))
+    oracle.destroy(h)
+    # the combine changes every key, and the fixture's similarities no longer reach 100 of 160 tables (SURVEY's argument
+    # for "off"): far fewer pairs pass the reference's threshold than with raw minima
+    cnt = oracle_np.collision_counts(keys)
+    assert (cnt[np.triu_indices(21, 1)] >= 100).sum() == 0
