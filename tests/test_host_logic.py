@@ -52,6 +52,30 @@ def test_partial_fit_numbers_rows_in_append_order(oracle_backed, fixture20, gold
     assert np.array_equal(mh.kneighbors(return_distance=False), golden20["idx_fast"])
 
 
+def test_block_combine_option_through_the_class(oracle_backed, fixture20):
+    """``shingle=1`` (upstream's separate switch; the reference does not pass it, so the default path is unchanged): the
+    class reports one signature column per table, the graph is built on the folded keys, the hyperopt prefix switch and
+    the sharded layer refuse the combination."""
+    from oracle import oracle_np
+    from schicexplorer_b200.dist import ShardedMinHash
+    X = fixture20[0]
+    kw = dict(n_neighbors=20, number_of_hash_functions=800, shingle_size=5, fast=True, minimal_blocks_in_common=2,
+              excess_factor=1, max_bin_size=100000)
+    plain = MinHash(**kw).fit(X)
+    folded = MinHash(shingle=1, **kw).fit(X)
+    assert plain.signatures().shape == (20, 800) and folded.signatures().shape == (20, 160)
+    assert np.array_equal(folded.signatures(), oracle_np.combine(plain.signatures(), 5))
+    g = folded.kneighbors_graph(mode="distance")
+    cnt = oracle_np.collision_counts(folded.signatures())
+    assert np.array_equal(np.diff(g.indptr), (cnt >= 2).sum(axis=1))
+    with pytest.raises(ValueError):
+        folded.set_number_of_hash_functions(400)
+    assert folded.get_params()["shingle"] == 1
+    import torch
+    with pytest.raises(NotImplementedError):
+        ShardedMinHash(oracle_backed, 20, [0, 20], torch.device("cpu"), shingle=1, **kw)
+
+
 def test_unknown_kwargs_warn_but_work(oracle_backed):
     with pytest.warns(UserWarning):
         MinHash(n_neighbors=3, some_new_upstream_flag=1)
