@@ -327,7 +327,6 @@ k3h_collision_kernel(const uint32_t* __restrict__ q16, int64_t nq, const uint32_
 // (Hw .. Hw_pad) hold the never-equal NaN pattern.
 // =================================================================================================
 constexpr int K3T_STAGE_WORDS = 2 * K3_JB * K3_TILE;        // query tile + database tile, uint32
-constexpr int K3T_MAX_BLOCKS = 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -487,35 +486,6 @@ k3t_collision_kernel(const __grid_constant__ CUtensorMap tmap, int q_row0, int64
                    reinterpret_cast<uint32_t*>(k3t_smem), full_bar);
 }
 
-// Several blocks in ONE launch (the pieces of a sharded symmetric count matrix: each is less than a wave of tiles, so
-// separate launches leave most of the GPU idle). Block i owns tiles [tile_begin[i], tile_begin[i + 1]) of a 1-D grid.
-struct K3TBlocks {
-    int n;
-    int q_row0[K3T_MAX_BLOCKS], nq[K3T_MAX_BLOCKS], d_row0[K3T_MAX_BLOCKS], nd[K3T_MAX_BLOCKS], tile_begin[K3T_MAX_BLOCKS + 1];
-    uint16_t* cnt[K3T_MAX_BLOCKS];
-    uint16_t* cnt_t[K3T_MAX_BLOCKS];
-    int64_t ld[K3T_MAX_BLOCKS], ld_t[K3T_MAX_BLOCKS];
-};
-
-__global__ void __launch_bounds__(K3_THREADS, 2)
-k3t_blocks_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K3TBlocks bl, int Hw_pad) {
-    extern __shared__ __align__(1024) unsigned char k3t_smem[];
-    __shared__ __align__(8) uint64_t full_bar[2];
-    int i = 0;
-    while (i + 1 < bl.n && (int)blockIdx.x >= bl.tile_begin[i + 1]) ++i;
-    const int t = (int)blockIdx.x - bl.tile_begin[i];
-    const int tiles_x = (bl.nd[i] + K3_TILE - 1) / K3_TILE;
-    const int tile_y = t / tiles_x, tile_x = t - tile_y * tiles_x;
-    uint32_t* stage = reinterpret_cast<uint32_t*>(k3t_smem);
-    const bool same = bl.q_row0[i] == bl.d_row0[i] && bl.nq[i] == bl.nd[i];
-    if (same)
-        k3t_tile<1>(tmap, bl.q_row0[i], bl.nq[i], bl.d_row0[i], bl.nd[i], Hw_pad, bl.cnt[i], bl.ld[i], nullptr, 0, tile_x, tile_y, stage, full_bar);
-    else if (bl.cnt_t[i])
-        k3t_tile<2>(tmap, bl.q_row0[i], bl.nq[i], bl.d_row0[i], bl.nd[i], Hw_pad, bl.cnt[i], bl.ld[i], bl.cnt_t[i], bl.ld_t[i], tile_x, tile_y, stage, full_bar);
-    else
-        k3t_tile<0>(tmap, bl.q_row0[i], bl.nq[i], bl.d_row0[i], bl.nd[i], Hw_pad, bl.cnt[i], bl.ld[i], nullptr, 0, tile_x, tile_y, stage, full_bar);
-}
-
 int k3t_padded_words(int H) { return ((k3h_padded_hashes(H) / 2) + K3_JB - 1) / K3_JB * K3_JB; }
 int64_t k3t_padded_rows(int64_t n) { return (n + 3) & ~(int64_t)3; }
 size_t k3t_transposed_elems(int64_t n, int H) { return (size_t)k3t_padded_words(H) * (size_t)k3t_padded_rows(n); }
@@ -575,31 +545,6 @@ int launch_collision_counts_tma(const void* map, int64_t q_row0, int64_t nq, int
         cudaFuncSetAttribute(k3t_collision_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k3t_collision_kernel<0><<<grid, K3_THREADS, smem, stream>>>(tm, (int)q_row0, nq, (int)d_row0, ndb, Hw_pad, d_cnt, ld_out, nullptr, 0);
     }
-    return 1;
-}
-
-// n blocks in one launch; every row offset must be a multiple of 4 (TMA box alignment). Arrays of length n.
-int launch_collision_blocks_tma(const void* map, int n, const int64_t* q_row0, const int64_t* nq, const int64_t* d_row0,
-                                const int64_t* nd, uint16_t* const* cnt, const int64_t* ld, uint16_t* const* cnt_t,
-                                const int64_t* ld_t, int H, cudaStream_t stream) {
-    if (n <= 0) return 0;
-    if (n > K3T_MAX_BLOCKS) return -1;
-    K3TBlocks bl;
-    bl.n = 0;
-    int tiles = 0;
-    for (int i = 0; i < n; ++i) {
-        if (nq[i] <= 0 || nd[i] <= 0) continue;
-        const int k = bl.n++;
-        bl.q_row0[k] = (int)q_row0[i]; bl.nq[k] = (int)nq[i]; bl.d_row0[k] = (int)d_row0[i]; bl.nd[k] = (int)nd[i];
-        bl.cnt[k] = cnt[i]; bl.ld[k] = ld[i]; bl.cnt_t[k] = cnt_t ? cnt_t[i] : nullptr; bl.ld_t[k] = ld_t ? ld_t[i] : 0;
-        bl.tile_begin[k] = tiles;
-        tiles += (int)(((nq[i] + K3_TILE - 1) / K3_TILE) * ((nd[i] + K3_TILE - 1) / K3_TILE));
-    }
-    if (bl.n == 0) return 0;
-    bl.tile_begin[bl.n] = tiles;
-    const size_t smem = (size_t)2 * K3T_STAGE_WORDS * 4 + 1024;
-    cudaFuncSetAttribute(k3t_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k3t_blocks_kernel<<<(unsigned)tiles, K3_THREADS, smem, stream>>>(*reinterpret_cast<const CUtensorMap*>(map), bl, k3t_padded_words(H));
     return 1;
 }
 
